@@ -1,0 +1,138 @@
+"""ctypes binding of libfdk (include/fdk.h).  There is no fallback: if the CUDA library is
+missing or fails to load, every entry point raises."""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_fdk.so")
+
+HEX8, TET4, TET10, QUAD4 = 0, 1, 2, 3
+ELEM_IDS = {"hex8": HEX8, "tet4": TET4, "tet10": TET10, "quad4": QUAD4}
+MATRIX, VECTOR, ALL = 1, 2, 3
+COMPUTE_FLAGS = {"matrix": MATRIX, "vector": VECTOR, "all": ALL}
+
+EXPORTS = [
+    "fdk_last_error_string", "fdk_version", "fdk_element_info", "fdk_element_table",
+    "fdk_sym_block_keys", "fdk_sym_block_csr", "fdk_sym_expand_csr",
+    "fdk_assemble_elastic_iso", "fdk_assemble_elastic_general", "fdk_assemble_heat",
+    "fdk_gp_strain_stress", "fdk_gp_temperature", "fdk_j2_update",
+    "fdk_gather_f64", "fdk_scatter_add_f64",
+]  # fmt: skip
+
+
+class FdkError(RuntimeError):
+    pass
+
+
+class PlanStruct(C.Structure):
+    """Mirror of ``struct fdk_plan`` (include/fdk.h)."""
+
+    _fields_ = [
+        ("elem_type", C.c_int32),
+        ("n_nodes", C.c_int32),
+        ("n_elems", C.c_int64),
+        ("n_clusters", C.c_int32),
+        ("nvar", C.c_int32),
+        ("blk_nnz", C.c_int64),
+        ("cap_te", C.c_int32),
+        ("cap_tn", C.c_int32),
+        ("cap_inc", C.c_int32),
+        ("cap_owned", C.c_int32),
+        ("cap_slots", C.c_int32),
+        ("cap_gent", C.c_int32),
+        ("cl_node_ptr", C.c_void_p),
+        ("cl_node", C.c_void_p),
+        ("cl_bptr", C.c_void_p),
+        ("cl_slot_ptr", C.c_void_p),
+        ("cl_inc_ptr", C.c_void_p),
+        ("inc_desc", C.c_void_p),
+        ("cl_te_ptr", C.c_void_p),
+        ("cl_te_elem", C.c_void_p),
+        ("cl_te_own", C.c_void_p),
+        ("cl_lconn", C.c_void_p),
+        ("cl_tn_ptr", C.c_void_p),
+        ("cl_tn_node", C.c_void_p),
+        ("cl_g_base", C.c_void_p),
+        ("g_off", C.c_void_p),
+        ("g_ent", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load libfdk; raises FdkError when the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FdkError(
+            f"{LIB_PATH} not found: build the CUDA extension first "
+            "(python -c 'import __graft_entry__ as g; g.build()' or python -m fedoo_b200.build)"
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    lib.fdk_last_error_string.restype = C.c_char_p
+    lib.fdk_last_error_string.argtypes = []
+    lib.fdk_version.restype = i32
+    lib.fdk_element_info.argtypes = [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    lib.fdk_element_table.argtypes = [i32, vp, vp, vp]
+    lib.fdk_sym_block_keys.argtypes = [i32, i64, i32, vp, vp, C.POINTER(i64), vp]
+    lib.fdk_sym_block_csr.argtypes = [i32, i64, vp, vp, vp, vp]
+    lib.fdk_sym_expand_csr.argtypes = [i32, i32, i32, i64, vp, vp, i32, vp, vp, vp]
+    pp = C.POINTER(PlanStruct)
+    lib.fdk_assemble_elastic_iso.argtypes = [pp, i32, vp, dbl, dbl, vp, vp, vp, vp, vp]
+    lib.fdk_assemble_elastic_general.argtypes = [pp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.fdk_assemble_heat.argtypes = [pp, i32, vp, vp, dbl, vp, vp, vp, vp, vp]
+    lib.fdk_gp_strain_stress.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.fdk_gp_temperature.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, vp]
+    lib.fdk_j2_update.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp]
+    lib.fdk_gather_f64.argtypes = [i64, vp, vp, vp, vp]
+    lib.fdk_scatter_add_f64.argtypes = [i64, vp, vp, vp, vp]
+    for name in EXPORTS:
+        if name not in ("fdk_last_error_string",):
+            getattr(lib, name).restype = i32
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().fdk_last_error_string().decode()
+        raise FdkError(f"{what} failed with code {rc}: {msg}")
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor / numpy array, NULL for None."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        assert t.is_contiguous(), "fdk buffers must be contiguous"
+        return C.c_void_p(t.data_ptr())
+    assert t.flags["C_CONTIGUOUS"] or t.flags["F_CONTIGUOUS"]
+    return C.c_void_p(t.ctypes.data)
+
+
+def current_stream():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def element_table(elem):
+    """(w, N, dN) of an element type as NumPy arrays, straight from the library."""
+    import numpy as np
+
+    lib = load()
+    eid = ELEM_IDS[elem] if isinstance(elem, str) else elem
+    nne, ngp, dim = C.c_int(), C.c_int(), C.c_int()
+    check(lib.fdk_element_info(eid, C.byref(nne), C.byref(ngp), C.byref(dim)), "fdk_element_info")
+    w = np.zeros(ngp.value)
+    N = np.zeros((ngp.value, nne.value))
+    dN = np.zeros((ngp.value, dim.value, nne.value))
+    check(lib.fdk_element_table(eid, ptr(w), ptr(N), ptr(dN)), "fdk_element_table")
+    return w, N, dN

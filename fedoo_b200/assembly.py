@@ -1,0 +1,394 @@
+"""``Assembly``: drop-in mirror of fedoo's global-operator assembly
+(fedoo/core/assembly.py:33-1663) whose ``assemble_global_mat`` runs the sm_100a cluster
+kernels of libfdk instead of NumPy/SciPy.
+
+Boundary kept:
+  * ``Assembly.create(weakform, mesh="", elm_type="", name="", **kargs)`` (assembly.py:1566)
+  * ``assemble_global_mat(compute)`` sets ``global_matrix`` / ``global_vector`` (:143-470);
+    ``compute`` in {"all", "matrix", "vector", "none"}; the vector is the scalar 0 when the weak
+    form has no vector term (:462-463)
+  * ``get_global_matrix() / get_global_vector()`` (fedoo/core/base.py:138-148)
+  * ``initialize / set_start / update / to_start / reset`` and the ``sv`` / ``sv_start`` dicts
+    (:672-753), ``get_gp_results``-style state (``sv["Strain"]``, ``sv["Stress"]``,
+    ``sv["DispGradient"]``, ``sv["TempGradient"]``, ``sv["Temp"]``)
+The matrix is returned as a device-resident ``DeviceCSR`` (materialised to scipy on demand),
+the vector as a NumPy array (device copy in ``global_vector_device``).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, symbolic
+from .constitutivelaw import ElasticAnisotropic, ElasticIsotrop, ElastoPlasticity
+from .core import DeviceCSR, GaussPointTensor, Mesh, _Named, as_device_f64, device
+from .weakform import WeakFormBase
+
+_DEFAULT_NGP = {"hex8": 8, "tet4": 4, "tet10": 15, "quad4": 4}  # fedoo/lib_elements/element_list.py:50-84
+
+
+class Assembly(_Named):
+    _dict = {}
+    # class-level symbolic cache keyed by (mesh object, element type), like the reference's
+    # _saved_elementary_operators (fedoo/core/assembly.py:56,928)
+    _saved_plans = {}
+
+    @staticmethod
+    def create(weakform, mesh="", elm_type="", name="", **kargs):
+        return Assembly(weakform, mesh, elm_type, name, **kargs)
+
+    @staticmethod
+    def delete_memory():
+        """fedoo/core/assembly.py:755-774."""
+        Assembly._saved_plans = {}
+
+    def __init__(self, weakform, mesh="", elm_type="", name="", **kargs):
+        if isinstance(weakform, str):
+            weakform = WeakFormBase.get_all()[weakform]
+        if isinstance(mesh, str):
+            mesh = Mesh.get_all()[mesh]
+        if not type(mesh) == Mesh:
+            raise TypeError("mesh should refers to a fedoo.Mesh object")
+        self.weakform = weakform
+        self.space = weakform.space
+        self.current = self
+        self.meshChange = kargs.pop("MeshChange", False)
+        self.mesh = mesh
+        if elm_type == "":
+            elm_type = mesh.elm_type
+        self.elm_type = elm_type.lower()
+        if self.elm_type not in _DEFAULT_NGP:
+            raise NotImplementedError(
+                f"element type '{self.elm_type}' is not on the accelerated path (hex8, tet4, tet10, quad4)"
+            )
+        self.n_elm_gp = kargs.pop("n_elm_gp", None) or _DEFAULT_NGP[self.elm_type]
+        if self.n_elm_gp != _DEFAULT_NGP[self.elm_type]:
+            raise NotImplementedError(f"{self.elm_type} is integrated with {_DEFAULT_NGP[self.elm_type]} Gauss points")
+        if mesh.elements.shape[1] != {"hex8": 8, "tet4": 4, "tet10": 10, "quad4": 4}[self.elm_type]:
+            raise ValueError("mesh connectivity does not match the element type")
+        if mesh.ndim != (2 if self.elm_type == "quad4" else 3) or self.space.ndim != mesh.ndim:
+            raise ValueError("mesh / modeling space dimension mismatch")
+        self.assume_sym = weakform.assembly_options.get("assume_sym", False)
+        self.sv, self.sv_start, self.sv_type, self.sv_component = {}, {}, {}, {}
+        self._nlgeom = None
+        self._pb = None
+        self.global_matrix = None
+        self.global_vector = None
+        self.global_vector_device = None
+        self._saved_bloc_structure = None
+        self._U_dev = None
+        self._T_start_dev = None
+        self._register(name)
+
+    # ------------------------------------------------------------------ sizes
+    @property
+    def n_gauss_points(self):
+        return self.mesh.n_elements * self.n_elm_gp
+
+    @property
+    def nvar(self):
+        return 1 if self.weakform.operator == "heat" else self.space.ndim
+
+    # ------------------------------------------------------------------ symbolic (one-time)
+    def _symbolic(self):
+        """Pattern, tiled CSR and cluster plan; cached per (mesh, element type) and per nvar."""
+        key = (id(self.mesh), self.elm_type)
+        if self.meshChange and self._saved_bloc_structure is not None:
+            self._saved_bloc_structure["coords"] = None  # node positions changed: re-upload only
+        entry = Assembly._saved_plans.get(key)
+        if entry is None:
+            coords, conn = self.mesh.device_arrays()
+            pattern = symbolic.build_pattern(conn, self.mesh.n_nodes)
+            plan = symbolic.build_plan(self.elm_type, coords, conn, pattern)
+            entry = {"pattern": pattern, "plan": plan, "csr": {}}
+            Assembly._saved_plans[key] = entry
+        nvar = self.nvar
+        n_glob = 0 if self._pb is None else getattr(self._pb, "n_global_dof", 0)
+        if (nvar, n_glob) not in entry["csr"]:
+            entry["csr"][(nvar, n_glob)] = symbolic.expand_csr(entry["pattern"], nvar, n_glob)
+        self._saved_bloc_structure = entry
+        return entry, entry["csr"][(nvar, n_glob)], n_glob
+
+    def _coords(self):
+        if self.meshChange:
+            self.mesh.invalidate_device()
+        return self.mesh.device_arrays()[0]
+
+    # ------------------------------------------------------------------ the hot path
+    def assemble_global_mat(self, compute="all"):
+        """fedoo/core/assembly.py:143-470."""
+        if compute == "none":
+            return
+        if compute not in ("all", "matrix", "vector"):
+            raise ValueError("compute must be 'all', 'matrix', 'vector' or 'none'")
+        lib = _lib.load()
+        entry, (indptr, indices), n_glob = self._symbolic()
+        plan, pattern = entry["plan"], entry["pattern"]
+        nvar = self.nvar
+        n_nodes = self.mesh.n_nodes
+        dev = device()
+        coords = self._coords()
+        want_mat = compute != "vector"
+        want_vec = compute != "matrix"
+        stream = _lib.current_stream()
+
+        if self.weakform.operator == "elastic":
+            law = self.weakform.constitutivelaw
+            dimension = self.space.get_dimension()
+            stress = self.sv.get("Stress", 0)
+            has_vec = want_vec and not (np.isscalar(stress) and stress == 0)
+            flags = (_lib.MATRIX if want_mat else 0) | (_lib.VECTOR if has_vec else 0)
+            K = torch.empty(nvar * nvar * pattern.blk_nnz, dtype=torch.float64, device=dev) if want_mat else None
+            D = torch.zeros(nvar * n_nodes + n_glob, dtype=torch.float64, device=dev) if has_vec else None
+            U_dev = stress_dev = None
+            if has_vec:
+                if isinstance(stress, _FusedElasticStress):
+                    U_dev = stress.U  # sigma = H eps(U) recomputed in the kernel, never materialised
+                else:
+                    stress_dev = stress.device_tensor
+            if flags:
+                tangent_dev = law.tangent_device(self) if hasattr(law, "tangent_device") else None
+                if isinstance(law, ElasticIsotrop) and tangent_dev is None:
+                    lam, mu = law.lame(dimension)
+                    rc = lib.fdk_assemble_elastic_iso(
+                        C.byref(plan.struct(nvar)), flags, _lib.ptr(coords), lam, mu, _lib.ptr(U_dev),
+                        _lib.ptr(stress_dev), _lib.ptr(K), _lib.ptr(D), stream,
+                    )  # fmt: skip
+                    _lib.check(rc, "fdk_assemble_elastic_iso")
+                else:
+                    H = self.sv["TangentMatrix"]
+                    C_h = None if tangent_dev is not None else np.ascontiguousarray(H, dtype=np.float64)
+                    rc = lib.fdk_assemble_elastic_general(
+                        C.byref(plan.struct(nvar)), flags, _lib.ptr(coords), _lib.ptr(C_h), _lib.ptr(tangent_dev),
+                        _lib.ptr(U_dev), _lib.ptr(stress_dev), _lib.ptr(K), _lib.ptr(D), stream,
+                    )  # fmt: skip
+                    _lib.check(rc, "fdk_assemble_elastic_general")
+        elif self.weakform.operator == "heat":
+            law = self.weakform.constitutivelaw
+            cond = np.ascontiguousarray(np.asarray(law.thermal_conductivity, dtype=np.float64).reshape(3, 3))
+            dtime = getattr(self._pb, "dtime", 0) if self._pb is not None else 0
+            rcdt = float(law.density * law.specific_heat / dtime) if (self.weakform.transient and dtime != 0) else 0.0
+            T_dev = self._U_dev
+            has_vec = want_vec and T_dev is not None
+            flags = (_lib.MATRIX if want_mat else 0) | (_lib.VECTOR if has_vec else 0)
+            K = torch.empty(pattern.blk_nnz, dtype=torch.float64, device=dev) if want_mat else None
+            D = torch.zeros(n_nodes + n_glob, dtype=torch.float64, device=dev) if has_vec else None
+            if flags:
+                rc = lib.fdk_assemble_heat(
+                    C.byref(plan.struct(1)), flags, _lib.ptr(coords), _lib.ptr(cond), rcdt, _lib.ptr(T_dev),
+                    _lib.ptr(self._T_start_dev if rcdt != 0.0 else None), _lib.ptr(K), _lib.ptr(D), stream,
+                )  # fmt: skip
+                _lib.check(rc, "fdk_assemble_heat")
+        else:
+            raise NotImplementedError(f"weak form operator '{self.weakform.operator}'")
+
+        if want_mat:
+            n_rows = nvar * n_nodes + n_glob
+            self.global_matrix = DeviceCSR(indptr, indices, K, (n_rows, n_rows))
+        if want_vec:
+            if has_vec:
+                self.global_vector_device = D
+                self.global_vector = D.cpu().numpy()
+            else:
+                self.global_vector_device = None
+                self.global_vector = 0
+
+    def get_global_matrix(self):
+        if self.global_matrix is None:
+            self.assemble_global_mat()
+        return self.global_matrix
+
+    def get_global_vector(self):
+        if self.global_vector is None:
+            self.assemble_global_mat()
+        return self.global_vector
+
+    def delete_global_mat(self):
+        self.global_matrix = self.global_vector = self.global_vector_device = None
+
+    # ------------------------------------------------------------------ lifecycle (assembly.py:672-753)
+    def initialize(self, pb):
+        self._pb = pb
+        self.weakform.initialize(self, pb)
+        if self.weakform.constitutivelaw is not None:
+            self.weakform.constitutivelaw.initialize(self, pb)
+        self.sv_start = dict(self.sv)
+
+    def set_start(self, pb):
+        self.weakform.set_start(self, pb)
+        if self.weakform.constitutivelaw is not None:
+            self.weakform.constitutivelaw.set_start(self, pb)
+        self.sv_start = dict(self.sv)
+        self.assemble_global_mat("all")
+
+    def update(self, pb, compute="all"):
+        self.weakform.update(self, pb)
+        if self.weakform.constitutivelaw is not None:
+            self.weakform.constitutivelaw.update(self, pb)
+        self.weakform.update_2(self, pb)
+        self.assemble_global_mat(compute)
+
+    def to_start(self, pb):
+        self.weakform.to_start(self, pb)
+        if self.weakform.constitutivelaw is not None:
+            self.weakform.constitutivelaw.to_start(self, pb)
+        self.sv = dict(self.sv_start)
+        self.assemble_global_mat("all")
+
+    def reset(self):
+        self.weakform.reset()
+        if self.weakform.constitutivelaw is not None:
+            self.weakform.constitutivelaw.reset()
+        self.delete_global_mat()
+        self.sv, self.sv_start, self.sv_type = {}, {}, {}
+
+    # ------------------------------------------------------------------ state update helpers
+    def _strain_update(self, U):
+        """StressEquilibrium.update (fedoo/weakform/stress_equilibrium.py:191-217): record the dof
+        vector; sv['Strain'] / sv['DispGradient'] are produced lazily by ``fdk_gp_strain_stress``."""
+        self._U_dev = as_device_f64(U)
+        self.sv["Strain"] = _LazyStrain(self, self._U_dev)
+        self.sv["DispGradient"] = _LazyGrad(self, self._U_dev)
+
+    def _elastic_stress_update(self, law):
+        """ElasticAnisotropic.update (fedoo/constitutivelaw/elastic_anisotropic.py:36-56)."""
+        strain = self.sv.get("Strain", 0)
+        if np.isscalar(strain) and strain == 0:
+            self.sv["Stress"] = 0
+            return
+        self.sv["Stress"] = _FusedElasticStress(self, law, strain.U)
+
+    def _gp_strain_stress(self, U_dev, want_grad=False, want_strain=False, want_stress=False, law=None):
+        lib = _lib.load()
+        coords, conn = self._coords(), self.mesh.device_arrays()[1]
+        N = self.n_gauss_points
+        dev = device()
+        grad = torch.empty((9, N), dtype=torch.float64, device=dev) if want_grad else None
+        strain = torch.empty((N, 6), dtype=torch.float64, device=dev) if want_strain else None
+        stress = torch.empty((N, 6), dtype=torch.float64, device=dev) if want_stress else None
+        C_h = tangent_dev = None
+        if want_stress:
+            tangent_dev = law.tangent_device(self)
+            if tangent_dev is None:
+                C_h = np.ascontiguousarray(self.sv["TangentMatrix"], dtype=np.float64)
+        _lib.check(
+            lib.fdk_gp_strain_stress(
+                _lib.ELEM_IDS[self.elm_type], self.mesh.n_nodes, self.mesh.n_elements, _lib.ptr(conn), _lib.ptr(coords),
+                _lib.ptr(U_dev), _lib.ptr(C_h), _lib.ptr(tangent_dev), _lib.ptr(grad), _lib.ptr(strain),
+                _lib.ptr(stress), _lib.current_stream(),
+            ),
+            "fdk_gp_strain_stress",
+        )  # fmt: skip
+        return grad, strain, stress
+
+    def get_grad_disp(self, U, type_output="GaussPoint"):
+        """fedoo/core/assembly.py:1285-1336: 3x3 list of (N,) arrays, gp-major."""
+        if type_output != "GaussPoint":
+            raise NotImplementedError("only Gauss-point output is on the accelerated path")
+        grad, _, _ = self._gp_strain_stress(as_device_f64(U), want_grad=True)
+        g = grad.cpu().numpy()
+        ndim = self.space.ndim
+        return [[g[a * 3 + b] if (a < ndim and b < ndim) else 0 for b in range(3)] for a in range(3)]
+
+    def _thermal_state_update(self, pb, initialize=False):
+        """SteadyHeatEquation.update / TemperatureTimeDerivative.update
+        (fedoo/weakform/heat_equation.py:54-70,140-152)."""
+        T = pb.get_dof_solution()
+        if np.isscalar(T):
+            self._U_dev = None
+            self.sv["TempGradient"] = [0, 0, 0]
+            self.sv["Temp"] = 0
+            if initialize:
+                self._T_start_dev = None
+            return
+        self._U_dev = as_device_f64(T)
+        if initialize:
+            self._T_start_dev = self._U_dev.clone()
+        self.sv["Temp"] = _LazyTemp(self, self._U_dev, 0)
+        self.sv["TempGradient"] = _LazyTemp(self, self._U_dev, 1)
+
+    def _thermal_set_start(self, pb):
+        """TemperatureTimeDerivative.set_start (fedoo/weakform/heat_equation.py:164-165)."""
+        self._T_start_dev = None if self._U_dev is None else self._U_dev.clone()
+
+    def _gp_temperature(self, T_dev):
+        lib = _lib.load()
+        coords, conn = self._coords(), self.mesh.device_arrays()[1]
+        N = self.n_gauss_points
+        dev = device()
+        temp = torch.empty(N, dtype=torch.float64, device=dev)
+        grad = torch.empty((3, N), dtype=torch.float64, device=dev)
+        _lib.check(
+            lib.fdk_gp_temperature(
+                _lib.ELEM_IDS[self.elm_type], self.mesh.n_nodes, self.mesh.n_elements, _lib.ptr(conn), _lib.ptr(coords),
+                _lib.ptr(T_dev), _lib.ptr(temp), _lib.ptr(grad), _lib.current_stream(),
+            ),
+            "fdk_gp_temperature",
+        )  # fmt: skip
+        return temp, grad
+
+
+class _LazyStrain(GaussPointTensor):
+    """sv['Strain'] of the current dof vector, computed on first access."""
+
+    def __init__(self, assembly, U):
+        self._asm, self.U, self.kind, self._host, self._dev = assembly, U, "strain", None, None
+
+    @property
+    def device_tensor(self):
+        if self._dev is None:
+            self._dev = self._asm._gp_strain_stress(self.U, want_strain=True)[1]
+        return self._dev
+
+
+class _FusedElasticStress(GaussPointTensor):
+    """sv['Stress'] = H eps(U) of a linear elastic law.  The residual kernel recomputes it on the
+    fly from U (no (6,N) array is written); it is materialised only if somebody reads it."""
+
+    def __init__(self, assembly, law, U):
+        self._asm, self._law, self.U, self.kind, self._host, self._dev = assembly, law, U, "stress", None, None
+
+    @property
+    def device_tensor(self):
+        if self._dev is None:
+            self._dev = self._asm._gp_strain_stress(self.U, want_stress=True, law=self._law)[2]
+        return self._dev
+
+
+class _LazyGrad:
+    def __init__(self, assembly, U):
+        self._asm, self.U, self._host = assembly, U, None
+
+    def _get(self):
+        if self._host is None:
+            self._host = self._asm._gp_strain_stress(self.U, want_grad=True)[0].cpu().numpy()
+        return self._host
+
+    def __getitem__(self, a):
+        g = self._get()
+        return [g[a * 3 + b] for b in range(3)]
+
+
+class _LazyTemp:
+    """sv['Temp'] (which=0, (N,)) or sv['TempGradient'] (which=1, list of 3 (N,))."""
+
+    def __init__(self, assembly, T, which):
+        self._asm, self.T, self.which, self._host = assembly, T, which, None
+
+    def _get(self):
+        if self._host is None:
+            temp, grad = self._asm._gp_temperature(self.T)
+            self._host = (temp if self.which == 0 else grad).cpu().numpy()
+        return self._host
+
+    def __array__(self, dtype=None, copy=None):
+        return self._get()
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    def __len__(self):
+        return len(self._get())

@@ -1,0 +1,248 @@
+"""Host-side mirror of the fedoo objects the assembly path touches: name registries,
+ModelingSpace, Mesh, and the device-resident containers returned at the boundary
+(``DeviceCSR`` for ``get_global_matrix()``, ``GaussPointTensor`` for ``sv["Stress"]`` /
+``sv["Strain"]``).
+
+Mirrors fedoo/core/base.py:79-148,210-260 (registries), fedoo/core/modelingspace.py:7-120
+(active space, variables), fedoo/core/mesh.py:70-200 (Mesh) and
+fedoo/util/voigt_tensors.py:150-321 (tensor lists) -- API only, none of their code.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise _lib.FdkError("fedoo_b200 needs a CUDA device: there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class _Named:
+    """Objects registered by name in a class-level dict (fedoo/core/base.py:79,109,213,276)."""
+
+    _dict: dict
+
+    def _register(self, name):
+        self.name = name
+        if name != "":
+            type(self)._registry()[name] = self
+
+    @classmethod
+    def _registry(cls):
+        for k in cls.__mro__:
+            if "_dict" in k.__dict__:
+                return k._dict
+        raise TypeError("no registry")
+
+    @classmethod
+    def get_all(cls):
+        return cls._registry()
+
+    def __class_getitem__(cls, item):
+        return cls._registry()[item]
+
+
+class ModelingSpace(_Named):
+    """fedoo/core/modelingspace.py:7-120: '3D', '2Dplane' (plane strain) or '2Dstress'."""
+
+    _dict = {}
+    _active = None
+
+    def __init__(self, dimension, name="Main"):
+        assert isinstance(dimension, str), "The dimension value must be a string"
+        assert dimension in ("3D", "2Dplane", "2Dstress"), "Dimension must be '3D', '2Dplane' or '2Dstress'"
+        self._dimension = dimension
+        self.ndim = 3 if dimension == "3D" else 2
+        self._variable = {}
+        self._register(name)
+        ModelingSpace._active = self
+
+    def get_dimension(self):
+        return self._dimension
+
+    @staticmethod
+    def get_active():
+        assert ModelingSpace._active is not None, "Define a ModelingSpace before constructing any model object"
+        return ModelingSpace._active
+
+    def new_variable(self, name):
+        if name not in self._variable:
+            self._variable[name] = len(self._variable)
+
+    def variable_rank(self, name):
+        return self._variable[name]
+
+    @property
+    def nvar(self):
+        return len(self._variable)
+
+    def list_variables(self):
+        return list(self._variable)
+
+
+class BoundingBox:
+    def __init__(self, nodes):
+        self.mins, self.maxs = nodes.min(axis=0), nodes.max(axis=0)
+        self.xmin, self.ymin = self.mins[0], self.mins[1]
+        self.xmax, self.ymax = self.maxs[0], self.maxs[1]
+        if nodes.shape[1] > 2:
+            self.zmin, self.zmax = self.mins[2], self.maxs[2]
+
+    def __iter__(self):
+        return iter((self.mins, self.maxs))
+
+
+class Mesh(_Named):
+    """fedoo/core/mesh.py:70: nodes (n, dim) float64, elements (n_el, nne) ints, elm_type."""
+
+    _dict = {}
+    SUPPORTED = ("hex8", "tet4", "tet10", "quad4")
+
+    def __init__(self, nodes, elements=None, elm_type=None, node_sets=None, element_sets=None, ndim=None, name=""):
+        self.nodes = np.ascontiguousarray(nodes, dtype=float)
+        self.elements = np.ascontiguousarray(elements)
+        self.elm_type = elm_type.lower() if elm_type else elm_type
+        self.node_sets = {} if node_sets is None else node_sets
+        self.element_sets = {} if element_sets is None else element_sets
+        self._dev = None
+        self._register(name)
+
+    @property
+    def n_nodes(self):
+        return self.nodes.shape[0]
+
+    @property
+    def n_elements(self):
+        return self.elements.shape[0]
+
+    @property
+    def n_elm_nodes(self):
+        return self.elements.shape[1]
+
+    @property
+    def ndim(self):
+        return self.nodes.shape[1]
+
+    @property
+    def bounding_box(self):
+        return BoundingBox(self.nodes)
+
+    def find_nodes(self, selection_criterion, value=0, tol=1e-6):
+        """Subset of fedoo/core/mesh.py find_nodes: 'X', 'Y', 'Z' planes."""
+        axis = {"X": 0, "Y": 1, "Z": 2}[selection_criterion.upper()]
+        return np.where(np.abs(self.nodes[:, axis] - value) < tol)[0]
+
+    def device_arrays(self):
+        """(coords float64 (n, dim), conn int32 (n_el, nne)) on the current CUDA device."""
+        if self._dev is None:
+            dev = device()
+            coords = torch.from_numpy(self.nodes).to(dev)
+            conn = torch.from_numpy(self.elements.astype(np.int32)).to(dev)
+            self._dev = (coords, conn)
+        return self._dev
+
+    def invalidate_device(self):
+        self._dev = None
+
+
+class DeviceCSR:
+    """Device-resident CSR matrix returned by ``Assembly.get_global_matrix()``.
+
+    The reference returns a host ``scipy.sparse.csr_matrix`` (fedoo/core/assembly.py:452-460).
+    At 8 M hex8 elements K is 15.6 GB of values + 7.8 GB of indices, so the matrix stays in HBM
+    and the scipy object is materialised on first host access (``tocsr()`` or any scipy-like
+    attribute); ``indptr`` / ``indices`` / ``data`` are the device tensors."""
+
+    def __init__(self, indptr, indices, data, shape):
+        self.indptr, self.indices, self.data = indptr, indices, data
+        self.shape = tuple(shape)
+        self._host = None
+
+    @property
+    def nnz(self):
+        return int(self.data.numel())
+
+    def tocsr(self):
+        if self._host is None:
+            from scipy import sparse
+
+            self._host = sparse.csr_matrix(
+                (self.data.cpu().numpy(), self.indices.cpu().numpy(), self.indptr.cpu().numpy()), shape=self.shape
+            )
+        return self._host
+
+    to_scipy = tocsr
+
+    def resize(self, *shape):
+        """In-place resize to account for global dofs (fedoo/core/problem.py:282-284): only
+        trailing empty rows/columns can be added."""
+        if len(shape) == 1:
+            shape = shape[0]
+        n = int(shape[0])
+        assert n >= self.shape[0] and shape[0] == shape[1]
+        extra = n - self.shape[0]
+        if extra:
+            self.indptr = torch.cat([self.indptr, self.indptr[-1:].expand(extra)])
+            self.shape = (n, n)
+            self._host = None
+
+    def __matmul__(self, x):
+        return self.tocsr() @ x
+
+    def __rmatmul__(self, x):
+        return x @ self.tocsr()
+
+    def diagonal(self):
+        return self.tocsr().diagonal()
+
+    def __getattr__(self, item):  # any other scipy attribute: materialise
+        if item.startswith("_"):
+            raise AttributeError(item)
+        return getattr(self.tocsr(), item)
+
+
+class GaussPointTensor:
+    """Voigt tensor field at the Gauss points kept on the device: the (6, N) Fortran-ordered
+    array of the reference's StressTensorList / StrainTensorList
+    (fedoo/util/voigt_tensors.py:150-321) stored as a contiguous (N, 6) CUDA tensor."""
+
+    def __init__(self, tensor, kind="stress"):
+        self.device_tensor = tensor  # (N, 6)
+        self.kind = kind
+        self._host = None
+
+    def asarray(self):
+        if self._host is None:
+            self._host = self.device_tensor.cpu().numpy().T  # (6, N), F-contiguous view
+        return self._host
+
+    @property
+    def array(self):
+        return self.asarray()
+
+    def __getitem__(self, i):
+        return self.asarray()[i]
+
+    def __len__(self):
+        return 6
+
+    def von_mises(self):
+        """fedoo/util/voigt_tensors.py:270-283 (stress convention)."""
+        s = self.asarray()
+        return np.sqrt(
+            0.5 * ((s[0] - s[1]) ** 2 + (s[1] - s[2]) ** 2 + (s[0] - s[2]) ** 2 + 6 * (s[3] ** 2 + s[4] ** 2 + s[5] ** 2))
+        )
+
+
+def as_device_f64(x, dev=None):
+    """numpy / torch (host or device) -> contiguous float64 CUDA tensor."""
+    dev = dev or device()
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=torch.float64, non_blocking=True).contiguous()
+    a = np.ascontiguousarray(x, dtype=np.float64)
+    return torch.from_numpy(a).to(dev, non_blocking=True)

@@ -1,0 +1,218 @@
+// fdk_api.cu -- the C ABI of libfdk (see include/fdk.h).  Single translation unit: the kernels
+// live in the .cuh files included below.
+#include "fdk_assemble.cuh"
+#include "fdk_gp.cuh"
+#include "fdk_symbolic.cuh"
+
+using namespace fdk;
+
+namespace {
+
+int check_plan(const fdk_plan* p) {
+  FDK_REQUIRE(p != nullptr, FDK_EINVAL, "plan is NULL");
+  int nne, ngp, dim;
+  if (int rc = elem_dims(p->elem_type, &nne, &ngp, &dim)) return rc;
+  FDK_REQUIRE(p->n_clusters >= 0 && p->n_nodes >= 0 && p->n_elems >= 0, FDK_EINVAL, "negative size in plan");
+  if (p->n_clusters > 0)
+    FDK_REQUIRE(p->cl_node_ptr && p->cl_node && p->cl_bptr && p->cl_slot_ptr && p->cl_inc_ptr && p->inc_desc &&
+                    p->cl_te_ptr && p->cl_te_elem && p->cl_lconn && p->cl_tn_ptr && p->cl_tn_node &&
+                    p->cl_g_base && p->g_off && p->g_ent,
+                FDK_EINVAL, "plan has NULL arrays");
+  return 0;
+}
+
+int check_io(int compute, const double* coords, const double* K, const double* D) {
+  FDK_REQUIRE(compute >= 1 && compute <= 3, FDK_EINVAL, "compute must be FDK_MATRIX, FDK_VECTOR or FDK_ALL");
+  FDK_REQUIRE(coords != nullptr, FDK_EINVAL, "coords is NULL");
+  FDK_REQUIRE(!(compute & FDK_MATRIX) || K != nullptr, FDK_EINVAL, "K_values is NULL but the matrix is requested");
+  FDK_REQUIRE(!(compute & FDK_VECTOR) || D != nullptr, FDK_EINVAL, "D is NULL but the vector is requested");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fdk_last_error_string(void) { return g_err; }
+int fdk_version(void) { return 100; }
+
+int fdk_element_info(int elem_type, int* nne, int* ngp, int* dim) { return elem_dims(elem_type, nne, ngp, dim); }
+
+int fdk_element_table(int elem_type, double* w, double* N, double* dN) {
+  int nne, ngp, dim;
+  if (int rc = elem_dims(elem_type, &nne, &ngp, &dim)) return rc;
+  const ElemTable& t = host_table(elem_type);
+  for (int g = 0; g < ngp; ++g) w[g] = t.w[g];
+  for (int i = 0; i < ngp * nne; ++i) N[i] = t.N[i];
+  for (int i = 0; i < ngp * dim * nne; ++i) dN[i] = t.dN[i];
+  return 0;
+}
+
+int fdk_sym_block_keys(int n_nodes, int64_t n_elems, int nne, const int32_t* conn, uint64_t* keys_out,
+                       int64_t* blk_nnz_h, fdk_stream_t stream) {
+  FDK_REQUIRE(n_nodes >= 0 && n_elems >= 0 && nne > 0 && nne <= MAX_NNE, FDK_EINVAL, "bad sizes");
+  FDK_REQUIRE(blk_nnz_h != nullptr, FDK_EINVAL, "blk_nnz_h is NULL");
+  FDK_REQUIRE(n_elems == 0 || (conn && keys_out), FDK_EINVAL, "NULL buffer");
+  return sym_block_keys(n_nodes, n_elems, nne, conn, keys_out, blk_nnz_h, (cudaStream_t)stream);
+}
+
+int fdk_sym_block_csr(int n_nodes, int64_t blk_nnz, const uint64_t* keys, int64_t* blk_indptr, int32_t* blk_indices,
+                      fdk_stream_t stream) {
+  FDK_REQUIRE(n_nodes >= 0 && blk_nnz >= 0 && blk_indptr, FDK_EINVAL, "bad arguments");
+  return sym_block_csr(n_nodes, blk_nnz, keys, blk_indptr, blk_indices, (cudaStream_t)stream);
+}
+
+int fdk_sym_expand_csr(int n_nodes, int nvar, int n_global_dof, int64_t blk_nnz, const int64_t* blk_indptr,
+                       const int32_t* blk_indices, int index_bytes, void* indptr, void* indices, fdk_stream_t stream) {
+  FDK_REQUIRE(n_nodes >= 0 && nvar > 0 && n_global_dof >= 0 && indptr, FDK_EINVAL, "bad arguments");
+  return sym_expand_csr(n_nodes, nvar, n_global_dof, blk_nnz, blk_indptr, blk_indices, index_bytes, indptr, indices,
+                        (cudaStream_t)stream);
+}
+
+int fdk_assemble_elastic_iso(const fdk_plan* plan, int compute, const double* coords, double lambda, double mu,
+                             const double* U, const double* stress_gp, double* K_values, double* D,
+                             fdk_stream_t stream) {
+  if (int rc = check_plan(plan)) return rc;
+  if (int rc = check_io(compute, coords, K_values, D)) return rc;
+  FDK_REQUIRE(!(compute & FDK_VECTOR) || U || stress_gp, FDK_EINVAL, "the vector needs U or stress_gp");
+  AsmArgs a{};
+  a.p = *plan;
+  a.coords = coords;
+  a.U = U;
+  a.stress_gp = stress_gp;
+  a.K = K_values;
+  a.D = D;
+  a.lam = lambda;
+  a.mu = mu;
+  a.compute = compute;
+  return dispatch_assemble<PHYS_ISO>(a, (cudaStream_t)stream);
+}
+
+int fdk_assemble_elastic_general(const fdk_plan* plan, int compute, const double* coords, const double* C_h,
+                                 const double* tangent_gp, const double* U, const double* stress_gp,
+                                 double* K_values, double* D, fdk_stream_t stream) {
+  if (int rc = check_plan(plan)) return rc;
+  if (int rc = check_io(compute, coords, K_values, D)) return rc;
+  FDK_REQUIRE(C_h || tangent_gp, FDK_EINVAL, "need C_h or tangent_gp");
+  FDK_REQUIRE(!(compute & FDK_VECTOR) || U || stress_gp, FDK_EINVAL, "the vector needs U or stress_gp");
+  AsmArgs a{};
+  a.p = *plan;
+  a.coords = coords;
+  a.U = U;
+  a.stress_gp = stress_gp;
+  a.tangent_gp = tangent_gp;
+  a.K = K_values;
+  a.D = D;
+  if (C_h)
+    for (int i = 0; i < 36; ++i) a.C[i] = C_h[i];
+  a.compute = compute;
+  return dispatch_assemble<PHYS_GENERAL>(a, (cudaStream_t)stream);
+}
+
+int fdk_assemble_heat(const fdk_plan* plan, int compute, const double* coords, const double* cond_h,
+                      double rho_c_over_dt, const double* T, const double* T_start, double* K_values, double* D,
+                      fdk_stream_t stream) {
+  if (int rc = check_plan(plan)) return rc;
+  if (int rc = check_io(compute, coords, K_values, D)) return rc;
+  FDK_REQUIRE(cond_h != nullptr, FDK_EINVAL, "cond_h is NULL");
+  FDK_REQUIRE(!(compute & FDK_VECTOR) || T, FDK_EINVAL, "the vector needs T");
+  AsmArgs a{};
+  a.p = *plan;
+  a.coords = coords;
+  a.U = T;
+  a.U2 = T_start;
+  a.K = K_values;
+  a.D = D;
+  for (int i = 0; i < 9; ++i) a.cond[i] = cond_h[i];
+  a.rcdt = rho_c_over_dt;
+  a.compute = compute;
+  return dispatch_assemble<PHYS_HEAT>(a, (cudaStream_t)stream);
+}
+
+int fdk_gp_strain_stress(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                         const double* U, const double* C_h, const double* tangent_gp, double* grad_gp,
+                         double* strain_gp, double* stress_gp, fdk_stream_t stream) {
+  FDK_REQUIRE(conn && coords && U, FDK_EINVAL, "NULL input");
+  FDK_REQUIRE(!stress_gp || C_h || tangent_gp, FDK_EINVAL, "stress needs C_h or tangent_gp");
+  GpArgs a{};
+  a.n_nodes = n_nodes;
+  a.n_elems = n_elems;
+  a.conn = conn;
+  a.coords = coords;
+  a.U = U;
+  a.tangent_gp = tangent_gp;
+  a.grad_gp = grad_gp;
+  a.strain_gp = strain_gp;
+  a.stress_gp = stress_gp;
+  if (C_h)
+    for (int i = 0; i < 36; ++i) a.C[i] = C_h[i];
+  switch (elem_type) {
+    case FDK_HEX8: return launch_gp_strain_stress<Hex8>(a, (cudaStream_t)stream);
+    case FDK_TET4: return launch_gp_strain_stress<Tet4>(a, (cudaStream_t)stream);
+    case FDK_TET10: return launch_gp_strain_stress<Tet10>(a, (cudaStream_t)stream);
+    case FDK_QUAD4: return launch_gp_strain_stress<Quad4>(a, (cudaStream_t)stream);
+  }
+  set_error("unknown element type %d", elem_type);
+  return FDK_EINVAL;
+}
+
+int fdk_gp_temperature(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                       const double* T, double* temp_gp, double* temp_gradient_gp, fdk_stream_t stream) {
+  FDK_REQUIRE(conn && coords && T, FDK_EINVAL, "NULL input");
+  GpArgs a{};
+  a.n_nodes = n_nodes;
+  a.n_elems = n_elems;
+  a.conn = conn;
+  a.coords = coords;
+  a.U = T;
+  a.temp_gp = temp_gp;
+  a.temp_grad_gp = temp_gradient_gp;
+  switch (elem_type) {
+    case FDK_HEX8: return launch_gp_temperature<Hex8>(a, (cudaStream_t)stream);
+    case FDK_TET4: return launch_gp_temperature<Tet4>(a, (cudaStream_t)stream);
+    case FDK_TET10: return launch_gp_temperature<Tet10>(a, (cudaStream_t)stream);
+    case FDK_QUAD4: return launch_gp_temperature<Quad4>(a, (cudaStream_t)stream);
+  }
+  set_error("unknown element type %d", elem_type);
+  return FDK_EINVAL;
+}
+
+int fdk_j2_update(int64_t n_gp, const double* props_h, const double* strain_gp, const double* statev_start,
+                  double* stress_gp, double* statev, double* tangent_gp, fdk_stream_t stream) {
+  FDK_REQUIRE(props_h && strain_gp && statev_start && stress_gp && statev, FDK_EINVAL, "NULL argument");
+  FDK_REQUIRE(n_gp >= 0, FDK_EINVAL, "negative n_gp");
+  if (n_gp == 0) return 0;
+  J2Args a{};
+  a.n_gp = n_gp;
+  a.E = props_h[0];
+  a.nu = props_h[1];
+  a.sigY = props_h[3];
+  a.k = props_h[4];
+  a.m = props_h[5];
+  a.strain = strain_gp;
+  a.statev0 = statev_start;
+  a.stress = stress_gp;
+  a.statev = statev;
+  a.tangent = tangent_gp;
+  k_j2_update<<<(unsigned)((n_gp + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int fdk_gather_f64(int64_t n, const int64_t* index, const double* src, double* dst, fdk_stream_t stream) {
+  if (n <= 0) return 0;
+  FDK_REQUIRE(index && src && dst, FDK_EINVAL, "NULL argument");
+  k_gather_f64<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, index, src, dst);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int fdk_scatter_add_f64(int64_t n, const int64_t* index, const double* src, double* dst, fdk_stream_t stream) {
+  if (n <= 0) return 0;
+  FDK_REQUIRE(index && src && dst, FDK_EINVAL, "NULL argument");
+  k_scatter_add_f64<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, index, src, dst);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

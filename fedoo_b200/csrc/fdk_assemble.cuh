@@ -1,0 +1,566 @@
+// fdk_assemble.cuh -- owner-computes cluster kernels for K (CSR values) and D (global vector).
+//
+// One CTA per node cluster.  The cluster OWNS a compact set of nodes, hence the 3 (nvar)
+// CSR rows of each of them, and computes every contribution to those rows itself:
+//
+//   phase 0  stage tables, coordinates and dof values of the touched nodes in shared memory
+//   phase 1  one thread per (touched element, Gauss point): Jacobian, inverse, |det J| w and
+//            dN/dx (and w*sigma for the residual) -> shared memory, computed ONCE per cluster
+//            and reused by all incidences (the reference caches these as sparse operators,
+//            fedoo/core/assembly.py:776-928; here they never leave the SM)
+//   phase 2  one thread per incidence (owned node I, element e containing I): accumulates in
+//            registers, over the Gauss points, the nne blocks S_IJ = sum_g w G_I (x) G_J
+//            (isotropic closed form), B_I^T C_g B_J (general tangent) or the scalar conduction
+//            term (heat) -- the batched A^T diag(c) B of fedoo/core/_sparsematrix.py:83-89 --
+//            and the nodal force B_I^T sigma (fedoo/core/assembly.py:400-411)
+//   phase 3  slot-centric gather: one thread per CSR block slot (I, J) sums the blocks of the
+//            elements shared by I and J in a fixed order (the cluster-local analogue of the
+//            reference's Matrix_convertCOOtoCSR SpMV, fedoo/core/_sparsematrix.py:256-302),
+//            applies the constitutive closed form and writes the nvar x nvar scalars to their
+//            final positions of the variable-major tiled CSR (scipy.sparse.bmat layout).
+//
+// No floating-point atomics anywhere: each K value and each D entry is written exactly once,
+// so results are bit-reproducible run to run.  Rows are never exchanged between CTAs (or GPUs).
+#pragma once
+#include "fdk_common.cuh"
+#include "fdk_tables.cuh"
+
+namespace fdk {
+
+enum Physics { PHYS_ISO = 0, PHYS_GENERAL = 1, PHYS_HEAT = 2 };
+
+struct AsmArgs {
+  fdk_plan p;
+  const double* coords;
+  const double* U;           // elastic: dof vector; heat: T
+  const double* U2;          // heat: T_start
+  const double* stress_gp;   // optional given stress (6,N)
+  const double* tangent_gp;  // optional per-GP tangent (6,6,N)
+  double* K;
+  double* D;
+  double lam, mu;
+  double C[36];     // uniform tangent, row-major
+  double cond[9];   // conductivity, row-major
+  double rcdt;      // rho c / dt
+  int compute;
+  int big_doubles;  // size of the aliased geometry / block region
+};
+
+template <class El, int PHYS>
+struct Layout {
+  static constexpr int NNE = El::NNE, NGP = El::NGP, DIM = El::DIM;
+  static constexpr int NV = (PHYS == PHYS_HEAT) ? 1 : DIM;    // variables per node
+  static constexpr int NU = (PHYS == PHYS_HEAT) ? 2 : DIM;    // staged nodal values per touched node
+  static constexpr int BLK = NV * NV;                         // scalars per (I,J) block
+  static constexpr int NSIG = (PHYS == PHYS_HEAT) ? DIM + 1 : (DIM == 3 ? 6 : 3);
+  static constexpr int GSTR = DIM * NNE + 1 + NSIG;           // per (element, gp): G[k][d], w, w*sigma
+  static constexpr int ESTR = (NGP * GSTR) | 1;               // odd stride: spreads banks across elements
+  static constexpr int SSTR = (NNE * BLK + NV) | 1;           // per incidence: nne blocks + nodal force
+  static constexpr int TSTR = (DIM * NNE) | 1;                // padded dN table row
+  static constexpr int TAB_DOUBLES = NGP * TSTR + NGP * NNE + NGP + 1;
+
+  static size_t smem_bytes(const fdk_plan& p, int* big_doubles) {
+    long big = (long)p.cap_te * ESTR;
+    long s = (long)p.cap_inc * SSTR;
+    if (s > big) big = s;
+    big = (big + 1) & ~1L;
+    *big_doubles = (int)big;
+    long doubles = TAB_DOUBLES + (long)p.cap_tn * (DIM + NU) + big;
+    doubles = (doubles + 1) & ~1L;
+    return (size_t)doubles * 8 + (size_t)(2 * (p.cap_owned + 1)) * 4;
+  }
+};
+
+template <int DIM>
+__device__ __forceinline__ double invert(const double (&J)[DIM][DIM], double (&iJ)[DIM][DIM]);
+
+template <>
+__device__ __forceinline__ double invert<3>(const double (&J)[3][3], double (&iJ)[3][3]) {
+  const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+  const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+  const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+  const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+  const double r = 1.0 / det;
+  iJ[0][0] = c00 * r;
+  iJ[1][0] = c01 * r;
+  iJ[2][0] = c02 * r;
+  iJ[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * r;
+  iJ[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * r;
+  iJ[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * r;
+  iJ[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * r;
+  iJ[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * r;
+  iJ[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * r;
+  return det;
+}
+
+template <>
+__device__ __forceinline__ double invert<2>(const double (&J)[2][2], double (&iJ)[2][2]) {
+  const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+  const double r = 1.0 / det;
+  iJ[0][0] = J[1][1] * r;
+  iJ[0][1] = -J[0][1] * r;
+  iJ[1][0] = -J[1][0] * r;
+  iJ[1][1] = J[0][0] * r;
+  return det;
+}
+
+// Geometry of one (element, Gauss point): G[k][d] = dN_k/dx_d and w = w_g |det J|.
+// J[r][x] = sum_k dN_k/dxi_r X_k[x]  (fedoo/lib_elements/element_base.py:43-50),
+// G = J^-1 dN/dxi (fedoo/core/assembly.py:879-881).
+template <int NNE, int DIM>
+__device__ __forceinline__ double gp_geometry(const double* __restrict__ dN /*[DIM][NNE]*/, double wg,
+                                              const double (&X)[NNE][DIM], double (&G)[NNE][DIM]) {
+  double J[DIM][DIM];
+#pragma unroll
+  for (int r = 0; r < DIM; ++r)
+#pragma unroll
+    for (int x = 0; x < DIM; ++x) J[r][x] = 0.0;
+#pragma unroll
+  for (int k = 0; k < NNE; ++k)
+#pragma unroll
+    for (int r = 0; r < DIM; ++r) {
+      const double dn = dN[r * NNE + k];
+#pragma unroll
+      for (int x = 0; x < DIM; ++x) J[r][x] = fma(dn, X[k][x], J[r][x]);
+    }
+  double iJ[DIM][DIM];
+  const double det = invert<DIM>(J, iJ);
+#pragma unroll
+  for (int k = 0; k < NNE; ++k)
+#pragma unroll
+    for (int x = 0; x < DIM; ++x) {
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < DIM; ++r) s = fma(iJ[x][r], dN[r * NNE + k], s);
+      G[k][x] = s;
+    }
+  return wg * fabs(det);
+}
+
+// Voigt strain from the displacement gradient g[a][b] = du_a/dx_b (engineering shears).
+template <int DIM>
+__device__ __forceinline__ void voigt_strain(const double (&g)[DIM][DIM], double (&e)[6]) {
+  e[0] = g[0][0];
+  e[1] = g[1][1];
+  e[3] = g[0][1] + g[1][0];
+  if constexpr (DIM == 3) {
+    e[2] = g[2][2];
+    e[4] = g[0][2] + g[2][0];
+    e[5] = g[1][2] + g[2][1];
+  } else {
+    e[2] = 0.0;
+    e[4] = 0.0;
+    e[5] = 0.0;
+  }
+}
+
+// sigma_i = sum_j C_ij eps_j with C addressed as C[i*si + j*sj].
+__device__ __forceinline__ void apply_tangent(const double* __restrict__ C, int si, int sj, const double (&e)[6],
+                                              double (&s)[6]) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc = fma(C[i * si + j * sj], e[j], acc);
+    s[i] = acc;
+  }
+}
+
+template <class El, int PHYS>
+__global__ void __launch_bounds__(El::THREADS, 1) k_assemble(const __grid_constant__ AsmArgs a) {
+  using L = Layout<El, PHYS>;
+  constexpr int NNE = L::NNE, NGP = L::NGP, DIM = L::DIM, NV = L::NV, NU = L::NU, BLK = L::BLK;
+  constexpr int NSIG = L::NSIG, GSTR = L::GSTR, ESTR = L::ESTR, SSTR = L::SSTR, TSTR = L::TSTR;
+  constexpr int THREADS = El::THREADS;
+  const fdk_plan& p = a.p;
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const bool do_mat = (a.compute & FDK_MATRIX) != 0;
+  const bool do_vec = (a.compute & FDK_VECTOR) != 0;
+
+  const int q0 = p.cl_node_ptr[c], n_owned = p.cl_node_ptr[c + 1] - q0;
+  const int te0 = p.cl_te_ptr[c], n_te = p.cl_te_ptr[c + 1] - te0;
+  const int tn0 = p.cl_tn_ptr[c], n_tn = p.cl_tn_ptr[c + 1] - tn0;
+  const int inc0 = p.cl_inc_ptr[q0], n_inc = p.cl_inc_ptr[q0 + n_owned] - inc0;
+  const int64_t slot0 = p.cl_slot_ptr[q0];
+  const int n_slots = (int)(p.cl_slot_ptr[q0 + n_owned] - slot0);
+
+  extern __shared__ __align__(16) double smem[];
+  double* sdN = smem;
+  double* sN = sdN + NGP * TSTR;
+  double* sW = sN + NGP * NNE;
+  double* sX = smem + L::TAB_DOUBLES;
+  double* sU = sX + p.cap_tn * DIM;
+  double* sBig = sU + p.cap_tn * NU;
+  int* sSlotBase = reinterpret_cast<int*>(smem + ((L::TAB_DOUBLES + p.cap_tn * (DIM + NU) + a.big_doubles + 1) & ~1));
+  int* sIncPtr = sSlotBase + (p.cap_owned + 1);
+
+  // ---------------- phase 0: staging ----------------
+  {
+    const ElemTable& tab = c_tab[El::ID];
+    for (int t = tid; t < NGP * DIM * NNE; t += THREADS) {
+      const int g = t / (DIM * NNE), r = t - g * (DIM * NNE);
+      sdN[g * TSTR + r] = tab.dN[t];
+    }
+    for (int t = tid; t < NGP * NNE; t += THREADS) sN[t] = tab.N[t];
+    if (tid < NGP) sW[tid] = tab.w[tid];
+    for (int t = tid; t < n_tn; t += THREADS) {
+      const int node = p.cl_tn_node[tn0 + t];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) sX[t * DIM + d] = a.coords[(int64_t)node * DIM + d];
+      if (do_vec && a.U != nullptr) {
+        if constexpr (PHYS == PHYS_HEAT) {
+          const double T = a.U[node];
+          sU[t * 2 + 0] = T;
+          sU[t * 2 + 1] = T - (a.U2 ? a.U2[node] : 0.0);
+        } else {
+#pragma unroll
+          for (int v = 0; v < DIM; ++v) sU[t * DIM + v] = a.U[(int64_t)v * p.n_nodes + node];
+        }
+      }
+    }
+    for (int t = tid; t <= n_owned; t += THREADS) {
+      sSlotBase[t] = (int)(p.cl_slot_ptr[q0 + t] - slot0);
+      sIncPtr[t] = p.cl_inc_ptr[q0 + t] - inc0;
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase 1: geometry (+ w*sigma) per (touched element, gp) ----------------
+  for (int task = tid; task < n_te * NGP; task += THREADS) {
+    const int le = task / NGP, g = task - le * NGP;
+    const uint8_t* lc = p.cl_lconn + (int64_t)(te0 + le) * NNE;
+    int ln[NNE];
+    double X[NNE][DIM];
+#pragma unroll
+    for (int k = 0; k < NNE; ++k) {
+      ln[k] = lc[k];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) X[k][d] = sX[ln[k] * DIM + d];
+    }
+    double G[NNE][DIM];
+    const double w = gp_geometry<NNE, DIM>(sdN + g * TSTR, sW[g], X, G);
+    double* out = sBig + le * ESTR + g * GSTR;
+#pragma unroll
+    for (int k = 0; k < NNE; ++k)
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) out[k * DIM + d] = G[k][d];
+    out[DIM * NNE] = w;
+
+    if (do_vec) {
+      double* so = out + DIM * NNE + 1;
+      if constexpr (PHYS == PHYS_HEAT) {
+        double gT[DIM], dTg = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) gT[d] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NNE; ++k) {
+          const double T = sU[ln[k] * 2 + 0];
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) gT[d] = fma(T, G[k][d], gT[d]);
+          dTg = fma(sN[g * NNE + k], sU[ln[k] * 2 + 1], dTg);
+        }
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) {
+          double q = 0.0;
+#pragma unroll
+          for (int j = 0; j < DIM; ++j) q = fma(a.cond[i * 3 + j], gT[j], q);
+          so[i] = w * q;
+        }
+        so[DIM] = w * a.rcdt * dTg;
+      } else {
+        double sig[6];
+        if (a.stress_gp != nullptr) {
+          const int64_t e = p.cl_te_elem[te0 + le];
+          const double* sp = a.stress_gp + 6 * ((int64_t)g * p.n_elems + e);
+#pragma unroll
+          for (int s = 0; s < 6; ++s) sig[s] = sp[s];
+        } else {
+          double gu[DIM][DIM];
+#pragma unroll
+          for (int v = 0; v < DIM; ++v)
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) gu[v][d] = 0.0;
+#pragma unroll
+          for (int k = 0; k < NNE; ++k)
+#pragma unroll
+            for (int v = 0; v < DIM; ++v) {
+              const double u = sU[ln[k] * DIM + v];
+#pragma unroll
+              for (int d = 0; d < DIM; ++d) gu[v][d] = fma(u, G[k][d], gu[v][d]);
+            }
+          double eps[6];
+          voigt_strain<DIM>(gu, eps);
+          if constexpr (PHYS == PHYS_ISO) {
+            // sigma = lambda tr(eps) 1 + 2 mu eps  (H of fedoo/constitutivelaw/elastic_isotrop.py:57-66)
+            const double tr = eps[0] + eps[1] + eps[2];
+            const double lt = a.lam * tr, m2 = 2.0 * a.mu;
+            sig[0] = fma(m2, eps[0], lt);
+            sig[1] = fma(m2, eps[1], lt);
+            sig[2] = fma(m2, eps[2], lt);
+            sig[3] = a.mu * eps[3];
+            sig[4] = a.mu * eps[4];
+            sig[5] = a.mu * eps[5];
+          } else {
+            if (a.tangent_gp != nullptr) {
+              const int64_t e = p.cl_te_elem[te0 + le];
+              apply_tangent(a.tangent_gp + 36 * ((int64_t)g * p.n_elems + e), 1, 6, eps, sig);
+            } else {
+              apply_tangent(a.C, 6, 1, eps, sig);
+            }
+          }
+        }
+        if constexpr (DIM == 3) {
+#pragma unroll
+          for (int s = 0; s < 6; ++s) so[s] = w * sig[s];
+        } else {
+          so[0] = w * sig[0];
+          so[1] = w * sig[1];
+          so[2] = w * sig[3];
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase 2: per-incidence blocks in registers ----------------
+  double acc[NNE][BLK];
+  double f[NV];
+#pragma unroll
+  for (int j = 0; j < NNE; ++j)
+#pragma unroll
+    for (int b = 0; b < BLK; ++b) acc[j][b] = 0.0;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) f[v] = 0.0;
+
+  if (tid < n_inc) {
+    const unsigned desc = p.inc_desc[inc0 + tid];
+    const int le = desc & 0xFFF, i = desc >> 12;
+    const double* eb = sBig + le * ESTR;
+    [[maybe_unused]] int64_t e_glob = 0;
+    if constexpr (PHYS == PHYS_GENERAL) {
+      if (a.tangent_gp != nullptr) e_glob = p.cl_te_elem[te0 + le];
+    }
+#pragma unroll 1
+    for (int g = 0; g < NGP; ++g) {
+      const double* gb = eb + g * GSTR;
+      const double w = gb[DIM * NNE];
+      double gi[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) gi[d] = gb[i * DIM + d];
+
+      if (do_vec) {
+        const double* ws = gb + DIM * NNE + 1;
+        if constexpr (PHYS == PHYS_HEAT) {
+          double s = ws[DIM] * sN[g * NNE + i];
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) s = fma(ws[d], gi[d], s);
+          f[0] += s;
+        } else if constexpr (DIM == 3) {
+          f[0] += ws[0] * gi[0] + ws[3] * gi[1] + ws[4] * gi[2];
+          f[1] += ws[1] * gi[1] + ws[3] * gi[0] + ws[5] * gi[2];
+          f[2] += ws[2] * gi[2] + ws[4] * gi[0] + ws[5] * gi[1];
+        } else {
+          f[0] += ws[0] * gi[0] + ws[2] * gi[1];
+          f[1] += ws[1] * gi[1] + ws[2] * gi[0];
+        }
+      }
+
+      if (do_mat) {
+        if constexpr (PHYS == PHYS_ISO) {
+          double wgi[DIM];
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) wgi[d] = w * gi[d];
+#pragma unroll
+          for (int j = 0; j < NNE; ++j) {
+            double gj[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) gj[d] = gb[j * DIM + d];
+#pragma unroll
+            for (int cc = 0; cc < DIM; ++cc)
+#pragma unroll
+              for (int aa = 0; aa < DIM; ++aa) acc[j][cc * DIM + aa] = fma(wgi[cc], gj[aa], acc[j][cc * DIM + aa]);
+          }
+        } else if constexpr (PHYS == PHYS_HEAT) {
+          double kgi[DIM];
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) {
+            double s = 0.0;
+#pragma unroll
+            for (int d2 = 0; d2 < DIM; ++d2) s = fma(gi[d2], a.cond[d2 * 3 + d], s);
+            kgi[d] = w * s;
+          }
+          // lumped capacity: row sum of the consistent mass goes to the diagonal
+          double nsum = 0.0;
+#pragma unroll
+          for (int j = 0; j < NNE; ++j) nsum += sN[g * NNE + j];
+          const double m = a.rcdt * w * sN[g * NNE + i] * nsum;
+#pragma unroll
+          for (int j = 0; j < NNE; ++j) {
+            double s = (j == i) ? m : 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) s = fma(kgi[d], gb[j * DIM + d], s);
+            acc[j][0] += s;
+          }
+        } else {  // PHYS_GENERAL: t[c][s] = w sum_s' B_I[s'][c] C[s'][s]; acc[j][c][a] += sum_s t[c][s] B_J[s][a]
+          const double* Cg;
+          int si, sj;
+          if (a.tangent_gp != nullptr) {
+            Cg = a.tangent_gp + 36 * ((int64_t)g * p.n_elems + e_glob);
+            si = 1;
+            sj = 6;
+          } else {
+            Cg = a.C;
+            si = 6;
+            sj = 1;
+          }
+          double t[DIM][6];
+#pragma unroll
+          for (int s = 0; s < 6; ++s) {
+            if constexpr (DIM == 3) {
+              const double c0 = Cg[0 * si + s * sj], c1 = Cg[1 * si + s * sj], c2 = Cg[2 * si + s * sj];
+              const double c3 = Cg[3 * si + s * sj], c4 = Cg[4 * si + s * sj], c5 = Cg[5 * si + s * sj];
+              t[0][s] = w * (gi[0] * c0 + gi[1] * c3 + gi[2] * c4);
+              t[1][s] = w * (gi[1] * c1 + gi[0] * c3 + gi[2] * c5);
+              t[2][s] = w * (gi[2] * c2 + gi[0] * c4 + gi[1] * c5);
+            } else {
+              const double c0 = Cg[0 * si + s * sj], c1 = Cg[1 * si + s * sj], c3 = Cg[3 * si + s * sj];
+              t[0][s] = w * (gi[0] * c0 + gi[1] * c3);
+              t[1][s] = w * (gi[1] * c1 + gi[0] * c3);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < NNE; ++j) {
+            double gj[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) gj[d] = gb[j * DIM + d];
+#pragma unroll
+            for (int cc = 0; cc < DIM; ++cc) {
+              if constexpr (DIM == 3) {
+                acc[j][cc * 3 + 0] += t[cc][0] * gj[0] + t[cc][3] * gj[1] + t[cc][4] * gj[2];
+                acc[j][cc * 3 + 1] += t[cc][1] * gj[1] + t[cc][3] * gj[0] + t[cc][5] * gj[2];
+                acc[j][cc * 3 + 2] += t[cc][2] * gj[2] + t[cc][4] * gj[0] + t[cc][5] * gj[1];
+              } else {
+                acc[j][cc * 2 + 0] += t[cc][0] * gj[0] + t[cc][3] * gj[1];
+                acc[j][cc * 2 + 1] += t[cc][1] * gj[1] + t[cc][3] * gj[0];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();  // everyone is done reading the geometry region; it becomes the block region
+  if (tid < n_inc) {
+    double* sp = sBig + tid * SSTR;
+    if (do_mat) {
+#pragma unroll
+      for (int j = 0; j < NNE; ++j)
+#pragma unroll
+        for (int b = 0; b < BLK; ++b) sp[j * BLK + b] = acc[j][b];
+    }
+    if (do_vec) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) sp[NNE * BLK + v] = f[v];
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase 3: slot-centric gather, constitutive closed form, final stores ----------------
+  if (do_mat) {
+    const int64_t gbase = p.cl_g_base[c];
+    const uint16_t* goff = p.g_off + slot0 + c;
+    for (int s = tid; s < n_slots; s += THREADS) {
+      int lo = 0, hi = n_owned;  // owner node n: sSlotBase[n] <= s < sSlotBase[n+1]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (sSlotBase[mid] <= s) lo = mid; else hi = mid;
+      }
+      const int n = lo;
+      const int pcol = s - sSlotBase[n];
+      const int deg = sSlotBase[n + 1] - sSlotBase[n];
+      const int t0 = goff[s], t1 = goff[s + 1];
+      double S[BLK];
+#pragma unroll
+      for (int b = 0; b < BLK; ++b) S[b] = 0.0;
+      for (int t = t0; t < t1; ++t) {
+        const unsigned ent = p.g_ent[gbase + t];
+        const double* sp = sBig + (ent >> 4) * SSTR + (ent & 15) * BLK;
+#pragma unroll
+        for (int b = 0; b < BLK; ++b) S[b] += sp[b];
+      }
+      double Kb[BLK];
+      if constexpr (PHYS == PHYS_ISO) {
+        // K_IJ = lambda S + mu S^T + mu tr(S) 1
+        double tr = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) tr += S[d * DIM + d];
+#pragma unroll
+        for (int cc = 0; cc < DIM; ++cc)
+#pragma unroll
+          for (int aa = 0; aa < DIM; ++aa) {
+            double v = fma(a.lam, S[cc * DIM + aa], a.mu * S[aa * DIM + cc]);
+            if (cc == aa) v = fma(a.mu, tr, v);
+            Kb[cc * DIM + aa] = v;
+          }
+      } else {
+#pragma unroll
+        for (int b = 0; b < BLK; ++b) Kb[b] = S[b];
+      }
+      const int64_t bp = p.cl_bptr[q0 + n];
+#pragma unroll
+      for (int cc = 0; cc < NV; ++cc) {
+        double* row = a.K + ((int64_t)cc * NV * p.blk_nnz + (int64_t)NV * bp);
+#pragma unroll
+        for (int aa = 0; aa < NV; ++aa) __stcs(row + (int64_t)aa * deg + pcol, Kb[cc * NV + aa]);
+      }
+    }
+  }
+  if (do_vec) {
+    for (int n = tid; n < n_owned; n += THREADS) {
+      double s[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) s[v] = 0.0;
+      for (int k = sIncPtr[n]; k < sIncPtr[n + 1]; ++k)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) s[v] += sBig[k * SSTR + NNE * BLK + v];
+      const int node = p.cl_node[q0 + n];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) a.D[(int64_t)v * p.n_nodes + node] = -s[v];
+    }
+  }
+}
+
+// ---- host launcher -----------------------------------------------------------------------
+template <class El, int PHYS>
+int launch_assemble(AsmArgs& a, cudaStream_t stream) {
+  using L = Layout<El, PHYS>;
+  const fdk_plan& p = a.p;
+  FDK_REQUIRE(p.cap_inc <= El::THREADS, FDK_ECAP, "cluster with %d incidences exceeds CTA size %d", p.cap_inc,
+              El::THREADS);
+  FDK_REQUIRE(p.cap_te < 4096 && p.cap_tn <= 256 && p.cap_gent < 65536, FDK_ECAP,
+              "cluster capacity overflow (te=%d tn=%d gent=%d)", p.cap_te, p.cap_tn, p.cap_gent);
+  FDK_REQUIRE(p.nvar == L::NV, FDK_EINVAL, "plan nvar %d does not match the operator (%d)", p.nvar, L::NV);
+  const size_t smem = L::smem_bytes(p, &a.big_doubles);
+  FDK_REQUIRE(smem <= 227 * 1024, FDK_ECAP, "cluster needs %zu bytes of shared memory (> 227 KB)", smem);
+  if (p.n_clusters == 0) return 0;
+  if (int rc = ensure_device_tables()) return rc;
+  auto kern = k_assemble<El, PHYS>;
+  FDK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<p.n_clusters, El::THREADS, smem, stream>>>(a);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int PHYS>
+int dispatch_assemble(AsmArgs& a, cudaStream_t stream) {
+  switch (a.p.elem_type) {
+    case FDK_HEX8: return launch_assemble<Hex8, PHYS>(a, stream);
+    case FDK_TET4: return launch_assemble<Tet4, PHYS>(a, stream);
+    case FDK_TET10: return launch_assemble<Tet10, PHYS>(a, stream);
+    case FDK_QUAD4: return launch_assemble<Quad4, PHYS>(a, stream);
+  }
+  set_error("unknown element type %d", a.p.elem_type);
+  return FDK_EINVAL;
+}
+
+}  // namespace fdk

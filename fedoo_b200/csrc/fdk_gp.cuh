@@ -1,0 +1,295 @@
+// fdk_gp.cuh -- element-parallel Gauss-point kernels: strain/stress update, thermal state,
+// J2 radial return.  One thread per Gauss point, gp-major indexing n = g * n_elems + e so that a
+// warp handles 32 consecutive elements at the same Gauss point (uniform table reads from
+// constant memory, fully coalesced (6,N)/(8,N) column stores).
+#pragma once
+#include "fdk_assemble.cuh"
+
+namespace fdk {
+
+struct GpArgs {
+  int n_nodes;
+  int64_t n_elems;
+  const int32_t* conn;
+  const double* coords;
+  const double* U;
+  const double* tangent_gp;
+  double* grad_gp;
+  double* strain_gp;
+  double* stress_gp;
+  double* temp_gp;
+  double* temp_grad_gp;
+  double C[36];
+  int has_C;
+};
+
+// grad u -> strain -> stress.  Replaces the 9 SpMVs of Assembly.get_grad_disp
+// (fedoo/core/assembly.py:1285-1336), _comp_linear_strain
+// (fedoo/weakform/stress_equilibrium.py:589-601) and the 36 array multiplies of
+// ElasticAnisotropic.update (fedoo/constitutivelaw/elastic_anisotropic.py:48-56).
+template <class El>
+__global__ void __launch_bounds__(256) k_gp_strain_stress(const __grid_constant__ GpArgs a) {
+  constexpr int NNE = El::NNE, NGP = El::NGP, DIM = El::DIM;
+  const int64_t N = a.n_elems * NGP;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int g = (int)(n / a.n_elems);
+  const int64_t e = n - (int64_t)g * a.n_elems;
+  const ElemTable& tab = c_tab[El::ID];
+  int nd[NNE];
+  double X[NNE][DIM];
+#pragma unroll
+  for (int k = 0; k < NNE; ++k) {
+    nd[k] = a.conn[e * NNE + k];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) X[k][d] = a.coords[(int64_t)nd[k] * DIM + d];
+  }
+  double dN[DIM * NNE];
+#pragma unroll
+  for (int t = 0; t < DIM * NNE; ++t) dN[t] = tab.dN[g * DIM * NNE + t];
+  double G[NNE][DIM];
+  gp_geometry<NNE, DIM>(dN, 1.0, X, G);
+  double gu[DIM][DIM];
+#pragma unroll
+  for (int v = 0; v < DIM; ++v)
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) gu[v][d] = 0.0;
+#pragma unroll
+  for (int k = 0; k < NNE; ++k)
+#pragma unroll
+    for (int v = 0; v < DIM; ++v) {
+      const double u = a.U[(int64_t)v * a.n_nodes + nd[k]];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) gu[v][d] = fma(u, G[k][d], gu[v][d]);
+    }
+  if (a.grad_gp != nullptr) {
+#pragma unroll
+    for (int v = 0; v < 3; ++v)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        a.grad_gp[(int64_t)(v * 3 + d) * N + n] = (v < DIM && d < DIM) ? gu[v < DIM ? v : 0][d < DIM ? d : 0] : 0.0;
+      }
+  }
+  double eps[6];
+  voigt_strain<DIM>(gu, eps);
+  if (a.strain_gp != nullptr) {
+#pragma unroll
+    for (int s = 0; s < 6; ++s) a.strain_gp[6 * n + s] = eps[s];
+  }
+  if (a.stress_gp != nullptr) {
+    double sig[6];
+    if (a.tangent_gp != nullptr)
+      apply_tangent(a.tangent_gp + 36 * n, 1, 6, eps, sig);
+    else
+      apply_tangent(a.C, 6, 1, eps, sig);
+#pragma unroll
+    for (int s = 0; s < 6; ++s) a.stress_gp[6 * n + s] = sig[s];
+  }
+}
+
+// Temperature and its gradient at the Gauss points (fedoo/weakform/heat_equation.py:64-70,149-152).
+template <class El>
+__global__ void __launch_bounds__(256) k_gp_temperature(const __grid_constant__ GpArgs a) {
+  constexpr int NNE = El::NNE, NGP = El::NGP, DIM = El::DIM;
+  const int64_t N = a.n_elems * NGP;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int g = (int)(n / a.n_elems);
+  const int64_t e = n - (int64_t)g * a.n_elems;
+  const ElemTable& tab = c_tab[El::ID];
+  int nd[NNE];
+  double X[NNE][DIM];
+#pragma unroll
+  for (int k = 0; k < NNE; ++k) {
+    nd[k] = a.conn[e * NNE + k];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) X[k][d] = a.coords[(int64_t)nd[k] * DIM + d];
+  }
+  double dN[DIM * NNE];
+#pragma unroll
+  for (int t = 0; t < DIM * NNE; ++t) dN[t] = tab.dN[g * DIM * NNE + t];
+  double G[NNE][DIM];
+  gp_geometry<NNE, DIM>(dN, 1.0, X, G);
+  double Tg = 0.0, gT[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < NNE; ++k) {
+    const double T = a.U[nd[k]];
+    Tg = fma(tab.N[g * NNE + k], T, Tg);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) gT[d] = fma(T, G[k][d], gT[d]);
+  }
+  if (a.temp_gp != nullptr) a.temp_gp[n] = Tg;
+  if (a.temp_grad_gp != nullptr) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) a.temp_grad_gp[(int64_t)d * N + n] = gT[d];
+  }
+}
+
+template <class El>
+int launch_gp_strain_stress(const GpArgs& a, cudaStream_t stream) {
+  const int64_t N = a.n_elems * El::NGP;
+  if (N == 0) return 0;
+  if (int rc = ensure_device_tables()) return rc;
+  const int64_t blocks = (N + 255) / 256;
+  k_gp_strain_stress<El><<<(unsigned)blocks, 256, 0, stream>>>(a);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <class El>
+int launch_gp_temperature(const GpArgs& a, cudaStream_t stream) {
+  const int64_t N = a.n_elems * El::NGP;
+  if (N == 0) return 0;
+  if (int rc = ensure_device_tables()) return rc;
+  const int64_t blocks = (N + 255) / 256;
+  k_gp_temperature<El><<<(unsigned)blocks, 256, 0, stream>>>(a);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// J2 plasticity: radial return + consistent tangent, one thread per Gauss point.
+// props = [E, nu, alpha, sigmaY, k, m]; hardening R(p) = k p^m (EPICP,
+// fedoo/constitutivelaw/simcoon_umat.py:103-112); yield f = q - sigmaY - R(p)
+// (fedoo/constitutivelaw/elasto_plasticity.py:154-155); trial state sigma = H (eps - eps_p)
+// (:317-330); flow direction n = 3/2 s/q with engineering shear doubling (:160-164).
+// The legacy per-GP Python cutting-plane loop (:338-371) is replaced by a safeguarded scalar
+// Newton on g(dp) = q_tr - 3 mu dp - sigmaY - k (p0+dp)^m (same fixed point for J2 + isotropic
+// hardening), slope -(3 mu + R'(p)).
+// ---------------------------------------------------------------------------------------
+struct J2Args {
+  int64_t n_gp;
+  double E, nu, sigY, k, m;
+  const double* strain;
+  const double* statev0;
+  double* stress;
+  double* statev;
+  double* tangent;
+};
+
+__global__ void __launch_bounds__(256) k_j2_update(const __grid_constant__ J2Args a) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.n_gp) return;
+  const double mu = 0.5 * a.E / (1.0 + a.nu);
+  const double lam = a.E * a.nu / ((1.0 + a.nu) * (1.0 - 2.0 * a.nu));
+  const double kb = lam + 2.0 * mu / 3.0;  // bulk modulus
+  double eps[6], sv[8];
+  {
+    const double2* ep = reinterpret_cast<const double2*>(a.strain + 6 * n);
+    const double2* sp = reinterpret_cast<const double2*>(a.statev0 + 8 * n);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double2 v = ep[i];
+      eps[2 * i] = v.x;
+      eps[2 * i + 1] = v.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double2 v = sp[i];
+      sv[2 * i] = v.x;
+      sv[2 * i + 1] = v.y;
+    }
+  }
+  const double p0 = sv[1];
+  double ee[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) ee[i] = eps[i] - sv[2 + i];
+  const double tr = ee[0] + ee[1] + ee[2];
+  double sig[6];
+  sig[0] = lam * tr + 2.0 * mu * ee[0];
+  sig[1] = lam * tr + 2.0 * mu * ee[1];
+  sig[2] = lam * tr + 2.0 * mu * ee[2];
+  sig[3] = mu * ee[3];
+  sig[4] = mu * ee[4];
+  sig[5] = mu * ee[5];
+  const double pm = (sig[0] + sig[1] + sig[2]) / 3.0;
+  double s[6] = {sig[0] - pm, sig[1] - pm, sig[2] - pm, sig[3], sig[4], sig[5]};
+  const double q = sqrt(1.5 * (s[0] * s[0] + s[1] * s[1] + s[2] * s[2] + 2.0 * (s[3] * s[3] + s[4] * s[4] + s[5] * s[5])));
+  const double R0 = (p0 > 0.0) ? a.k * pow(p0, a.m) : 0.0;
+  const double ftr = q - a.sigY - R0;
+  double dp = 0.0;
+  double Rp = 0.0;
+  const bool plastic = ftr > 0.0;
+  if (plastic) {
+    const double m3 = 3.0 * mu;
+    double lo = 0.0, hi = ftr / m3, x = hi;
+    for (int it = 0; it < 60; ++it) {
+      const double pp = p0 + x;
+      const double pw = (pp > 0.0) ? pow(pp, a.m) : 0.0;
+      const double fx = q - m3 * x - a.sigY - a.k * pw;
+      if (fx < 0.0) hi = fmin(hi, x);
+      if (fx > 0.0) lo = fmax(lo, x);
+      const double dR = (pp > 0.0) ? a.k * a.m * pw / pp : 1e300;
+      double xn = x + fx / (m3 + dR);
+      if (!(xn > lo && xn < hi) || !isfinite(xn)) xn = 0.5 * (lo + hi);
+      const bool done = fabs(xn - x) <= 1e-14 * fmax(fabs(xn), 1e-300);
+      x = xn;
+      if (done) break;
+    }
+    dp = x;
+    const double pn = p0 + dp;
+    Rp = (pn > 0.0) ? a.k * a.m * pow(pn, a.m - 1.0) : 1e300;
+  }
+  const double qs = (q > 0.0) ? q : 1.0;
+  double nf[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) nf[i] = 1.5 * s[i] / qs;
+  double out_s[6], out_v[8];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) out_s[i] = sig[i] - 2.0 * mu * dp * nf[i];
+  out_v[0] = sv[0];
+  out_v[1] = p0 + dp;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) out_v[2 + i] = sv[2 + i] + dp * nf[i];
+#pragma unroll
+  for (int i = 3; i < 6; ++i) out_v[2 + i] = sv[2 + i] + 2.0 * dp * nf[i];
+  {
+    double2* so = reinterpret_cast<double2*>(a.stress + 6 * n);
+    double2* vo = reinterpret_cast<double2*>(a.statev + 8 * n);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) so[i] = make_double2(out_s[2 * i], out_s[2 * i + 1]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) vo[i] = make_double2(out_v[2 * i], out_v[2 * i + 1]);
+  }
+  if (a.tangent != nullptr) {
+    // C = K 1(x)1 + 2 mu beta I_dev - 2 mu gamma n^(x)n^   (elastic: beta = 1, gamma = 0)
+    double beta = 1.0, gam = 0.0;
+    if (plastic) {
+      beta = 1.0 - 3.0 * mu * dp / q;
+      gam = 1.0 / (1.0 + Rp / (3.0 * mu)) - (1.0 - beta);
+    }
+    const double sc = sqrt(1.5) / qs;
+    double nh[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) nh[i] = s[i] * sc;
+    double2* to = reinterpret_cast<double2*>(a.tangent + 36 * n);
+    const double m2b = 2.0 * mu * beta, m2g = 2.0 * mu * gam;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {  // column j (Fortran order: C_ij at i + 6 j)
+      double col[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        double v = -m2g * nh[i] * nh[j];
+        if (i < 3 && j < 3) v += kb - m2b / 3.0;
+        if (i == j) v += (i < 3) ? m2b : 0.5 * m2b;
+        col[i] = v;
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) to[3 * j + i] = make_double2(col[2 * i], col[2 * i + 1]);
+    }
+  }
+}
+
+__global__ void k_gather_f64(int64_t n, const int64_t* __restrict__ index, const double* __restrict__ src,
+                             double* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[index[i]];
+}
+
+__global__ void k_scatter_add_f64(int64_t n, const int64_t* __restrict__ index, const double* __restrict__ src,
+                                  double* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[index[i]] += src[i];  // indices are unique within one call (owner rows)
+}
+
+}  // namespace fdk

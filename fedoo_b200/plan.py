@@ -1,0 +1,334 @@
+"""Assembly plan: node clusters + per-cluster metadata consumed by the cluster kernels.
+
+The numeric kernels (csrc/fdk_assemble.cuh) are *owner-computes*: a CTA owns a compact
+cluster of nodes (hence their CSR rows) and needs, per cluster,
+  * the owned nodes, their block-row start and length,
+  * the touched elements (all elements incident to an owned node) with a cluster-local
+    connectivity, and the touched nodes,
+  * the incidences (owned node, touched element, local node index), one per thread,
+  * the gather lists: for every CSR block slot (I, J) of an owned row the list of
+    (incidence, local column node) whose element block contributes to it -- the
+    cluster-local analogue of the reference's ``Matrix_convertCOOtoCSR``
+    (fedoo/core/_sparsematrix.py:256-274), i.e. the transposed element->nnz-slot map.
+
+Everything here is one-time symbolic work expressed with torch tensor ops (sort / unique /
+searchsorted / cumsum), so it runs on the GPU in production and on the CPU in the unit
+tests.  Clusters are Morton blocks of a rank-bucketed node lattice, refined until each one
+fits the kernel's shared-memory / thread capacities.
+"""
+
+from __future__ import annotations
+
+import dataclasses
+
+import torch
+
+from . import _lib
+
+# per element type: CTA threads (= max incidences), max touched elements, first Morton shift
+# (log2 of lattice cells per cluster).  te_max keeps te_max * ESTR * 8 B <= ~160 KB.
+_CAPS = {
+    "hex8": dict(nne=8, ngp=8, dim=3, inc_max=256, te_max=80, shift=5),
+    "tet4": dict(nne=4, ngp=4, dim=3, inc_max=512, te_max=256, shift=4),
+    "tet10": dict(nne=10, ngp=15, dim=3, inc_max=200, te_max=36, shift=3),
+    "quad4": dict(nne=4, ngp=4, dim=2, inc_max=512, te_max=400, shift=6),
+}
+TN_MAX = 255
+GENT_MAX = 65535
+
+
+def _expand_ranges(starts, counts):
+    """Concatenate arange(starts[i], starts[i]+counts[i])."""
+    total = int(counts.sum())
+    if total == 0:
+        return torch.zeros(0, dtype=torch.int64, device=starts.device)
+    ends = torch.cumsum(counts, 0)
+    seg = torch.repeat_interleave(torch.arange(len(counts), device=starts.device), counts)
+    within = torch.arange(total, device=starts.device) - (ends - counts)[seg]
+    return starts[seg] + within
+
+
+def _part1by2(x):
+    x = x & 0x1FFFFF
+    x = (x | (x << 32)) & 0x1F00000000FFFF
+    x = (x | (x << 16)) & 0x1F0000FF0000FF
+    x = (x | (x << 8)) & 0x100F00F00F00F00F
+    x = (x | (x << 4)) & 0x10C30C30C30C30C3
+    x = (x | (x << 2)) & 0x1249249249249249
+    return x
+
+
+def _part1by1(x):
+    x = x & 0xFFFFFFFF
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFF
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FF
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0F
+    x = (x | (x << 2)) & 0x3333333333333333
+    x = (x | (x << 1)) & 0x5555555555555555
+    return x
+
+
+def morton_order(coords):
+    """Locality-preserving node order: per-axis rank buckets -> Morton key -> stable sort.
+
+    For a structured (even jittered) box the buckets are the lattice indices, so Morton
+    blocks are compact bricks of nodes."""
+    n, dim = coords.shape
+    nb = max(1, int(round(n ** (1.0 / dim))))
+    comps = []
+    for d in range(dim):
+        x = coords[:, d]
+        n_unique = int(torch.unique(x).numel())
+        nbd = min(n_unique, nb)
+        if n_unique <= nb:  # structured axis: bucket = index of the coordinate value
+            _, inv = torch.unique(x, sorted=True, return_inverse=True)
+            comps.append(inv.to(torch.int64))
+        else:
+            rank = torch.empty(n, dtype=torch.int64, device=coords.device)
+            rank[torch.argsort(x, stable=True)] = torch.arange(n, device=coords.device)
+            comps.append(rank * nbd // n)
+    if dim == 3:
+        key = _part1by2(comps[0]) | (_part1by2(comps[1]) << 1) | (_part1by2(comps[2]) << 2)
+    else:
+        key = _part1by1(comps[0]) | (_part1by1(comps[1]) << 1)
+    order = torch.argsort(key, stable=True)
+    return order, key[order]
+
+
+@dataclasses.dataclass
+class Pattern:
+    """Block (node-node) CSR pattern and its sorted unique keys I*n_nodes+J."""
+
+    n_nodes: int
+    blk_indptr: torch.Tensor  # int64 [n_nodes+1]
+    blk_indices: torch.Tensor  # int32 [blk_nnz]
+    keys: torch.Tensor  # int64 [blk_nnz] sorted unique
+
+    @property
+    def blk_nnz(self):
+        return int(self.blk_indices.numel())
+
+
+class Plan:
+    """Cluster plan for one (mesh connectivity, element type).  Holds the device tensors and
+    the C struct handed to the kernels."""
+
+    def __init__(self, elem_type, coords, conn, pattern, caps=None, verbose=False):
+        cap = dict(_CAPS[elem_type])
+        if caps:
+            cap.update(caps)
+        self.elem_type = elem_type
+        dev = conn.device
+        n_el, nne = conn.shape
+        assert nne == cap["nne"]
+        n_nodes = pattern.n_nodes
+        self.n_nodes, self.n_elems, self.nne = n_nodes, n_el, nne
+        self.pattern = pattern
+        conn64 = conn.to(torch.int64)
+        M = n_el * nne
+        assert M < 2**31, "incidence count must fit int32"
+
+        # ---- node -> incidences, grouped by node, element-ascending ----
+        nid = conn64.reshape(-1)
+        perm = torch.argsort(nid, stable=True)
+        inc_e_by_node = perm // nne
+        inc_l_by_node = perm % nne
+        inc_count = torch.bincount(nid, minlength=n_nodes)
+        inc_ptr_node = torch.zeros(n_nodes + 1, dtype=torch.int64, device=dev)
+        inc_ptr_node[1:] = torch.cumsum(inc_count, 0)
+        deg = pattern.blk_indptr[1:] - pattern.blk_indptr[:-1]
+
+        # ---- Morton order with unique keys ----
+        order, mk = morton_order(coords)
+        if n_nodes > 0:
+            first = torch.ones(n_nodes, dtype=torch.bool, device=dev)
+            first[1:] = mk[1:] != mk[:-1]
+            run_start = torch.cummax(torch.where(first, torch.arange(n_nodes, device=dev), 0), 0).values
+            within = torch.arange(n_nodes, device=dev) - run_start
+            rbits = max(1, int(within.max()).bit_length())
+        else:
+            within = mk
+            rbits = 1
+        mk = (mk << rbits) | within
+        shift = torch.full((n_nodes,), cap["shift"] + rbits, dtype=torch.int64, device=dev)
+        inc_count_o = inc_count[order]
+        deg_o = deg[order]
+
+        # ---- refine clusters until every one fits ----
+        for it in range(80):
+            ck = mk >> shift
+            b = torch.ones(n_nodes, dtype=torch.bool, device=dev)
+            if n_nodes > 1:
+                b[1:] = (ck[1:] != ck[:-1]) | (shift[1:] != shift[:-1])
+            cl_of_pos = torch.cumsum(b.to(torch.int64), 0) - 1
+            n_cl = int(cl_of_pos[-1]) + 1 if n_nodes > 0 else 0
+            stats = self._cluster_stats(cl_of_pos, n_cl, order, inc_count_o, deg_o, inc_ptr_node, inc_e_by_node, conn64)
+            n_inc_c, n_te_c, n_tn_c = stats["n_inc"], stats["n_te"], stats["n_tn"]
+            bad = (
+                (n_inc_c > cap["inc_max"])
+                | (n_te_c > cap["te_max"])
+                | (n_tn_c > TN_MAX)
+                | (n_inc_c * nne > GENT_MAX)
+            )
+            n_bad = int(bad.sum())
+            if verbose:
+                print(f"[plan] iter {it}: {n_cl} clusters, {n_bad} over capacity")
+            if n_bad == 0:
+                break
+            bad_pos = bad[cl_of_pos]
+            if bool((bad_pos & (shift == 0)).any()):
+                raise _lib.FdkError(
+                    "a single node exceeds the cluster capacity of the kernel "
+                    f"(incidences > {cap['inc_max']} or touched elements > {cap['te_max']})"
+                )
+            shift = torch.where(bad_pos, shift - 1, shift)
+        else:
+            raise _lib.FdkError("cluster refinement did not converge")
+
+        self.n_clusters = n_cl
+        counts_c = torch.bincount(cl_of_pos, minlength=n_cl)
+        cl_node_ptr = torch.zeros(n_cl + 1, dtype=torch.int64, device=dev)
+        cl_node_ptr[1:] = torch.cumsum(counts_c, 0)
+
+        # ---- incidences in cluster order ----
+        cl_inc_ptr = torch.zeros(n_nodes + 1, dtype=torch.int64, device=dev)
+        cl_inc_ptr[1:] = torch.cumsum(inc_count_o, 0)
+        src = _expand_ranges(inc_ptr_node[order], inc_count_o)
+        inc_e = inc_e_by_node[src]
+        inc_l = inc_l_by_node[src]
+        inc_q = torch.repeat_interleave(torch.arange(n_nodes, device=dev), inc_count_o)
+        inc_cl = cl_of_pos[inc_q]
+
+        # ---- touched elements ----
+        te_keys = torch.unique(inc_cl * n_el + inc_e)  # sorted
+        te_cl = te_keys // max(n_el, 1)
+        te_elem = te_keys - te_cl * n_el
+        cl_te_ptr = torch.zeros(n_cl + 1, dtype=torch.int64, device=dev)
+        cl_te_ptr[1:] = torch.cumsum(torch.bincount(te_cl, minlength=n_cl), 0)
+        le = torch.searchsorted(te_keys, inc_cl * n_el + inc_e) - cl_te_ptr[inc_cl]
+        assert M == 0 or int(le.max()) < 4096
+        inc_desc = le | (inc_l << 12)
+        cl_of_node = torch.empty(n_nodes, dtype=torch.int64, device=dev)
+        cl_of_node[order] = cl_of_pos
+        te_own = cl_of_node[conn64[te_elem, 0]] == te_cl if len(te_elem) else torch.zeros(0, dtype=torch.bool, device=dev)
+
+        # ---- touched nodes + local connectivity ----
+        tn_all = te_cl[:, None] * n_nodes + conn64[te_elem]  # (n_te_total, nne)
+        tn_keys = torch.unique(tn_all.reshape(-1))
+        tn_cl = tn_keys // max(n_nodes, 1)
+        tn_node = tn_keys - tn_cl * n_nodes
+        cl_tn_ptr = torch.zeros(n_cl + 1, dtype=torch.int64, device=dev)
+        cl_tn_ptr[1:] = torch.cumsum(torch.bincount(tn_cl, minlength=n_cl), 0)
+        lconn = torch.searchsorted(tn_keys, tn_all.reshape(-1)).reshape(-1, nne) - cl_tn_ptr[te_cl][:, None]
+
+        # ---- slots (block rows in cluster order) ----
+        cl_slot_ptr = torch.zeros(n_nodes + 1, dtype=torch.int64, device=dev)
+        cl_slot_ptr[1:] = torch.cumsum(deg_o, 0)
+        cl_bptr = pattern.blk_indptr[:-1][order]
+        total_slots = int(cl_slot_ptr[-1])
+        assert total_slots == pattern.blk_nnz
+
+        # ---- gather lists ----
+        I = order[inc_q]  # row node of each incidence
+        cl_inc_start = cl_inc_ptr[cl_node_ptr[:-1]]  # first incidence of each cluster
+        k_local = torch.arange(M, device=dev) - cl_inc_start[inc_cl]
+        J = conn64[inc_e]  # (M, nne)
+        pos = torch.searchsorted(pattern.keys, (I[:, None] * n_nodes + J).reshape(-1)).reshape(-1, nne)
+        pcol = pos - pattern.blk_indptr[I][:, None]
+        slot = cl_slot_ptr[inc_q][:, None] + pcol  # cluster-order slot id
+        payload = (k_local[:, None] << 4) | torch.arange(nne, device=dev)[None, :]
+        assert M == 0 or int(payload.max()) < 65536
+        packed = torch.sort(((slot << 16) | payload).reshape(-1)).values
+        g_ent = packed & 0xFFFF
+        g_slot = packed >> 16
+        gcum = torch.zeros(total_slots + 1, dtype=torch.int64, device=dev)
+        gcum[1:] = torch.cumsum(torch.bincount(g_slot, minlength=total_slots), 0)
+        slot0_c = cl_slot_ptr[cl_node_ptr]  # (n_cl+1) first slot of each cluster (+ end)
+        cl_g_base = gcum[slot0_c]
+        g_off = torch.zeros(total_slots + n_cl, dtype=torch.int64, device=dev)
+        if total_slots:
+            cl_of_slot = torch.repeat_interleave(cl_of_pos, deg_o)
+            sl = torch.arange(total_slots, device=dev)
+            g_off[sl + cl_of_slot] = gcum[:-1] - cl_g_base[cl_of_slot]
+        if n_cl:
+            cidx = torch.arange(n_cl, device=dev)
+            g_off[slot0_c[1:] + cidx] = cl_g_base[1:] - cl_g_base[:-1]
+        assert n_cl == 0 or int(g_off.max()) <= GENT_MAX
+
+        # ---- capacities ----
+        def cmax(x):
+            return int(x.max()) if x.numel() else 0
+
+        n_slots_c = slot0_c[1:] - slot0_c[:-1]
+        self.caps = dict(
+            cap_te=cmax(cl_te_ptr[1:] - cl_te_ptr[:-1]),
+            cap_tn=cmax(cl_tn_ptr[1:] - cl_tn_ptr[:-1]),
+            cap_inc=cmax(cl_inc_ptr[cl_node_ptr[1:]] - cl_inc_ptr[cl_node_ptr[:-1]]),
+            cap_owned=cmax(counts_c),
+            cap_slots=cmax(n_slots_c),
+            cap_gent=cmax(cl_g_base[1:] - cl_g_base[:-1]),
+        )
+        self.stats = dict(
+            n_clusters=n_cl,
+            touched_elems_total=int(len(te_elem)),
+            redundancy=float(len(te_elem)) / max(n_el, 1),
+            mean_owned=float(n_nodes) / max(n_cl, 1),
+        )
+
+        # ---- device arrays in their kernel dtypes ----
+        i32, u16, u8 = torch.int32, torch.uint16, torch.uint8
+        self.t = dict(
+            cl_node_ptr=cl_node_ptr.to(i32),
+            cl_node=order.to(i32),
+            cl_bptr=cl_bptr.contiguous(),
+            cl_slot_ptr=cl_slot_ptr,
+            cl_inc_ptr=cl_inc_ptr.to(i32),
+            inc_desc=inc_desc.to(u16),
+            cl_te_ptr=cl_te_ptr.to(i32),
+            cl_te_elem=te_elem.to(i32),
+            cl_te_own=te_own.to(u8),
+            cl_lconn=lconn.to(u8).contiguous(),
+            cl_tn_ptr=cl_tn_ptr.to(i32),
+            cl_tn_node=tn_node.to(i32),
+            cl_g_base=cl_g_base,
+            g_off=g_off.to(u16),
+            g_ent=g_ent.to(u16),
+        )
+        self._structs = {}
+
+    @staticmethod
+    def _cluster_stats(cl_of_pos, n_cl, order, inc_count_o, deg_o, inc_ptr_node, inc_e_by_node, conn64):
+        dev = cl_of_pos.device
+        n_nodes = len(order)
+        n_el = conn64.shape[0]
+        n_inc = torch.zeros(n_cl, dtype=torch.int64, device=dev).index_add_(0, cl_of_pos, inc_count_o)
+        src = _expand_ranges(inc_ptr_node[order], inc_count_o)
+        inc_e = inc_e_by_node[src]
+        inc_cl = torch.repeat_interleave(cl_of_pos, inc_count_o)
+        te_keys = torch.unique(inc_cl * n_el + inc_e)
+        te_cl = te_keys // max(n_el, 1)
+        n_te = torch.bincount(te_cl, minlength=n_cl)
+        te_elem = te_keys - te_cl * n_el
+        tn_keys = torch.unique((te_cl[:, None] * n_nodes + conn64[te_elem]).reshape(-1))
+        n_tn = torch.bincount(tn_keys // max(n_nodes, 1), minlength=n_cl)
+        return dict(n_inc=n_inc, n_te=n_te, n_tn=n_tn)
+
+    def struct(self, nvar):
+        """C struct for an operator with ``nvar`` variables per node."""
+        if nvar not in self._structs:
+            s = _lib.PlanStruct()
+            s.elem_type = _lib.ELEM_IDS[self.elem_type]
+            s.n_nodes = self.n_nodes
+            s.n_elems = self.n_elems
+            s.n_clusters = self.n_clusters
+            s.nvar = nvar
+            s.blk_nnz = self.pattern.blk_nnz
+            for k, v in self.caps.items():
+                setattr(s, k, v)
+            for k, v in self.t.items():
+                setattr(s, k, v.data_ptr())
+            self._structs[nvar] = s
+        return self._structs[nvar]
+
+    def metadata_bytes(self):
+        return sum(v.numel() * v.element_size() for v in self.t.values())

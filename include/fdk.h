@@ -1,0 +1,188 @@
+/*
+ * fdk.h -- C ABI of libfdk (fedoo_b200/_fdk.so): B200-native (sm_100a) kernels for
+ * fedoo's global-operator assembly hot path.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _h;
+ *   - every function returns 0 on success or a negative FDK_E* / a positive
+ *     cudaError_t; fdk_last_error_string() describes the last failure on the
+ *     calling thread;
+ *   - nothing here allocates or frees caller buffers; the symbolic functions
+ *     allocate and release their own temporary workspace;
+ *   - all numeric kernels are launched on the given stream and return
+ *     asynchronously; they are deterministic (no floating-point atomics): every
+ *     CSR value and every entry of the global vector is written exactly once.
+ *   - dof ordering is variable-major: dof = var * n_nodes + node
+ *     (fedoo/core/problem.py:89-91); Gauss-point ordering is gp-major:
+ *     gp_index = gp * n_elems + elem (fedoo/core/mesh.py:1137-1140); Voigt order
+ *     [xx, yy, zz, xy, xz, yz] with engineering shear strains
+ *     (fedoo/core/modelingspace.py:289-316).
+ *
+ * Each entry point names the reference interface it replaces.
+ */
+#ifndef FDK_H
+#define FDK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fdk_stream_t; /* cudaStream_t */
+
+enum fdk_elem_type { FDK_HEX8 = 0, FDK_TET4 = 1, FDK_TET10 = 2, FDK_QUAD4 = 3 };
+
+enum fdk_error {
+  FDK_OK = 0,
+  FDK_EINVAL = -1,   /* bad argument */
+  FDK_ECAP = -2,     /* a cluster exceeds the shared-memory capacity of the kernel */
+  FDK_EOVERFLOW = -3 /* an index does not fit its integer type */
+};
+
+/* compute flags of fdk_assemble_* (fedoo/core/assembly.py:143-151: compute = all|matrix|vector) */
+enum fdk_compute { FDK_MATRIX = 1, FDK_VECTOR = 2, FDK_ALL = 3 };
+
+const char* fdk_last_error_string(void);
+int fdk_version(void);
+
+/* element table accessors (host): what the kernels integrate with.
+ * Replaces fedoo/lib_elements/{hexahedron,tetrahedron,quadrangle}.py tables
+ * (hexahedron.py:22-27,134-135,178-248; tetrahedron.py:21-61,72-97,106-208;
+ * quadrangle.py:24-26,125-167).  out_dN_h: [ngp][dim][nne], out_N_h: [ngp][nne]. */
+int fdk_element_info(int elem_type, int* nne, int* ngp, int* dim);
+int fdk_element_table(int elem_type, double* out_w_h, double* out_N_h, double* out_dN_h);
+
+/* ------------------------------------------------------------------------- *
+ * Symbolic phase (one-time): CSR pattern, bit-exact with the reference's
+ * scipy-built one.  Replaces _BlocSparse.tocsr symbolic part
+ * (fedoo/core/_sparsematrix.py:225-284: key = row*n_cols+col, unique, bincount)
+ * and scipy.sparse.bmat tiling (:310-315).
+ * ------------------------------------------------------------------------- */
+
+/* Step 1: number of distinct (I,J) node pairs sharing an element.
+ * conn: [n_elems][nne] int32.  keys_out: caller buffer of n_elems*nne*nne uint64
+ * receiving the sorted unique keys I*n_nodes+J in its first *blk_nnz_h entries. */
+int fdk_sym_block_keys(int n_nodes, int64_t n_elems, int nne, const int32_t* conn, uint64_t* keys_out,
+                       int64_t* blk_nnz_h, fdk_stream_t stream);
+
+/* Step 2: block CSR from the unique keys: blk_indptr [n_nodes+1] int64, blk_indices [blk_nnz] int32. */
+int fdk_sym_block_csr(int n_nodes, int64_t blk_nnz, const uint64_t* keys, int64_t* blk_indptr, int32_t* blk_indices,
+                      fdk_stream_t stream);
+
+/* Step 3: nvar x nvar tiling -> global CSR of shape (nvar*n_nodes + n_global_dof)^2.
+ * index_bytes = 4 (int32) or 8 (int64): the caller applies scipy's get_index_dtype rule
+ * (int32 iff max(nnz, n_rows) <= 2^31-1).  indptr has nvar*n_nodes+n_global_dof+1 entries. */
+int fdk_sym_expand_csr(int n_nodes, int nvar, int n_global_dof, int64_t blk_nnz, const int64_t* blk_indptr,
+                       const int32_t* blk_indices, int index_bytes, void* indptr, void* indices, fdk_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Assembly plan: node clusters (one CTA each) with everything the numeric
+ * kernels need, built once per mesh by the host (fedoo_b200/plan.py).
+ * ------------------------------------------------------------------------- */
+typedef struct fdk_plan {
+  int32_t elem_type;  /* enum fdk_elem_type */
+  int32_t n_nodes;
+  int64_t n_elems;
+  int32_t n_clusters;
+  int32_t nvar;       /* variables per node of the assembled operator (dim for elasticity, 1 for heat) */
+  int64_t blk_nnz;    /* nnz of the node-node block pattern */
+  /* capacities = max over clusters (sizes the dynamic shared memory) */
+  int32_t cap_te, cap_tn, cap_inc, cap_owned, cap_slots, cap_gent;
+  const int32_t* cl_node_ptr;  /* [n_clusters+1] range of owned nodes (cluster order)            */
+  const int32_t* cl_node;      /* [n_nodes]  global id of the q-th owned node                     */
+  const int64_t* cl_bptr;      /* [n_nodes]  blk_indptr[cl_node[q]]                               */
+  const int64_t* cl_slot_ptr;  /* [n_nodes+1] exclusive cumsum of block-row lengths, cluster order */
+  const int32_t* cl_inc_ptr;   /* [n_nodes+1] range of incidences of the q-th owned node          */
+  const uint16_t* inc_desc;    /* [n_elems*nne] local touched-element index | local node << 12    */
+  const int32_t* cl_te_ptr;    /* [n_clusters+1] range of touched elements                        */
+  const int32_t* cl_te_elem;   /* global element id of each touched element                       */
+  const uint8_t* cl_te_own;    /* 1 if this cluster is the unique owner of the touched element    */
+  const uint8_t* cl_lconn;     /* [n_te_total][nne] local (cluster) index of each element node    */
+  const int32_t* cl_tn_ptr;    /* [n_clusters+1] range of touched nodes                           */
+  const int32_t* cl_tn_node;   /* global node id of each touched node                             */
+  const int64_t* cl_g_base;    /* [n_clusters+1] range of gather entries                          */
+  const uint16_t* g_off;       /* per cluster n_slots+1 offsets at index cl_slot_ptr[q0] + cluster */
+  const uint16_t* g_ent;       /* gather entries: local incidence << 4 | local column node j      */
+} fdk_plan;
+
+/* ------------------------------------------------------------------------- *
+ * Numeric assembly (per step).  Replaces Assembly.assemble_global_mat
+ * (fedoo/core/assembly.py:143-470) + _BlocSparse.addToBlocATB / tocsr numeric part
+ * (fedoo/core/_sparsematrix.py:55-174, 286-315) + the vector branch
+ * (fedoo/core/assembly.py:400-411) for StressEquilibrium (small strain,
+ * fedoo/weakform/stress_equilibrium.py:92-145) and HeatEquation
+ * (fedoo/weakform/heat_equation.py:78-119,168-187).
+ *
+ * coords: [n_nodes][dim] double (fedoo Mesh.nodes layout).
+ * K_values: CSR data of the tiled pattern (nvar*nvar*blk_nnz doubles) or NULL.
+ * D: global vector (nvar*n_nodes doubles) or NULL; D = -int B^T sigma.
+ * ------------------------------------------------------------------------- */
+
+/* Isotropic linear elasticity, uniform (lambda, mu): K from the closed form
+ * K[(c,I),(a,J)] = sum_g w (lambda G_cI G_aJ + mu G_aI G_cJ + mu d_ca G_I.G_J)
+ * (= ElasticIsotrop tangent, fedoo/constitutivelaw/elastic_isotrop.py:35-68; for plane
+ * stress pass lambda = nu E/(1-nu^2)).  The residual uses sigma = C eps(U) computed on
+ * the fly (fused update, fedoo/weakform/stress_equilibrium.py:485-524,589-601 +
+ * fedoo/constitutivelaw/elastic_anisotropic.py:36-56) unless stress_gp != NULL, in
+ * which case sigma is read from stress_gp [6][n_gp] (column-major (6,N), gp-major
+ * columns = sv["Stress"] layout). */
+int fdk_assemble_elastic_iso(const fdk_plan* plan, int compute, const double* coords, double lambda, double mu,
+                             const double* U, const double* stress_gp, double* K_values, double* D,
+                             fdk_stream_t stream);
+
+/* General tangent: C is 6x6 row-major uniform (tangent_gp == NULL) or per Gauss point
+ * tangent_gp [(6,6,N) Fortran order: C_ij of GP n at i + 6 j + 36 n] = sv["TangentMatrix"]
+ * (fedoo/constitutivelaw/simcoon_umat.py:556-580, elastic_anisotropic.py:19-31).
+ * K = sum_g w B^T C_g B (full, no symmetry assumption). Residual as above. */
+int fdk_assemble_elastic_general(const fdk_plan* plan, int compute, const double* coords, const double* C_h,
+                                 const double* tangent_gp, const double* U, const double* stress_gp,
+                                 double* K_values, double* D, fdk_stream_t stream);
+
+/* Heat equation: K_IJ = sum_g w grad N_I . k grad N_J + d_IJ (rho c/dt) sum_g w N_I sum_J N_J
+ * (row-sum lumping, fedoo/core/_sparsematrix.py:91-98); D_I = -sum_g w [grad N_I . k grad T
+ * + (rho c/dt) N_I (T_g - Tstart_g)].  cond_h: 3x3 row-major host array. rho_c_over_dt = 0 for
+ * the steady problem. */
+int fdk_assemble_heat(const fdk_plan* plan, int compute, const double* coords, const double* cond_h,
+                      double rho_c_over_dt, const double* T, const double* T_start, double* K_values, double* D,
+                      fdk_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Gauss-point state update.  Replaces Assembly.get_gp_results / get_grad_disp
+ * (fedoo/core/assembly.py:1045-1112,1285-1336), _comp_linear_strain
+ * (fedoo/weakform/stress_equilibrium.py:589-601) and ElasticAnisotropic.update
+ * (fedoo/constitutivelaw/elastic_anisotropic.py:36-56).
+ * conn: [n_elems][nne] int32. Outputs (any may be NULL): grad_gp [9][n_gp] rows a*3+b = du_a/dx_b
+ * (row-major (9,N)), strain_gp / stress_gp column-major (6,N).  C_h 6x6 row-major host,
+ * or tangent_gp per GP as above. */
+int fdk_gp_strain_stress(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                         const double* U, const double* C_h, const double* tangent_gp, double* grad_gp,
+                         double* strain_gp, double* stress_gp, fdk_stream_t stream);
+
+/* Thermal state: temp_gp [n_gp] and temp_gradient_gp [3][n_gp] (row-major)
+ * (fedoo/weakform/heat_equation.py:64-70,149-152). */
+int fdk_gp_temperature(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                       const double* T, double* temp_gp, double* temp_gradient_gp, fdk_stream_t stream);
+
+/* J2 plasticity (isotropic power-law hardening sigma_Y + k p^m), backward-Euler radial
+ * return + consistent tangent, one thread per Gauss point.  Follows the Simcoon("EPICP")
+ * state-variable protocol of fedoo/constitutivelaw/simcoon_umat.py:463-580 (props
+ * [E, nu, alpha, sigmaY, k, m], statev [T, p, EP(6)] :103-113) and the algorithm sketch of
+ * fedoo/constitutivelaw/elasto_plasticity.py:275-376.  All arrays column-major with gp-major
+ * columns: strain_gp (6,N) total strain, statev_start (8,N) -> stress_gp (6,N), statev (8,N),
+ * tangent_gp (6,6,N) or NULL. */
+int fdk_j2_update(int64_t n_gp, const double* props_h, const double* strain_gp, const double* statev_start,
+                  double* stress_gp, double* statev, double* tangent_gp, fdk_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Multi-GPU helpers: pack / unpack-add of owned or halo entries around an NCCL
+ * exchange of the global vector (no reference counterpart: the reference is
+ * single-process).
+ * ------------------------------------------------------------------------- */
+int fdk_gather_f64(int64_t n, const int64_t* index, const double* src, double* dst, fdk_stream_t stream);
+int fdk_scatter_add_f64(int64_t n, const int64_t* index, const double* src, double* dst, fdk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDK_H */

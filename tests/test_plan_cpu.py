@@ -1,0 +1,86 @@
+"""CPU tests of the cluster plan (host logic): partition properties, capacities and a NumPy
+emulation of the kernel that must reproduce the reference K from the plan arrays alone."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from fedoo_b200 import meshgen
+from fedoo_b200.plan import TN_MAX, _CAPS
+from oracle import fedoo_oracle as fo
+
+from plan_emulator import emulate_iso, make_plan
+
+
+def _mesh(kind):
+    if kind == "hex8":
+        nodes, el = meshgen.box_hex8(9, 7, 6)
+        return meshgen.jitter_nodes(nodes, 9, 7, 6), el
+    if kind == "tet4":
+        nodes, hexes = meshgen.box_hex8(6, 5, 5)
+        return meshgen.jitter_nodes(nodes, 6, 5, 5), meshgen.hex8_to_tet4(hexes)
+    if kind == "tet10":
+        nodes, hexes = meshgen.box_hex8(4, 4, 3)
+        nodes = meshgen.jitter_nodes(nodes, 4, 4, 3)
+        return meshgen.tet4_to_tet10(nodes, meshgen.hex8_to_tet4(hexes), bulge=0.03)
+    nodes, el = meshgen.rect_quad4(12, 9)
+    return meshgen.jitter_nodes_2d(nodes, 12, 9), el
+
+
+@pytest.mark.parametrize("kind", ["hex8", "tet4", "tet10", "quad4"])
+def test_plan_reproduces_reference_K(kind):
+    nodes, el = _mesh(kind)
+    plan, pat = make_plan(kind, nodes, el)
+    dim = nodes.shape[1]
+    lam, mu = 115384.61538461539, 76923.07692307692
+    K = emulate_iso(plan, pat, nodes, el, lam, mu)
+    H = fo.elastic_isotropic_H(200e3, 0.3)
+    Kref = fo.assemble_stiffness(nodes, el, kind, H, dim)
+    assert np.array_equal(Kref.indptr[: len(nodes) + 1] // dim, pat.blk_indptr.numpy())
+    assert np.abs(K - Kref.data).max() <= 1e-12 * np.abs(Kref.data).max()
+
+
+@pytest.mark.parametrize("kind", ["hex8", "tet4", "tet10", "quad4"])
+def test_plan_partition_and_caps(kind):
+    nodes, el = _mesh(kind)
+    plan, pat = make_plan(kind, nodes, el)
+    t = plan.t
+    order = t["cl_node"].numpy()
+    assert np.array_equal(np.sort(order), np.arange(len(nodes)))  # every node owned exactly once
+    cap = _CAPS[kind]
+    assert plan.caps["cap_inc"] <= cap["inc_max"]
+    assert plan.caps["cap_te"] <= cap["te_max"]
+    assert plan.caps["cap_tn"] <= TN_MAX
+    # every element is owned by exactly one cluster
+    own = t["cl_te_own"].numpy().astype(bool)
+    te = t["cl_te_elem"].numpy()
+    assert np.array_equal(np.sort(te[own]), np.arange(len(el)))
+    assert plan.stats["redundancy"] >= 1.0
+
+
+def test_plan_forced_refinement():
+    """Tiny capacities force many refinement rounds; result must stay exact."""
+    nodes, el = _mesh("hex8")
+    plan, pat = make_plan("hex8", nodes, el, caps=dict(inc_max=40, te_max=20))
+    assert plan.caps["cap_inc"] <= 40 and plan.caps["cap_te"] <= 20
+    K = emulate_iso(plan, pat, nodes, el, 1.5, 0.7)
+    G, wdet = fo.geometry(nodes, el, "hex8")
+    H = np.zeros((6, 6))
+    H[:3, :3] = 1.5
+    H[np.arange(3), np.arange(3)] += 1.4
+    H[np.arange(3, 6), np.arange(3, 6)] = 0.7
+    Kref = fo.assemble_stiffness(nodes, el, "hex8", H, 3)
+    assert np.abs(K - Kref.data).max() <= 1e-12 * np.abs(Kref.data).max()
+
+
+def test_plan_unreferenced_nodes_and_single_node_overflow():
+    nodes, el = _mesh("hex8")
+    nodes = np.vstack([nodes, [[5.0, 5.0, 5.0], [6.0, 6.0, 6.0]]])  # two isolated nodes
+    plan, pat = make_plan("hex8", nodes, el)
+    assert plan.n_nodes == len(nodes)
+    from fedoo_b200._lib import FdkError
+
+    with pytest.raises(FdkError):
+        make_plan("hex8", nodes, el, caps=dict(inc_max=4, te_max=80))  # interior nodes have 8 incidences
