@@ -113,7 +113,9 @@ class Plan:
     """Cluster plan for one (mesh connectivity, element type).  Holds the device tensors and
     the C struct handed to the kernels."""
 
-    def __init__(self, elem_type, coords, conn, pattern, caps=None, verbose=False):
+    def __init__(self, elem_type, coords, conn, pattern, caps=None, verbose=False, owned=None):
+        """``owned``: optional bool mask (n_nodes,) -- only these nodes get clusters (their rows are
+        assembled); used by the multi-GPU partition where a rank's local mesh carries halo nodes."""
         cap = dict(_CAPS[elem_type])
         if caps:
             cap.update(caps)
@@ -140,6 +142,11 @@ class Plan:
 
         # ---- Morton order with unique keys ----
         order, mk = morton_order(coords)
+        if owned is not None:
+            keep = owned.to(dev)[order]
+            order, mk = order[keep], mk[keep]
+        n_mesh_nodes = n_nodes
+        n_nodes = int(order.numel())  # from here on: number of OWNED nodes (cluster order)
         if n_nodes > 0:
             first = torch.ones(n_nodes, dtype=torch.bool, device=dev)
             first[1:] = mk[1:] != mk[:-1]
@@ -206,17 +213,17 @@ class Plan:
         cl_te_ptr = torch.zeros(n_cl + 1, dtype=torch.int64, device=dev)
         cl_te_ptr[1:] = torch.cumsum(torch.bincount(te_cl, minlength=n_cl), 0)
         le = torch.searchsorted(te_keys, inc_cl * n_el + inc_e) - cl_te_ptr[inc_cl]
-        assert M == 0 or int(le.max()) < 4096
+        assert le.numel() == 0 or int(le.max()) < 4096
         inc_desc = le | (inc_l << 12)
-        cl_of_node = torch.empty(n_nodes, dtype=torch.int64, device=dev)
+        cl_of_node = torch.full((n_mesh_nodes,), -1, dtype=torch.int64, device=dev)
         cl_of_node[order] = cl_of_pos
         te_own = cl_of_node[conn64[te_elem, 0]] == te_cl if len(te_elem) else torch.zeros(0, dtype=torch.bool, device=dev)
 
         # ---- touched nodes + local connectivity ----
-        tn_all = te_cl[:, None] * n_nodes + conn64[te_elem]  # (n_te_total, nne)
+        tn_all = te_cl[:, None] * n_mesh_nodes + conn64[te_elem]  # (n_te_total, nne)
         tn_keys = torch.unique(tn_all.reshape(-1))
-        tn_cl = tn_keys // max(n_nodes, 1)
-        tn_node = tn_keys - tn_cl * n_nodes
+        tn_cl = tn_keys // max(n_mesh_nodes, 1)
+        tn_node = tn_keys - tn_cl * n_mesh_nodes
         cl_tn_ptr = torch.zeros(n_cl + 1, dtype=torch.int64, device=dev)
         cl_tn_ptr[1:] = torch.cumsum(torch.bincount(tn_cl, minlength=n_cl), 0)
         lconn = torch.searchsorted(tn_keys, tn_all.reshape(-1)).reshape(-1, nne) - cl_tn_ptr[te_cl][:, None]
@@ -226,18 +233,18 @@ class Plan:
         cl_slot_ptr[1:] = torch.cumsum(deg_o, 0)
         cl_bptr = pattern.blk_indptr[:-1][order]
         total_slots = int(cl_slot_ptr[-1])
-        assert total_slots == pattern.blk_nnz
+        assert owned is not None or total_slots == pattern.blk_nnz
 
         # ---- gather lists ----
         I = order[inc_q]  # row node of each incidence
         cl_inc_start = cl_inc_ptr[cl_node_ptr[:-1]]  # first incidence of each cluster
-        k_local = torch.arange(M, device=dev) - cl_inc_start[inc_cl]
+        k_local = torch.arange(inc_e.numel(), device=dev) - cl_inc_start[inc_cl]
         J = conn64[inc_e]  # (M, nne)
-        pos = torch.searchsorted(pattern.keys, (I[:, None] * n_nodes + J).reshape(-1)).reshape(-1, nne)
+        pos = torch.searchsorted(pattern.keys, (I[:, None] * n_mesh_nodes + J).reshape(-1)).reshape(-1, nne)
         pcol = pos - pattern.blk_indptr[I][:, None]
         slot = cl_slot_ptr[inc_q][:, None] + pcol  # cluster-order slot id
         payload = (k_local[:, None] << 4) | torch.arange(nne, device=dev)[None, :]
-        assert M == 0 or int(payload.max()) < 65536
+        assert payload.numel() == 0 or int(payload.max()) < 65536
         packed = torch.sort(((slot << 16) | payload).reshape(-1)).values
         g_ent = packed & 0xFFFF
         g_slot = packed >> 16
@@ -273,7 +280,9 @@ class Plan:
             touched_elems_total=int(len(te_elem)),
             redundancy=float(len(te_elem)) / max(n_el, 1),
             mean_owned=float(n_nodes) / max(n_cl, 1),
+            n_owned=n_nodes,
         )
+        self.n_owned = n_nodes
 
         # ---- device arrays in their kernel dtypes ----
         i32, u16, u8 = torch.int32, torch.uint16, torch.uint8
@@ -299,7 +308,7 @@ class Plan:
     @staticmethod
     def _cluster_stats(cl_of_pos, n_cl, order, inc_count_o, deg_o, inc_ptr_node, inc_e_by_node, conn64):
         dev = cl_of_pos.device
-        n_nodes = len(order)
+        n_nodes = int(inc_ptr_node.numel()) - 1  # mesh nodes
         n_el = conn64.shape[0]
         n_inc = torch.zeros(n_cl, dtype=torch.int64, device=dev).index_add_(0, cl_of_pos, inc_count_o)
         src = _expand_ranges(inc_ptr_node[order], inc_count_o)
