@@ -56,6 +56,14 @@ class Assembly(_Named):
         self.space = weakform.space
         self.current = self
         self.meshChange = kargs.pop("MeshChange", False)
+        # multi-GPU: bool mask of the nodes whose rows this rank assembles (fedoo_b200/dist.py)
+        self.owned_nodes = kargs.pop("owned_nodes", None)
+        # reuse the K / D device buffers (and a pinned host buffer for D) across assemblies
+        # instead of replacing them (the reference replaces; useful for 15 GB matrices)
+        self.reuse_buffers = kargs.pop("reuse_buffers", False)
+        # leave the global vector in HBM (``global_vector`` is then the CUDA tensor): no D2H copy
+        self.vector_on_device = kargs.pop("vector_on_device", False)
+        self._bufs = {}
         self.mesh = mesh
         if elm_type == "":
             elm_type = mesh.elm_type
@@ -95,14 +103,13 @@ class Assembly(_Named):
     # ------------------------------------------------------------------ symbolic (one-time)
     def _symbolic(self):
         """Pattern, tiled CSR and cluster plan; cached per (mesh, element type) and per nvar."""
-        key = (id(self.mesh), self.elm_type)
-        if self.meshChange and self._saved_bloc_structure is not None:
-            self._saved_bloc_structure["coords"] = None  # node positions changed: re-upload only
+        key = (id(self.mesh), self.elm_type, id(self.owned_nodes))
         entry = Assembly._saved_plans.get(key)
         if entry is None:
             coords, conn = self.mesh.device_arrays()
             pattern = symbolic.build_pattern(conn, self.mesh.n_nodes)
-            plan = symbolic.build_plan(self.elm_type, coords, conn, pattern)
+            owned = None if self.owned_nodes is None else torch.from_numpy(np.asarray(self.owned_nodes, dtype=bool))
+            plan = symbolic.build_plan(self.elm_type, coords, conn, pattern, owned=owned)
             entry = {"pattern": pattern, "plan": plan, "csr": {}}
             Assembly._saved_plans[key] = entry
         nvar = self.nvar
@@ -141,8 +148,8 @@ class Assembly(_Named):
             stress = self.sv.get("Stress", 0)
             has_vec = want_vec and not (np.isscalar(stress) and stress == 0)
             flags = (_lib.MATRIX if want_mat else 0) | (_lib.VECTOR if has_vec else 0)
-            K = torch.empty(nvar * nvar * pattern.blk_nnz, dtype=torch.float64, device=dev) if want_mat else None
-            D = torch.zeros(nvar * n_nodes + n_glob, dtype=torch.float64, device=dev) if has_vec else None
+            K = self._buffer("K", nvar * nvar * pattern.blk_nnz) if want_mat else None
+            D = self._buffer("D", nvar * n_nodes + n_glob, zero=True) if has_vec else None
             U_dev = stress_dev = None
             if has_vec:
                 if isinstance(stress, _FusedElasticStress):
@@ -174,8 +181,8 @@ class Assembly(_Named):
             T_dev = self._U_dev
             has_vec = want_vec and T_dev is not None
             flags = (_lib.MATRIX if want_mat else 0) | (_lib.VECTOR if has_vec else 0)
-            K = torch.empty(pattern.blk_nnz, dtype=torch.float64, device=dev) if want_mat else None
-            D = torch.zeros(n_nodes + n_glob, dtype=torch.float64, device=dev) if has_vec else None
+            K = self._buffer("K", pattern.blk_nnz) if want_mat else None
+            D = self._buffer("D", n_nodes + n_glob, zero=True) if has_vec else None
             if flags:
                 rc = lib.fdk_assemble_heat(
                     C.byref(plan.struct(1)), flags, _lib.ptr(coords), _lib.ptr(cond), rcdt, _lib.ptr(T_dev),
@@ -191,10 +198,33 @@ class Assembly(_Named):
         if want_vec:
             if has_vec:
                 self.global_vector_device = D
-                self.global_vector = D.cpu().numpy()
+                self.global_vector = D if self.vector_on_device else self._to_host(D)
             else:
                 self.global_vector_device = None
                 self.global_vector = 0
+
+    def _buffer(self, tag, n, zero=False):
+        """Device output buffer.  Entries the kernels do not write (global dofs, halo nodes of a
+        rank-local mesh) must read 0, hence ``zero`` on (first) allocation."""
+        dev = device()
+        if not self.reuse_buffers:
+            return (torch.zeros if zero else torch.empty)(n, dtype=torch.float64, device=dev)
+        b = self._bufs.get(tag)
+        if b is None or b.numel() != n:
+            b = (torch.zeros if zero else torch.empty)(n, dtype=torch.float64, device=dev)
+            self._bufs[tag] = b
+        return b
+
+    def _to_host(self, D):
+        if not self.reuse_buffers:
+            return D.cpu().numpy()
+        h = self._bufs.get("D_host")
+        if h is None or h.numel() != D.numel():
+            h = torch.empty(D.numel(), dtype=torch.float64, pin_memory=True)
+            self._bufs["D_host"] = h
+        h.copy_(D, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return h.numpy()
 
     def get_global_matrix(self):
         if self.global_matrix is None:
