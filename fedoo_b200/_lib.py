@@ -42,22 +42,27 @@ class PlanStruct(C.Structure):
         ("cap_inc", C.c_int32),
         ("cap_owned", C.c_int32),
         ("cap_slots", C.c_int32),
-        ("cap_gent", C.c_int32),
+        ("cap_ent", C.c_int32),
+        ("threads", C.c_int32),
+        ("reserved", C.c_int32),
         ("cl_node_ptr", C.c_void_p),
         ("cl_node", C.c_void_p),
         ("cl_bptr", C.c_void_p),
         ("cl_slot_ptr", C.c_void_p),
+        ("cl_finc_ptr", C.c_void_p),
         ("cl_inc_ptr", C.c_void_p),
         ("inc_desc", C.c_void_p),
+        ("inc_dst", C.c_void_p),
+        ("inc_fdst", C.c_void_p),
         ("cl_te_ptr", C.c_void_p),
         ("cl_te_elem", C.c_void_p),
         ("cl_te_own", C.c_void_p),
         ("cl_lconn", C.c_void_p),
         ("cl_tn_ptr", C.c_void_p),
         ("cl_tn_node", C.c_void_p),
-        ("cl_g_base", C.c_void_p),
-        ("g_off", C.c_void_p),
-        ("g_ent", C.c_void_p),
+        ("slot_off", C.c_void_p),
+        ("cl_heavy_ptr", C.c_void_p),
+        ("heavy_slot", C.c_void_p),
     ]
 
 

@@ -1,23 +1,29 @@
 // fdk_assemble.cuh -- owner-computes cluster kernels for K (CSR values) and D (global vector).
 //
-// One CTA per node cluster.  The cluster OWNS a compact set of nodes, hence the 3 (nvar)
-// CSR rows of each of them, and computes every contribution to those rows itself:
+// One CTA per node cluster.  The cluster OWNS a compact set of nodes, hence the nvar CSR rows
+// of each of them, and computes every contribution to those rows itself:
 //
-//   phase 0  stage tables, coordinates and dof values of the touched nodes in shared memory
-//   phase 1  one thread per (touched element, Gauss point): Jacobian, inverse, |det J| w and
+//   phase 0  stage tables, coordinates, dof values, local connectivity and the slot offsets of
+//            the cluster in shared memory; every thread prefetches the descriptor of "its"
+//            incidence (owned node I, element e containing I) into registers
+//   phase 1  one task per (touched element, Gauss point): Jacobian, inverse, |det J| w and
 //            dN/dx (and w*sigma for the residual) -> shared memory, computed ONCE per cluster
 //            and reused by all incidences (the reference caches these as sparse operators,
 //            fedoo/core/assembly.py:776-928; here they never leave the SM)
-//   phase 2  one thread per incidence (owned node I, element e containing I): accumulates in
+//   phase 2  one thread per incidence, in ELEMENT-major order so that the lanes of one element
+//            read the same dN/dx rows (shared-memory broadcast, 128-bit loads): accumulates in
 //            registers, over the Gauss points, the nne blocks S_IJ = sum_g w G_I (x) G_J
 //            (isotropic closed form), B_I^T C_g B_J (general tangent) or the scalar conduction
 //            term (heat) -- the batched A^T diag(c) B of fedoo/core/_sparsematrix.py:83-89 --
-//            and the nodal force B_I^T sigma (fedoo/core/assembly.py:400-411)
-//   phase 3  slot-centric gather: one thread per CSR block slot (I, J) sums the blocks of the
-//            elements shared by I and J in a fixed order (the cluster-local analogue of the
-//            reference's Matrix_convertCOOtoCSR SpMV, fedoo/core/_sparsematrix.py:256-302),
-//            applies the constitutive closed form and writes the nvar x nvar scalars to their
-//            final positions of the variable-major tiled CSR (scipy.sparse.bmat layout).
+//            and the nodal force B_I^T sigma (fedoo/core/assembly.py:400-411); then scatters the
+//            blocks into a staging array SORTED BY CSR SLOT (positions precomputed by the plan)
+//   phase 3  slot-centric gather: one thread per CSR block slot (I, J) sums the contiguous run
+//            of staged blocks of the elements shared by I and J in a fixed order (the
+//            cluster-local analogue of the reference's Matrix_convertCOOtoCSR SpMV,
+//            fedoo/core/_sparsematrix.py:256-302), applies the constitutive closed form and
+//            writes the nvar x nvar scalars to their final positions of the variable-major tiled
+//            CSR (scipy.sparse.bmat layout).  Slots with many contributions (the diagonal) are
+//            pre-reduced by a lane-balanced pass so that the main pass diverges little.
 //
 // No floating-point atomics anywhere: each K value and each D entry is written exactly once,
 // so results are bit-reproducible run to run.  Rows are never exchanged between CTAs (or GPUs).
@@ -28,6 +34,8 @@
 namespace fdk {
 
 enum Physics { PHYS_ISO = 0, PHYS_GENERAL = 1, PHYS_HEAT = 2 };
+
+constexpr int HEAVY_T = 4;  // slots with more contributions are pre-reduced (must match plan.py)
 
 struct AsmArgs {
   fdk_plan p;
@@ -43,7 +51,7 @@ struct AsmArgs {
   double cond[9];   // conductivity, row-major
   double rcdt;      // rho c / dt
   int compute;
-  int big_doubles;  // size of the aliased geometry / block region
+  int big_doubles;  // size of the aliased geometry / staging region
 };
 
 template <class El, int PHYS>
@@ -52,22 +60,32 @@ struct Layout {
   static constexpr int NV = (PHYS == PHYS_HEAT) ? 1 : DIM;    // variables per node
   static constexpr int NU = (PHYS == PHYS_HEAT) ? 2 : DIM;    // staged nodal values per touched node
   static constexpr int BLK = NV * NV;                         // scalars per (I,J) block
+  static constexpr int BLKP = BLK | 1;                        // odd staging stride (bank spread)
   static constexpr int NSIG = (PHYS == PHYS_HEAT) ? DIM + 1 : (DIM == 3 ? 6 : 3);
-  static constexpr int GSTR = DIM * NNE + 1 + NSIG;           // per (element, gp): G[k][d], w, w*sigma
-  static constexpr int ESTR = (NGP * GSTR) | 1;               // odd stride: spreads banks across elements
-  static constexpr int SSTR = (NNE * BLK + NV) | 1;           // per incidence: nne blocks + nodal force
-  static constexpr int TSTR = (DIM * NNE) | 1;                // padded dN table row
-  static constexpr int TAB_DOUBLES = NGP * TSTR + NGP * NNE + NGP + 1;
+  static constexpr int GROW = DIM * NNE;                      // dN/dx of one (element, gp): [k][d]
+  static_assert(GROW % 2 == 0, "128-bit rows");
+  static constexpr int ESTR = NGP * GROW + 2;                 // +16 B: consecutive elements hit different banks
+  static constexpr int TSTR = GROW | 1;                       // padded dN table row
+  static constexpr int TAB_DOUBLES = (NGP * TSTR + NGP * NNE + NGP + 1) & ~1;
+
+  // doubles of the geometry view of the big region
+  static long geo_doubles(const fdk_plan& p) { return (long)p.cap_te * (ESTR + NGP + NGP * NSIG); }
+  // doubles of the staging view
+  static long stage_doubles(const fdk_plan& p) { return (long)p.cap_ent * BLKP + (long)p.cap_inc * NV; }
 
   static size_t smem_bytes(const fdk_plan& p, int* big_doubles) {
-    long big = (long)p.cap_te * ESTR;
-    long s = (long)p.cap_inc * SSTR;
+    long big = geo_doubles(p);
+    const long s = stage_doubles(p);
     if (s > big) big = s;
     big = (big + 1) & ~1L;
     *big_doubles = (int)big;
-    long doubles = TAB_DOUBLES + (long)p.cap_tn * (DIM + NU) + big;
-    doubles = (doubles + 1) & ~1L;
-    return (size_t)doubles * 8 + (size_t)(2 * (p.cap_owned + 1)) * 4;
+    long doubles = TAB_DOUBLES + (((long)p.cap_tn * (DIM + NU) + 1) & ~1L) + big;
+    size_t bytes = (size_t)doubles * 8;
+    bytes += (size_t)(2 * (p.cap_owned + 1)) * 4;     // sSlotBase, sFinc
+    bytes += (size_t)((p.cap_slots + 2) & ~1) * 2;    // sOff (u16)
+    bytes += (size_t)((p.cap_slots + 3) & ~3);        // sOwner (u8)
+    bytes += (size_t)((p.cap_te * NNE + 3) & ~3);     // sLconn (u8)
+    return bytes;
   }
 };
 
@@ -166,12 +184,11 @@ __device__ __forceinline__ void apply_tangent(const double* __restrict__ C, int 
   }
 }
 
-template <class El, int PHYS>
-__global__ void __launch_bounds__(El::THREADS, 1) k_assemble(const __grid_constant__ AsmArgs a) {
+template <class El, int PHYS, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constant__ AsmArgs a) {
   using L = Layout<El, PHYS>;
-  constexpr int NNE = L::NNE, NGP = L::NGP, DIM = L::DIM, NV = L::NV, NU = L::NU, BLK = L::BLK;
-  constexpr int NSIG = L::NSIG, GSTR = L::GSTR, ESTR = L::ESTR, SSTR = L::SSTR, TSTR = L::TSTR;
-  constexpr int THREADS = El::THREADS;
+  constexpr int NNE = L::NNE, NGP = L::NGP, DIM = L::DIM, NV = L::NV, NU = L::NU, BLK = L::BLK, BLKP = L::BLKP;
+  constexpr int NSIG = L::NSIG, GROW = L::GROW, ESTR = L::ESTR, TSTR = L::TSTR;
   const fdk_plan& p = a.p;
   const int c = blockIdx.x, tid = threadIdx.x;
   const bool do_mat = (a.compute & FDK_MATRIX) != 0;
@@ -180,9 +197,37 @@ __global__ void __launch_bounds__(El::THREADS, 1) k_assemble(const __grid_consta
   const int q0 = p.cl_node_ptr[c], n_owned = p.cl_node_ptr[c + 1] - q0;
   const int te0 = p.cl_te_ptr[c], n_te = p.cl_te_ptr[c + 1] - te0;
   const int tn0 = p.cl_tn_ptr[c], n_tn = p.cl_tn_ptr[c + 1] - tn0;
-  const int inc0 = p.cl_inc_ptr[q0], n_inc = p.cl_inc_ptr[q0 + n_owned] - inc0;
+  const int inc0 = p.cl_inc_ptr[c], n_inc = p.cl_inc_ptr[c + 1] - inc0;
   const int64_t slot0 = p.cl_slot_ptr[q0];
   const int n_slots = (int)(p.cl_slot_ptr[q0 + n_owned] - slot0);
+
+  // ---- this thread's incidence (long-latency loads issued first, consumed in phase 2) ----
+  unsigned my_desc = 0, my_fdst = 0;
+  unsigned short my_dst[NNE];
+  if (tid < n_inc) {
+    my_desc = p.inc_desc[inc0 + tid];
+    my_fdst = p.inc_fdst[inc0 + tid];
+    const unsigned short* dp = p.inc_dst + (int64_t)(inc0 + tid) * NNE;
+    if constexpr (NNE % 4 == 0) {
+      const uint2* d2 = reinterpret_cast<const uint2*>(dp);
+#pragma unroll
+      for (int j = 0; j < NNE / 4; ++j) {
+        const uint2 v = d2[j];
+        my_dst[4 * j + 0] = (unsigned short)(v.x & 0xFFFF);
+        my_dst[4 * j + 1] = (unsigned short)(v.x >> 16);
+        my_dst[4 * j + 2] = (unsigned short)(v.y & 0xFFFF);
+        my_dst[4 * j + 3] = (unsigned short)(v.y >> 16);
+      }
+    } else {
+      const unsigned* d1 = reinterpret_cast<const unsigned*>(dp);  // NNE even: 4-byte aligned
+#pragma unroll
+      for (int j = 0; j < NNE / 2; ++j) {
+        const unsigned v = d1[j];
+        my_dst[2 * j + 0] = (unsigned short)(v & 0xFFFF);
+        my_dst[2 * j + 1] = (unsigned short)(v >> 16);
+      }
+    }
+  }
 
   extern __shared__ __align__(16) double smem[];
   double* sdN = smem;
@@ -190,15 +235,25 @@ __global__ void __launch_bounds__(El::THREADS, 1) k_assemble(const __grid_consta
   double* sW = sN + NGP * NNE;
   double* sX = smem + L::TAB_DOUBLES;
   double* sU = sX + p.cap_tn * DIM;
-  double* sBig = sU + p.cap_tn * NU;
-  int* sSlotBase = reinterpret_cast<int*>(smem + ((L::TAB_DOUBLES + p.cap_tn * (DIM + NU) + a.big_doubles + 1) & ~1));
-  int* sIncPtr = sSlotBase + (p.cap_owned + 1);
+  double* sBig = smem + L::TAB_DOUBLES + ((p.cap_tn * (DIM + NU) + 1) & ~1);
+  // geometry view
+  double* sG = sBig;                               // [n_te][ESTR]
+  double* sWd = sG + (long)p.cap_te * ESTR;        // [n_te][NGP]       w_g |det J|
+  double* sSig = sWd + (long)p.cap_te * NGP;       // [n_te][NGP][NSIG] w * sigma
+  // staging view (aliases the geometry once phase 2 has read it)
+  double* sBlk = sBig;                             // [cap_ent][BLKP]
+  double* sF = sBlk + (long)p.cap_ent * BLKP;      // [cap_inc][NV]
+  int* sSlotBase = reinterpret_cast<int*>(sBig + a.big_doubles);
+  int* sFinc = sSlotBase + (p.cap_owned + 1);
+  unsigned short* sOff = reinterpret_cast<unsigned short*>(sFinc + (p.cap_owned + 1));
+  unsigned char* sOwner = reinterpret_cast<unsigned char*>(sOff + ((p.cap_slots + 2) & ~1));
+  unsigned char* sLconn = sOwner + ((p.cap_slots + 3) & ~3);
 
   // ---------------- phase 0: staging ----------------
   {
     const ElemTable& tab = c_tab[El::ID];
-    for (int t = tid; t < NGP * DIM * NNE; t += THREADS) {
-      const int g = t / (DIM * NNE), r = t - g * (DIM * NNE);
+    for (int t = tid; t < NGP * GROW; t += THREADS) {
+      const int g = t / GROW, r = t - g * GROW;
       sdN[g * TSTR + r] = tab.dN[t];
     }
     for (int t = tid; t < NGP * NNE; t += THREADS) sN[t] = tab.N[t];
@@ -218,9 +273,21 @@ __global__ void __launch_bounds__(El::THREADS, 1) k_assemble(const __grid_consta
         }
       }
     }
+    {
+      const unsigned char* lc = p.cl_lconn + (int64_t)te0 * NNE;
+      for (int t = tid; t < n_te * NNE; t += THREADS) sLconn[t] = lc[t];
+    }
+    {
+      const unsigned short* go = p.slot_off + slot0 + c;
+      for (int t = tid; t <= n_slots; t += THREADS) sOff[t] = go[t];
+    }
     for (int t = tid; t <= n_owned; t += THREADS) {
       sSlotBase[t] = (int)(p.cl_slot_ptr[q0 + t] - slot0);
-      sIncPtr[t] = p.cl_inc_ptr[q0 + t] - inc0;
+      sFinc[t] = p.cl_finc_ptr[q0 + t] - p.cl_finc_ptr[q0];
+    }
+    for (int t = tid; t < n_owned; t += THREADS) {
+      const int b0 = (int)(p.cl_slot_ptr[q0 + t] - slot0), b1 = (int)(p.cl_slot_ptr[q0 + t + 1] - slot0);
+      for (int s = b0; s < b1; ++s) sOwner[s] = (unsigned char)t;
     }
   }
   __syncthreads();
@@ -228,7 +295,7 @@ __global__ void __launch_bounds__(El::THREADS, 1) k_assemble(const __grid_consta
   // ---------------- phase 1: geometry (+ w*sigma) per (touched element, gp) ----------------
   for (int task = tid; task < n_te * NGP; task += THREADS) {
     const int le = task / NGP, g = task - le * NGP;
-    const uint8_t* lc = p.cl_lconn + (int64_t)(te0 + le) * NNE;
+    const unsigned char* lc = sLconn + le * NNE;
     int ln[NNE];
     double X[NNE][DIM];
 #pragma unroll
@@ -239,15 +306,18 @@ __global__ void __launch_bounds__(El::THREADS, 1) k_assemble(const __grid_consta
     }
     double G[NNE][DIM];
     const double w = gp_geometry<NNE, DIM>(sdN + g * TSTR, sW[g], X, G);
-    double* out = sBig + le * ESTR + g * GSTR;
+    {
+      double2* out = reinterpret_cast<double2*>(sG + le * ESTR + g * GROW);
 #pragma unroll
-    for (int k = 0; k < NNE; ++k)
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) out[k * DIM + d] = G[k][d];
-    out[DIM * NNE] = w;
+      for (int t = 0; t < GROW / 2; ++t) {
+        const int k0 = (2 * t) / DIM, d0 = (2 * t) % DIM, k1 = (2 * t + 1) / DIM, d1 = (2 * t + 1) % DIM;
+        out[t] = make_double2(G[k0][d0], G[k1][d1]);
+      }
+    }
+    sWd[le * NGP + g] = w;
 
     if (do_vec) {
-      double* so = out + DIM * NNE + 1;
+      double* so = sSig + (le * NGP + g) * NSIG;
       if constexpr (PHYS == PHYS_HEAT) {
         double gT[DIM], dTg = 0.0;
 #pragma unroll
@@ -333,23 +403,33 @@ __global__ void __launch_bounds__(El::THREADS, 1) k_assemble(const __grid_consta
   for (int v = 0; v < NV; ++v) f[v] = 0.0;
 
   if (tid < n_inc) {
-    const unsigned desc = p.inc_desc[inc0 + tid];
-    const int le = desc & 0xFFF, i = desc >> 12;
-    const double* eb = sBig + le * ESTR;
+    const int le = my_desc & 0xFFF, i = my_desc >> 12;
+    const double* eb = sG + le * ESTR;
     [[maybe_unused]] int64_t e_glob = 0;
     if constexpr (PHYS == PHYS_GENERAL) {
       if (a.tangent_gp != nullptr) e_glob = p.cl_te_elem[te0 + le];
     }
 #pragma unroll 1
     for (int g = 0; g < NGP; ++g) {
-      const double* gb = eb + g * GSTR;
-      const double w = gb[DIM * NNE];
+      const double* gb = eb + g * GROW;
+      // all dN/dx of the element at this gp: the lanes of one element read the same addresses
+      double Gr[GROW];
+      {
+        const double2* g2 = reinterpret_cast<const double2*>(gb);
+#pragma unroll
+        for (int t = 0; t < GROW / 2; ++t) {
+          const double2 v = g2[t];
+          Gr[2 * t] = v.x;
+          Gr[2 * t + 1] = v.y;
+        }
+      }
+      const double w = sWd[le * NGP + g];
       double gi[DIM];
 #pragma unroll
       for (int d = 0; d < DIM; ++d) gi[d] = gb[i * DIM + d];
 
       if (do_vec) {
-        const double* ws = gb + DIM * NNE + 1;
+        const double* ws = sSig + (le * NGP + g) * NSIG;
         if constexpr (PHYS == PHYS_HEAT) {
           double s = ws[DIM] * sN[g * NNE + i];
 #pragma unroll
@@ -372,13 +452,11 @@ __global__ void __launch_bounds__(El::THREADS, 1) k_assemble(const __grid_consta
           for (int d = 0; d < DIM; ++d) wgi[d] = w * gi[d];
 #pragma unroll
           for (int j = 0; j < NNE; ++j) {
-            double gj[DIM];
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) gj[d] = gb[j * DIM + d];
 #pragma unroll
             for (int cc = 0; cc < DIM; ++cc)
 #pragma unroll
-              for (int aa = 0; aa < DIM; ++aa) acc[j][cc * DIM + aa] = fma(wgi[cc], gj[aa], acc[j][cc * DIM + aa]);
+              for (int aa = 0; aa < DIM; ++aa)
+                acc[j][cc * DIM + aa] = fma(wgi[cc], Gr[j * DIM + aa], acc[j][cc * DIM + aa]);
           }
         } else if constexpr (PHYS == PHYS_HEAT) {
           double kgi[DIM];
@@ -398,7 +476,7 @@ __global__ void __launch_bounds__(El::THREADS, 1) k_assemble(const __grid_consta
           for (int j = 0; j < NNE; ++j) {
             double s = (j == i) ? m : 0.0;
 #pragma unroll
-            for (int d = 0; d < DIM; ++d) s = fma(kgi[d], gb[j * DIM + d], s);
+            for (int d = 0; d < DIM; ++d) s = fma(kgi[d], Gr[j * DIM + d], s);
             acc[j][0] += s;
           }
         } else {  // PHYS_GENERAL: t[c][s] = w sum_s' B_I[s'][c] C[s'][s]; acc[j][c][a] += sum_s t[c][s] B_J[s][a]
@@ -432,7 +510,7 @@ __global__ void __launch_bounds__(El::THREADS, 1) k_assemble(const __grid_consta
           for (int j = 0; j < NNE; ++j) {
             double gj[DIM];
 #pragma unroll
-            for (int d = 0; d < DIM; ++d) gj[d] = gb[j * DIM + d];
+            for (int d = 0; d < DIM; ++d) gj[d] = Gr[j * DIM + d];
 #pragma unroll
             for (int cc = 0; cc < DIM; ++cc) {
               if constexpr (DIM == 3) {
@@ -449,42 +527,56 @@ __global__ void __launch_bounds__(El::THREADS, 1) k_assemble(const __grid_consta
       }
     }
   }
-  __syncthreads();  // everyone is done reading the geometry region; it becomes the block region
+  __syncthreads();  // everyone is done reading the geometry region; it becomes the staging region
   if (tid < n_inc) {
-    double* sp = sBig + tid * SSTR;
     if (do_mat) {
 #pragma unroll
-      for (int j = 0; j < NNE; ++j)
+      for (int j = 0; j < NNE; ++j) {
+        double* sp = sBlk + (int)my_dst[j] * BLKP;
 #pragma unroll
-        for (int b = 0; b < BLK; ++b) sp[j * BLK + b] = acc[j][b];
+        for (int b = 0; b < BLK; ++b) sp[b] = acc[j][b];
+      }
     }
     if (do_vec) {
 #pragma unroll
-      for (int v = 0; v < NV; ++v) sp[NNE * BLK + v] = f[v];
+      for (int v = 0; v < NV; ++v) sF[my_fdst * NV + v] = f[v];
     }
   }
   __syncthreads();
 
-  // ---------------- phase 3: slot-centric gather, constitutive closed form, final stores ----------------
   if (do_mat) {
-    const int64_t gbase = p.cl_g_base[c];
-    const uint16_t* goff = p.g_off + slot0 + c;
-    for (int s = tid; s < n_slots; s += THREADS) {
-      int lo = 0, hi = n_owned;  // owner node n: sSlotBase[n] <= s < sSlotBase[n+1]
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (sSlotBase[mid] <= s) lo = mid; else hi = mid;
+    // ---------------- phase 3a: lane-balanced pre-reduction of the heavy slots ----------------
+    {
+      const int h0 = p.cl_heavy_ptr[c], n_heavy = p.cl_heavy_ptr[c + 1] - h0;
+      if (n_heavy > 0) {  // uniform over the CTA
+        for (int t = tid; t < n_heavy * BLK; t += THREADS) {
+          const int h = t / BLK, b = t - h * BLK;
+          const int s = p.heavy_slot[h0 + h];
+          const int n = sOwner[s];
+          const int e0 = sOff[s];
+          const int e1 = (int)sOff[s + 1] - ((s + 1 == sSlotBase[n + 1]) ? 1 : 0);
+          double v = 0.0;
+          for (int e = e0; e < e1; ++e) v += sBlk[e * BLKP + b];
+          sBlk[e0 * BLKP + b] = v;
+        }
+        __syncthreads();
       }
-      const int n = lo;
-      const int pcol = s - sSlotBase[n];
-      const int deg = sSlotBase[n + 1] - sSlotBase[n];
-      const int t0 = goff[s], t1 = goff[s + 1];
+    }
+    // ---------------- phase 3b: slot gather, constitutive closed form, final stores ----------------
+    for (int s = tid; s < n_slots; s += THREADS) {
+      const int n = sOwner[s];
+      const int sb = sSlotBase[n];
+      const int deg = sSlotBase[n + 1] - sb;
+      const int pcol = s - sb;
+      const int e0 = sOff[s];
+      int cnt = (int)sOff[s + 1] - e0 - ((pcol == deg - 1) ? 1 : 0);  // one gap entry after each row
+      if (cnt > HEAVY_T) cnt = 1;                                    // pre-reduced in 3a
       double S[BLK];
+      const double* sp = sBlk + e0 * BLKP;
 #pragma unroll
-      for (int b = 0; b < BLK; ++b) S[b] = 0.0;
-      for (int t = t0; t < t1; ++t) {
-        const unsigned ent = p.g_ent[gbase + t];
-        const double* sp = sBig + (ent >> 4) * SSTR + (ent & 15) * BLK;
+      for (int b = 0; b < BLK; ++b) S[b] = (cnt > 0) ? sp[b] : 0.0;
+      for (int t = 1; t < cnt; ++t) {
+        sp += BLKP;
 #pragma unroll
         for (int b = 0; b < BLK; ++b) S[b] += sp[b];
       }
@@ -520,9 +612,9 @@ __global__ void __launch_bounds__(El::THREADS, 1) k_assemble(const __grid_consta
       double s[NV];
 #pragma unroll
       for (int v = 0; v < NV; ++v) s[v] = 0.0;
-      for (int k = sIncPtr[n]; k < sIncPtr[n + 1]; ++k)
+      for (int k = sFinc[n]; k < sFinc[n + 1]; ++k)
 #pragma unroll
-        for (int v = 0; v < NV; ++v) s[v] += sBig[k * SSTR + NNE * BLK + v];
+        for (int v = 0; v < NV; ++v) s[v] += sF[k * NV + v];
       const int node = p.cl_node[q0 + n];
 #pragma unroll
       for (int v = 0; v < NV; ++v) a.D[(int64_t)v * p.n_nodes + node] = -s[v];
@@ -531,24 +623,34 @@ __global__ void __launch_bounds__(El::THREADS, 1) k_assemble(const __grid_consta
 }
 
 // ---- host launcher -----------------------------------------------------------------------
-template <class El, int PHYS>
-int launch_assemble(AsmArgs& a, cudaStream_t stream) {
+template <class El, int PHYS, int THREADS, int MINB>
+int launch_assemble_t(AsmArgs& a, cudaStream_t stream) {
   using L = Layout<El, PHYS>;
   const fdk_plan& p = a.p;
-  FDK_REQUIRE(p.cap_inc <= El::THREADS, FDK_ECAP, "cluster with %d incidences exceeds CTA size %d", p.cap_inc,
-              El::THREADS);
-  FDK_REQUIRE(p.cap_te < 4096 && p.cap_tn <= 256 && p.cap_gent < 65536, FDK_ECAP,
-              "cluster capacity overflow (te=%d tn=%d gent=%d)", p.cap_te, p.cap_tn, p.cap_gent);
+  FDK_REQUIRE(p.cap_inc <= THREADS, FDK_ECAP, "cluster with %d incidences exceeds CTA size %d", p.cap_inc, THREADS);
+  FDK_REQUIRE(p.cap_te < 4096 && p.cap_tn <= 256 && p.cap_owned <= 256 && p.cap_ent < 65536 && p.cap_slots < 65536,
+              FDK_ECAP, "cluster capacity overflow (te=%d tn=%d owned=%d ent=%d slots=%d)", p.cap_te, p.cap_tn,
+              p.cap_owned, p.cap_ent, p.cap_slots);
   FDK_REQUIRE(p.nvar == L::NV, FDK_EINVAL, "plan nvar %d does not match the operator (%d)", p.nvar, L::NV);
   const size_t smem = L::smem_bytes(p, &a.big_doubles);
   FDK_REQUIRE(smem <= 227 * 1024, FDK_ECAP, "cluster needs %zu bytes of shared memory (> 227 KB)", smem);
   if (p.n_clusters == 0) return 0;
   if (int rc = ensure_device_tables()) return rc;
-  auto kern = k_assemble<El, PHYS>;
+  auto kern = k_assemble<El, PHYS, THREADS, MINB>;
   FDK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<p.n_clusters, El::THREADS, smem, stream>>>(a);
+  kern<<<p.n_clusters, THREADS, smem, stream>>>(a);
   FDK_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <class El, int PHYS>
+int launch_assemble(AsmArgs& a, cudaStream_t stream) {
+  // the plan states the CTA size it was built for (fedoo_b200/plan.py); small CTAs run 2 per SM
+  if (a.p.threads == El::THREADS) return launch_assemble_t<El, PHYS, El::THREADS, 1>(a, stream);
+  if (a.p.threads == El::THREADS / 2) return launch_assemble_t<El, PHYS, El::THREADS / 2, 2>(a, stream);
+  set_error("plan built for %d threads per cluster; this element supports %d or %d", a.p.threads, El::THREADS,
+            El::THREADS / 2);
+  return FDK_EINVAL;
 }
 
 template <int PHYS>

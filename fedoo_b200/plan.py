@@ -33,8 +33,17 @@ _CAPS = {
     "tet10": dict(nne=10, ngp=15, dim=3, inc_max=200, te_max=36, shift=3),
     "quad4": dict(nne=4, ngp=4, dim=2, inc_max=512, te_max=400, shift=6),
 }
+# CTA sizes the kernels are instantiated for (csrc/fdk_common.cuh ElemTraits::THREADS and half of it)
+_THREADS = {"hex8": 256, "tet4": 512, "tet10": 256, "quad4": 512}
+# "small" variant: half-size CTAs, two resident per SM (phases of different clusters overlap)
+_CAPS_SMALL = {
+    "hex8": dict(inc_max=128, te_max=45, shift=4),
+    "tet4": dict(inc_max=256, te_max=128, shift=3),
+    "quad4": dict(inc_max=256, te_max=200, shift=5),
+}
+HEAVY_T = 4  # slots with more contributions are pre-reduced by a balanced pass (csrc/fdk_assemble.cuh)
 TN_MAX = 255
-GENT_MAX = 65535
+ENT_MAX = 65535
 
 
 def _expand_ranges(starts, counts):
@@ -113,12 +122,22 @@ class Plan:
     """Cluster plan for one (mesh connectivity, element type).  Holds the device tensors and
     the C struct handed to the kernels."""
 
-    def __init__(self, elem_type, coords, conn, pattern, caps=None, verbose=False, owned=None):
+    def __init__(self, elem_type, coords, conn, pattern, caps=None, verbose=False, owned=None, small=None):
         """``owned``: optional bool mask (n_nodes,) -- only these nodes get clusters (their rows are
-        assembled); used by the multi-GPU partition where a rank's local mesh carries halo nodes."""
+        assembled); used by the multi-GPU partition where a rank's local mesh carries halo nodes.
+        ``small``: half-size clusters / CTAs, two resident per SM (default: env FDK_SMALL_CTA, else on)."""
+        import os
+
+        if small is None:
+            small = os.environ.get("FDK_SMALL_CTA", "1") != "0"
         cap = dict(_CAPS[elem_type])
+        self.threads = _THREADS[elem_type]
+        if small and elem_type in _CAPS_SMALL:  # tet10: one vertex node alone can touch > 18 elements
+            cap.update(_CAPS_SMALL[elem_type])
+            self.threads //= 2
         if caps:
             cap.update(caps)
+        assert cap["inc_max"] <= self.threads
         self.elem_type = elem_type
         dev = conn.device
         n_el, nne = conn.shape
@@ -175,7 +194,7 @@ class Plan:
                 (n_inc_c > cap["inc_max"])
                 | (n_te_c > cap["te_max"])
                 | (n_tn_c > TN_MAX)
-                | (n_inc_c * nne > GENT_MAX)
+                | (n_inc_c * nne + 256 > ENT_MAX)
             )
             n_bad = int(bad.sum())
             if verbose:
@@ -197,14 +216,16 @@ class Plan:
         cl_node_ptr = torch.zeros(n_cl + 1, dtype=torch.int64, device=dev)
         cl_node_ptr[1:] = torch.cumsum(counts_c, 0)
 
-        # ---- incidences in cluster order ----
-        cl_inc_ptr = torch.zeros(n_nodes + 1, dtype=torch.int64, device=dev)
-        cl_inc_ptr[1:] = torch.cumsum(inc_count_o, 0)
+        # ---- incidences in cluster order, node-major (grouped by owned node, element-ascending) ----
+        cl_finc_ptr = torch.zeros(n_nodes + 1, dtype=torch.int64, device=dev)
+        cl_finc_ptr[1:] = torch.cumsum(inc_count_o, 0)
         src = _expand_ranges(inc_ptr_node[order], inc_count_o)
         inc_e = inc_e_by_node[src]
         inc_l = inc_l_by_node[src]
         inc_q = torch.repeat_interleave(torch.arange(n_nodes, device=dev), inc_count_o)
         inc_cl = cl_of_pos[inc_q]
+        n_inc_tot = int(inc_e.numel())
+        cl_inc_ptr = cl_finc_ptr[cl_node_ptr]  # (n_cl+1) incidence range of each cluster (either order)
 
         # ---- touched elements ----
         te_keys = torch.unique(inc_cl * n_el + inc_e)  # sorted
@@ -212,12 +233,20 @@ class Plan:
         te_elem = te_keys - te_cl * n_el
         cl_te_ptr = torch.zeros(n_cl + 1, dtype=torch.int64, device=dev)
         cl_te_ptr[1:] = torch.cumsum(torch.bincount(te_cl, minlength=n_cl), 0)
-        le = torch.searchsorted(te_keys, inc_cl * n_el + inc_e) - cl_te_ptr[inc_cl]
+        te_idx = torch.searchsorted(te_keys, inc_cl * n_el + inc_e)
+        le = te_idx - cl_te_ptr[inc_cl]
         assert le.numel() == 0 or int(le.max()) < 4096
         inc_desc = le | (inc_l << 12)
         cl_of_node = torch.full((n_mesh_nodes,), -1, dtype=torch.int64, device=dev)
         cl_of_node[order] = cl_of_pos
         te_own = cl_of_node[conn64[te_elem, 0]] == te_cl if len(te_elem) else torch.zeros(0, dtype=torch.bool, device=dev)
+
+        # ---- kernel thread order: element-major (cluster, touched element, local node) ----
+        # the lanes of one element then read the same dN/dx rows in phase 2 (shared-memory broadcast)
+        em_perm = torch.argsort(te_idx * nne + inc_l)  # te_idx already sorts by cluster first
+        em_pos = torch.empty_like(em_perm)
+        em_pos[em_perm] = torch.arange(n_inc_tot, device=dev)
+        nm_rank = torch.arange(n_inc_tot, device=dev) - cl_inc_ptr[inc_cl]  # node-major rank in the cluster
 
         # ---- touched nodes + local connectivity ----
         tn_all = te_cl[:, None] * n_mesh_nodes + conn64[te_elem]  # (n_te_total, nne)
@@ -235,45 +264,65 @@ class Plan:
         total_slots = int(cl_slot_ptr[-1])
         assert owned is not None or total_slots == pattern.blk_nnz
 
-        # ---- gather lists ----
+        # ---- staging entries: every (incidence, local column node j) block, sorted by CSR slot ----
+        # entry position inside the cluster = rank among the cluster's entries in (slot, thread, j)
+        # order + one gap entry per preceding block row (spreads the rows over the smem banks)
         I = order[inc_q]  # row node of each incidence
-        cl_inc_start = cl_inc_ptr[cl_node_ptr[:-1]]  # first incidence of each cluster
-        k_local = torch.arange(inc_e.numel(), device=dev) - cl_inc_start[inc_cl]
         J = conn64[inc_e]  # (M, nne)
         pos = torch.searchsorted(pattern.keys, (I[:, None] * n_mesh_nodes + J).reshape(-1)).reshape(-1, nne)
         pcol = pos - pattern.blk_indptr[I][:, None]
-        slot = cl_slot_ptr[inc_q][:, None] + pcol  # cluster-order slot id
-        payload = (k_local[:, None] << 4) | torch.arange(nne, device=dev)[None, :]
-        assert payload.numel() == 0 or int(payload.max()) < 65536
-        packed = torch.sort(((slot << 16) | payload).reshape(-1)).values
-        g_ent = packed & 0xFFFF
-        g_slot = packed >> 16
+        slot = (cl_slot_ptr[inc_q][:, None] + pcol).reshape(-1)  # cluster-order slot id of every entry
+        del pos, pcol, J, I
+        n_ent_tot = n_inc_tot * nne
+        tie = (em_pos[:, None] * nne + torch.arange(nne, device=dev)[None, :]).reshape(-1)
+        ent_order = torch.argsort(slot * max(n_ent_tot, 1) + tie)
+        rank = torch.empty_like(ent_order)
+        rank[ent_order] = torch.arange(n_ent_tot, device=dev)
+        del ent_order, tie
+        row_local = inc_q - cl_node_ptr[inc_cl]  # local index of the row node in its cluster
+        dst = rank.reshape(-1, nne) - (cl_inc_ptr[inc_cl] * nne)[:, None] + row_local[:, None]
+        del rank
+        assert dst.numel() == 0 or (int(dst.max()) <= ENT_MAX and int(dst.min()) >= 0)
         gcum = torch.zeros(total_slots + 1, dtype=torch.int64, device=dev)
-        gcum[1:] = torch.cumsum(torch.bincount(g_slot, minlength=total_slots), 0)
+        gcum[1:] = torch.cumsum(torch.bincount(slot, minlength=total_slots), 0)
+        del slot
         slot0_c = cl_slot_ptr[cl_node_ptr]  # (n_cl+1) first slot of each cluster (+ end)
-        cl_g_base = gcum[slot0_c]
-        g_off = torch.zeros(total_slots + n_cl, dtype=torch.int64, device=dev)
+        ent0_c = gcum[slot0_c]  # == cl_inc_ptr * nne
+        counts_c = cl_node_ptr[1:] - cl_node_ptr[:-1]
+        slot_off = torch.zeros(total_slots + n_cl, dtype=torch.int64, device=dev)
+        slot_cnt = gcum[1:] - gcum[:-1]
         if total_slots:
-            cl_of_slot = torch.repeat_interleave(cl_of_pos, deg_o)
+            q_of_slot = torch.repeat_interleave(torch.arange(n_nodes, device=dev), deg_o)
+            cl_of_slot = cl_of_pos[q_of_slot]
             sl = torch.arange(total_slots, device=dev)
-            g_off[sl + cl_of_slot] = gcum[:-1] - cl_g_base[cl_of_slot]
+            slot_off[sl + cl_of_slot] = gcum[:-1] - ent0_c[cl_of_slot] + (q_of_slot - cl_node_ptr[cl_of_slot])
+            # heavy slots (cluster-local index), cluster by cluster
+            heavy = torch.nonzero(slot_cnt > HEAVY_T).reshape(-1)
+            heavy_slot = heavy - slot0_c[cl_of_slot[heavy]]
+            cl_heavy_ptr = torch.zeros(n_cl + 1, dtype=torch.int64, device=dev)
+            cl_heavy_ptr[1:] = torch.cumsum(torch.bincount(cl_of_slot[heavy], minlength=n_cl), 0)
+            del q_of_slot, cl_of_slot, sl
+        else:
+            heavy_slot = torch.zeros(0, dtype=torch.int64, device=dev)
+            cl_heavy_ptr = torch.zeros(n_cl + 1, dtype=torch.int64, device=dev)
         if n_cl:
             cidx = torch.arange(n_cl, device=dev)
-            g_off[slot0_c[1:] + cidx] = cl_g_base[1:] - cl_g_base[:-1]
-        assert n_cl == 0 or int(g_off.max()) <= GENT_MAX
+            slot_off[slot0_c[1:] + cidx] = (ent0_c[1:] - ent0_c[:-1]) + counts_c  # end sentinel (incl. all gaps)
+        assert n_cl == 0 or int(slot_off.max()) <= ENT_MAX
 
         # ---- capacities ----
         def cmax(x):
             return int(x.max()) if x.numel() else 0
 
         n_slots_c = slot0_c[1:] - slot0_c[:-1]
+        n_inc_c = cl_inc_ptr[1:] - cl_inc_ptr[:-1]
         self.caps = dict(
             cap_te=cmax(cl_te_ptr[1:] - cl_te_ptr[:-1]),
             cap_tn=cmax(cl_tn_ptr[1:] - cl_tn_ptr[:-1]),
-            cap_inc=cmax(cl_inc_ptr[cl_node_ptr[1:]] - cl_inc_ptr[cl_node_ptr[:-1]]),
+            cap_inc=cmax(n_inc_c),
             cap_owned=cmax(counts_c),
             cap_slots=cmax(n_slots_c),
-            cap_gent=cmax(cl_g_base[1:] - cl_g_base[:-1]),
+            cap_ent=cmax(n_inc_c * nne + counts_c),
         )
         self.stats = dict(
             n_clusters=n_cl,
@@ -284,24 +333,27 @@ class Plan:
         )
         self.n_owned = n_nodes
 
-        # ---- device arrays in their kernel dtypes ----
+        # ---- device arrays in their kernel dtypes (per-incidence arrays in kernel thread order) ----
         i32, u16, u8 = torch.int32, torch.uint16, torch.uint8
         self.t = dict(
             cl_node_ptr=cl_node_ptr.to(i32),
             cl_node=order.to(i32),
             cl_bptr=cl_bptr.contiguous(),
             cl_slot_ptr=cl_slot_ptr,
+            cl_finc_ptr=cl_finc_ptr.to(i32),
             cl_inc_ptr=cl_inc_ptr.to(i32),
-            inc_desc=inc_desc.to(u16),
+            inc_desc=inc_desc[em_perm].to(u16),
+            inc_dst=dst[em_perm].to(u16).contiguous(),
+            inc_fdst=nm_rank[em_perm].to(u16),
             cl_te_ptr=cl_te_ptr.to(i32),
             cl_te_elem=te_elem.to(i32),
             cl_te_own=te_own.to(u8),
             cl_lconn=lconn.to(u8).contiguous(),
             cl_tn_ptr=cl_tn_ptr.to(i32),
             cl_tn_node=tn_node.to(i32),
-            cl_g_base=cl_g_base,
-            g_off=g_off.to(u16),
-            g_ent=g_ent.to(u16),
+            slot_off=slot_off.to(u16),
+            cl_heavy_ptr=cl_heavy_ptr.to(i32),
+            heavy_slot=heavy_slot.to(u16),
         )
         self._structs = {}
 
@@ -332,6 +384,7 @@ class Plan:
             s.n_clusters = self.n_clusters
             s.nvar = nvar
             s.blk_nnz = self.pattern.blk_nnz
+            s.threads = self.threads
             for k, v in self.caps.items():
                 setattr(s, k, v)
             for k, v in self.t.items():

@@ -88,22 +88,28 @@ typedef struct fdk_plan {
   int32_t nvar;       /* variables per node of the assembled operator (dim for elasticity, 1 for heat) */
   int64_t blk_nnz;    /* nnz of the node-node block pattern */
   /* capacities = max over clusters (sizes the dynamic shared memory) */
-  int32_t cap_te, cap_tn, cap_inc, cap_owned, cap_slots, cap_gent;
-  const int32_t* cl_node_ptr;  /* [n_clusters+1] range of owned nodes (cluster order)            */
-  const int32_t* cl_node;      /* [n_nodes]  global id of the q-th owned node                     */
-  const int64_t* cl_bptr;      /* [n_nodes]  blk_indptr[cl_node[q]]                               */
-  const int64_t* cl_slot_ptr;  /* [n_nodes+1] exclusive cumsum of block-row lengths, cluster order */
-  const int32_t* cl_inc_ptr;   /* [n_nodes+1] range of incidences of the q-th owned node          */
-  const uint16_t* inc_desc;    /* [n_elems*nne] local touched-element index | local node << 12    */
-  const int32_t* cl_te_ptr;    /* [n_clusters+1] range of touched elements                        */
-  const int32_t* cl_te_elem;   /* global element id of each touched element                       */
-  const uint8_t* cl_te_own;    /* 1 if this cluster is the unique owner of the touched element    */
-  const uint8_t* cl_lconn;     /* [n_te_total][nne] local (cluster) index of each element node    */
-  const int32_t* cl_tn_ptr;    /* [n_clusters+1] range of touched nodes                           */
-  const int32_t* cl_tn_node;   /* global node id of each touched node                             */
-  const int64_t* cl_g_base;    /* [n_clusters+1] range of gather entries                          */
-  const uint16_t* g_off;       /* per cluster n_slots+1 offsets at index cl_slot_ptr[q0] + cluster */
-  const uint16_t* g_ent;       /* gather entries: local incidence << 4 | local column node j      */
+  int32_t cap_te, cap_tn, cap_inc, cap_owned, cap_slots, cap_ent;
+  int32_t threads;    /* CTA size the clusters were sized for (cap_inc <= threads) */
+  int32_t reserved;
+  const int32_t* cl_node_ptr;  /* [n_clusters+1] range of owned nodes (cluster order)                    */
+  const int32_t* cl_node;      /* [n_owned]  global id of the q-th owned node                             */
+  const int64_t* cl_bptr;      /* [n_owned]  blk_indptr[cl_node[q]]                                       */
+  const int64_t* cl_slot_ptr;  /* [n_owned+1] exclusive cumsum of block-row lengths, cluster order        */
+  const int32_t* cl_finc_ptr;  /* [n_owned+1] exclusive cumsum of incidences per owned node               */
+  const int32_t* cl_inc_ptr;   /* [n_clusters+1] range of incidences (= threads), element-major order     */
+  const uint16_t* inc_desc;    /* [n_inc] local touched-element index | local node << 12                  */
+  const uint16_t* inc_dst;     /* [n_inc][nne] staging entry (slot-sorted) of the block (I, node j of e)  */
+  const uint16_t* inc_fdst;    /* [n_inc] node-major rank of the incidence inside its cluster             */
+  const int32_t* cl_te_ptr;    /* [n_clusters+1] range of touched elements                                */
+  const int32_t* cl_te_elem;   /* global element id of each touched element                               */
+  const uint8_t* cl_te_own;    /* 1 if this cluster is the unique owner of the touched element            */
+  const uint8_t* cl_lconn;     /* [n_te_total][nne] local (cluster) index of each element node            */
+  const int32_t* cl_tn_ptr;    /* [n_clusters+1] range of touched nodes                                   */
+  const int32_t* cl_tn_node;   /* global node id of each touched node                                     */
+  const uint16_t* slot_off;    /* per cluster n_slots+1 staging offsets (first entry of each slot; one gap
+                                  entry after every block row) at index cl_slot_ptr[q0] + cluster         */
+  const int32_t* cl_heavy_ptr; /* [n_clusters+1] range of heavy slots (more than 4 contributions)         */
+  const uint16_t* heavy_slot;  /* cluster-local slot index of each heavy slot                             */
 } fdk_plan;
 
 /* ------------------------------------------------------------------------- *

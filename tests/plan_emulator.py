@@ -29,6 +29,10 @@ def make_plan(elem_type, nodes, elements, **kw):
 
 
 def emulate_iso(plan, pat, nodes, elements, lam, mu, allow_unwritten=False):
+    """Follows csrc/fdk_assemble.cuh: threads = incidences in element-major order, blocks scattered to
+    the slot-sorted staging array (inc_dst), heavy slots pre-reduced, slot gather by contiguous runs."""
+    from fedoo_b200.plan import HEAVY_T
+
     t = {k: v.numpy() if v.dtype != torch.uint16 else v.view(torch.int16).numpy().astype(np.int64) & 0xFFFF for k, v in plan.t.items()}
     elements = np.asarray(elements)
     G, wdet = fo.geometry(nodes, elements, plan.elem_type)
@@ -38,41 +42,67 @@ def emulate_iso(plan, pat, nodes, elements, lam, mu, allow_unwritten=False):
     blk_nnz = pat.blk_nnz
     K = np.full(nv * nv * blk_nnz, np.nan)
     written = np.zeros(nv * nv * blk_nnz, dtype=np.int32)
+    inc_dst = t["inc_dst"].reshape(-1, nne)
     for c in range(plan.n_clusters):
         q0, q1 = t["cl_node_ptr"][c], t["cl_node_ptr"][c + 1]
+        n_owned = q1 - q0
         te0 = t["cl_te_ptr"][c]
         tn0 = t["cl_tn_ptr"][c]
-        inc0, inc1 = t["cl_inc_ptr"][q0], t["cl_inc_ptr"][q1]
+        inc0, inc1 = t["cl_inc_ptr"][c], t["cl_inc_ptr"][c + 1]
+        n_inc = inc1 - inc0
+        assert n_inc <= plan.threads
+        assert n_inc == t["cl_finc_ptr"][q1] - t["cl_finc_ptr"][q0]
         slot0 = t["cl_slot_ptr"][q0]
-        S = np.zeros((inc1 - inc0, nne, dim, dim))
-        for n in range(q1 - q0):
-            node = t["cl_node"][q0 + n]
-            for m in range(t["cl_inc_ptr"][q0 + n], t["cl_inc_ptr"][q0 + n + 1]):
-                desc = int(t["inc_desc"][m])
-                le, i = desc & 0xFFF, desc >> 12
-                e = t["cl_te_elem"][te0 + le]
-                assert elements[e, i] == node
-                lc = t["cl_lconn"][te0 + le]
-                assert np.array_equal(t["cl_tn_node"][tn0 + lc.astype(np.int64)], elements[e])
-                S[m - inc0] = np.einsum("g,gc,gaj->jca", wdet[e], G[e, :, :, i], G[e])
-        gbase = t["cl_g_base"][c]
-        goff = t["g_off"][slot0 + c : slot0 + c + (t["cl_slot_ptr"][q1] - slot0) + 1]
-        assert goff[-1] == t["cl_g_base"][c + 1] - gbase
-        for n in range(q1 - q0):
+        n_slots = t["cl_slot_ptr"][q1] - slot0
+        off = t["slot_off"][slot0 + c : slot0 + c + n_slots + 1]
+        assert off[-1] == n_inc * nne + n_owned <= plan.caps["cap_ent"]
+        stage = np.full((plan.caps["cap_ent"], dim, dim), np.nan)
+        fdst_seen = np.zeros(n_inc, dtype=int)
+        owned_nodes = t["cl_node"][q0:q1]
+        prev_le = -1
+        for m in range(inc0, inc1):  # one kernel thread each
+            desc = int(t["inc_desc"][m])
+            le, i = desc & 0xFFF, desc >> 12
+            assert le >= prev_le  # element-major thread order
+            prev_le = le
+            e = t["cl_te_elem"][te0 + le]
+            node = elements[e, i]
+            n = int(np.nonzero(owned_nodes == node)[0][0])  # the row node is owned by this cluster
+            lc = t["cl_lconn"][te0 + le]
+            assert np.array_equal(t["cl_tn_node"][tn0 + lc.astype(np.int64)], elements[e])
+            fd = int(t["inc_fdst"][m])
+            assert t["cl_finc_ptr"][q0 + n] - t["cl_finc_ptr"][q0] <= fd < t["cl_finc_ptr"][q0 + n + 1] - t["cl_finc_ptr"][q0]
+            fdst_seen[fd] += 1
+            S = np.einsum("g,gc,gaj->jca", wdet[e], G[e, :, :, i], G[e])
+            for j in range(nne):
+                d = int(inc_dst[m, j])
+                assert np.isnan(stage[d, 0, 0]), "two blocks staged at the same entry"
+                stage[d] = S[j]
+        assert (fdst_seen == 1).all()
+        # heavy slots
+        h0, h1 = t["cl_heavy_ptr"][c], t["cl_heavy_ptr"][c + 1]
+        heavy = set(int(x) for x in t["heavy_slot"][h0:h1])
+        for n in range(n_owned):
             sb0 = t["cl_slot_ptr"][q0 + n] - slot0
             deg = t["cl_slot_ptr"][q0 + n + 1] - t["cl_slot_ptr"][q0 + n]
             bp = t["cl_bptr"][q0 + n]
+            I = owned_nodes[n]
             for pcol in range(deg):
                 s = sb0 + pcol
-                acc = np.zeros((dim, dim))
-                for tt in range(goff[s], goff[s + 1]):
-                    ent = int(t["g_ent"][gbase + tt])
-                    acc += S[ent >> 4, ent & 15]
+                e0 = int(off[s])
+                cnt = int(off[s + 1]) - e0 - (1 if pcol == deg - 1 else 0)
+                assert (cnt > HEAVY_T) == (s in heavy)
+                acc = stage[e0 : e0 + cnt].sum(axis=0) if cnt else np.zeros((dim, dim))
+                assert not np.isnan(acc).any()
+                Jn = pat.blk_indices[bp + pcol].item()
+                assert cnt == np.sum((elements == I).any(axis=1) & (elements == Jn).any(axis=1))
                 Kb = lam * acc + mu * acc.T + mu * np.trace(acc) * np.eye(dim)
                 for cc in range(nv):
                     for aa in range(nv):
                         dst = cc * nv * blk_nnz + nv * bp + aa * deg + pcol
                         K[dst] = Kb[cc, aa]
                         written[dst] += 1
+            # the gap entry after the row is never staged
+            assert np.isnan(stage[int(off[sb0 + deg]) - 1, 0, 0])
     assert (written <= 1).all() and (allow_unwritten or (written == 1).all()), "every CSR value must be written exactly once"
     return K
