@@ -61,6 +61,7 @@ class PlanStruct(C.Structure):
         ("cl_tn_ptr", C.c_void_p),
         ("cl_tn_node", C.c_void_p),
         ("slot_off", C.c_void_p),
+        ("slot_tn", C.c_void_p),
         ("cl_heavy_ptr", C.c_void_p),
         ("heavy_slot", C.c_void_p),
     ]

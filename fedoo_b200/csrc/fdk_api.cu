@@ -1,5 +1,7 @@
 // fdk_api.cu -- the C ABI of libfdk (see include/fdk.h).  Single translation unit: the kernels
 // live in the .cuh files included below.
+#include <cstdlib>
+
 #include "fdk_assemble.cuh"
 #include "fdk_gp.cuh"
 #include "fdk_symbolic.cuh"
@@ -7,6 +9,12 @@
 using namespace fdk;
 
 namespace {
+
+// FDK_NO_FUSE_KU=1 forces the B^T sigma residual path (tests compare both)
+const bool g_no_fuse = [] {
+  const char* e = getenv("FDK_NO_FUSE_KU");
+  return e != nullptr && e[0] == '1';
+}();
 
 int check_plan(const fdk_plan* p) {
   FDK_REQUIRE(p != nullptr, FDK_EINVAL, "plan is NULL");
@@ -16,7 +24,7 @@ int check_plan(const fdk_plan* p) {
   if (p->n_clusters > 0)
     FDK_REQUIRE(p->cl_node_ptr && p->cl_node && p->cl_bptr && p->cl_slot_ptr && p->cl_inc_ptr && p->inc_desc &&
                     p->cl_te_ptr && p->cl_te_elem && p->cl_lconn && p->cl_tn_ptr && p->cl_tn_node &&
-                    p->cl_finc_ptr && p->inc_dst && p->inc_fdst && p->slot_off && p->cl_heavy_ptr,
+                    p->cl_finc_ptr && p->inc_dst && p->inc_fdst && p->slot_off && p->slot_tn && p->cl_heavy_ptr,
                 FDK_EINVAL, "plan has NULL arrays");
   return 0;
 }
@@ -85,6 +93,9 @@ int fdk_assemble_elastic_iso(const fdk_plan* plan, int compute, const double* co
   a.lam = lambda;
   a.mu = mu;
   a.compute = compute;
+  // linear law and both outputs requested: the residual -int B^T C eps(U) equals -(K U) row by row,
+  // so it is taken from the assembled rows in the gather phase instead of a second B^T sigma pass
+  a.fuse_ku = (compute == FDK_ALL && U != nullptr && stress_gp == nullptr && !g_no_fuse) ? 1 : 0;
   return dispatch_assemble<PHYS_ISO>(a, (cudaStream_t)stream);
 }
 
@@ -106,6 +117,8 @@ int fdk_assemble_elastic_general(const fdk_plan* plan, int compute, const double
   if (C_h)
     for (int i = 0; i < 36; ++i) a.C[i] = C_h[i];
   a.compute = compute;
+  a.fuse_ku =
+      (compute == FDK_ALL && U != nullptr && stress_gp == nullptr && tangent_gp == nullptr && !g_no_fuse) ? 1 : 0;
   return dispatch_assemble<PHYS_GENERAL>(a, (cudaStream_t)stream);
 }
 

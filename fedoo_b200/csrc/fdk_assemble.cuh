@@ -52,6 +52,7 @@ struct AsmArgs {
   double rcdt;      // rho c / dt
   int compute;
   int big_doubles;  // size of the aliased geometry / staging region
+  int fuse_ku;      // linear law, K and D both requested: D = -(assembled rows) . U in the gather phase
 };
 
 template <class El, int PHYS>
@@ -64,14 +65,22 @@ struct Layout {
   static constexpr int NSIG = (PHYS == PHYS_HEAT) ? DIM + 1 : (DIM == 3 ? 6 : 3);
   static constexpr int GROW = DIM * NNE;                      // dN/dx of one (element, gp): [k][d]
   static_assert(GROW % 2 == 0, "128-bit rows");
-  static constexpr int ESTR = NGP * GROW + 2;                 // +16 B: consecutive elements hit different banks
+  // shared-memory strides chosen so that (stride / 16 B) is odd: the 128-bit rows of the 8 Gauss
+  // points of an element, and of consecutive elements, start in different bank groups
+  static constexpr int GSTR = ((GROW + 2) / 2) % 2 ? GROW + 2 : GROW + 4;
+  static constexpr int ESTR = ((NGP * GSTR) / 2) % 2 ? NGP * GSTR : NGP * GSTR + 2;
+  static constexpr int WSTR = NGP | 1;                        // w_g |det J| per element
+  static constexpr int SSTR = (NGP * NSIG) | 1;               // w sigma per element
   static constexpr int TSTR = GROW | 1;                       // padded dN table row
   static constexpr int TAB_DOUBLES = (NGP * TSTR + NGP * NNE + NGP + 1) & ~1;
 
   // doubles of the geometry view of the big region
-  static long geo_doubles(const fdk_plan& p) { return (long)p.cap_te * (ESTR + NGP + NGP * NSIG); }
+  static long geo_doubles(const fdk_plan& p) { return (long)p.cap_te * (ESTR + WSTR + SSTR); }
   // doubles of the staging view
-  static long stage_doubles(const fdk_plan& p) { return (long)p.cap_ent * BLKP + (long)p.cap_inc * NV; }
+  static long stage_doubles(const fdk_plan& p) {
+    const long nf = p.cap_inc > p.cap_slots ? p.cap_inc : p.cap_slots;  // nodal forces / per-slot K.u products
+    return (long)p.cap_ent * BLKP + nf * NV;
+  }
 
   static size_t smem_bytes(const fdk_plan& p, int* big_doubles) {
     long big = geo_doubles(p);
@@ -184,15 +193,26 @@ __device__ __forceinline__ void apply_tangent(const double* __restrict__ C, int 
   }
 }
 
+// Ampere-style asynchronous global -> shared copy (LDGSTS); BYTES = 4, 8 or 16, both sides aligned.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <class El, int PHYS, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constant__ AsmArgs a) {
   using L = Layout<El, PHYS>;
   constexpr int NNE = L::NNE, NGP = L::NGP, DIM = L::DIM, NV = L::NV, NU = L::NU, BLK = L::BLK, BLKP = L::BLKP;
-  constexpr int NSIG = L::NSIG, GROW = L::GROW, ESTR = L::ESTR, TSTR = L::TSTR;
+  constexpr int NSIG = L::NSIG, GROW = L::GROW, GSTR = L::GSTR, ESTR = L::ESTR, WSTR = L::WSTR, SSTR = L::SSTR;
+  constexpr int TSTR = L::TSTR;
   const fdk_plan& p = a.p;
   const int c = blockIdx.x, tid = threadIdx.x;
   const bool do_mat = (a.compute & FDK_MATRIX) != 0;
   const bool do_vec = (a.compute & FDK_VECTOR) != 0;
+  const bool fuse_ku = a.fuse_ku != 0;           // residual from the assembled rows (phase 3)
+  const bool do_bts = do_vec && !fuse_ku;        // residual as B^T sigma (phases 1-2)
 
   const int q0 = p.cl_node_ptr[c], n_owned = p.cl_node_ptr[c + 1] - q0;
   const int te0 = p.cl_te_ptr[c], n_te = p.cl_te_ptr[c + 1] - te0;
@@ -238,11 +258,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   double* sBig = smem + L::TAB_DOUBLES + ((p.cap_tn * (DIM + NU) + 1) & ~1);
   // geometry view
   double* sG = sBig;                               // [n_te][ESTR]
-  double* sWd = sG + (long)p.cap_te * ESTR;        // [n_te][NGP]       w_g |det J|
-  double* sSig = sWd + (long)p.cap_te * NGP;       // [n_te][NGP][NSIG] w * sigma
+  double* sWd = sG + (long)p.cap_te * ESTR;        // [n_te][WSTR]      w_g |det J|
+  double* sSig = sWd + (long)p.cap_te * WSTR;      // [n_te][SSTR]      w * sigma
   // staging view (aliases the geometry once phase 2 has read it)
   double* sBlk = sBig;                             // [cap_ent][BLKP]
-  double* sF = sBlk + (long)p.cap_ent * BLKP;      // [cap_inc][NV]
+  double* sF = sBlk + (long)p.cap_ent * BLKP;      // [max(cap_inc, cap_slots)][NV]
+  double* sR = sF;                                 // per-slot K.u products (fuse_ku: sF is unused)
   int* sSlotBase = reinterpret_cast<int*>(sBig + a.big_doubles);
   int* sFinc = sSlotBase + (p.cap_owned + 1);
   unsigned short* sOff = reinterpret_cast<unsigned short*>(sFinc + (p.cap_owned + 1));
@@ -250,7 +271,34 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   unsigned char* sLconn = sOwner + ((p.cap_slots + 3) & ~3);
 
   // ---------------- phase 0: staging ----------------
+  // All global loads are issued before the first shared-memory store that depends on one (node ids
+  // and offsets into registers, coordinates / dofs / connectivity through cp.async), so the CTA
+  // pays about two memory latencies here instead of one per array.
   {
+    constexpr int RT = (256 + THREADS - 1) / THREADS;  // cap_tn <= 256
+    int node_r[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const int t = tid + r * THREADS;
+      node_r[r] = (t < n_tn) ? p.cl_tn_node[tn0 + t] : -1;
+    }
+    constexpr int RS = 4;
+    unsigned short off_r[RS];
+    const unsigned short* go = p.slot_off + slot0 + c;
+#pragma unroll
+    for (int r = 0; r < RS; ++r) {
+      const int t = tid + r * THREADS;
+      off_r[r] = (t <= n_slots) ? go[t] : (unsigned short)0;
+    }
+    // connectivity bytes: 4-byte cp.async when the element rows are 4-byte multiples
+    {
+      const unsigned char* lc = p.cl_lconn + (int64_t)te0 * NNE;
+      if constexpr (NNE % 4 == 0) {
+        for (int t = tid; t < n_te * NNE / 4; t += THREADS) cp_async<4>(sLconn + 4 * t, lc + 4 * t);
+      } else {
+        for (int t = tid; t < n_te * NNE; t += THREADS) sLconn[t] = lc[t];
+      }
+    }
     const ElemTable& tab = c_tab[El::ID];
     for (int t = tid; t < NGP * GROW; t += THREADS) {
       const int g = t / GROW, r = t - g * GROW;
@@ -258,29 +306,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
     }
     for (int t = tid; t < NGP * NNE; t += THREADS) sN[t] = tab.N[t];
     if (tid < NGP) sW[tid] = tab.w[tid];
-    for (int t = tid; t < n_tn; t += THREADS) {
-      const int node = p.cl_tn_node[tn0 + t];
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) sX[t * DIM + d] = a.coords[(int64_t)node * DIM + d];
-      if (do_vec && a.U != nullptr) {
-        if constexpr (PHYS == PHYS_HEAT) {
-          const double T = a.U[node];
-          sU[t * 2 + 0] = T;
-          sU[t * 2 + 1] = T - (a.U2 ? a.U2[node] : 0.0);
-        } else {
-#pragma unroll
-          for (int v = 0; v < DIM; ++v) sU[t * DIM + v] = a.U[(int64_t)v * p.n_nodes + node];
-        }
-      }
-    }
-    {
-      const unsigned char* lc = p.cl_lconn + (int64_t)te0 * NNE;
-      for (int t = tid; t < n_te * NNE; t += THREADS) sLconn[t] = lc[t];
-    }
-    {
-      const unsigned short* go = p.slot_off + slot0 + c;
-      for (int t = tid; t <= n_slots; t += THREADS) sOff[t] = go[t];
-    }
     for (int t = tid; t <= n_owned; t += THREADS) {
       sSlotBase[t] = (int)(p.cl_slot_ptr[q0 + t] - slot0);
       sFinc[t] = p.cl_finc_ptr[q0 + t] - p.cl_finc_ptr[q0];
@@ -289,6 +314,33 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
       const int b0 = (int)(p.cl_slot_ptr[q0 + t] - slot0), b1 = (int)(p.cl_slot_ptr[q0 + t + 1] - slot0);
       for (int s = b0; s < b1; ++s) sOwner[s] = (unsigned char)t;
     }
+#pragma unroll
+    for (int r = 0; r < RS; ++r) {
+      const int t = tid + r * THREADS;
+      if (t <= n_slots) sOff[t] = off_r[r];
+    }
+    for (int t = tid + RS * THREADS; t <= n_slots; t += THREADS) sOff[t] = go[t];
+    const bool need_u = do_vec && a.U != nullptr;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const int t = tid + r * THREADS;
+      const int node = node_r[r];
+      if (node >= 0) {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) cp_async<8>(sX + t * DIM + d, a.coords + (int64_t)node * DIM + d);
+        if (need_u) {
+          if constexpr (PHYS == PHYS_HEAT) {
+            const double T = a.U[node];
+            sU[t * 2 + 0] = T;
+            sU[t * 2 + 1] = T - (a.U2 ? a.U2[node] : 0.0);
+          } else {
+#pragma unroll
+            for (int v = 0; v < DIM; ++v) cp_async<8>(sU + t * DIM + v, a.U + (int64_t)v * p.n_nodes + node);
+          }
+        }
+      }
+    }
+    cp_async_wait_all();
   }
   __syncthreads();
 
@@ -307,17 +359,17 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
     double G[NNE][DIM];
     const double w = gp_geometry<NNE, DIM>(sdN + g * TSTR, sW[g], X, G);
     {
-      double2* out = reinterpret_cast<double2*>(sG + le * ESTR + g * GROW);
+      double2* out = reinterpret_cast<double2*>(sG + le * ESTR + g * GSTR);
 #pragma unroll
       for (int t = 0; t < GROW / 2; ++t) {
         const int k0 = (2 * t) / DIM, d0 = (2 * t) % DIM, k1 = (2 * t + 1) / DIM, d1 = (2 * t + 1) % DIM;
         out[t] = make_double2(G[k0][d0], G[k1][d1]);
       }
     }
-    sWd[le * NGP + g] = w;
+    sWd[le * WSTR + g] = w;
 
-    if (do_vec) {
-      double* so = sSig + (le * NGP + g) * NSIG;
+    if (do_bts) {
+      double* so = sSig + le * SSTR + g * NSIG;
       if constexpr (PHYS == PHYS_HEAT) {
         double gT[DIM], dTg = 0.0;
 #pragma unroll
@@ -411,7 +463,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
     }
 #pragma unroll 1
     for (int g = 0; g < NGP; ++g) {
-      const double* gb = eb + g * GROW;
+      const double* gb = eb + g * GSTR;
       // all dN/dx of the element at this gp: the lanes of one element read the same addresses
       double Gr[GROW];
       {
@@ -423,13 +475,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
           Gr[2 * t + 1] = v.y;
         }
       }
-      const double w = sWd[le * NGP + g];
+      const double w = sWd[le * WSTR + g];
       double gi[DIM];
 #pragma unroll
       for (int d = 0; d < DIM; ++d) gi[d] = gb[i * DIM + d];
 
-      if (do_vec) {
-        const double* ws = sSig + (le * NGP + g) * NSIG;
+      if (do_bts) {
+        const double* ws = sSig + le * SSTR + g * NSIG;
         if constexpr (PHYS == PHYS_HEAT) {
           double s = ws[DIM] * sN[g * NNE + i];
 #pragma unroll
@@ -537,7 +589,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
         for (int b = 0; b < BLK; ++b) sp[b] = acc[j][b];
       }
     }
-    if (do_vec) {
+    if (do_bts) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) sF[my_fdst * NV + v] = f[v];
     }
@@ -564,6 +616,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
     }
     // ---------------- phase 3b: slot gather, constitutive closed form, final stores ----------------
     for (int s = tid; s < n_slots; s += THREADS) {
+      [[maybe_unused]] unsigned slot_tn = 0;
+      if constexpr (PHYS != PHYS_HEAT) {
+        if (fuse_ku) slot_tn = p.slot_tn[slot0 + s];
+      }
       const int n = sOwner[s];
       const int sb = sSlotBase[n];
       const int deg = sSlotBase[n + 1] - sb;
@@ -605,16 +661,31 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
 #pragma unroll
         for (int aa = 0; aa < NV; ++aa) __stcs(row + (int64_t)aa * deg + pcol, Kb[cc * NV + aa]);
       }
+      if constexpr (PHYS != PHYS_HEAT) {
+        if (fuse_ku) {  // this slot's share of (K U)_I: the assembled block times the dofs of its column node
+          const double* uj = sU + (int)slot_tn * DIM;
+#pragma unroll
+          for (int cc = 0; cc < NV; ++cc) {
+            double r = 0.0;
+#pragma unroll
+            for (int aa = 0; aa < NV; ++aa) r = fma(Kb[cc * NV + aa], uj[aa], r);
+            sR[s * NV + cc] = r;
+          }
+        }
+      }
     }
   }
+  if (fuse_ku) __syncthreads();  // sR complete (uniform)
   if (do_vec) {
     for (int n = tid; n < n_owned; n += THREADS) {
       double s[NV];
 #pragma unroll
       for (int v = 0; v < NV; ++v) s[v] = 0.0;
-      for (int k = sFinc[n]; k < sFinc[n + 1]; ++k)
+      const int k0 = fuse_ku ? sSlotBase[n] : sFinc[n], k1 = fuse_ku ? sSlotBase[n + 1] : sFinc[n + 1];
+      const double* src = fuse_ku ? sR : sF;
+      for (int k = k0; k < k1; ++k)
 #pragma unroll
-        for (int v = 0; v < NV; ++v) s[v] += sF[k * NV + v];
+        for (int v = 0; v < NV; ++v) s[v] += src[k * NV + v];
       const int node = p.cl_node[q0 + n];
 #pragma unroll
       for (int v = 0; v < NV; ++v) a.D[(int64_t)v * p.n_nodes + node] = -s[v];

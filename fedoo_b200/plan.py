@@ -296,6 +296,10 @@ class Plan:
             cl_of_slot = cl_of_pos[q_of_slot]
             sl = torch.arange(total_slots, device=dev)
             slot_off[sl + cl_of_slot] = gcum[:-1] - ent0_c[cl_of_slot] + (q_of_slot - cl_node_ptr[cl_of_slot])
+            # cluster-local touched-node index of every slot's column node (K.u residual in phase 3)
+            J_of_slot = pattern.blk_indices.to(torch.int64)[_expand_ranges(cl_bptr, deg_o)]
+            slot_tn = torch.searchsorted(tn_keys, cl_of_slot * n_mesh_nodes + J_of_slot) - cl_tn_ptr[cl_of_slot]
+            del J_of_slot
             # heavy slots (cluster-local index), cluster by cluster
             heavy = torch.nonzero(slot_cnt > HEAVY_T).reshape(-1)
             heavy_slot = heavy - slot0_c[cl_of_slot[heavy]]
@@ -304,6 +308,7 @@ class Plan:
             del q_of_slot, cl_of_slot, sl
         else:
             heavy_slot = torch.zeros(0, dtype=torch.int64, device=dev)
+            slot_tn = torch.zeros(0, dtype=torch.int64, device=dev)
             cl_heavy_ptr = torch.zeros(n_cl + 1, dtype=torch.int64, device=dev)
         if n_cl:
             cidx = torch.arange(n_cl, device=dev)
@@ -352,6 +357,7 @@ class Plan:
             cl_tn_ptr=cl_tn_ptr.to(i32),
             cl_tn_node=tn_node.to(i32),
             slot_off=slot_off.to(u16),
+            slot_tn=slot_tn.to(u8),
             cl_heavy_ptr=cl_heavy_ptr.to(i32),
             heavy_slot=heavy_slot.to(u16),
         )

@@ -108,6 +108,8 @@ typedef struct fdk_plan {
   const int32_t* cl_tn_node;   /* global node id of each touched node                                     */
   const uint16_t* slot_off;    /* per cluster n_slots+1 staging offsets (first entry of each slot; one gap
                                   entry after every block row) at index cl_slot_ptr[q0] + cluster         */
+  const uint8_t* slot_tn;      /* [n_slots_total] cluster-local touched-node index of the slot's column
+                                  node (dofs staged in shared memory; residual from the assembled rows)   */
   const int32_t* cl_heavy_ptr; /* [n_clusters+1] range of heavy slots (more than 4 contributions)         */
   const uint16_t* heavy_slot;  /* cluster-local slot index of each heavy slot                             */
 } fdk_plan;

@@ -95,6 +95,7 @@ def emulate_iso(plan, pat, nodes, elements, lam, mu, allow_unwritten=False):
                 acc = stage[e0 : e0 + cnt].sum(axis=0) if cnt else np.zeros((dim, dim))
                 assert not np.isnan(acc).any()
                 Jn = pat.blk_indices[bp + pcol].item()
+                assert t["cl_tn_node"][tn0 + int(t["slot_tn"][slot0 + s])] == Jn
                 assert cnt == np.sum((elements == I).any(axis=1) & (elements == Jn).any(axis=1))
                 Kb = lam * acc + mu * acc.T + mu * np.trace(acc) * np.eye(dim)
                 for cc in range(nv):
