@@ -43,8 +43,8 @@ class PlanStruct(C.Structure):
         ("cap_owned", C.c_int32),
         ("cap_slots", C.c_int32),
         ("cap_ent", C.c_int32),
+        ("cap_heavy", C.c_int32),
         ("threads", C.c_int32),
-        ("reserved", C.c_int32),
         ("cl_node_ptr", C.c_void_p),
         ("cl_node", C.c_void_p),
         ("cl_bptr", C.c_void_p),
@@ -60,8 +60,7 @@ class PlanStruct(C.Structure):
         ("cl_lconn", C.c_void_p),
         ("cl_tn_ptr", C.c_void_p),
         ("cl_tn_node", C.c_void_p),
-        ("slot_off", C.c_void_p),
-        ("slot_tn", C.c_void_p),
+        ("slot_rec", C.c_void_p),
         ("cl_heavy_ptr", C.c_void_p),
         ("heavy_slot", C.c_void_p),
     ]

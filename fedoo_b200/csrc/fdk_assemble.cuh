@@ -74,26 +74,26 @@ struct Layout {
   static constexpr int TSTR = GROW | 1;                       // padded dN table row
   static constexpr int TAB_DOUBLES = (NGP * TSTR + NGP * NNE + NGP + 1) & ~1;
 
-  // doubles of the geometry view of the big region
-  static long geo_doubles(const fdk_plan& p) { return (long)p.cap_te * (ESTR + WSTR + SSTR); }
+  // doubles of the geometry view of the big region (w*sigma only on the B^T sigma residual path)
+  static long geo_doubles(const fdk_plan& p, bool bts) { return (long)p.cap_te * (ESTR + WSTR + (bts ? SSTR : 0)); }
   // doubles of the staging view
   static long stage_doubles(const fdk_plan& p) {
     const long nf = p.cap_inc > p.cap_slots ? p.cap_inc : p.cap_slots;  // nodal forces / per-slot K.u products
     return (long)p.cap_ent * BLKP + nf * NV;
   }
 
-  static size_t smem_bytes(const fdk_plan& p, int* big_doubles) {
-    long big = geo_doubles(p);
+  static size_t smem_bytes(const fdk_plan& p, bool bts, int* big_doubles) {
+    long big = geo_doubles(p, bts);
     const long s = stage_doubles(p);
     if (s > big) big = s;
     big = (big + 1) & ~1L;
     *big_doubles = (int)big;
-    long doubles = TAB_DOUBLES + (((long)p.cap_tn * (DIM + NU) + 1) & ~1L) + big;
+    long doubles = TAB_DOUBLES + (((long)p.cap_tn * (DIM + NU) + 1) & ~1L) + big + p.cap_owned;  // + sBptr
     size_t bytes = (size_t)doubles * 8;
     bytes += (size_t)(2 * (p.cap_owned + 1)) * 4;     // sSlotBase, sFinc
-    bytes += (size_t)((p.cap_slots + 2) & ~1) * 2;    // sOff (u16)
-    bytes += (size_t)((p.cap_slots + 3) & ~3);        // sOwner (u8)
-    bytes += (size_t)((p.cap_te * NNE + 3) & ~3);     // sLconn (u8)
+    bytes += (size_t)(p.cap_slots + 1) * 4;           // sRec
+    bytes += (size_t)((p.cap_heavy + 1) & ~1) * 2;    // sHeavy
+    bytes += (size_t)((p.cap_te * NNE + 3) & ~3);     // sLconn
     return bytes;
   }
 };
@@ -207,6 +207,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   constexpr int NNE = L::NNE, NGP = L::NGP, DIM = L::DIM, NV = L::NV, NU = L::NU, BLK = L::BLK, BLKP = L::BLKP;
   constexpr int NSIG = L::NSIG, GROW = L::GROW, GSTR = L::GSTR, ESTR = L::ESTR, WSTR = L::WSTR, SSTR = L::SSTR;
   constexpr int TSTR = L::TSTR;
+  constexpr int HT = THREADS / 2;  // incidences per cluster <= HT: two threads per incidence in phase 2
+  constexpr int NH = NNE / 2;      // column blocks per thread
+  static_assert(NNE % 2 == 0 && HT % 32 == 0, "half rows, warp-uniform halves");
   const fdk_plan& p = a.p;
   const int c = blockIdx.x, tid = threadIdx.x;
   const bool do_mat = (a.compute & FDK_MATRIX) != 0;
@@ -218,35 +221,24 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   const int te0 = p.cl_te_ptr[c], n_te = p.cl_te_ptr[c + 1] - te0;
   const int tn0 = p.cl_tn_ptr[c], n_tn = p.cl_tn_ptr[c + 1] - tn0;
   const int inc0 = p.cl_inc_ptr[c], n_inc = p.cl_inc_ptr[c + 1] - inc0;
+  const int h0 = p.cl_heavy_ptr[c], n_heavy = p.cl_heavy_ptr[c + 1] - h0;
   const int64_t slot0 = p.cl_slot_ptr[q0];
   const int n_slots = (int)(p.cl_slot_ptr[q0 + n_owned] - slot0);
 
-  // ---- this thread's incidence (long-latency loads issued first, consumed in phase 2) ----
+  // ---- this thread's half incidence (long-latency loads issued first, consumed in phase 2) ----
+  const int half = tid / HT;       // warp-uniform
+  const int it = tid - half * HT;  // incidence of this thread
+  const int j0 = half * NH;        // its column blocks: j0 .. j0 + NH - 1
   unsigned my_desc = 0, my_fdst = 0;
-  unsigned short my_dst[NNE];
-  if (tid < n_inc) {
-    my_desc = p.inc_desc[inc0 + tid];
-    my_fdst = p.inc_fdst[inc0 + tid];
-    const unsigned short* dp = p.inc_dst + (int64_t)(inc0 + tid) * NNE;
-    if constexpr (NNE % 4 == 0) {
-      const uint2* d2 = reinterpret_cast<const uint2*>(dp);
+  unsigned short my_dst[NH];
 #pragma unroll
-      for (int j = 0; j < NNE / 4; ++j) {
-        const uint2 v = d2[j];
-        my_dst[4 * j + 0] = (unsigned short)(v.x & 0xFFFF);
-        my_dst[4 * j + 1] = (unsigned short)(v.x >> 16);
-        my_dst[4 * j + 2] = (unsigned short)(v.y & 0xFFFF);
-        my_dst[4 * j + 3] = (unsigned short)(v.y >> 16);
-      }
-    } else {
-      const unsigned* d1 = reinterpret_cast<const unsigned*>(dp);  // NNE even: 4-byte aligned
+  for (int j = 0; j < NH; ++j) my_dst[j] = 0;
+  if (it < n_inc) {
+    my_desc = p.inc_desc[inc0 + it];
+    if (do_bts) my_fdst = p.inc_fdst[inc0 + it];
+    const unsigned short* dp = p.inc_dst + (int64_t)(inc0 + it) * NNE + j0;
 #pragma unroll
-      for (int j = 0; j < NNE / 2; ++j) {
-        const unsigned v = d1[j];
-        my_dst[2 * j + 0] = (unsigned short)(v & 0xFFFF);
-        my_dst[2 * j + 1] = (unsigned short)(v >> 16);
-      }
-    }
+    for (int j = 0; j < NH; ++j) my_dst[j] = dp[j];
   }
 
   extern __shared__ __align__(16) double smem[];
@@ -259,21 +251,22 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   // geometry view
   double* sG = sBig;                               // [n_te][ESTR]
   double* sWd = sG + (long)p.cap_te * ESTR;        // [n_te][WSTR]      w_g |det J|
-  double* sSig = sWd + (long)p.cap_te * WSTR;      // [n_te][SSTR]      w * sigma
+  double* sSig = sWd + (long)p.cap_te * WSTR;      // [n_te][SSTR]      w * sigma (B^T sigma path only)
   // staging view (aliases the geometry once phase 2 has read it)
   double* sBlk = sBig;                             // [cap_ent][BLKP]
   double* sF = sBlk + (long)p.cap_ent * BLKP;      // [max(cap_inc, cap_slots)][NV]
   double* sR = sF;                                 // per-slot K.u products (fuse_ku: sF is unused)
-  int* sSlotBase = reinterpret_cast<int*>(sBig + a.big_doubles);
-  int* sFinc = sSlotBase + (p.cap_owned + 1);
-  unsigned short* sOff = reinterpret_cast<unsigned short*>(sFinc + (p.cap_owned + 1));
-  unsigned char* sOwner = reinterpret_cast<unsigned char*>(sOff + ((p.cap_slots + 2) & ~1));
-  unsigned char* sLconn = sOwner + ((p.cap_slots + 3) & ~3);
+  long long* sBptr = reinterpret_cast<long long*>(sBig + a.big_doubles);   // [cap_owned]
+  int* sSlotBase = reinterpret_cast<int*>(sBptr + p.cap_owned);            // [cap_owned+1]
+  int* sFinc = sSlotBase + (p.cap_owned + 1);                              // [cap_owned+1]
+  unsigned* sRec = reinterpret_cast<unsigned*>(sFinc + (p.cap_owned + 1)); // [cap_slots+1]
+  unsigned short* sHeavy = reinterpret_cast<unsigned short*>(sRec + (p.cap_slots + 1));  // [cap_heavy]
+  unsigned char* sLconn = reinterpret_cast<unsigned char*>(sHeavy + ((p.cap_heavy + 1) & ~1));
 
   // ---------------- phase 0: staging ----------------
   // All global loads are issued before the first shared-memory store that depends on one (node ids
-  // and offsets into registers, coordinates / dofs / connectivity through cp.async), so the CTA
-  // pays about two memory latencies here instead of one per array.
+  // into registers, everything else through cp.async), so the CTA pays about two memory latencies
+  // here instead of one per array.
   {
     constexpr int RT = (256 + THREADS - 1) / THREADS;  // cap_tn <= 256
     int node_r[RT];
@@ -282,22 +275,21 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
       const int t = tid + r * THREADS;
       node_r[r] = (t < n_tn) ? p.cl_tn_node[tn0 + t] : -1;
     }
-    constexpr int RS = 4;
-    unsigned short off_r[RS];
-    const unsigned short* go = p.slot_off + slot0 + c;
-#pragma unroll
-    for (int r = 0; r < RS; ++r) {
-      const int t = tid + r * THREADS;
-      off_r[r] = (t <= n_slots) ? go[t] : (unsigned short)0;
-    }
-    // connectivity bytes: 4-byte cp.async when the element rows are 4-byte multiples
     {
+      const unsigned* rec = p.slot_rec + slot0 + c;
+      for (int t = tid; t <= n_slots; t += THREADS) cp_async<4>(sRec + t, rec + t);
+      for (int t = tid; t < n_owned; t += THREADS) cp_async<8>(sBptr + t, p.cl_bptr + q0 + t);
       const unsigned char* lc = p.cl_lconn + (int64_t)te0 * NNE;
       if constexpr (NNE % 4 == 0) {
         for (int t = tid; t < n_te * NNE / 4; t += THREADS) cp_async<4>(sLconn + 4 * t, lc + 4 * t);
       } else {
         for (int t = tid; t < n_te * NNE; t += THREADS) sLconn[t] = lc[t];
       }
+    }
+    for (int t = tid; t < n_heavy; t += THREADS) sHeavy[t] = p.heavy_slot[h0 + t];
+    for (int t = tid; t <= n_owned; t += THREADS) {
+      sSlotBase[t] = (int)(p.cl_slot_ptr[q0 + t] - slot0);
+      sFinc[t] = p.cl_finc_ptr[q0 + t] - p.cl_finc_ptr[q0];
     }
     const ElemTable& tab = c_tab[El::ID];
     for (int t = tid; t < NGP * GROW; t += THREADS) {
@@ -306,20 +298,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
     }
     for (int t = tid; t < NGP * NNE; t += THREADS) sN[t] = tab.N[t];
     if (tid < NGP) sW[tid] = tab.w[tid];
-    for (int t = tid; t <= n_owned; t += THREADS) {
-      sSlotBase[t] = (int)(p.cl_slot_ptr[q0 + t] - slot0);
-      sFinc[t] = p.cl_finc_ptr[q0 + t] - p.cl_finc_ptr[q0];
-    }
-    for (int t = tid; t < n_owned; t += THREADS) {
-      const int b0 = (int)(p.cl_slot_ptr[q0 + t] - slot0), b1 = (int)(p.cl_slot_ptr[q0 + t + 1] - slot0);
-      for (int s = b0; s < b1; ++s) sOwner[s] = (unsigned char)t;
-    }
-#pragma unroll
-    for (int r = 0; r < RS; ++r) {
-      const int t = tid + r * THREADS;
-      if (t <= n_slots) sOff[t] = off_r[r];
-    }
-    for (int t = tid + RS * THREADS; t <= n_slots; t += THREADS) sOff[t] = go[t];
     const bool need_u = do_vec && a.U != nullptr;
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
@@ -444,17 +422,18 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   }
   __syncthreads();
 
-  // ---------------- phase 2: per-incidence blocks in registers ----------------
-  double acc[NNE][BLK];
+  // ---------------- phase 2: per-incidence half rows in registers ----------------
+  double acc[NH][BLK];
   double f[NV];
 #pragma unroll
-  for (int j = 0; j < NNE; ++j)
+  for (int j = 0; j < NH; ++j)
 #pragma unroll
     for (int b = 0; b < BLK; ++b) acc[j][b] = 0.0;
 #pragma unroll
   for (int v = 0; v < NV; ++v) f[v] = 0.0;
+  const bool do_f = do_bts && half == 0;  // the nodal force is accumulated by the first half thread only
 
-  if (tid < n_inc) {
+  if (it < n_inc) {
     const int le = my_desc & 0xFFF, i = my_desc >> 12;
     const double* eb = sG + le * ESTR;
     [[maybe_unused]] int64_t e_glob = 0;
@@ -464,15 +443,20 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
 #pragma unroll 1
     for (int g = 0; g < NGP; ++g) {
       const double* gb = eb + g * GSTR;
-      // all dN/dx of the element at this gp: the lanes of one element read the same addresses
-      double Gr[GROW];
+      // dN/dx of this thread's column nodes: the lanes of one element read the same addresses
+      double Gr[NH * DIM];
       {
-        const double2* g2 = reinterpret_cast<const double2*>(gb);
+        if constexpr ((NH * DIM) % 2 == 0) {
+          const double2* g2 = reinterpret_cast<const double2*>(gb + j0 * DIM);
 #pragma unroll
-        for (int t = 0; t < GROW / 2; ++t) {
-          const double2 v = g2[t];
-          Gr[2 * t] = v.x;
-          Gr[2 * t + 1] = v.y;
+          for (int t = 0; t < NH * DIM / 2; ++t) {
+            const double2 v = g2[t];
+            Gr[2 * t] = v.x;
+            Gr[2 * t + 1] = v.y;
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < NH * DIM; ++t) Gr[t] = gb[j0 * DIM + t];
         }
       }
       const double w = sWd[le * WSTR + g];
@@ -480,7 +464,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
 #pragma unroll
       for (int d = 0; d < DIM; ++d) gi[d] = gb[i * DIM + d];
 
-      if (do_bts) {
+      if (do_f) {
         const double* ws = sSig + le * SSTR + g * NSIG;
         if constexpr (PHYS == PHYS_HEAT) {
           double s = ws[DIM] * sN[g * NNE + i];
@@ -503,7 +487,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
 #pragma unroll
           for (int d = 0; d < DIM; ++d) wgi[d] = w * gi[d];
 #pragma unroll
-          for (int j = 0; j < NNE; ++j) {
+          for (int j = 0; j < NH; ++j) {
 #pragma unroll
             for (int cc = 0; cc < DIM; ++cc)
 #pragma unroll
@@ -525,8 +509,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
           for (int j = 0; j < NNE; ++j) nsum += sN[g * NNE + j];
           const double m = a.rcdt * w * sN[g * NNE + i] * nsum;
 #pragma unroll
-          for (int j = 0; j < NNE; ++j) {
-            double s = (j == i) ? m : 0.0;
+          for (int j = 0; j < NH; ++j) {
+            double s = (j0 + j == i) ? m : 0.0;
 #pragma unroll
             for (int d = 0; d < DIM; ++d) s = fma(kgi[d], Gr[j * DIM + d], s);
             acc[j][0] += s;
@@ -559,7 +543,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
             }
           }
 #pragma unroll
-          for (int j = 0; j < NNE; ++j) {
+          for (int j = 0; j < NH; ++j) {
             double gj[DIM];
 #pragma unroll
             for (int d = 0; d < DIM; ++d) gj[d] = Gr[j * DIM + d];
@@ -580,53 +564,50 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
     }
   }
   __syncthreads();  // everyone is done reading the geometry region; it becomes the staging region
-  if (tid < n_inc) {
+  if (it < n_inc) {
     if (do_mat) {
 #pragma unroll
-      for (int j = 0; j < NNE; ++j) {
+      for (int j = 0; j < NH; ++j) {
         double* sp = sBlk + (int)my_dst[j] * BLKP;
 #pragma unroll
         for (int b = 0; b < BLK; ++b) sp[b] = acc[j][b];
       }
     }
-    if (do_bts) {
+    if (do_f) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) sF[my_fdst * NV + v] = f[v];
     }
   }
   __syncthreads();
 
+  // slot record: first staging entry | local touched-node index of the column node << 16 | owner << 24;
+  // the run of a slot ends where the next one starts (minus the gap entry that closes a block row)
   if (do_mat) {
     // ---------------- phase 3a: lane-balanced pre-reduction of the heavy slots ----------------
-    {
-      const int h0 = p.cl_heavy_ptr[c], n_heavy = p.cl_heavy_ptr[c + 1] - h0;
-      if (n_heavy > 0) {  // uniform over the CTA
-        for (int t = tid; t < n_heavy * BLK; t += THREADS) {
-          const int h = t / BLK, b = t - h * BLK;
-          const int s = p.heavy_slot[h0 + h];
-          const int n = sOwner[s];
-          const int e0 = sOff[s];
-          const int e1 = (int)sOff[s + 1] - ((s + 1 == sSlotBase[n + 1]) ? 1 : 0);
-          double v = 0.0;
-          for (int e = e0; e < e1; ++e) v += sBlk[e * BLKP + b];
-          sBlk[e0 * BLKP + b] = v;
-        }
-        __syncthreads();
+    if (n_heavy > 0) {  // uniform over the CTA
+      for (int t = tid; t < n_heavy * BLK; t += THREADS) {
+        const int h = t / BLK, b = t - h * BLK;
+        const int s = sHeavy[h];
+        const unsigned r0 = sRec[s], r1 = sRec[s + 1];
+        const int e0 = r0 & 0xFFFF;
+        const int e1 = (int)(r1 & 0xFFFF) - (((r0 ^ r1) >> 24) ? 1 : 0);
+        double v = 0.0;
+        for (int e = e0; e < e1; ++e) v += sBlk[e * BLKP + b];
+        sBlk[e0 * BLKP + b] = v;
       }
+      __syncthreads();
     }
     // ---------------- phase 3b: slot gather, constitutive closed form, final stores ----------------
     for (int s = tid; s < n_slots; s += THREADS) {
-      [[maybe_unused]] unsigned slot_tn = 0;
-      if constexpr (PHYS != PHYS_HEAT) {
-        if (fuse_ku) slot_tn = p.slot_tn[slot0 + s];
-      }
-      const int n = sOwner[s];
+      const unsigned r0 = sRec[s], r1 = sRec[s + 1];
+      const int e0 = r0 & 0xFFFF;
+      const int n = r0 >> 24;
+      int cnt = (int)(r1 & 0xFFFF) - e0 - (((r0 ^ r1) >> 24) ? 1 : 0);  // one gap entry after each row
+      if (cnt > HEAVY_T) cnt = 1;                                       // pre-reduced in 3a
       const int sb = sSlotBase[n];
       const int deg = sSlotBase[n + 1] - sb;
       const int pcol = s - sb;
-      const int e0 = sOff[s];
-      int cnt = (int)sOff[s + 1] - e0 - ((pcol == deg - 1) ? 1 : 0);  // one gap entry after each row
-      if (cnt > HEAVY_T) cnt = 1;                                    // pre-reduced in 3a
+      const int64_t bp = sBptr[n];
       double S[BLK];
       const double* sp = sBlk + e0 * BLKP;
 #pragma unroll
@@ -654,7 +635,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
 #pragma unroll
         for (int b = 0; b < BLK; ++b) Kb[b] = S[b];
       }
-      const int64_t bp = p.cl_bptr[q0 + n];
 #pragma unroll
       for (int cc = 0; cc < NV; ++cc) {
         double* row = a.K + ((int64_t)cc * NV * p.blk_nnz + (int64_t)NV * bp);
@@ -663,7 +643,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
       }
       if constexpr (PHYS != PHYS_HEAT) {
         if (fuse_ku) {  // this slot's share of (K U)_I: the assembled block times the dofs of its column node
-          const double* uj = sU + (int)slot_tn * DIM;
+          const double* uj = sU + (int)((r0 >> 16) & 0xFF) * DIM;
 #pragma unroll
           for (int cc = 0; cc < NV; ++cc) {
             double r = 0.0;
@@ -698,17 +678,23 @@ template <class El, int PHYS, int THREADS, int MINB>
 int launch_assemble_t(AsmArgs& a, cudaStream_t stream) {
   using L = Layout<El, PHYS>;
   const fdk_plan& p = a.p;
-  FDK_REQUIRE(p.cap_inc <= THREADS, FDK_ECAP, "cluster with %d incidences exceeds CTA size %d", p.cap_inc, THREADS);
-  FDK_REQUIRE(p.cap_te < 4096 && p.cap_tn <= 256 && p.cap_owned <= 256 && p.cap_ent < 65536 && p.cap_slots < 65536,
+  FDK_REQUIRE(2 * p.cap_inc <= THREADS, FDK_ECAP, "cluster with %d incidences exceeds half the CTA size %d",
+              p.cap_inc, THREADS);
+  FDK_REQUIRE(p.cap_te < 4096 && p.cap_tn <= 256 && p.cap_owned < 255 && p.cap_ent < 65536 && p.cap_slots < 65535,
               FDK_ECAP, "cluster capacity overflow (te=%d tn=%d owned=%d ent=%d slots=%d)", p.cap_te, p.cap_tn,
               p.cap_owned, p.cap_ent, p.cap_slots);
   FDK_REQUIRE(p.nvar == L::NV, FDK_EINVAL, "plan nvar %d does not match the operator (%d)", p.nvar, L::NV);
-  const size_t smem = L::smem_bytes(p, &a.big_doubles);
+  const bool bts = (a.compute & FDK_VECTOR) && !a.fuse_ku;
+  const size_t smem = L::smem_bytes(p, bts, &a.big_doubles);
   FDK_REQUIRE(smem <= 227 * 1024, FDK_ECAP, "cluster needs %zu bytes of shared memory (> 227 KB)", smem);
   if (p.n_clusters == 0) return 0;
   if (int rc = ensure_device_tables()) return rc;
   auto kern = k_assemble<El, PHYS, THREADS, MINB>;
-  FDK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static thread_local size_t smem_set = 0;  // per instantiation
+  if (smem > smem_set) {
+    FDK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
   kern<<<p.n_clusters, THREADS, smem, stream>>>(a);
   FDK_CUDA(cudaGetLastError());
   return 0;

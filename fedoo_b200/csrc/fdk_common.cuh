@@ -28,12 +28,13 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 // ---- element traits ------------------------------------------------------------------
-// THREADS = CTA size of the cluster kernels = max incidences (node, element) per cluster.
+// THREADS = CTA size of the cluster kernels = 2 x max incidences (node, element) per cluster
+// (phase 2 runs two threads per incidence, half a block row each); half-size variant: THREADS / 2.
 template <int ID_, int NNE_, int NGP_, int DIM_, int THREADS_>
 struct ElemTraits {
   static constexpr int ID = ID_, NNE = NNE_, NGP = NGP_, DIM = DIM_, THREADS = THREADS_;
 };
-using Hex8 = ElemTraits<FDK_HEX8, 8, 8, 3, 256>;
+using Hex8 = ElemTraits<FDK_HEX8, 8, 8, 3, 512>;
 using Tet4 = ElemTraits<FDK_TET4, 4, 4, 3, 512>;
 using Tet10 = ElemTraits<FDK_TET10, 10, 15, 3, 256>;
 using Quad4 = ElemTraits<FDK_QUAD4, 4, 4, 2, 512>;

@@ -29,17 +29,18 @@ from . import _lib
 # (log2 of lattice cells per cluster).  te_max keeps te_max * ESTR * 8 B <= ~160 KB.
 _CAPS = {
     "hex8": dict(nne=8, ngp=8, dim=3, inc_max=256, te_max=80, shift=5),
-    "tet4": dict(nne=4, ngp=4, dim=3, inc_max=512, te_max=256, shift=4),
-    "tet10": dict(nne=10, ngp=15, dim=3, inc_max=200, te_max=36, shift=3),
-    "quad4": dict(nne=4, ngp=4, dim=2, inc_max=512, te_max=400, shift=6),
+    "tet4": dict(nne=4, ngp=4, dim=3, inc_max=256, te_max=256, shift=4),
+    "tet10": dict(nne=10, ngp=15, dim=3, inc_max=128, te_max=36, shift=3),
+    "quad4": dict(nne=4, ngp=4, dim=2, inc_max=256, te_max=400, shift=6),
 }
-# CTA sizes the kernels are instantiated for (csrc/fdk_common.cuh ElemTraits::THREADS and half of it)
-_THREADS = {"hex8": 256, "tet4": 512, "tet10": 256, "quad4": 512}
-# "small" variant: half-size CTAs, two resident per SM (phases of different clusters overlap)
+# CTA sizes the kernels are instantiated for (csrc/fdk_common.cuh ElemTraits::THREADS and half of it):
+# two threads per incidence (half a block row each), so threads = 2 * inc_max
+_THREADS = {"hex8": 512, "tet4": 512, "tet10": 256, "quad4": 512}
+# "small" variant: half-size clusters / CTAs, two resident per SM (phases of different clusters overlap)
 _CAPS_SMALL = {
     "hex8": dict(inc_max=128, te_max=45, shift=4),
-    "tet4": dict(inc_max=256, te_max=128, shift=3),
-    "quad4": dict(inc_max=256, te_max=200, shift=5),
+    "tet4": dict(inc_max=128, te_max=128, shift=3),
+    "quad4": dict(inc_max=128, te_max=200, shift=5),
 }
 HEAVY_T = 4  # slots with more contributions are pre-reduced by a balanced pass (csrc/fdk_assemble.cuh)
 TN_MAX = 255
@@ -137,7 +138,7 @@ class Plan:
             self.threads //= 2
         if caps:
             cap.update(caps)
-        assert cap["inc_max"] <= self.threads
+        assert 2 * cap["inc_max"] <= self.threads
         self.elem_type = elem_type
         dev = conn.device
         n_el, nne = conn.shape
@@ -289,31 +290,36 @@ class Plan:
         slot0_c = cl_slot_ptr[cl_node_ptr]  # (n_cl+1) first slot of each cluster (+ end)
         ent0_c = gcum[slot0_c]  # == cl_inc_ptr * nne
         counts_c = cl_node_ptr[1:] - cl_node_ptr[:-1]
-        slot_off = torch.zeros(total_slots + n_cl, dtype=torch.int64, device=dev)
+        # slot records (csrc/fdk_assemble.cuh phase 3): first staging entry | column-node local index << 16
+        # | owner local index << 24; one end sentinel (owner 0xFF) per cluster
+        slot_rec = torch.zeros(total_slots + n_cl, dtype=torch.int64, device=dev)
         slot_cnt = gcum[1:] - gcum[:-1]
         if total_slots:
             q_of_slot = torch.repeat_interleave(torch.arange(n_nodes, device=dev), deg_o)
             cl_of_slot = cl_of_pos[q_of_slot]
             sl = torch.arange(total_slots, device=dev)
-            slot_off[sl + cl_of_slot] = gcum[:-1] - ent0_c[cl_of_slot] + (q_of_slot - cl_node_ptr[cl_of_slot])
+            n_loc = q_of_slot - cl_node_ptr[cl_of_slot]
+            e0 = gcum[:-1] - ent0_c[cl_of_slot] + n_loc
             # cluster-local touched-node index of every slot's column node (K.u residual in phase 3)
             J_of_slot = pattern.blk_indices.to(torch.int64)[_expand_ranges(cl_bptr, deg_o)]
             slot_tn = torch.searchsorted(tn_keys, cl_of_slot * n_mesh_nodes + J_of_slot) - cl_tn_ptr[cl_of_slot]
             del J_of_slot
+            assert int(e0.max()) <= ENT_MAX and int(slot_tn.max()) <= 0xFF and int(n_loc.max()) < 0xFF
+            slot_rec[sl + cl_of_slot] = e0 | (slot_tn << 16) | (n_loc << 24)
             # heavy slots (cluster-local index), cluster by cluster
             heavy = torch.nonzero(slot_cnt > HEAVY_T).reshape(-1)
             heavy_slot = heavy - slot0_c[cl_of_slot[heavy]]
             cl_heavy_ptr = torch.zeros(n_cl + 1, dtype=torch.int64, device=dev)
             cl_heavy_ptr[1:] = torch.cumsum(torch.bincount(cl_of_slot[heavy], minlength=n_cl), 0)
-            del q_of_slot, cl_of_slot, sl
+            del q_of_slot, cl_of_slot, sl, n_loc, e0, slot_tn
         else:
             heavy_slot = torch.zeros(0, dtype=torch.int64, device=dev)
-            slot_tn = torch.zeros(0, dtype=torch.int64, device=dev)
             cl_heavy_ptr = torch.zeros(n_cl + 1, dtype=torch.int64, device=dev)
         if n_cl:
             cidx = torch.arange(n_cl, device=dev)
-            slot_off[slot0_c[1:] + cidx] = (ent0_c[1:] - ent0_c[:-1]) + counts_c  # end sentinel (incl. all gaps)
-        assert n_cl == 0 or int(slot_off.max()) <= ENT_MAX
+            end = (ent0_c[1:] - ent0_c[:-1]) + counts_c  # end sentinel (incl. all gaps)
+            assert int(end.max()) <= ENT_MAX
+            slot_rec[slot0_c[1:] + cidx] = end | (0xFF << 24)
 
         # ---- capacities ----
         def cmax(x):
@@ -328,6 +334,7 @@ class Plan:
             cap_owned=cmax(counts_c),
             cap_slots=cmax(n_slots_c),
             cap_ent=cmax(n_inc_c * nne + counts_c),
+            cap_heavy=cmax(cl_heavy_ptr[1:] - cl_heavy_ptr[:-1]),
         )
         self.stats = dict(
             n_clusters=n_cl,
@@ -356,8 +363,7 @@ class Plan:
             cl_lconn=lconn.to(u8).contiguous(),
             cl_tn_ptr=cl_tn_ptr.to(i32),
             cl_tn_node=tn_node.to(i32),
-            slot_off=slot_off.to(u16),
-            slot_tn=slot_tn.to(u8),
+            slot_rec=slot_rec.to(torch.uint32),
             cl_heavy_ptr=cl_heavy_ptr.to(i32),
             heavy_slot=heavy_slot.to(u16),
         )

@@ -88,9 +88,8 @@ typedef struct fdk_plan {
   int32_t nvar;       /* variables per node of the assembled operator (dim for elasticity, 1 for heat) */
   int64_t blk_nnz;    /* nnz of the node-node block pattern */
   /* capacities = max over clusters (sizes the dynamic shared memory) */
-  int32_t cap_te, cap_tn, cap_inc, cap_owned, cap_slots, cap_ent;
-  int32_t threads;    /* CTA size the clusters were sized for (cap_inc <= threads) */
-  int32_t reserved;
+  int32_t cap_te, cap_tn, cap_inc, cap_owned, cap_slots, cap_ent, cap_heavy;
+  int32_t threads;    /* CTA size the clusters were sized for (2 * cap_inc <= threads) */
   const int32_t* cl_node_ptr;  /* [n_clusters+1] range of owned nodes (cluster order)                    */
   const int32_t* cl_node;      /* [n_owned]  global id of the q-th owned node                             */
   const int64_t* cl_bptr;      /* [n_owned]  blk_indptr[cl_node[q]]                                       */
@@ -106,10 +105,11 @@ typedef struct fdk_plan {
   const uint8_t* cl_lconn;     /* [n_te_total][nne] local (cluster) index of each element node            */
   const int32_t* cl_tn_ptr;    /* [n_clusters+1] range of touched nodes                                   */
   const int32_t* cl_tn_node;   /* global node id of each touched node                                     */
-  const uint16_t* slot_off;    /* per cluster n_slots+1 staging offsets (first entry of each slot; one gap
-                                  entry after every block row) at index cl_slot_ptr[q0] + cluster         */
-  const uint8_t* slot_tn;      /* [n_slots_total] cluster-local touched-node index of the slot's column
-                                  node (dofs staged in shared memory; residual from the assembled rows)   */
+  const uint32_t* slot_rec;    /* per cluster n_slots+1 records at index cl_slot_ptr[q0] + cluster:
+                                  first staging entry of the slot (entries are slot-sorted, one gap entry
+                                  after every block row) | cluster-local touched-node index of the slot's
+                                  column node << 16 | cluster-local index of the owner (row) node << 24;
+                                  the last record of a cluster is an end sentinel with owner 0xFF          */
   const int32_t* cl_heavy_ptr; /* [n_clusters+1] range of heavy slots (more than 4 contributions)         */
   const uint16_t* heavy_slot;  /* cluster-local slot index of each heavy slot                             */
 } fdk_plan;

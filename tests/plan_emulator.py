@@ -33,7 +33,14 @@ def emulate_iso(plan, pat, nodes, elements, lam, mu, allow_unwritten=False):
     the slot-sorted staging array (inc_dst), heavy slots pre-reduced, slot gather by contiguous runs."""
     from fedoo_b200.plan import HEAVY_T
 
-    t = {k: v.numpy() if v.dtype != torch.uint16 else v.view(torch.int16).numpy().astype(np.int64) & 0xFFFF for k, v in plan.t.items()}
+    def host(v):
+        if v.dtype == torch.uint16:
+            return v.view(torch.int16).numpy().astype(np.int64) & 0xFFFF
+        if v.dtype == torch.uint32:
+            return v.view(torch.int32).numpy().astype(np.int64) & 0xFFFFFFFF
+        return v.numpy()
+
+    t = {k: host(v) for k, v in plan.t.items()}
     elements = np.asarray(elements)
     G, wdet = fo.geometry(nodes, elements, plan.elem_type)
     dim = G.shape[2]
@@ -50,12 +57,13 @@ def emulate_iso(plan, pat, nodes, elements, lam, mu, allow_unwritten=False):
         tn0 = t["cl_tn_ptr"][c]
         inc0, inc1 = t["cl_inc_ptr"][c], t["cl_inc_ptr"][c + 1]
         n_inc = inc1 - inc0
-        assert n_inc <= plan.threads
+        assert 2 * n_inc <= plan.threads
         assert n_inc == t["cl_finc_ptr"][q1] - t["cl_finc_ptr"][q0]
         slot0 = t["cl_slot_ptr"][q0]
         n_slots = t["cl_slot_ptr"][q1] - slot0
-        off = t["slot_off"][slot0 + c : slot0 + c + n_slots + 1]
-        assert off[-1] == n_inc * nne + n_owned <= plan.caps["cap_ent"]
+        rec = t["slot_rec"][slot0 + c : slot0 + c + n_slots + 1]
+        off = rec & 0xFFFF
+        assert off[-1] == n_inc * nne + n_owned <= plan.caps["cap_ent"] and rec[-1] >> 24 == 0xFF
         stage = np.full((plan.caps["cap_ent"], dim, dim), np.nan)
         fdst_seen = np.zeros(n_inc, dtype=int)
         owned_nodes = t["cl_node"][q0:q1]
@@ -90,12 +98,13 @@ def emulate_iso(plan, pat, nodes, elements, lam, mu, allow_unwritten=False):
             for pcol in range(deg):
                 s = sb0 + pcol
                 e0 = int(off[s])
-                cnt = int(off[s + 1]) - e0 - (1 if pcol == deg - 1 else 0)
+                assert rec[s] >> 24 == n
+                cnt = int(off[s + 1]) - e0 - (1 if (rec[s] >> 24) != (rec[s + 1] >> 24) else 0)
                 assert (cnt > HEAVY_T) == (s in heavy)
                 acc = stage[e0 : e0 + cnt].sum(axis=0) if cnt else np.zeros((dim, dim))
                 assert not np.isnan(acc).any()
                 Jn = pat.blk_indices[bp + pcol].item()
-                assert t["cl_tn_node"][tn0 + int(t["slot_tn"][slot0 + s])] == Jn
+                assert t["cl_tn_node"][tn0 + int((rec[s] >> 16) & 0xFF)] == Jn
                 assert cnt == np.sum((elements == I).any(axis=1) & (elements == Jn).any(axis=1))
                 Kb = lam * acc + mu * acc.T + mu * np.trace(acc) * np.eye(dim)
                 for cc in range(nv):
