@@ -15,7 +15,7 @@ MATRIX, VECTOR, ALL = 1, 2, 3
 COMPUTE_FLAGS = {"matrix": MATRIX, "vector": VECTOR, "all": ALL}
 
 EXPORTS = [
-    "fdk_last_error_string", "fdk_version", "fdk_element_info", "fdk_element_table",
+    "fdk_last_error_string", "fdk_version", "fdk_set_option", "fdk_get_option", "fdk_element_info", "fdk_element_table",
     "fdk_sym_block_keys", "fdk_sym_block_csr", "fdk_sym_expand_csr",
     "fdk_assemble_elastic_iso", "fdk_assemble_elastic_general", "fdk_assemble_heat",
     "fdk_gp_strain_stress", "fdk_gp_temperature", "fdk_j2_update",
@@ -58,6 +58,8 @@ class PlanStruct(C.Structure):
         ("cl_te_elem", C.c_void_p),
         ("cl_te_own", C.c_void_p),
         ("cl_lconn", C.c_void_p),
+        ("te_inc", C.c_void_p),
+        ("te_mask", C.c_void_p),
         ("cl_tn_ptr", C.c_void_p),
         ("cl_tn_node", C.c_void_p),
         ("slot_rec", C.c_void_p),
@@ -84,6 +86,8 @@ def load():
     lib.fdk_last_error_string.restype = C.c_char_p
     lib.fdk_last_error_string.argtypes = []
     lib.fdk_version.restype = i32
+    lib.fdk_set_option.argtypes = [C.c_char_p, i32]
+    lib.fdk_get_option.argtypes = [C.c_char_p, C.POINTER(i32)]
     lib.fdk_element_info.argtypes = [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.fdk_element_table.argtypes = [i32, vp, vp, vp]
     lib.fdk_sym_block_keys.argtypes = [i32, i64, i32, vp, vp, C.POINTER(i64), vp]
@@ -103,6 +107,17 @@ def load():
             getattr(lib, name).restype = i32
     _lib = lib
     return lib
+
+
+def set_option(key, value):
+    """Process-wide kernel option (include/fdk.h: fdk_set_option): 'fuse_ku', 'mma'."""
+    check(load().fdk_set_option(key.encode(), int(value)), "fdk_set_option")
+
+
+def get_option(key):
+    v = C.c_int(0)
+    check(load().fdk_get_option(key.encode(), C.byref(v)), "fdk_get_option")
+    return v.value
 
 
 def check(rc, what=""):

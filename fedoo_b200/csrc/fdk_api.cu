@@ -10,11 +10,17 @@ using namespace fdk;
 
 namespace {
 
-// FDK_NO_FUSE_KU=1 forces the B^T sigma residual path (tests compare both)
-const bool g_no_fuse = [] {
-  const char* e = getenv("FDK_NO_FUSE_KU");
-  return e != nullptr && e[0] == '1';
-}();
+// Runtime options (fdk_set_option); defaults from the environment at load time.
+//   fuse_ku : take the residual of a linear law from the assembled rows (D = -K_row . U) when K and D are
+//             both requested (default 1; FDK_NO_FUSE_KU=1 -> 0: always integrate B^T sigma)
+//   mma     : hex8 + isotropic law: form the element matrices with FP64 tensor-core DMMA instead of
+//             CUDA-core FMAs (default 0; FDK_MMA=1 -> 1).  Measured at parity on B200.
+int env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e == nullptr ? dflt : (e[0] == '1');
+}
+int g_opt_fuse = env_flag("FDK_NO_FUSE_KU", 0) ? 0 : 1;
+int g_opt_mma = env_flag("FDK_MMA", 0);
 
 int check_plan(const fdk_plan* p) {
   FDK_REQUIRE(p != nullptr, FDK_EINVAL, "plan is NULL");
@@ -24,7 +30,7 @@ int check_plan(const fdk_plan* p) {
   if (p->n_clusters > 0)
     FDK_REQUIRE(p->cl_node_ptr && p->cl_node && p->cl_bptr && p->cl_slot_ptr && p->cl_inc_ptr && p->inc_desc &&
                     p->cl_te_ptr && p->cl_te_elem && p->cl_lconn && p->cl_tn_ptr && p->cl_tn_node &&
-                    p->cl_finc_ptr && p->inc_dst && p->inc_fdst && p->slot_rec && p->cl_heavy_ptr,
+                    p->cl_finc_ptr && p->inc_dst && p->inc_fdst && p->slot_rec && p->cl_heavy_ptr && p->te_inc && p->te_mask,
                 FDK_EINVAL, "plan has NULL arrays");
   return 0;
 }
@@ -42,7 +48,23 @@ int check_io(int compute, const double* coords, const double* K, const double* D
 extern "C" {
 
 const char* fdk_last_error_string(void) { return g_err; }
-int fdk_version(void) { return 100; }
+int fdk_version(void) { return 110; }
+
+int fdk_set_option(const char* key, int value) {
+  FDK_REQUIRE(key != nullptr, FDK_EINVAL, "option key is NULL");
+  if (strcmp(key, "fuse_ku") == 0) { g_opt_fuse = value != 0; return 0; }
+  if (strcmp(key, "mma") == 0) { g_opt_mma = value != 0; return 0; }
+  set_error("unknown option '%s' (known: fuse_ku, mma)", key);
+  return FDK_EINVAL;
+}
+
+int fdk_get_option(const char* key, int* value) {
+  FDK_REQUIRE(key != nullptr && value != nullptr, FDK_EINVAL, "NULL argument");
+  if (strcmp(key, "fuse_ku") == 0) { *value = g_opt_fuse; return 0; }
+  if (strcmp(key, "mma") == 0) { *value = g_opt_mma; return 0; }
+  set_error("unknown option '%s' (known: fuse_ku, mma)", key);
+  return FDK_EINVAL;
+}
 
 int fdk_element_info(int elem_type, int* nne, int* ngp, int* dim) { return elem_dims(elem_type, nne, ngp, dim); }
 
@@ -95,7 +117,8 @@ int fdk_assemble_elastic_iso(const fdk_plan* plan, int compute, const double* co
   a.compute = compute;
   // linear law and both outputs requested: the residual -int B^T C eps(U) equals -(K U) row by row,
   // so it is taken from the assembled rows in the gather phase instead of a second B^T sigma pass
-  a.fuse_ku = (compute == FDK_ALL && U != nullptr && stress_gp == nullptr && !g_no_fuse) ? 1 : 0;
+  a.fuse_ku = (compute == FDK_ALL && U != nullptr && stress_gp == nullptr && g_opt_fuse) ? 1 : 0;
+  a.no_mma = g_opt_mma ? 0 : 1;
   return dispatch_assemble<PHYS_ISO>(a, (cudaStream_t)stream);
 }
 
@@ -118,7 +141,7 @@ int fdk_assemble_elastic_general(const fdk_plan* plan, int compute, const double
     for (int i = 0; i < 36; ++i) a.C[i] = C_h[i];
   a.compute = compute;
   a.fuse_ku =
-      (compute == FDK_ALL && U != nullptr && stress_gp == nullptr && tangent_gp == nullptr && !g_no_fuse) ? 1 : 0;
+      (compute == FDK_ALL && U != nullptr && stress_gp == nullptr && tangent_gp == nullptr && g_opt_fuse) ? 1 : 0;
   return dispatch_assemble<PHYS_GENERAL>(a, (cudaStream_t)stream);
 }
 

@@ -53,6 +53,7 @@ struct AsmArgs {
   int compute;
   int big_doubles;  // size of the aliased geometry / staging region
   int fuse_ku;      // linear law, K and D both requested: D = -(assembled rows) . U in the gather phase
+  int no_mma;       // FDK_NO_MMA=1: keep the CUDA-core producer even where the tensor-core one applies
 };
 
 template <class El, int PHYS>
@@ -77,19 +78,26 @@ struct Layout {
   // doubles of the geometry view of the big region (w*sigma only on the B^T sigma residual path)
   static long geo_doubles(const fdk_plan& p, bool bts) { return (long)p.cap_te * (ESTR + WSTR + (bts ? SSTR : 0)); }
   // doubles of the staging view
-  static long stage_doubles(const fdk_plan& p) {
+  static long stage_doubles(const fdk_plan& p, bool mma = false) {
     const long nf = p.cap_inc > p.cap_slots ? p.cap_inc : p.cap_slots;  // nodal forces / per-slot K.u products
-    return (long)p.cap_ent * BLKP + nf * NV;
+    return (long)p.cap_ent * BLKP + (mma ? 0 : nf * NV);                 // (tensor-core path: products reuse sJ)
   }
 
-  static size_t smem_bytes(const fdk_plan& p, bool bts, int* big_doubles) {
-    long big = geo_doubles(p, bts);
-    const long s = stage_doubles(p);
+  static constexpr int JSTR = NGP * 10;  // tensor-core path: inverse Jacobian (9) + w per Gauss point
+
+  static size_t smem_bytes(const fdk_plan& p, bool bts, bool mma, int* big_doubles) {
+    long big = mma ? 0 : geo_doubles(p, bts);
+    const long s = stage_doubles(p, mma);
     if (s > big) big = s;
     big = (big + 1) & ~1L;
     *big_doubles = (int)big;
     long doubles = TAB_DOUBLES + (((long)p.cap_tn * (DIM + NU) + 1) & ~1L) + big + p.cap_owned;  // + sBptr
+    if (mma) {  // sJ lives beside the staging region (not aliased); the K.u products reuse it in phase 3
+      const long nj = (long)p.cap_te * JSTR, nr = (long)p.cap_slots * NV;
+      doubles += (nj > nr ? nj : nr) + 1;
+    }
     size_t bytes = (size_t)doubles * 8;
+    if (mma) bytes += (size_t)p.cap_inc * NNE * 2 + (size_t)((p.cap_te * 3 + 3) & ~3);  // sDst, sTeInc/sTeMask
     bytes += (size_t)(2 * (p.cap_owned + 1)) * 4;     // sSlotBase, sFinc
     bytes += (size_t)(p.cap_slots + 1) * 4;           // sRec
     bytes += (size_t)((p.cap_heavy + 1) & ~1) * 2;    // sHeavy
@@ -201,8 +209,24 @@ __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <class El, int PHYS, int THREADS, int MINB>
+// One m8n8k4 FP64 tensor-core MMA (SASS DMMA.8x8x4): D(8x8) += A(8x4) B(4x8).  Fragments: a = A[lane>>2][lane&3],
+// b = B[lane&3][lane>>2], d0/d1 = D[lane>>2][2*(lane&3) + 0/1].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// MMA = true (hex8, isotropic law, matrix requested, no B^T sigma pass): phases 1-2 are replaced by
+//   phase 1m  one task per (touched element, gp): inverse Jacobian and w only -> shared memory
+//   phase 2m  one WARP per touched element: every lane rebuilds "its" six dN/dx values
+//             (node lane>>2, Gauss points lane&3 and (lane&3)+4) in registers and the element matrix
+//             S^e = sum_g w G^T G (24 x 24, component-major) is formed by 12 DMMA.8x8x4 on the six
+//             upper (c <= a) 8x8 tiles -- operands never touch shared memory; the fragments are
+//             scattered to the same slot-sorted staging entries as in the CUDA-core path.
+template <class El, int PHYS, int THREADS, int MINB, bool MMA>
 __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constant__ AsmArgs a) {
+  static_assert(!MMA || (El::NNE == 8 && El::NGP == 8 && El::DIM == 3 && PHYS == PHYS_ISO), "MMA path: hex8 isotropic");
   using L = Layout<El, PHYS>;
   constexpr int NNE = L::NNE, NGP = L::NGP, DIM = L::DIM, NV = L::NV, NU = L::NU, BLK = L::BLK, BLKP = L::BLKP;
   constexpr int NSIG = L::NSIG, GROW = L::GROW, GSTR = L::GSTR, ESTR = L::ESTR, WSTR = L::WSTR, SSTR = L::SSTR;
@@ -233,7 +257,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   unsigned short my_dst[NH];
 #pragma unroll
   for (int j = 0; j < NH; ++j) my_dst[j] = 0;
-  if (it < n_inc) {
+  if (!MMA && it < n_inc) {
     my_desc = p.inc_desc[inc0 + it];
     if (do_bts) my_fdst = p.inc_fdst[inc0 + it];
     const unsigned short* dp = p.inc_dst + (int64_t)(inc0 + it) * NNE + j0;
@@ -262,6 +286,23 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   unsigned* sRec = reinterpret_cast<unsigned*>(sFinc + (p.cap_owned + 1)); // [cap_slots+1]
   unsigned short* sHeavy = reinterpret_cast<unsigned short*>(sRec + (p.cap_slots + 1));  // [cap_heavy]
   unsigned char* sLconn = reinterpret_cast<unsigned char*>(sHeavy + ((p.cap_heavy + 1) & ~1));
+  // tensor-core path extras
+  [[maybe_unused]] double* sJ = reinterpret_cast<double*>(sBptr + ((p.cap_owned + 1) & ~1));  // [cap_te][JSTR]
+  [[maybe_unused]] unsigned short* sDst = nullptr;
+  [[maybe_unused]] unsigned short* sTeInc = nullptr;
+  [[maybe_unused]] unsigned char* sTeMask = nullptr;
+  if constexpr (MMA) {
+    sR = sJ;  // sJ is dead once phase 2m is over
+    const long nj = (long)p.cap_te * L::JSTR, nr = (long)p.cap_slots * NV;
+    sSlotBase = reinterpret_cast<int*>(sJ + (nj > nr ? nj : nr));
+    sFinc = sSlotBase + (p.cap_owned + 1);
+    sRec = reinterpret_cast<unsigned*>(sFinc + (p.cap_owned + 1));
+    sHeavy = reinterpret_cast<unsigned short*>(sRec + (p.cap_slots + 1));
+    sLconn = reinterpret_cast<unsigned char*>(sHeavy + ((p.cap_heavy + 1) & ~1));
+    sDst = reinterpret_cast<unsigned short*>(sLconn + ((p.cap_te * NNE + 3) & ~3));
+    sTeInc = sDst + (long)p.cap_inc * NNE;
+    sTeMask = reinterpret_cast<unsigned char*>(sTeInc + p.cap_te);
+  }
 
   // ---------------- phase 0: staging ----------------
   // All global loads are issued before the first shared-memory store that depends on one (node ids
@@ -287,6 +328,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
       }
     }
     for (int t = tid; t < n_heavy; t += THREADS) sHeavy[t] = p.heavy_slot[h0 + t];
+    if constexpr (MMA) {
+      const unsigned short* dsrc = p.inc_dst + (int64_t)inc0 * NNE;  // 16-byte aligned rows
+      for (int t = tid; t < n_inc * NNE / 2; t += THREADS) cp_async<4>(sDst + 2 * t, dsrc + 2 * t);
+      for (int t = tid; t < n_te; t += THREADS) {
+        sTeInc[t] = p.te_inc[te0 + t];
+        sTeMask[t] = p.te_mask[te0 + t];
+      }
+    }
     for (int t = tid; t <= n_owned; t += THREADS) {
       sSlotBase[t] = (int)(p.cl_slot_ptr[q0 + t] - slot0);
       sFinc[t] = p.cl_finc_ptr[q0 + t] - p.cl_finc_ptr[q0];
@@ -322,260 +371,371 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   }
   __syncthreads();
 
-  // ---------------- phase 1: geometry (+ w*sigma) per (touched element, gp) ----------------
-  for (int task = tid; task < n_te * NGP; task += THREADS) {
-    const int le = task / NGP, g = task - le * NGP;
-    const unsigned char* lc = sLconn + le * NNE;
-    int ln[NNE];
-    double X[NNE][DIM];
-#pragma unroll
-    for (int k = 0; k < NNE; ++k) {
-      ln[k] = lc[k];
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) X[k][d] = sX[ln[k] * DIM + d];
-    }
-    double G[NNE][DIM];
-    const double w = gp_geometry<NNE, DIM>(sdN + g * TSTR, sW[g], X, G);
-    {
-      double2* out = reinterpret_cast<double2*>(sG + le * ESTR + g * GSTR);
-#pragma unroll
-      for (int t = 0; t < GROW / 2; ++t) {
-        const int k0 = (2 * t) / DIM, d0 = (2 * t) % DIM, k1 = (2 * t + 1) / DIM, d1 = (2 * t + 1) % DIM;
-        out[t] = make_double2(G[k0][d0], G[k1][d1]);
+  if constexpr (!MMA) {
+    // ---------------- phase 1: geometry (+ w*sigma) per (touched element, gp) ----------------
+    for (int task = tid; task < n_te * NGP; task += THREADS) {
+      const int le = task / NGP, g = task - le * NGP;
+      const unsigned char* lc = sLconn + le * NNE;
+      int ln[NNE];
+      double X[NNE][DIM];
+  #pragma unroll
+      for (int k = 0; k < NNE; ++k) {
+        ln[k] = lc[k];
+  #pragma unroll
+        for (int d = 0; d < DIM; ++d) X[k][d] = sX[ln[k] * DIM + d];
       }
-    }
-    sWd[le * WSTR + g] = w;
-
-    if (do_bts) {
-      double* so = sSig + le * SSTR + g * NSIG;
-      if constexpr (PHYS == PHYS_HEAT) {
-        double gT[DIM], dTg = 0.0;
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) gT[d] = 0.0;
-#pragma unroll
-        for (int k = 0; k < NNE; ++k) {
-          const double T = sU[ln[k] * 2 + 0];
-#pragma unroll
-          for (int d = 0; d < DIM; ++d) gT[d] = fma(T, G[k][d], gT[d]);
-          dTg = fma(sN[g * NNE + k], sU[ln[k] * 2 + 1], dTg);
-        }
-#pragma unroll
-        for (int i = 0; i < DIM; ++i) {
-          double q = 0.0;
-#pragma unroll
-          for (int j = 0; j < DIM; ++j) q = fma(a.cond[i * 3 + j], gT[j], q);
-          so[i] = w * q;
-        }
-        so[DIM] = w * a.rcdt * dTg;
-      } else {
-        double sig[6];
-        if (a.stress_gp != nullptr) {
-          const int64_t e = p.cl_te_elem[te0 + le];
-          const double* sp = a.stress_gp + 6 * ((int64_t)g * p.n_elems + e);
-#pragma unroll
-          for (int s = 0; s < 6; ++s) sig[s] = sp[s];
-        } else {
-          double gu[DIM][DIM];
-#pragma unroll
-          for (int v = 0; v < DIM; ++v)
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) gu[v][d] = 0.0;
-#pragma unroll
-          for (int k = 0; k < NNE; ++k)
-#pragma unroll
-            for (int v = 0; v < DIM; ++v) {
-              const double u = sU[ln[k] * DIM + v];
-#pragma unroll
-              for (int d = 0; d < DIM; ++d) gu[v][d] = fma(u, G[k][d], gu[v][d]);
-            }
-          double eps[6];
-          voigt_strain<DIM>(gu, eps);
-          if constexpr (PHYS == PHYS_ISO) {
-            // sigma = lambda tr(eps) 1 + 2 mu eps  (H of fedoo/constitutivelaw/elastic_isotrop.py:57-66)
-            const double tr = eps[0] + eps[1] + eps[2];
-            const double lt = a.lam * tr, m2 = 2.0 * a.mu;
-            sig[0] = fma(m2, eps[0], lt);
-            sig[1] = fma(m2, eps[1], lt);
-            sig[2] = fma(m2, eps[2], lt);
-            sig[3] = a.mu * eps[3];
-            sig[4] = a.mu * eps[4];
-            sig[5] = a.mu * eps[5];
-          } else {
-            if (a.tangent_gp != nullptr) {
-              const int64_t e = p.cl_te_elem[te0 + le];
-              apply_tangent(a.tangent_gp + 36 * ((int64_t)g * p.n_elems + e), 1, 6, eps, sig);
-            } else {
-              apply_tangent(a.C, 6, 1, eps, sig);
-            }
-          }
-        }
-        if constexpr (DIM == 3) {
-#pragma unroll
-          for (int s = 0; s < 6; ++s) so[s] = w * sig[s];
-        } else {
-          so[0] = w * sig[0];
-          so[1] = w * sig[1];
-          so[2] = w * sig[3];
-        }
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---------------- phase 2: per-incidence half rows in registers ----------------
-  double acc[NH][BLK];
-  double f[NV];
-#pragma unroll
-  for (int j = 0; j < NH; ++j)
-#pragma unroll
-    for (int b = 0; b < BLK; ++b) acc[j][b] = 0.0;
-#pragma unroll
-  for (int v = 0; v < NV; ++v) f[v] = 0.0;
-  const bool do_f = do_bts && half == 0;  // the nodal force is accumulated by the first half thread only
-
-  if (it < n_inc) {
-    const int le = my_desc & 0xFFF, i = my_desc >> 12;
-    const double* eb = sG + le * ESTR;
-    [[maybe_unused]] int64_t e_glob = 0;
-    if constexpr (PHYS == PHYS_GENERAL) {
-      if (a.tangent_gp != nullptr) e_glob = p.cl_te_elem[te0 + le];
-    }
-#pragma unroll 1
-    for (int g = 0; g < NGP; ++g) {
-      const double* gb = eb + g * GSTR;
-      // dN/dx of this thread's column nodes: the lanes of one element read the same addresses
-      double Gr[NH * DIM];
+      double G[NNE][DIM];
+      const double w = gp_geometry<NNE, DIM>(sdN + g * TSTR, sW[g], X, G);
       {
-        if constexpr ((NH * DIM) % 2 == 0) {
-          const double2* g2 = reinterpret_cast<const double2*>(gb + j0 * DIM);
-#pragma unroll
-          for (int t = 0; t < NH * DIM / 2; ++t) {
-            const double2 v = g2[t];
-            Gr[2 * t] = v.x;
-            Gr[2 * t + 1] = v.y;
-          }
-        } else {
-#pragma unroll
-          for (int t = 0; t < NH * DIM; ++t) Gr[t] = gb[j0 * DIM + t];
+        double2* out = reinterpret_cast<double2*>(sG + le * ESTR + g * GSTR);
+  #pragma unroll
+        for (int t = 0; t < GROW / 2; ++t) {
+          const int k0 = (2 * t) / DIM, d0 = (2 * t) % DIM, k1 = (2 * t + 1) / DIM, d1 = (2 * t + 1) % DIM;
+          out[t] = make_double2(G[k0][d0], G[k1][d1]);
         }
       }
-      const double w = sWd[le * WSTR + g];
-      double gi[DIM];
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) gi[d] = gb[i * DIM + d];
+      sWd[le * WSTR + g] = w;
 
-      if (do_f) {
-        const double* ws = sSig + le * SSTR + g * NSIG;
+      if (do_bts) {
+        double* so = sSig + le * SSTR + g * NSIG;
         if constexpr (PHYS == PHYS_HEAT) {
-          double s = ws[DIM] * sN[g * NNE + i];
-#pragma unroll
-          for (int d = 0; d < DIM; ++d) s = fma(ws[d], gi[d], s);
-          f[0] += s;
-        } else if constexpr (DIM == 3) {
-          f[0] += ws[0] * gi[0] + ws[3] * gi[1] + ws[4] * gi[2];
-          f[1] += ws[1] * gi[1] + ws[3] * gi[0] + ws[5] * gi[2];
-          f[2] += ws[2] * gi[2] + ws[4] * gi[0] + ws[5] * gi[1];
+          double gT[DIM], dTg = 0.0;
+  #pragma unroll
+          for (int d = 0; d < DIM; ++d) gT[d] = 0.0;
+  #pragma unroll
+          for (int k = 0; k < NNE; ++k) {
+            const double T = sU[ln[k] * 2 + 0];
+  #pragma unroll
+            for (int d = 0; d < DIM; ++d) gT[d] = fma(T, G[k][d], gT[d]);
+            dTg = fma(sN[g * NNE + k], sU[ln[k] * 2 + 1], dTg);
+          }
+  #pragma unroll
+          for (int i = 0; i < DIM; ++i) {
+            double q = 0.0;
+  #pragma unroll
+            for (int j = 0; j < DIM; ++j) q = fma(a.cond[i * 3 + j], gT[j], q);
+            so[i] = w * q;
+          }
+          so[DIM] = w * a.rcdt * dTg;
         } else {
-          f[0] += ws[0] * gi[0] + ws[2] * gi[1];
-          f[1] += ws[1] * gi[1] + ws[2] * gi[0];
-        }
-      }
-
-      if (do_mat) {
-        if constexpr (PHYS == PHYS_ISO) {
-          double wgi[DIM];
-#pragma unroll
-          for (int d = 0; d < DIM; ++d) wgi[d] = w * gi[d];
-#pragma unroll
-          for (int j = 0; j < NH; ++j) {
-#pragma unroll
-            for (int cc = 0; cc < DIM; ++cc)
-#pragma unroll
-              for (int aa = 0; aa < DIM; ++aa)
-                acc[j][cc * DIM + aa] = fma(wgi[cc], Gr[j * DIM + aa], acc[j][cc * DIM + aa]);
-          }
-        } else if constexpr (PHYS == PHYS_HEAT) {
-          double kgi[DIM];
-#pragma unroll
-          for (int d = 0; d < DIM; ++d) {
-            double s = 0.0;
-#pragma unroll
-            for (int d2 = 0; d2 < DIM; ++d2) s = fma(gi[d2], a.cond[d2 * 3 + d], s);
-            kgi[d] = w * s;
-          }
-          // lumped capacity: row sum of the consistent mass goes to the diagonal
-          double nsum = 0.0;
-#pragma unroll
-          for (int j = 0; j < NNE; ++j) nsum += sN[g * NNE + j];
-          const double m = a.rcdt * w * sN[g * NNE + i] * nsum;
-#pragma unroll
-          for (int j = 0; j < NH; ++j) {
-            double s = (j0 + j == i) ? m : 0.0;
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) s = fma(kgi[d], Gr[j * DIM + d], s);
-            acc[j][0] += s;
-          }
-        } else {  // PHYS_GENERAL: t[c][s] = w sum_s' B_I[s'][c] C[s'][s]; acc[j][c][a] += sum_s t[c][s] B_J[s][a]
-          const double* Cg;
-          int si, sj;
-          if (a.tangent_gp != nullptr) {
-            Cg = a.tangent_gp + 36 * ((int64_t)g * p.n_elems + e_glob);
-            si = 1;
-            sj = 6;
+          double sig[6];
+          if (a.stress_gp != nullptr) {
+            const int64_t e = p.cl_te_elem[te0 + le];
+            const double* sp = a.stress_gp + 6 * ((int64_t)g * p.n_elems + e);
+  #pragma unroll
+            for (int s = 0; s < 6; ++s) sig[s] = sp[s];
           } else {
-            Cg = a.C;
-            si = 6;
-            sj = 1;
-          }
-          double t[DIM][6];
-#pragma unroll
-          for (int s = 0; s < 6; ++s) {
-            if constexpr (DIM == 3) {
-              const double c0 = Cg[0 * si + s * sj], c1 = Cg[1 * si + s * sj], c2 = Cg[2 * si + s * sj];
-              const double c3 = Cg[3 * si + s * sj], c4 = Cg[4 * si + s * sj], c5 = Cg[5 * si + s * sj];
-              t[0][s] = w * (gi[0] * c0 + gi[1] * c3 + gi[2] * c4);
-              t[1][s] = w * (gi[1] * c1 + gi[0] * c3 + gi[2] * c5);
-              t[2][s] = w * (gi[2] * c2 + gi[0] * c4 + gi[1] * c5);
+            double gu[DIM][DIM];
+  #pragma unroll
+            for (int v = 0; v < DIM; ++v)
+  #pragma unroll
+              for (int d = 0; d < DIM; ++d) gu[v][d] = 0.0;
+  #pragma unroll
+            for (int k = 0; k < NNE; ++k)
+  #pragma unroll
+              for (int v = 0; v < DIM; ++v) {
+                const double u = sU[ln[k] * DIM + v];
+  #pragma unroll
+                for (int d = 0; d < DIM; ++d) gu[v][d] = fma(u, G[k][d], gu[v][d]);
+              }
+            double eps[6];
+            voigt_strain<DIM>(gu, eps);
+            if constexpr (PHYS == PHYS_ISO) {
+              // sigma = lambda tr(eps) 1 + 2 mu eps  (H of fedoo/constitutivelaw/elastic_isotrop.py:57-66)
+              const double tr = eps[0] + eps[1] + eps[2];
+              const double lt = a.lam * tr, m2 = 2.0 * a.mu;
+              sig[0] = fma(m2, eps[0], lt);
+              sig[1] = fma(m2, eps[1], lt);
+              sig[2] = fma(m2, eps[2], lt);
+              sig[3] = a.mu * eps[3];
+              sig[4] = a.mu * eps[4];
+              sig[5] = a.mu * eps[5];
             } else {
-              const double c0 = Cg[0 * si + s * sj], c1 = Cg[1 * si + s * sj], c3 = Cg[3 * si + s * sj];
-              t[0][s] = w * (gi[0] * c0 + gi[1] * c3);
-              t[1][s] = w * (gi[1] * c1 + gi[0] * c3);
+              if (a.tangent_gp != nullptr) {
+                const int64_t e = p.cl_te_elem[te0 + le];
+                apply_tangent(a.tangent_gp + 36 * ((int64_t)g * p.n_elems + e), 1, 6, eps, sig);
+              } else {
+                apply_tangent(a.C, 6, 1, eps, sig);
+              }
             }
           }
-#pragma unroll
-          for (int j = 0; j < NH; ++j) {
-            double gj[DIM];
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) gj[d] = Gr[j * DIM + d];
-#pragma unroll
-            for (int cc = 0; cc < DIM; ++cc) {
+          if constexpr (DIM == 3) {
+  #pragma unroll
+            for (int s = 0; s < 6; ++s) so[s] = w * sig[s];
+          } else {
+            so[0] = w * sig[0];
+            so[1] = w * sig[1];
+            so[2] = w * sig[3];
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: per-incidence half rows in registers ----------------
+    double acc[NH][BLK];
+    double f[NV];
+  #pragma unroll
+    for (int j = 0; j < NH; ++j)
+  #pragma unroll
+      for (int b = 0; b < BLK; ++b) acc[j][b] = 0.0;
+  #pragma unroll
+    for (int v = 0; v < NV; ++v) f[v] = 0.0;
+    const bool do_f = do_bts && half == 0;  // the nodal force is accumulated by the first half thread only
+
+    if (it < n_inc) {
+      const int le = my_desc & 0xFFF, i = my_desc >> 12;
+      const double* eb = sG + le * ESTR;
+      [[maybe_unused]] int64_t e_glob = 0;
+      if constexpr (PHYS == PHYS_GENERAL) {
+        if (a.tangent_gp != nullptr) e_glob = p.cl_te_elem[te0 + le];
+      }
+  #pragma unroll 1
+      for (int g = 0; g < NGP; ++g) {
+        const double* gb = eb + g * GSTR;
+        // dN/dx of this thread's column nodes: the lanes of one element read the same addresses
+        double Gr[NH * DIM];
+        {
+          if constexpr ((NH * DIM) % 2 == 0) {
+            const double2* g2 = reinterpret_cast<const double2*>(gb + j0 * DIM);
+  #pragma unroll
+            for (int t = 0; t < NH * DIM / 2; ++t) {
+              const double2 v = g2[t];
+              Gr[2 * t] = v.x;
+              Gr[2 * t + 1] = v.y;
+            }
+          } else {
+  #pragma unroll
+            for (int t = 0; t < NH * DIM; ++t) Gr[t] = gb[j0 * DIM + t];
+          }
+        }
+        const double w = sWd[le * WSTR + g];
+        double gi[DIM];
+  #pragma unroll
+        for (int d = 0; d < DIM; ++d) gi[d] = gb[i * DIM + d];
+
+        if (do_f) {
+          const double* ws = sSig + le * SSTR + g * NSIG;
+          if constexpr (PHYS == PHYS_HEAT) {
+            double s = ws[DIM] * sN[g * NNE + i];
+  #pragma unroll
+            for (int d = 0; d < DIM; ++d) s = fma(ws[d], gi[d], s);
+            f[0] += s;
+          } else if constexpr (DIM == 3) {
+            f[0] += ws[0] * gi[0] + ws[3] * gi[1] + ws[4] * gi[2];
+            f[1] += ws[1] * gi[1] + ws[3] * gi[0] + ws[5] * gi[2];
+            f[2] += ws[2] * gi[2] + ws[4] * gi[0] + ws[5] * gi[1];
+          } else {
+            f[0] += ws[0] * gi[0] + ws[2] * gi[1];
+            f[1] += ws[1] * gi[1] + ws[2] * gi[0];
+          }
+        }
+
+        if (do_mat) {
+          if constexpr (PHYS == PHYS_ISO) {
+            double wgi[DIM];
+  #pragma unroll
+            for (int d = 0; d < DIM; ++d) wgi[d] = w * gi[d];
+  #pragma unroll
+            for (int j = 0; j < NH; ++j) {
+  #pragma unroll
+              for (int cc = 0; cc < DIM; ++cc)
+  #pragma unroll
+                for (int aa = 0; aa < DIM; ++aa)
+                  acc[j][cc * DIM + aa] = fma(wgi[cc], Gr[j * DIM + aa], acc[j][cc * DIM + aa]);
+            }
+          } else if constexpr (PHYS == PHYS_HEAT) {
+            double kgi[DIM];
+  #pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+              double s = 0.0;
+  #pragma unroll
+              for (int d2 = 0; d2 < DIM; ++d2) s = fma(gi[d2], a.cond[d2 * 3 + d], s);
+              kgi[d] = w * s;
+            }
+            // lumped capacity: row sum of the consistent mass goes to the diagonal
+            double nsum = 0.0;
+  #pragma unroll
+            for (int j = 0; j < NNE; ++j) nsum += sN[g * NNE + j];
+            const double m = a.rcdt * w * sN[g * NNE + i] * nsum;
+  #pragma unroll
+            for (int j = 0; j < NH; ++j) {
+              double s = (j0 + j == i) ? m : 0.0;
+  #pragma unroll
+              for (int d = 0; d < DIM; ++d) s = fma(kgi[d], Gr[j * DIM + d], s);
+              acc[j][0] += s;
+            }
+          } else {  // PHYS_GENERAL: t[c][s] = w sum_s' B_I[s'][c] C[s'][s]; acc[j][c][a] += sum_s t[c][s] B_J[s][a]
+            const double* Cg;
+            int si, sj;
+            if (a.tangent_gp != nullptr) {
+              Cg = a.tangent_gp + 36 * ((int64_t)g * p.n_elems + e_glob);
+              si = 1;
+              sj = 6;
+            } else {
+              Cg = a.C;
+              si = 6;
+              sj = 1;
+            }
+            double t[DIM][6];
+  #pragma unroll
+            for (int s = 0; s < 6; ++s) {
               if constexpr (DIM == 3) {
-                acc[j][cc * 3 + 0] += t[cc][0] * gj[0] + t[cc][3] * gj[1] + t[cc][4] * gj[2];
-                acc[j][cc * 3 + 1] += t[cc][1] * gj[1] + t[cc][3] * gj[0] + t[cc][5] * gj[2];
-                acc[j][cc * 3 + 2] += t[cc][2] * gj[2] + t[cc][4] * gj[0] + t[cc][5] * gj[1];
+                const double c0 = Cg[0 * si + s * sj], c1 = Cg[1 * si + s * sj], c2 = Cg[2 * si + s * sj];
+                const double c3 = Cg[3 * si + s * sj], c4 = Cg[4 * si + s * sj], c5 = Cg[5 * si + s * sj];
+                t[0][s] = w * (gi[0] * c0 + gi[1] * c3 + gi[2] * c4);
+                t[1][s] = w * (gi[1] * c1 + gi[0] * c3 + gi[2] * c5);
+                t[2][s] = w * (gi[2] * c2 + gi[0] * c4 + gi[1] * c5);
               } else {
-                acc[j][cc * 2 + 0] += t[cc][0] * gj[0] + t[cc][3] * gj[1];
-                acc[j][cc * 2 + 1] += t[cc][1] * gj[1] + t[cc][3] * gj[0];
+                const double c0 = Cg[0 * si + s * sj], c1 = Cg[1 * si + s * sj], c3 = Cg[3 * si + s * sj];
+                t[0][s] = w * (gi[0] * c0 + gi[1] * c3);
+                t[1][s] = w * (gi[1] * c1 + gi[0] * c3);
+              }
+            }
+  #pragma unroll
+            for (int j = 0; j < NH; ++j) {
+              double gj[DIM];
+  #pragma unroll
+              for (int d = 0; d < DIM; ++d) gj[d] = Gr[j * DIM + d];
+  #pragma unroll
+              for (int cc = 0; cc < DIM; ++cc) {
+                if constexpr (DIM == 3) {
+                  acc[j][cc * 3 + 0] += t[cc][0] * gj[0] + t[cc][3] * gj[1] + t[cc][4] * gj[2];
+                  acc[j][cc * 3 + 1] += t[cc][1] * gj[1] + t[cc][3] * gj[0] + t[cc][5] * gj[2];
+                  acc[j][cc * 3 + 2] += t[cc][2] * gj[2] + t[cc][4] * gj[0] + t[cc][5] * gj[1];
+                } else {
+                  acc[j][cc * 2 + 0] += t[cc][0] * gj[0] + t[cc][3] * gj[1];
+                  acc[j][cc * 2 + 1] += t[cc][1] * gj[1] + t[cc][3] * gj[0];
+                }
               }
             }
           }
         }
       }
     }
-  }
-  __syncthreads();  // everyone is done reading the geometry region; it becomes the staging region
-  if (it < n_inc) {
-    if (do_mat) {
-#pragma unroll
-      for (int j = 0; j < NH; ++j) {
-        double* sp = sBlk + (int)my_dst[j] * BLKP;
-#pragma unroll
-        for (int b = 0; b < BLK; ++b) sp[b] = acc[j][b];
+    __syncthreads();  // everyone is done reading the geometry region; it becomes the staging region
+    if (it < n_inc) {
+      if (do_mat) {
+  #pragma unroll
+        for (int j = 0; j < NH; ++j) {
+          double* sp = sBlk + (int)my_dst[j] * BLKP;
+  #pragma unroll
+          for (int b = 0; b < BLK; ++b) sp[b] = acc[j][b];
+        }
+      }
+      if (do_f) {
+  #pragma unroll
+        for (int v = 0; v < NV; ++v) sF[my_fdst * NV + v] = f[v];
       }
     }
-    if (do_f) {
+  } else {
+    // ---------------- phase 1m: inverse Jacobian and w per (touched element, gp) ----------------
+    for (int task = tid; task < n_te * NGP; task += THREADS) {
+      const int le = task / NGP, g = task - le * NGP;
+      const unsigned char* lc = sLconn + le * NNE;
+      const double* dN = sdN + g * TSTR;
+      double J[DIM][DIM];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) sF[my_fdst * NV + v] = f[v];
+      for (int r = 0; r < DIM; ++r)
+#pragma unroll
+        for (int x = 0; x < DIM; ++x) J[r][x] = 0.0;
+#pragma unroll
+      for (int k = 0; k < NNE; ++k) {
+        const double* xk = sX + (int)lc[k] * DIM;
+        const double x0 = xk[0], x1 = xk[1], x2 = xk[2];
+#pragma unroll
+        for (int r = 0; r < DIM; ++r) {
+          const double dn = dN[r * NNE + k];
+          J[r][0] = fma(dn, x0, J[r][0]);
+          J[r][1] = fma(dn, x1, J[r][1]);
+          J[r][2] = fma(dn, x2, J[r][2]);
+        }
+      }
+      double iJ[DIM][DIM];
+      const double det = invert<DIM>(J, iJ);
+      double2* out = reinterpret_cast<double2*>(sJ + le * L::JSTR + g * 10);
+      out[0] = make_double2(iJ[0][0], iJ[0][1]);
+      out[1] = make_double2(iJ[0][2], iJ[1][0]);
+      out[2] = make_double2(iJ[1][1], iJ[1][2]);
+      out[3] = make_double2(iJ[2][0], iJ[2][1]);
+      out[4] = make_double2(iJ[2][2], sW[g] * fabs(det));
+    }
+    __syncthreads();
+
+    // ---------------- phase 2m: one warp per touched element, S^e by DMMA ----------------
+    {
+      const int lane = tid & 31, warp = tid >> 5;
+      const int r = lane >> 2, q = lane & 3;  // node (MMA row / column) and Gauss point pair (MMA k index)
+      // reference gradients of node r at the two Gauss points of this lane (constant for the kernel)
+      double dn0[DIM], dn1[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        dn0[d] = sdN[q * TSTR + d * NNE + r];
+        dn1[d] = sdN[(q + 4) * TSTR + d * NNE + r];
+      }
+      for (int le = warp; le < n_te; le += THREADS / 32) {
+        const double2* j0p = reinterpret_cast<const double2*>(sJ + le * L::JSTR + q * 10);
+        const double2* j1p = j0p + 20;  // Gauss point q + 4
+        double G0[DIM], G1[DIM], w0, w1;
+        {
+          const double2 a0 = j0p[0], a1 = j0p[1], a2 = j0p[2], a3 = j0p[3], a4 = j0p[4];
+          G0[0] = fma(a0.x, dn0[0], fma(a0.y, dn0[1], a1.x * dn0[2]));
+          G0[1] = fma(a1.y, dn0[0], fma(a2.x, dn0[1], a2.y * dn0[2]));
+          G0[2] = fma(a3.x, dn0[0], fma(a3.y, dn0[1], a4.x * dn0[2]));
+          w0 = a4.y;
+          const double2 b0 = j1p[0], b1 = j1p[1], b2 = j1p[2], b3 = j1p[3], b4 = j1p[4];
+          G1[0] = fma(b0.x, dn1[0], fma(b0.y, dn1[1], b1.x * dn1[2]));
+          G1[1] = fma(b1.y, dn1[0], fma(b2.x, dn1[1], b2.y * dn1[2]));
+          G1[2] = fma(b3.x, dn1[0], fma(b3.y, dn1[1], b4.x * dn1[2]));
+          w1 = b4.y;
+        }
+        double A0[DIM], A1[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          A0[d] = w0 * G0[d];
+          A1[d] = w1 * G1[d];
+        }
+        // six upper tiles (c <= a): d[t][jj] = S^e_{I=r, J=2q+jj}[c][a]
+        double d[6][2];
+        {
+          int t = 0;
+#pragma unroll
+          for (int cc = 0; cc < DIM; ++cc)
+#pragma unroll
+            for (int aa = cc; aa < DIM; ++aa, ++t) {
+              d[t][0] = 0.0;
+              d[t][1] = 0.0;
+              dmma884(d[t][0], d[t][1], A0[cc], G0[aa]);
+              dmma884(d[t][0], d[t][1], A1[cc], G1[aa]);
+            }
+        }
+        // scatter: block (I=r, J) upper entries go to the staging entry of (row r, column J); its
+        // transposed upper entries are the strictly-lower entries of block (J, r)
+        const unsigned mask = sTeMask[le];
+        const int base = sTeInc[le];
+        const bool own_r = (mask >> r) & 1u;
+        const int row_r = base + __popc(mask & ((1u << r) - 1u));
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int Jn = 2 * q + jj;
+          if (own_r) {
+            double* sp = sBlk + (int)sDst[row_r * NNE + Jn] * BLKP;
+            sp[0] = d[0][jj];
+            sp[1] = d[1][jj];
+            sp[2] = d[2][jj];
+            sp[4] = d[3][jj];
+            sp[5] = d[4][jj];
+            sp[8] = d[5][jj];
+          }
+          if ((mask >> Jn) & 1u) {
+            const int row_j = base + __popc(mask & ((1u << Jn) - 1u));
+            double* sp = sBlk + (int)sDst[row_j * NNE + r] * BLKP;
+            sp[3] = d[1][jj];  // S_{J r}[1][0] = S_{r J}[0][1]
+            sp[6] = d[2][jj];  // [2][0] = [0][2]
+            sp[7] = d[4][jj];  // [2][1] = [1][2]
+          }
+        }
+      }
     }
   }
   __syncthreads();
@@ -674,7 +834,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
 }
 
 // ---- host launcher -----------------------------------------------------------------------
-template <class El, int PHYS, int THREADS, int MINB>
+template <class El, int PHYS, int THREADS, int MINB, bool MMA>
 int launch_assemble_t(AsmArgs& a, cudaStream_t stream) {
   using L = Layout<El, PHYS>;
   const fdk_plan& p = a.p;
@@ -685,11 +845,11 @@ int launch_assemble_t(AsmArgs& a, cudaStream_t stream) {
               p.cap_owned, p.cap_ent, p.cap_slots);
   FDK_REQUIRE(p.nvar == L::NV, FDK_EINVAL, "plan nvar %d does not match the operator (%d)", p.nvar, L::NV);
   const bool bts = (a.compute & FDK_VECTOR) && !a.fuse_ku;
-  const size_t smem = L::smem_bytes(p, bts, &a.big_doubles);
+  const size_t smem = L::smem_bytes(p, bts, MMA, &a.big_doubles);
   FDK_REQUIRE(smem <= 227 * 1024, FDK_ECAP, "cluster needs %zu bytes of shared memory (> 227 KB)", smem);
   if (p.n_clusters == 0) return 0;
   if (int rc = ensure_device_tables()) return rc;
-  auto kern = k_assemble<El, PHYS, THREADS, MINB>;
+  auto kern = k_assemble<El, PHYS, THREADS, MINB, MMA>;
   static thread_local size_t smem_set = 0;  // per instantiation
   if (smem > smem_set) {
     FDK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -702,9 +862,17 @@ int launch_assemble_t(AsmArgs& a, cudaStream_t stream) {
 
 template <class El, int PHYS>
 int launch_assemble(AsmArgs& a, cudaStream_t stream) {
+  // hex8 + isotropic law + matrix requested + no B^T sigma pass: FP64 tensor-core producer
+  if constexpr (El::ID == FDK_HEX8 && PHYS == PHYS_ISO) {
+    const bool bts = (a.compute & FDK_VECTOR) && !a.fuse_ku;
+    if ((a.compute & FDK_MATRIX) && !bts && !a.no_mma) {
+      if (a.p.threads == El::THREADS) return launch_assemble_t<El, PHYS, El::THREADS, 1, true>(a, stream);
+      if (a.p.threads == El::THREADS / 2) return launch_assemble_t<El, PHYS, El::THREADS / 2, 2, true>(a, stream);
+    }
+  }
   // the plan states the CTA size it was built for (fedoo_b200/plan.py); small CTAs run 2 per SM
-  if (a.p.threads == El::THREADS) return launch_assemble_t<El, PHYS, El::THREADS, 1>(a, stream);
-  if (a.p.threads == El::THREADS / 2) return launch_assemble_t<El, PHYS, El::THREADS / 2, 2>(a, stream);
+  if (a.p.threads == El::THREADS) return launch_assemble_t<El, PHYS, El::THREADS, 1, false>(a, stream);
+  if (a.p.threads == El::THREADS / 2) return launch_assemble_t<El, PHYS, El::THREADS / 2, 2, false>(a, stream);
   set_error("plan built for %d threads per cluster; this element supports %d or %d", a.p.threads, El::THREADS,
             El::THREADS / 2);
   return FDK_EINVAL;

@@ -248,6 +248,12 @@ class Plan:
         em_pos = torch.empty_like(em_perm)
         em_pos[em_perm] = torch.arange(n_inc_tot, device=dev)
         nm_rank = torch.arange(n_inc_tot, device=dev) - cl_inc_ptr[inc_cl]  # node-major rank in the cluster
+        # per touched element: its first thread (cluster-local) and the mask of its owned local nodes
+        n_te_tot = int(te_keys.numel())
+        te_inc = torch.full((n_te_tot,), 1 << 40, dtype=torch.int64, device=dev)
+        te_inc.scatter_reduce_(0, te_idx, em_pos - cl_inc_ptr[inc_cl], reduce="amin")
+        te_mask = torch.zeros(n_te_tot, dtype=torch.int64, device=dev)
+        te_mask.scatter_add_(0, te_idx, torch.ones_like(inc_l) << inc_l)
 
         # ---- touched nodes + local connectivity ----
         tn_all = te_cl[:, None] * n_mesh_nodes + conn64[te_elem]  # (n_te_total, nne)
@@ -361,6 +367,8 @@ class Plan:
             cl_te_elem=te_elem.to(i32),
             cl_te_own=te_own.to(u8),
             cl_lconn=lconn.to(u8).contiguous(),
+            te_inc=te_inc.to(u16),
+            te_mask=te_mask.to(u8),
             cl_tn_ptr=cl_tn_ptr.to(i32),
             cl_tn_node=tn_node.to(i32),
             slot_rec=slot_rec.to(torch.uint32),

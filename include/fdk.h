@@ -46,6 +46,12 @@ enum fdk_compute { FDK_MATRIX = 1, FDK_VECTOR = 2, FDK_ALL = 3 };
 const char* fdk_last_error_string(void);
 int fdk_version(void);
 
+/* Runtime options (process-wide): "fuse_ku" (default 1): for a linear law with K and D both requested the
+ * residual is taken from the assembled rows, D = -K_row . U, instead of a second B^T sigma integration;
+ * "mma" (default 0): hex8 + isotropic law, element matrices by FP64 tensor-core DMMA.m8n8k4. */
+int fdk_set_option(const char* key, int value);
+int fdk_get_option(const char* key, int* value);
+
 /* element table accessors (host): what the kernels integrate with.
  * Replaces fedoo/lib_elements/{hexahedron,tetrahedron,quadrangle}.py tables
  * (hexahedron.py:22-27,134-135,178-248; tetrahedron.py:21-61,72-97,106-208;
@@ -103,6 +109,9 @@ typedef struct fdk_plan {
   const int32_t* cl_te_elem;   /* global element id of each touched element                               */
   const uint8_t* cl_te_own;    /* 1 if this cluster is the unique owner of the touched element            */
   const uint8_t* cl_lconn;     /* [n_te_total][nne] local (cluster) index of each element node            */
+  const uint16_t* te_inc;      /* [n_te_total] cluster-local index of the element's first incidence (the
+                                  incidences of one element are consecutive: element-major thread order)  */
+  const uint8_t* te_mask;      /* [n_te_total] bit i set: local node i of the element is owned here       */
   const int32_t* cl_tn_ptr;    /* [n_clusters+1] range of touched nodes                                   */
   const int32_t* cl_tn_node;   /* global node id of each touched node                                     */
   const uint32_t* slot_rec;    /* per cluster n_slots+1 records at index cl_slot_ptr[q0] + cluster:

@@ -87,6 +87,17 @@ def emulate_iso(plan, pat, nodes, elements, lam, mu, allow_unwritten=False):
                 assert np.isnan(stage[d, 0, 0]), "two blocks staged at the same entry"
                 stage[d] = S[j]
         assert (fdst_seen == 1).all()
+        # per touched element: first thread and owned-node mask (tensor-core producer, hex8)
+        if nne <= 8:
+            descs = t["inc_desc"][inc0:inc1]
+            for le in range(t["cl_te_ptr"][c + 1] - te0):
+                mine = np.nonzero((descs & 0xFFF) == le)[0]
+                assert len(mine) > 0 and mine[0] == t["te_inc"][te0 + le] and (np.diff(mine) == 1).all()
+                mask = 0
+                for m in mine:
+                    mask |= 1 << int(descs[m] >> 12)
+                assert mask == t["te_mask"][te0 + le]
+                assert list(descs[mine] >> 12) == sorted(descs[mine] >> 12)
         # heavy slots
         h0, h1 = t["cl_heavy_ptr"][c], t["cl_heavy_ptr"][c + 1]
         heavy = set(int(x) for x in t["heavy_slot"][h0:h1])

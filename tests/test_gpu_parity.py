@@ -97,6 +97,34 @@ def test_elastic_against_reference(fd, golden_dir, name, elm, space):
     a.assemble_global_mat("none")
 
 
+@pytest.mark.parametrize("name", ["hex8_cantilever", "hex8_jitter"])
+@pytest.mark.parametrize("small", [True, False])
+def test_hex8_tensor_core_producer(fd, golden_dir, name, small, monkeypatch):
+    """hex8 + isotropic law with the DMMA.8x8x4 producer (option 'mma') and with both cluster sizes:
+    same CSR values and residual as the reference; the CUDA-core producer agrees to rounding."""
+    from fedoo_b200 import _lib
+
+    monkeypatch.setenv("FDK_SMALL_CTA", "1" if small else "0")
+    g = load(golden_dir, name)
+    out = {}
+    for mma in (1, 0):
+        _lib.set_option("mma", mma)
+        try:
+            law = fd.constitutivelaw.ElasticIsotrop(float(g["E"]), float(g["nu"]), name="law")
+            mesh, a, pb = _elastic_setup(fd, "3D", g["nodes"], g["elements"], "hex8", law)
+            pb.set_X(g["U"])
+            a.update(pb, compute="all")
+            K = a.get_global_matrix().tocsr()
+            out[mma] = (K.data.copy(), np.array(a.get_global_vector()))
+            assert np.array_equal(K.indptr, g["K_indptr"]) and np.array_equal(K.indices, g["K_indices"])
+            assert nrm(K.data, g["K_data"]) <= TOL and nrm(out[mma][1], g["D"]) <= TOL
+            a.assemble_global_mat("matrix")
+            assert np.array_equal(a.get_global_matrix().tocsr().data, K.data)  # deterministic
+        finally:
+            _lib.set_option("mma", 0)
+    assert nrm(out[1][0], out[0][0]) <= 1e-14 and nrm(out[1][1], out[0][1]) <= 1e-13
+
+
 def test_zero_displacement_vector_is_scalar_zero(fd, golden_dir):
     """fedoo/core/assembly.py:462-463: no vector term -> global_vector == 0 (scalar)."""
     g = load(golden_dir, "hex8_jitter")
