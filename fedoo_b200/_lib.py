@@ -45,11 +45,14 @@ class PlanStruct(C.Structure):
         ("cap_ent", C.c_int32),
         ("cap_heavy", C.c_int32),
         ("threads", C.c_int32),
+        ("cl_hdr", C.c_void_p),
         ("cl_node_ptr", C.c_void_p),
         ("cl_node", C.c_void_p),
         ("cl_bptr", C.c_void_p),
         ("cl_slot_ptr", C.c_void_p),
         ("cl_finc_ptr", C.c_void_p),
+        ("cl_slot_loc", C.c_void_p),
+        ("cl_finc_loc", C.c_void_p),
         ("cl_inc_ptr", C.c_void_p),
         ("inc_desc", C.c_void_p),
         ("inc_dst", C.c_void_p),
@@ -58,8 +61,7 @@ class PlanStruct(C.Structure):
         ("cl_te_elem", C.c_void_p),
         ("cl_te_own", C.c_void_p),
         ("cl_lconn", C.c_void_p),
-        ("te_inc", C.c_void_p),
-        ("te_mask", C.c_void_p),
+        ("te_desc", C.c_void_p),
         ("cl_tn_ptr", C.c_void_p),
         ("cl_tn_node", C.c_void_p),
         ("slot_rec", C.c_void_p),

@@ -91,17 +91,17 @@ struct Layout {
     if (s > big) big = s;
     big = (big + 1) & ~1L;
     *big_doubles = (int)big;
-    long doubles = TAB_DOUBLES + (((long)p.cap_tn * (DIM + NU) + 1) & ~1L) + big + p.cap_owned;  // + sBptr
+    long doubles = TAB_DOUBLES + 2 * (((long)p.cap_tn * (DIM + NU) + 1) & ~1L) + big + p.cap_owned;  // + sBptr
     if (mma) {  // sJ lives beside the staging region (not aliased); the K.u products reuse it in phase 3
       const long nj = (long)p.cap_te * JSTR, nr = (long)p.cap_slots * NV;
       doubles += (nj > nr ? nj : nr) + 1;
     }
     size_t bytes = (size_t)doubles * 8;
-    if (mma) bytes += (size_t)p.cap_inc * NNE * 2 + (size_t)((p.cap_te * 3 + 3) & ~3);  // sDst, sTeInc/sTeMask
+    if (mma) bytes += (size_t)p.cap_inc * NNE * 2 + (size_t)p.cap_te * 4;  // sDst, sTe
     bytes += (size_t)(2 * (p.cap_owned + 1)) * 4;     // sSlotBase, sFinc
     bytes += (size_t)(p.cap_slots + 1) * 4;           // sRec
-    bytes += (size_t)((p.cap_heavy + 1) & ~1) * 2;    // sHeavy
-    bytes += (size_t)((p.cap_te * NNE + 3) & ~3);     // sLconn
+    bytes += (size_t)p.cap_heavy * 4;                 // sHeavy
+    bytes += 2 * (size_t)((p.cap_te * NNE + 3) & ~3); // sLconn (double-buffered)
     return bytes;
   }
 };
@@ -208,6 +208,27 @@ __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Per-cluster header (fdk_plan::cl_hdr, 16 int32 per cluster): one 64-byte load instead of a chain of
+// dependent loads through the individual range arrays.
+struct ClusterHdr {
+  int q0, n_owned, te0, n_te, tn0, n_tn, inc0, n_inc, h0, n_heavy, n_slots;
+  int64_t slot0;
+};
+__device__ __forceinline__ ClusterHdr load_hdr(const int32_t* __restrict__ hdr, int c) {
+  const int4* h4 = reinterpret_cast<const int4*>(hdr + (int64_t)c * 16);
+  const int4 a = h4[0], b = h4[1], d = h4[2], e = h4[3];
+  ClusterHdr h;
+  h.q0 = a.x; h.n_owned = a.y; h.te0 = a.z; h.n_te = a.w;
+  h.tn0 = b.x; h.n_tn = b.y; h.inc0 = b.z; h.n_inc = b.w;
+  h.h0 = d.x; h.n_heavy = d.y;
+  h.slot0 = (int64_t)(((uint64_t)(uint32_t)d.w << 32) | (uint32_t)d.z);
+  h.n_slots = e.x;
+  return h;
+}
 
 // One m8n8k4 FP64 tensor-core MMA (SASS DMMA.8x8x4): D(8x8) += A(8x4) B(4x8).  Fragments: a = A[lane>>2][lane&3],
 // b = B[lane&3][lane>>2], d0/d1 = D[lane>>2][2*(lane&3) + 0/1].
@@ -235,43 +256,26 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   constexpr int NH = NNE / 2;      // column blocks per thread
   static_assert(NNE % 2 == 0 && HT % 32 == 0, "half rows, warp-uniform halves");
   const fdk_plan& p = a.p;
-  const int c = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   const bool do_mat = (a.compute & FDK_MATRIX) != 0;
   const bool do_vec = (a.compute & FDK_VECTOR) != 0;
   const bool fuse_ku = a.fuse_ku != 0;           // residual from the assembled rows (phase 3)
   const bool do_bts = do_vec && !fuse_ku;        // residual as B^T sigma (phases 1-2)
 
-  const int q0 = p.cl_node_ptr[c], n_owned = p.cl_node_ptr[c + 1] - q0;
-  const int te0 = p.cl_te_ptr[c], n_te = p.cl_te_ptr[c + 1] - te0;
-  const int tn0 = p.cl_tn_ptr[c], n_tn = p.cl_tn_ptr[c + 1] - tn0;
-  const int inc0 = p.cl_inc_ptr[c], n_inc = p.cl_inc_ptr[c + 1] - inc0;
-  const int h0 = p.cl_heavy_ptr[c], n_heavy = p.cl_heavy_ptr[c + 1] - h0;
-  const int64_t slot0 = p.cl_slot_ptr[q0];
-  const int n_slots = (int)(p.cl_slot_ptr[q0 + n_owned] - slot0);
-
-  // ---- this thread's half incidence (long-latency loads issued first, consumed in phase 2) ----
+  // ---- persistent CTA: clusters blockIdx.x, blockIdx.x + gridDim.x, ... ----
   const int half = tid / HT;       // warp-uniform
-  const int it = tid - half * HT;  // incidence of this thread
+  const int it = tid - half * HT;  // incidence of this thread (phase 2)
   const int j0 = half * NH;        // its column blocks: j0 .. j0 + NH - 1
-  unsigned my_desc = 0, my_fdst = 0;
-  unsigned short my_dst[NH];
-#pragma unroll
-  for (int j = 0; j < NH; ++j) my_dst[j] = 0;
-  if (!MMA && it < n_inc) {
-    my_desc = p.inc_desc[inc0 + it];
-    if (do_bts) my_fdst = p.inc_fdst[inc0 + it];
-    const unsigned short* dp = p.inc_dst + (int64_t)(inc0 + it) * NNE + j0;
-#pragma unroll
-    for (int j = 0; j < NH; ++j) my_dst[j] = dp[j];
-  }
 
   extern __shared__ __align__(16) double smem[];
   double* sdN = smem;
   double* sN = sdN + NGP * TSTR;
   double* sW = sN + NGP * NNE;
-  double* sX = smem + L::TAB_DOUBLES;
-  double* sU = sX + p.cap_tn * DIM;
-  double* sBig = smem + L::TAB_DOUBLES + ((p.cap_tn * (DIM + NU) + 1) & ~1);
+  // phase-1 inputs are double-buffered: the next cluster's coordinates / dofs / connectivity are
+  // fetched (cp.async) while the current cluster computes
+  const int xu_doubles = (p.cap_tn * (DIM + NU) + 1) & ~1;
+  double* sXbuf = smem + L::TAB_DOUBLES;  // [2][xu_doubles]
+  double* sBig = sXbuf + 2 * xu_doubles;
   // geometry view
   double* sG = sBig;                               // [n_te][ESTR]
   double* sWd = sG + (long)p.cap_te * ESTR;        // [n_te][WSTR]      w_g |det J|
@@ -284,62 +288,27 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   int* sSlotBase = reinterpret_cast<int*>(sBptr + p.cap_owned);            // [cap_owned+1]
   int* sFinc = sSlotBase + (p.cap_owned + 1);                              // [cap_owned+1]
   unsigned* sRec = reinterpret_cast<unsigned*>(sFinc + (p.cap_owned + 1)); // [cap_slots+1]
-  unsigned short* sHeavy = reinterpret_cast<unsigned short*>(sRec + (p.cap_slots + 1));  // [cap_heavy]
-  unsigned char* sLconn = reinterpret_cast<unsigned char*>(sHeavy + ((p.cap_heavy + 1) & ~1));
+  unsigned* sHeavy = sRec + (p.cap_slots + 1);                             // [cap_heavy]
+  unsigned char* sLbuf = reinterpret_cast<unsigned char*>(sHeavy + p.cap_heavy);  // [2][lc_bytes]
+  const int lc_bytes = (p.cap_te * NNE + 3) & ~3;
   // tensor-core path extras
   [[maybe_unused]] double* sJ = reinterpret_cast<double*>(sBptr + ((p.cap_owned + 1) & ~1));  // [cap_te][JSTR]
   [[maybe_unused]] unsigned short* sDst = nullptr;
-  [[maybe_unused]] unsigned short* sTeInc = nullptr;
-  [[maybe_unused]] unsigned char* sTeMask = nullptr;
+  [[maybe_unused]] unsigned* sTe = nullptr;  // per touched element: first thread | owned-node mask << 16
   if constexpr (MMA) {
     sR = sJ;  // sJ is dead once phase 2m is over
     const long nj = (long)p.cap_te * L::JSTR, nr = (long)p.cap_slots * NV;
     sSlotBase = reinterpret_cast<int*>(sJ + (nj > nr ? nj : nr));
     sFinc = sSlotBase + (p.cap_owned + 1);
     sRec = reinterpret_cast<unsigned*>(sFinc + (p.cap_owned + 1));
-    sHeavy = reinterpret_cast<unsigned short*>(sRec + (p.cap_slots + 1));
-    sLconn = reinterpret_cast<unsigned char*>(sHeavy + ((p.cap_heavy + 1) & ~1));
-    sDst = reinterpret_cast<unsigned short*>(sLconn + ((p.cap_te * NNE + 3) & ~3));
-    sTeInc = sDst + (long)p.cap_inc * NNE;
-    sTeMask = reinterpret_cast<unsigned char*>(sTeInc + p.cap_te);
+    sHeavy = sRec + (p.cap_slots + 1);
+    sLbuf = reinterpret_cast<unsigned char*>(sHeavy + p.cap_heavy);
+    sTe = reinterpret_cast<unsigned*>(sLbuf + 2 * lc_bytes);
+    sDst = reinterpret_cast<unsigned short*>(sTe + p.cap_te);
   }
 
-  // ---------------- phase 0: staging ----------------
-  // All global loads are issued before the first shared-memory store that depends on one (node ids
-  // into registers, everything else through cp.async), so the CTA pays about two memory latencies
-  // here instead of one per array.
+  // ---------------- prologue: tables (once per CTA) and the first cluster's phase-1 inputs ----------------
   {
-    constexpr int RT = (256 + THREADS - 1) / THREADS;  // cap_tn <= 256
-    int node_r[RT];
-#pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      const int t = tid + r * THREADS;
-      node_r[r] = (t < n_tn) ? p.cl_tn_node[tn0 + t] : -1;
-    }
-    {
-      const unsigned* rec = p.slot_rec + slot0 + c;
-      for (int t = tid; t <= n_slots; t += THREADS) cp_async<4>(sRec + t, rec + t);
-      for (int t = tid; t < n_owned; t += THREADS) cp_async<8>(sBptr + t, p.cl_bptr + q0 + t);
-      const unsigned char* lc = p.cl_lconn + (int64_t)te0 * NNE;
-      if constexpr (NNE % 4 == 0) {
-        for (int t = tid; t < n_te * NNE / 4; t += THREADS) cp_async<4>(sLconn + 4 * t, lc + 4 * t);
-      } else {
-        for (int t = tid; t < n_te * NNE; t += THREADS) sLconn[t] = lc[t];
-      }
-    }
-    for (int t = tid; t < n_heavy; t += THREADS) sHeavy[t] = p.heavy_slot[h0 + t];
-    if constexpr (MMA) {
-      const unsigned short* dsrc = p.inc_dst + (int64_t)inc0 * NNE;  // 16-byte aligned rows
-      for (int t = tid; t < n_inc * NNE / 2; t += THREADS) cp_async<4>(sDst + 2 * t, dsrc + 2 * t);
-      for (int t = tid; t < n_te; t += THREADS) {
-        sTeInc[t] = p.te_inc[te0 + t];
-        sTeMask[t] = p.te_mask[te0 + t];
-      }
-    }
-    for (int t = tid; t <= n_owned; t += THREADS) {
-      sSlotBase[t] = (int)(p.cl_slot_ptr[q0 + t] - slot0);
-      sFinc[t] = p.cl_finc_ptr[q0 + t] - p.cl_finc_ptr[q0];
-    }
     const ElemTable& tab = c_tab[El::ID];
     for (int t = tid; t < NGP * GROW; t += THREADS) {
       const int g = t / GROW, r = t - g * GROW;
@@ -347,28 +316,101 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
     }
     for (int t = tid; t < NGP * NNE; t += THREADS) sN[t] = tab.N[t];
     if (tid < NGP) sW[tid] = tab.w[tid];
-    const bool need_u = do_vec && a.U != nullptr;
+  }
+  const bool need_u = do_vec && a.U != nullptr;
+  constexpr int RT = (256 + THREADS - 1) / THREADS;  // cap_tn <= 256
+  int node_r[RT];
+  // issue the phase-1 inputs of one cluster into buffer b (node ids already in registers)
+  auto fetch_inputs = [&](const ClusterHdr& h, int b) {
+    double* dX = sXbuf + b * xu_doubles;
+    double* dU = dX + p.cap_tn * DIM;
+    unsigned char* dL = sLbuf + b * lc_bytes;
+    const unsigned char* lc = p.cl_lconn + (int64_t)h.te0 * NNE;
+    if constexpr (NNE % 4 == 0) {
+      for (int t = tid; t < h.n_te * NNE / 4; t += THREADS) cp_async<4>(dL + 4 * t, lc + 4 * t);
+    } else {
+      for (int t = tid; t < h.n_te * NNE; t += THREADS) dL[t] = lc[t];
+    }
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
       const int t = tid + r * THREADS;
       const int node = node_r[r];
       if (node >= 0) {
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) cp_async<8>(sX + t * DIM + d, a.coords + (int64_t)node * DIM + d);
+        for (int d = 0; d < DIM; ++d) cp_async<8>(dX + t * DIM + d, a.coords + (int64_t)node * DIM + d);
         if (need_u) {
           if constexpr (PHYS == PHYS_HEAT) {
             const double T = a.U[node];
-            sU[t * 2 + 0] = T;
-            sU[t * 2 + 1] = T - (a.U2 ? a.U2[node] : 0.0);
+            dU[t * 2 + 0] = T;
+            dU[t * 2 + 1] = T - (a.U2 ? a.U2[node] : 0.0);
           } else {
 #pragma unroll
-            for (int v = 0; v < DIM; ++v) cp_async<8>(sU + t * DIM + v, a.U + (int64_t)v * p.n_nodes + node);
+            for (int v = 0; v < DIM; ++v) cp_async<8>(dU + t * DIM + v, a.U + (int64_t)v * p.n_nodes + node);
           }
         }
       }
     }
-    cp_async_wait_all();
+    cp_async_commit();
+  };
+  auto load_node_ids = [&](const ClusterHdr& h) {
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const int t = tid + r * THREADS;
+      node_r[r] = (t < h.n_tn) ? p.cl_tn_node[h.tn0 + t] : -1;
+    }
+  };
+  ClusterHdr cur = load_hdr(p.cl_hdr, blockIdx.x);
+  load_node_ids(cur);
+  fetch_inputs(cur, 0);
+
+  int buf = 0;
+  for (int c = blockIdx.x; c < p.n_clusters; c += gridDim.x, buf ^= 1) {
+  const int q0 = cur.q0, n_owned = cur.n_owned, te0 = cur.te0, n_te = cur.n_te, n_inc = cur.n_inc;
+  const int inc0 = cur.inc0, h0 = cur.h0, n_heavy = cur.n_heavy, n_slots = cur.n_slots;
+  const int64_t slot0 = cur.slot0;
+  const double* sX = sXbuf + buf * xu_doubles;
+  const double* sU = sX + p.cap_tn * DIM;
+  const unsigned char* sLconn = sLbuf + buf * lc_bytes;
+  const int c_next = c + gridDim.x;
+  const bool has_next = c_next < p.n_clusters;
+  ClusterHdr nxt = cur;
+  if (has_next) nxt = load_hdr(p.cl_hdr, c_next);  // consumed after phase 1
+
+  // ---------------- phase 0: this cluster's phase-2/3 descriptors (latency hidden behind phase 1) ----------------
+  unsigned my_desc = 0, my_fdst = 0;
+  unsigned short my_dst[NH];
+#pragma unroll
+  for (int j = 0; j < NH; ++j) my_dst[j] = 0;
+  if (!MMA && it < n_inc) {
+    my_desc = p.inc_desc[inc0 + it];
+    if (do_bts) my_fdst = p.inc_fdst[inc0 + it];
+    const unsigned short* dp = p.inc_dst + (int64_t)(inc0 + it) * NNE + j0;
+#pragma unroll
+    for (int j = 0; j < NH; ++j) my_dst[j] = dp[j];
   }
+  {
+    const unsigned* rec = p.slot_rec + slot0 + c;
+    for (int t = tid; t <= n_slots; t += THREADS) cp_async<4>(sRec + t, rec + t);
+    for (int t = tid; t < n_owned; t += THREADS) cp_async<8>(sBptr + t, p.cl_bptr + q0 + t);
+    if constexpr (MMA) {
+      const unsigned short* dsrc = p.inc_dst + (int64_t)inc0 * NNE;  // 16-byte aligned rows
+      for (int t = tid; t < n_inc * NNE / 2; t += THREADS) cp_async<4>(sDst + 2 * t, dsrc + 2 * t);
+    }
+    for (int t = tid; t < n_heavy; t += THREADS) cp_async<4>(sHeavy + t, p.heavy_slot + h0 + t);
+    if constexpr (MMA) {
+      for (int t = tid; t < n_te; t += THREADS) cp_async<4>(sTe + t, p.te_desc + te0 + t);
+    }
+    for (int t = tid; t < n_owned; t += THREADS) {
+      cp_async<4>(sSlotBase + t, p.cl_slot_loc + q0 + t);
+      cp_async<4>(sFinc + t, p.cl_finc_loc + q0 + t);
+    }
+    cp_async_commit();
+    if (tid == 0) {  // end markers come from the header
+      sSlotBase[n_owned] = n_slots;
+      sFinc[n_owned] = n_inc;
+    }
+  }
+  cp_async_wait_group<1>();  // the phase-1 inputs of this cluster (issued one cluster ago) have landed
   __syncthreads();
 
   if constexpr (!MMA) {
@@ -470,6 +512,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
         }
       }
     }
+    if (has_next) load_node_ids(nxt);  // consumed after phase 2
+    cp_async_wait_group<0>();          // this cluster's descriptors
     __syncthreads();
 
     // ---------------- phase 2: per-incidence half rows in registers ----------------
@@ -660,6 +704,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
       out[3] = make_double2(iJ[2][0], iJ[2][1]);
       out[4] = make_double2(iJ[2][2], sW[g] * fabs(det));
     }
+    if (has_next) load_node_ids(nxt);  // consumed after phase 2m
+    cp_async_wait_group<0>();          // this cluster's descriptors
     __syncthreads();
 
     // ---------------- phase 2m: one warp per touched element, S^e by DMMA ----------------
@@ -711,8 +757,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
         }
         // scatter: block (I=r, J) upper entries go to the staging entry of (row r, column J); its
         // transposed upper entries are the strictly-lower entries of block (J, r)
-        const unsigned mask = sTeMask[le];
-        const int base = sTeInc[le];
+        const unsigned ted = sTe[le];
+        const unsigned mask = ted >> 16;
+        const int base = ted & 0xFFFF;
         const bool own_r = (mask >> r) & 1u;
         const int row_r = base + __popc(mask & ((1u << r) - 1u));
 #pragma unroll
@@ -738,6 +785,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
       }
     }
   }
+  if (has_next) fetch_inputs(nxt, buf ^ 1);  // lands during phase 3 and the next cluster's phase 0
+  else cp_async_commit();
   __syncthreads();
 
   // slot record: first staging entry | local touched-node index of the column node << 16 | owner << 24;
@@ -831,6 +880,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
       for (int v = 0; v < NV; ++v) a.D[(int64_t)v * p.n_nodes + node] = -s[v];
     }
   }
+  __syncthreads();  // staging, descriptors and row buffers are free for the next cluster
+  cur = nxt;
+  }  // cluster loop
 }
 
 // ---- host launcher -----------------------------------------------------------------------
@@ -855,7 +907,17 @@ int launch_assemble_t(AsmArgs& a, cudaStream_t stream) {
     FDK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  kern<<<p.n_clusters, THREADS, smem, stream>>>(a);
+  // persistent CTAs: as many as are resident at once, each walking the cluster list with stride gridDim
+  static thread_local int resident = 0;
+  if (resident == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    FDK_CUDA(cudaGetDevice(&dev));
+    FDK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+    resident = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  const int grid = p.n_clusters < resident ? p.n_clusters : resident;
+  kern<<<grid, THREADS, smem, stream>>>(a);
   FDK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -130,7 +130,10 @@ class Plan:
         import os
 
         if small is None:
-            small = os.environ.get("FDK_SMALL_CTA", "1") != "0"
+            # measured on B200: hex8 runs best with 32-node clusters / 512-thread
+            # persistent CTAs (tensor-core producer); the other elements keep the half-size variant
+            env = os.environ.get("FDK_SMALL_CTA")
+            small = (elem_type != "hex8") if env is None else (env != "0")
         cap = dict(_CAPS[elem_type])
         self.threads = _THREADS[elem_type]
         if small and elem_type in _CAPS_SMALL:  # tet10: one vertex node alone can touch > 18 elements
@@ -351,14 +354,35 @@ class Plan:
         )
         self.n_owned = n_nodes
 
+        # ---- packed per-cluster header (one 64-byte load per cluster in the kernel) ----
+        hdr = torch.zeros((n_cl, 16), dtype=torch.int64, device=dev)
+        if n_cl:
+            hdr[:, 0] = cl_node_ptr[:-1]
+            hdr[:, 1] = counts_c
+            hdr[:, 2] = cl_te_ptr[:-1]
+            hdr[:, 3] = cl_te_ptr[1:] - cl_te_ptr[:-1]
+            hdr[:, 4] = cl_tn_ptr[:-1]
+            hdr[:, 5] = cl_tn_ptr[1:] - cl_tn_ptr[:-1]
+            hdr[:, 6] = cl_inc_ptr[:-1]
+            hdr[:, 7] = n_inc_c
+            hdr[:, 8] = cl_heavy_ptr[:-1]
+            hdr[:, 9] = cl_heavy_ptr[1:] - cl_heavy_ptr[:-1]
+            hdr[:, 10] = slot0_c[:-1] & 0xFFFFFFFF
+            hdr[:, 11] = slot0_c[:-1] >> 32
+            hdr[:, 12] = n_slots_c
+        hdr = torch.where(hdr >= 2**31, hdr - 2**32, hdr).to(torch.int32).contiguous()  # low words as int32 bits
+
         # ---- device arrays in their kernel dtypes (per-incidence arrays in kernel thread order) ----
         i32, u16, u8 = torch.int32, torch.uint16, torch.uint8
         self.t = dict(
+            cl_hdr=hdr,
             cl_node_ptr=cl_node_ptr.to(i32),
             cl_node=order.to(i32),
             cl_bptr=cl_bptr.contiguous(),
             cl_slot_ptr=cl_slot_ptr,
             cl_finc_ptr=cl_finc_ptr.to(i32),
+            cl_slot_loc=(cl_slot_ptr[:-1] - slot0_c[cl_of_pos]).to(i32) if n_nodes else cl_slot_ptr[:0].to(i32),
+            cl_finc_loc=(cl_finc_ptr[:-1] - cl_inc_ptr[cl_of_pos]).to(i32) if n_nodes else cl_slot_ptr[:0].to(i32),
             cl_inc_ptr=cl_inc_ptr.to(i32),
             inc_desc=inc_desc[em_perm].to(u16),
             inc_dst=dst[em_perm].to(u16).contiguous(),
@@ -367,13 +391,12 @@ class Plan:
             cl_te_elem=te_elem.to(i32),
             cl_te_own=te_own.to(u8),
             cl_lconn=lconn.to(u8).contiguous(),
-            te_inc=te_inc.to(u16),
-            te_mask=te_mask.to(u8),
+            te_desc=((te_inc & 0xFFFF) | ((te_mask & 0xFFFF) << 16)).to(torch.uint32),
             cl_tn_ptr=cl_tn_ptr.to(i32),
             cl_tn_node=tn_node.to(i32),
             slot_rec=slot_rec.to(torch.uint32),
             cl_heavy_ptr=cl_heavy_ptr.to(i32),
-            heavy_slot=heavy_slot.to(u16),
+            heavy_slot=heavy_slot.to(torch.uint32),
         )
         self._structs = {}
 

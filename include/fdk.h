@@ -48,7 +48,7 @@ int fdk_version(void);
 
 /* Runtime options (process-wide): "fuse_ku" (default 1): for a linear law with K and D both requested the
  * residual is taken from the assembled rows, D = -K_row . U, instead of a second B^T sigma integration;
- * "mma" (default 0): hex8 + isotropic law, element matrices by FP64 tensor-core DMMA.m8n8k4. */
+ * "mma" (default 1): hex8 + isotropic law, element matrices by FP64 tensor-core DMMA.m8n8k4. */
 int fdk_set_option(const char* key, int value);
 int fdk_get_option(const char* key, int* value);
 
@@ -96,11 +96,15 @@ typedef struct fdk_plan {
   /* capacities = max over clusters (sizes the dynamic shared memory) */
   int32_t cap_te, cap_tn, cap_inc, cap_owned, cap_slots, cap_ent, cap_heavy;
   int32_t threads;    /* CTA size the clusters were sized for (2 * cap_inc <= threads) */
+  const int32_t* cl_hdr;       /* [n_clusters][16] packed per-cluster header: q0, n_owned, te0, n_te, tn0,
+                                  n_tn, inc0, n_inc, heavy0, n_heavy, slot0 (lo, hi), n_slots, 0, 0, 0     */
   const int32_t* cl_node_ptr;  /* [n_clusters+1] range of owned nodes (cluster order)                    */
   const int32_t* cl_node;      /* [n_owned]  global id of the q-th owned node                             */
   const int64_t* cl_bptr;      /* [n_owned]  blk_indptr[cl_node[q]]                                       */
   const int64_t* cl_slot_ptr;  /* [n_owned+1] exclusive cumsum of block-row lengths, cluster order        */
   const int32_t* cl_finc_ptr;  /* [n_owned+1] exclusive cumsum of incidences per owned node               */
+  const int32_t* cl_slot_loc;  /* [n_owned] cl_slot_ptr relative to the first slot of the node's cluster  */
+  const int32_t* cl_finc_loc;  /* [n_owned] cl_finc_ptr relative to the first incidence of the cluster    */
   const int32_t* cl_inc_ptr;   /* [n_clusters+1] range of incidences (= threads), element-major order     */
   const uint16_t* inc_desc;    /* [n_inc] local touched-element index | local node << 12                  */
   const uint16_t* inc_dst;     /* [n_inc][nne] staging entry (slot-sorted) of the block (I, node j of e)  */
@@ -109,9 +113,9 @@ typedef struct fdk_plan {
   const int32_t* cl_te_elem;   /* global element id of each touched element                               */
   const uint8_t* cl_te_own;    /* 1 if this cluster is the unique owner of the touched element            */
   const uint8_t* cl_lconn;     /* [n_te_total][nne] local (cluster) index of each element node            */
-  const uint16_t* te_inc;      /* [n_te_total] cluster-local index of the element's first incidence (the
-                                  incidences of one element are consecutive: element-major thread order)  */
-  const uint8_t* te_mask;      /* [n_te_total] bit i set: local node i of the element is owned here       */
+  const uint32_t* te_desc;     /* [n_te_total] cluster-local index of the element's first incidence (the
+                                  incidences of one element are consecutive: element-major thread order)
+                                  | mask << 16, bit i of mask set: local node i is owned by the cluster   */
   const int32_t* cl_tn_ptr;    /* [n_clusters+1] range of touched nodes                                   */
   const int32_t* cl_tn_node;   /* global node id of each touched node                                     */
   const uint32_t* slot_rec;    /* per cluster n_slots+1 records at index cl_slot_ptr[q0] + cluster:
@@ -120,7 +124,7 @@ typedef struct fdk_plan {
                                   column node << 16 | cluster-local index of the owner (row) node << 24;
                                   the last record of a cluster is an end sentinel with owner 0xFF          */
   const int32_t* cl_heavy_ptr; /* [n_clusters+1] range of heavy slots (more than 4 contributions)         */
-  const uint16_t* heavy_slot;  /* cluster-local slot index of each heavy slot                             */
+  const uint32_t* heavy_slot;  /* cluster-local slot index of each heavy slot                             */
 } fdk_plan;
 
 /* ------------------------------------------------------------------------- *

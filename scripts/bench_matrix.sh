@@ -1,5 +1,5 @@
 for n in 100 200; do for mma in 0 1; do for s in 1 0; do
-FDK_NO_MMA=$((1-mma)) FDK_SMALL_CTA=$s python bench.py --n $n --steps 5 --no-cpu-baseline > gpurun_out/mx.log 2>&1
+FDK_MMA=$mma FDK_SMALL_CTA=$s python bench.py --n $n --steps 5 --no-cpu-baseline > gpurun_out/mx.log 2>&1
 python - <<PY
 import json
 l=[x for x in open("gpurun_out/mx.log") if x.startswith("{")]

@@ -28,6 +28,10 @@ def make_plan(elem_type, nodes, elements, **kw):
     return plan, pat
 
 
+def slot0_chk(t, q0):
+    return t["cl_slot_ptr"][q0]
+
+
 def emulate_iso(plan, pat, nodes, elements, lam, mu, allow_unwritten=False):
     """Follows csrc/fdk_assemble.cuh: threads = incidences in element-major order, blocks scattered to
     the slot-sorted staging array (inc_dst), heavy slots pre-reduced, slot gather by contiguous runs."""
@@ -58,6 +62,13 @@ def emulate_iso(plan, pat, nodes, elements, lam, mu, allow_unwritten=False):
         inc0, inc1 = t["cl_inc_ptr"][c], t["cl_inc_ptr"][c + 1]
         n_inc = inc1 - inc0
         assert 2 * n_inc <= plan.threads
+        hdr = t["cl_hdr"][c].astype(np.int64)
+        assert list(hdr[:10]) == [q0, n_owned, te0, t["cl_te_ptr"][c + 1] - te0, tn0, t["cl_tn_ptr"][c + 1] - tn0,
+                                  inc0, n_inc, t["cl_heavy_ptr"][c], t["cl_heavy_ptr"][c + 1] - t["cl_heavy_ptr"][c]]
+        assert ((hdr[11] & 0xFFFFFFFF) << 32 | (hdr[10] & 0xFFFFFFFF)) == t["cl_slot_ptr"][q0]
+        assert hdr[12] == t["cl_slot_ptr"][q1] - t["cl_slot_ptr"][q0]
+        assert np.array_equal(t["cl_slot_loc"][q0:q1], t["cl_slot_ptr"][q0:q1] - slot0_chk(t, q0))
+        assert np.array_equal(t["cl_finc_loc"][q0:q1], t["cl_finc_ptr"][q0:q1] - t["cl_finc_ptr"][q0])
         assert n_inc == t["cl_finc_ptr"][q1] - t["cl_finc_ptr"][q0]
         slot0 = t["cl_slot_ptr"][q0]
         n_slots = t["cl_slot_ptr"][q1] - slot0
@@ -92,11 +103,11 @@ def emulate_iso(plan, pat, nodes, elements, lam, mu, allow_unwritten=False):
             descs = t["inc_desc"][inc0:inc1]
             for le in range(t["cl_te_ptr"][c + 1] - te0):
                 mine = np.nonzero((descs & 0xFFF) == le)[0]
-                assert len(mine) > 0 and mine[0] == t["te_inc"][te0 + le] and (np.diff(mine) == 1).all()
+                assert len(mine) > 0 and mine[0] == (t["te_desc"][te0 + le] & 0xFFFF) and (np.diff(mine) == 1).all()
                 mask = 0
                 for m in mine:
                     mask |= 1 << int(descs[m] >> 12)
-                assert mask == t["te_mask"][te0 + le]
+                assert mask == t["te_desc"][te0 + le] >> 16
                 assert list(descs[mine] >> 12) == sorted(descs[mine] >> 12)
         # heavy slots
         h0, h1 = t["cl_heavy_ptr"][c], t["cl_heavy_ptr"][c + 1]

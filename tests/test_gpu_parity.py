@@ -121,7 +121,7 @@ def test_hex8_tensor_core_producer(fd, golden_dir, name, small, monkeypatch):
             a.assemble_global_mat("matrix")
             assert np.array_equal(a.get_global_matrix().tocsr().data, K.data)  # deterministic
         finally:
-            _lib.set_option("mma", 0)
+            _lib.set_option("mma", 1)
     assert nrm(out[1][0], out[0][0]) <= 1e-14 and nrm(out[1][1], out[0][1]) <= 1e-13
 
 
