@@ -55,7 +55,7 @@ class PlanStruct(C.Structure):
         ("cl_finc_loc", C.c_void_p),
         ("cl_inc_ptr", C.c_void_p),
         ("inc_desc", C.c_void_p),
-        ("inc_dst", C.c_void_p),
+        ("ent_src", C.c_void_p),
         ("inc_fdst", C.c_void_p),
         ("cl_te_ptr", C.c_void_p),
         ("cl_te_elem", C.c_void_p),

@@ -30,7 +30,7 @@ int check_plan(const fdk_plan* p) {
   if (p->n_clusters > 0)
     FDK_REQUIRE(p->cl_hdr && p->cl_node_ptr && p->cl_node && p->cl_bptr && p->cl_slot_ptr && p->cl_inc_ptr && p->inc_desc &&
                     p->cl_te_ptr && p->cl_te_elem && p->cl_lconn && p->cl_tn_ptr && p->cl_tn_node &&
-                    p->cl_finc_ptr && p->inc_dst && p->inc_fdst && p->slot_rec && p->cl_heavy_ptr && p->te_desc && p->cl_slot_loc && p->cl_finc_loc,
+                    p->cl_finc_ptr && p->ent_src && p->inc_fdst && p->slot_rec && p->cl_heavy_ptr && p->te_desc && p->cl_slot_loc && p->cl_finc_loc,
                 FDK_EINVAL, "plan has NULL arrays");
   return 0;
 }

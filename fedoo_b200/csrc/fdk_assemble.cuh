@@ -62,7 +62,8 @@ struct Layout {
   static constexpr int NV = (PHYS == PHYS_HEAT) ? 1 : DIM;    // variables per node
   static constexpr int NU = (PHYS == PHYS_HEAT) ? 2 : DIM;    // staged nodal values per touched node
   static constexpr int BLK = NV * NV;                         // scalars per (I,J) block
-  static constexpr int BLKP = BLK | 1;                        // odd staging stride (bank spread)
+  static constexpr int ISTR = (NNE * BLK) | 1;                // staging stride of one incidence (its nne blocks):
+                                                              // odd, so that the lanes of a store hit distinct banks
   static constexpr int NSIG = (PHYS == PHYS_HEAT) ? DIM + 1 : (DIM == 3 ? 6 : 3);
   static constexpr int GROW = DIM * NNE;                      // dN/dx of one (element, gp): [k][d]
   static_assert(GROW % 2 == 0, "128-bit rows");
@@ -80,7 +81,7 @@ struct Layout {
   // doubles of the staging view
   static long stage_doubles(const fdk_plan& p, bool mma = false) {
     const long nf = p.cap_inc > p.cap_slots ? p.cap_inc : p.cap_slots;  // nodal forces / per-slot K.u products
-    return (long)p.cap_ent * BLKP + (mma ? 0 : nf * NV);                 // (tensor-core path: products reuse sJ)
+    return (long)p.cap_inc * ISTR + (mma ? 0 : nf * NV);                 // (tensor-core path: products reuse sJ)
   }
 
   static constexpr int JSTR = NGP * 10;  // tensor-core path: inverse Jacobian (9) + w per Gauss point
@@ -97,7 +98,8 @@ struct Layout {
       doubles += (nj > nr ? nj : nr) + 1;
     }
     size_t bytes = (size_t)doubles * 8;
-    if (mma) bytes += (size_t)p.cap_inc * NNE * 2 + (size_t)p.cap_te * 4;  // sDst, sTe
+    bytes += (size_t)((p.cap_ent + 3) & ~3) * 2;      // sEnt
+    if (mma) bytes += (size_t)p.cap_te * 4;           // sTe
     bytes += (size_t)(2 * (p.cap_owned + 1)) * 4;     // sSlotBase, sFinc
     bytes += (size_t)(p.cap_slots + 1) * 4;           // sRec
     bytes += (size_t)p.cap_heavy * 4;                 // sHeavy
@@ -215,7 +217,7 @@ __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.w
 // Per-cluster header (fdk_plan::cl_hdr, 16 int32 per cluster): one 64-byte load instead of a chain of
 // dependent loads through the individual range arrays.
 struct ClusterHdr {
-  int q0, n_owned, te0, n_te, tn0, n_tn, inc0, n_inc, h0, n_heavy, n_slots;
+  int q0, n_owned, te0, n_te, tn0, n_tn, inc0, n_inc, h0, n_heavy, n_slots, ent0;
   int64_t slot0;
 };
 __device__ __forceinline__ ClusterHdr load_hdr(const int32_t* __restrict__ hdr, int c) {
@@ -227,6 +229,7 @@ __device__ __forceinline__ ClusterHdr load_hdr(const int32_t* __restrict__ hdr, 
   h.h0 = d.x; h.n_heavy = d.y;
   h.slot0 = (int64_t)(((uint64_t)(uint32_t)d.w << 32) | (uint32_t)d.z);
   h.n_slots = e.x;
+  h.ent0 = e.y;
   return h;
 }
 
@@ -249,7 +252,7 @@ template <class El, int PHYS, int THREADS, int MINB, bool MMA>
 __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constant__ AsmArgs a) {
   static_assert(!MMA || (El::NNE == 8 && El::NGP == 8 && El::DIM == 3 && PHYS == PHYS_ISO), "MMA path: hex8 isotropic");
   using L = Layout<El, PHYS>;
-  constexpr int NNE = L::NNE, NGP = L::NGP, DIM = L::DIM, NV = L::NV, NU = L::NU, BLK = L::BLK, BLKP = L::BLKP;
+  constexpr int NNE = L::NNE, NGP = L::NGP, DIM = L::DIM, NV = L::NV, NU = L::NU, BLK = L::BLK, ISTR = L::ISTR;
   constexpr int NSIG = L::NSIG, GROW = L::GROW, GSTR = L::GSTR, ESTR = L::ESTR, WSTR = L::WSTR, SSTR = L::SSTR;
   constexpr int TSTR = L::TSTR;
   constexpr int HT = THREADS / 2;  // incidences per cluster <= HT: two threads per incidence in phase 2
@@ -281,8 +284,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   double* sWd = sG + (long)p.cap_te * ESTR;        // [n_te][WSTR]      w_g |det J|
   double* sSig = sWd + (long)p.cap_te * WSTR;      // [n_te][SSTR]      w * sigma (B^T sigma path only)
   // staging view (aliases the geometry once phase 2 has read it)
-  double* sBlk = sBig;                             // [cap_ent][BLKP]
-  double* sF = sBlk + (long)p.cap_ent * BLKP;      // [max(cap_inc, cap_slots)][NV]
+  double* sBlk = sBig;                             // [cap_inc][ISTR]: the nne blocks of every incidence
+  double* sF = sBlk + (long)p.cap_inc * ISTR;      // [max(cap_inc, cap_slots)][NV]
   double* sR = sF;                                 // per-slot K.u products (fuse_ku: sF is unused)
   long long* sBptr = reinterpret_cast<long long*>(sBig + a.big_doubles);   // [cap_owned]
   int* sSlotBase = reinterpret_cast<int*>(sBptr + p.cap_owned);            // [cap_owned+1]
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   const int lc_bytes = (p.cap_te * NNE + 3) & ~3;
   // tensor-core path extras
   [[maybe_unused]] double* sJ = reinterpret_cast<double*>(sBptr + ((p.cap_owned + 1) & ~1));  // [cap_te][JSTR]
-  [[maybe_unused]] unsigned short* sDst = nullptr;
+  unsigned short* sEnt = reinterpret_cast<unsigned short*>(sLbuf + 2 * lc_bytes);  // [cap_ent] slot-sorted sources
   [[maybe_unused]] unsigned* sTe = nullptr;  // per touched element: first thread | owned-node mask << 16
   if constexpr (MMA) {
     sR = sJ;  // sJ is dead once phase 2m is over
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
     sHeavy = sRec + (p.cap_slots + 1);
     sLbuf = reinterpret_cast<unsigned char*>(sHeavy + p.cap_heavy);
     sTe = reinterpret_cast<unsigned*>(sLbuf + 2 * lc_bytes);
-    sDst = reinterpret_cast<unsigned short*>(sTe + p.cap_te);
+    sEnt = reinterpret_cast<unsigned short*>(sTe + p.cap_te);
   }
 
   // ---------------- prologue: tables (once per CTA) and the first cluster's phase-1 inputs ----------------
@@ -378,23 +381,18 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
 
   // ---------------- phase 0: this cluster's phase-2/3 descriptors (latency hidden behind phase 1) ----------------
   unsigned my_desc = 0, my_fdst = 0;
-  unsigned short my_dst[NH];
-#pragma unroll
-  for (int j = 0; j < NH; ++j) my_dst[j] = 0;
   if (!MMA && it < n_inc) {
     my_desc = p.inc_desc[inc0 + it];
     if (do_bts) my_fdst = p.inc_fdst[inc0 + it];
-    const unsigned short* dp = p.inc_dst + (int64_t)(inc0 + it) * NNE + j0;
-#pragma unroll
-    for (int j = 0; j < NH; ++j) my_dst[j] = dp[j];
   }
   {
     const unsigned* rec = p.slot_rec + slot0 + c;
     for (int t = tid; t <= n_slots; t += THREADS) cp_async<4>(sRec + t, rec + t);
     for (int t = tid; t < n_owned; t += THREADS) cp_async<8>(sBptr + t, p.cl_bptr + q0 + t);
-    if constexpr (MMA) {
-      const unsigned short* dsrc = p.inc_dst + (int64_t)inc0 * NNE;  // 16-byte aligned rows
-      for (int t = tid; t < n_inc * NNE / 2; t += THREADS) cp_async<4>(sDst + 2 * t, dsrc + 2 * t);
+    {
+      const unsigned short* esrc = p.ent_src + cur.ent0;  // even offset: 4-byte aligned
+      const int n_ent = n_inc * NNE + n_owned;
+      for (int t = tid; t < (n_ent + 1) / 2; t += THREADS) cp_async<4>(sEnt + 2 * t, esrc + 2 * t);
     }
     for (int t = tid; t < n_heavy; t += THREADS) cp_async<4>(sHeavy + t, p.heavy_slot + h0 + t);
     if constexpr (MMA) {
@@ -662,7 +660,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
       if (do_mat) {
   #pragma unroll
         for (int j = 0; j < NH; ++j) {
-          double* sp = sBlk + (int)my_dst[j] * BLKP;
+          double* sp = sBlk + it * ISTR + (j0 + j) * BLK;
   #pragma unroll
           for (int b = 0; b < BLK; ++b) sp[b] = acc[j][b];
         }
@@ -674,10 +672,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
     }
   } else {
     // ---------------- phase 1m: inverse Jacobian and w per (touched element, gp) ----------------
+    static_assert(THREADS % NGP == 0, "the Gauss point of a thread's tasks is fixed");
+    double dNr[DIM * NNE];  // reference gradients at this thread's Gauss point
+#pragma unroll
+    for (int t = 0; t < DIM * NNE; ++t) dNr[t] = sdN[(tid % NGP) * TSTR + t];
     for (int task = tid; task < n_te * NGP; task += THREADS) {
       const int le = task / NGP, g = task - le * NGP;
       const unsigned char* lc = sLconn + le * NNE;
-      const double* dN = sdN + g * TSTR;
+      const double* dN = dNr;
       double J[DIM][DIM];
 #pragma unroll
       for (int r = 0; r < DIM; ++r)
@@ -741,46 +743,28 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
           A0[d] = w0 * G0[d];
           A1[d] = w1 * G1[d];
         }
-        // six upper tiles (c <= a): d[t][jj] = S^e_{I=r, J=2q+jj}[c][a]
-        double d[6][2];
-        {
-          int t = 0;
+        // nine 8x8 tiles: d[c*3+a][jj] = S^e_{I=r, J=2q+jj}[c][a] (the lower tiles are the transposes of the
+        // upper ones; computing them keeps every 3x3 block whole in one lane, so the stores below are
+        // contiguous and bank-conflict free -- the FP64 pipe has the headroom, shared memory does not)
+        double d[9][2];
 #pragma unroll
-          for (int cc = 0; cc < DIM; ++cc)
+        for (int cc = 0; cc < DIM; ++cc)
 #pragma unroll
-            for (int aa = cc; aa < DIM; ++aa, ++t) {
-              d[t][0] = 0.0;
-              d[t][1] = 0.0;
-              dmma884(d[t][0], d[t][1], A0[cc], G0[aa]);
-              dmma884(d[t][0], d[t][1], A1[cc], G1[aa]);
-            }
-        }
-        // scatter: block (I=r, J) upper entries go to the staging entry of (row r, column J); its
-        // transposed upper entries are the strictly-lower entries of block (J, r)
+          for (int aa = 0; aa < DIM; ++aa) {
+            d[cc * 3 + aa][0] = 0.0;
+            d[cc * 3 + aa][1] = 0.0;
+            dmma884(d[cc * 3 + aa][0], d[cc * 3 + aa][1], A0[cc], G0[aa]);
+            dmma884(d[cc * 3 + aa][0], d[cc * 3 + aa][1], A1[cc], G1[aa]);
+          }
+        // rows of owned nodes go to the incidence-major staging (the element's incidences are consecutive)
         const unsigned ted = sTe[le];
         const unsigned mask = ted >> 16;
-        const int base = ted & 0xFFFF;
-        const bool own_r = (mask >> r) & 1u;
-        const int row_r = base + __popc(mask & ((1u << r) - 1u));
+        if ((mask >> r) & 1u) {
+          double* sp = sBlk + ((int)(ted & 0xFFFF) + __popc(mask & ((1u << r) - 1u))) * ISTR + (2 * q) * BLK;
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-          const int Jn = 2 * q + jj;
-          if (own_r) {
-            double* sp = sBlk + (int)sDst[row_r * NNE + Jn] * BLKP;
-            sp[0] = d[0][jj];
-            sp[1] = d[1][jj];
-            sp[2] = d[2][jj];
-            sp[4] = d[3][jj];
-            sp[5] = d[4][jj];
-            sp[8] = d[5][jj];
-          }
-          if ((mask >> Jn) & 1u) {
-            const int row_j = base + __popc(mask & ((1u << Jn) - 1u));
-            double* sp = sBlk + (int)sDst[row_j * NNE + r] * BLKP;
-            sp[3] = d[1][jj];  // S_{J r}[1][0] = S_{r J}[0][1]
-            sp[6] = d[2][jj];  // [2][0] = [0][2]
-            sp[7] = d[4][jj];  // [2][1] = [1][2]
-          }
+          for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int b = 0; b < BLK; ++b) sp[jj * BLK + b] = d[b][jj];
         }
       }
     }
@@ -801,8 +785,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
         const int e0 = r0 & 0xFFFF;
         const int e1 = (int)(r1 & 0xFFFF) - (((r0 ^ r1) >> 24) ? 1 : 0);
         double v = 0.0;
-        for (int e = e0; e < e1; ++e) v += sBlk[e * BLKP + b];
-        sBlk[e0 * BLKP + b] = v;
+        for (int e = e0; e < e1; ++e) {
+          const int src = sEnt[e];
+          v += sBlk[(src / NNE) * ISTR + (src % NNE) * BLK + b];
+        }
+        const int src0 = sEnt[e0];
+        sBlk[(src0 / NNE) * ISTR + (src0 % NNE) * BLK + b] = v;
       }
       __syncthreads();
     }
@@ -817,14 +805,23 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
       const int deg = sSlotBase[n + 1] - sb;
       const int pcol = s - sb;
       const int64_t bp = sBptr[n];
+      // at most HEAVY_T contributions: all source lookups, then all block loads, are issued together
+      // (two shared-memory latencies per slot instead of two per contribution)
+      const double* bp_[HEAVY_T];
+#pragma unroll
+      for (int t = 0; t < HEAVY_T; ++t) {
+        const int src = sEnt[e0 + (t < cnt ? t : 0)];
+        bp_[t] = sBlk + (src / NNE) * ISTR + (src % NNE) * BLK;
+      }
       double S[BLK];
-      const double* sp = sBlk + e0 * BLKP;
 #pragma unroll
-      for (int b = 0; b < BLK; ++b) S[b] = (cnt > 0) ? sp[b] : 0.0;
-      for (int t = 1; t < cnt; ++t) {
-        sp += BLKP;
+      for (int b = 0; b < BLK; ++b) S[b] = 0.0;
 #pragma unroll
-        for (int b = 0; b < BLK; ++b) S[b] += sp[b];
+      for (int t = 0; t < HEAVY_T; ++t) {
+        if (t < cnt) {
+#pragma unroll
+          for (int b = 0; b < BLK; ++b) S[b] += bp_[t][b];
+        }
       }
       double Kb[BLK];
       if constexpr (PHYS == PHYS_ISO) {

@@ -354,6 +354,19 @@ class Plan:
         )
         self.n_owned = n_nodes
 
+        # ---- gather lists: the inverse of dst, per cluster at an even offset ent0 ----
+        n_ent_c = n_inc_c * nne + counts_c
+        n_ent_pad = (n_ent_c + 1) & ~1
+        ent0_pad = torch.zeros(n_cl + 1, dtype=torch.int64, device=dev)
+        ent0_pad[1:] = torch.cumsum(n_ent_pad, 0)
+        assert int(ent0_pad[-1]) < 2**31
+        ent_src = torch.zeros(int(ent0_pad[-1]), dtype=torch.int64, device=dev)
+        if n_inc_tot:
+            thread_loc = em_pos - cl_inc_ptr[inc_cl]  # element-major thread index of every incidence
+            val = thread_loc[:, None] * nne + torch.arange(nne, device=dev)[None, :]
+            ent_src[(ent0_pad[inc_cl][:, None] + dst).reshape(-1)] = val.reshape(-1)
+            del val, thread_loc
+
         # ---- packed per-cluster header (one 64-byte load per cluster in the kernel) ----
         hdr = torch.zeros((n_cl, 16), dtype=torch.int64, device=dev)
         if n_cl:
@@ -370,6 +383,7 @@ class Plan:
             hdr[:, 10] = slot0_c[:-1] & 0xFFFFFFFF
             hdr[:, 11] = slot0_c[:-1] >> 32
             hdr[:, 12] = n_slots_c
+            hdr[:, 13] = ent0_pad[:-1]
         hdr = torch.where(hdr >= 2**31, hdr - 2**32, hdr).to(torch.int32).contiguous()  # low words as int32 bits
 
         # ---- device arrays in their kernel dtypes (per-incidence arrays in kernel thread order) ----
@@ -385,7 +399,7 @@ class Plan:
             cl_finc_loc=(cl_finc_ptr[:-1] - cl_inc_ptr[cl_of_pos]).to(i32) if n_nodes else cl_slot_ptr[:0].to(i32),
             cl_inc_ptr=cl_inc_ptr.to(i32),
             inc_desc=inc_desc[em_perm].to(u16),
-            inc_dst=dst[em_perm].to(u16).contiguous(),
+            ent_src=ent_src.to(u16),
             inc_fdst=nm_rank[em_perm].to(u16),
             cl_te_ptr=cl_te_ptr.to(i32),
             cl_te_elem=te_elem.to(i32),

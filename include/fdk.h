@@ -97,7 +97,7 @@ typedef struct fdk_plan {
   int32_t cap_te, cap_tn, cap_inc, cap_owned, cap_slots, cap_ent, cap_heavy;
   int32_t threads;    /* CTA size the clusters were sized for (2 * cap_inc <= threads) */
   const int32_t* cl_hdr;       /* [n_clusters][16] packed per-cluster header: q0, n_owned, te0, n_te, tn0,
-                                  n_tn, inc0, n_inc, heavy0, n_heavy, slot0 (lo, hi), n_slots, 0, 0, 0     */
+                                  n_tn, inc0, n_inc, heavy0, n_heavy, slot0 (lo, hi), n_slots, ent0, 0, 0  */
   const int32_t* cl_node_ptr;  /* [n_clusters+1] range of owned nodes (cluster order)                    */
   const int32_t* cl_node;      /* [n_owned]  global id of the q-th owned node                             */
   const int64_t* cl_bptr;      /* [n_owned]  blk_indptr[cl_node[q]]                                       */
@@ -107,7 +107,9 @@ typedef struct fdk_plan {
   const int32_t* cl_finc_loc;  /* [n_owned] cl_finc_ptr relative to the first incidence of the cluster    */
   const int32_t* cl_inc_ptr;   /* [n_clusters+1] range of incidences (= threads), element-major order     */
   const uint16_t* inc_desc;    /* [n_inc] local touched-element index | local node << 12                  */
-  const uint16_t* inc_dst;     /* [n_inc][nne] staging entry (slot-sorted) of the block (I, node j of e)  */
+  const uint16_t* ent_src;     /* gather lists: for every cluster, at ent0, its (incidence, local column
+                                  node) blocks sorted by CSR slot, as local_thread * nne + j; one unused
+                                  gap entry closes every block row; ent0 is even                          */
   const uint16_t* inc_fdst;    /* [n_inc] node-major rank of the incidence inside its cluster             */
   const int32_t* cl_te_ptr;    /* [n_clusters+1] range of touched elements                                */
   const int32_t* cl_te_elem;   /* global element id of each touched element                               */
@@ -119,7 +121,7 @@ typedef struct fdk_plan {
   const int32_t* cl_tn_ptr;    /* [n_clusters+1] range of touched nodes                                   */
   const int32_t* cl_tn_node;   /* global node id of each touched node                                     */
   const uint32_t* slot_rec;    /* per cluster n_slots+1 records at index cl_slot_ptr[q0] + cluster:
-                                  first staging entry of the slot (entries are slot-sorted, one gap entry
+                                  first gather-list entry of the slot (entries are slot-sorted, one gap entry
                                   after every block row) | cluster-local touched-node index of the slot's
                                   column node << 16 | cluster-local index of the owner (row) node << 24;
                                   the last record of a cluster is an end sentinel with owner 0xFF          */

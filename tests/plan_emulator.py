@@ -53,7 +53,6 @@ def emulate_iso(plan, pat, nodes, elements, lam, mu, allow_unwritten=False):
     blk_nnz = pat.blk_nnz
     K = np.full(nv * nv * blk_nnz, np.nan)
     written = np.zeros(nv * nv * blk_nnz, dtype=np.int32)
-    inc_dst = t["inc_dst"].reshape(-1, nne)
     for c in range(plan.n_clusters):
         q0, q1 = t["cl_node_ptr"][c], t["cl_node_ptr"][c + 1]
         n_owned = q1 - q0
@@ -75,7 +74,11 @@ def emulate_iso(plan, pat, nodes, elements, lam, mu, allow_unwritten=False):
         rec = t["slot_rec"][slot0 + c : slot0 + c + n_slots + 1]
         off = rec & 0xFFFF
         assert off[-1] == n_inc * nne + n_owned <= plan.caps["cap_ent"] and rec[-1] >> 24 == 0xFF
-        stage = np.full((plan.caps["cap_ent"], dim, dim), np.nan)
+        ent0 = int(hdr[13])
+        assert ent0 % 2 == 0
+        n_ent = n_inc * nne + n_owned
+        ent_src = t["ent_src"][ent0 : ent0 + n_ent]
+        blocks = np.full((n_inc, nne, dim, dim), np.nan)  # incidence-major staging (kernel thread order)
         fdst_seen = np.zeros(n_inc, dtype=int)
         owned_nodes = t["cl_node"][q0:q1]
         prev_le = -1
@@ -92,11 +95,7 @@ def emulate_iso(plan, pat, nodes, elements, lam, mu, allow_unwritten=False):
             fd = int(t["inc_fdst"][m])
             assert t["cl_finc_ptr"][q0 + n] - t["cl_finc_ptr"][q0] <= fd < t["cl_finc_ptr"][q0 + n + 1] - t["cl_finc_ptr"][q0]
             fdst_seen[fd] += 1
-            S = np.einsum("g,gc,gaj->jca", wdet[e], G[e, :, :, i], G[e])
-            for j in range(nne):
-                d = int(inc_dst[m, j])
-                assert np.isnan(stage[d, 0, 0]), "two blocks staged at the same entry"
-                stage[d] = S[j]
+            blocks[m - inc0] = np.einsum("g,gc,gaj->jca", wdet[e], G[e, :, :, i], G[e])
         assert (fdst_seen == 1).all()
         # per touched element: first thread and owned-node mask (tensor-core producer, hex8)
         if nne <= 8:
@@ -109,6 +108,7 @@ def emulate_iso(plan, pat, nodes, elements, lam, mu, allow_unwritten=False):
                     mask |= 1 << int(descs[m] >> 12)
                 assert mask == t["te_desc"][te0 + le] >> 16
                 assert list(descs[mine] >> 12) == sorted(descs[mine] >> 12)
+        used = np.zeros(n_inc * nne, dtype=int)
         # heavy slots
         h0, h1 = t["cl_heavy_ptr"][c], t["cl_heavy_ptr"][c + 1]
         heavy = set(int(x) for x in t["heavy_slot"][h0:h1])
@@ -123,7 +123,11 @@ def emulate_iso(plan, pat, nodes, elements, lam, mu, allow_unwritten=False):
                 assert rec[s] >> 24 == n
                 cnt = int(off[s + 1]) - e0 - (1 if (rec[s] >> 24) != (rec[s + 1] >> 24) else 0)
                 assert (cnt > HEAVY_T) == (s in heavy)
-                acc = stage[e0 : e0 + cnt].sum(axis=0) if cnt else np.zeros((dim, dim))
+                acc = np.zeros((dim, dim))
+                for ent in ent_src[e0 : e0 + cnt]:
+                    assert used[ent] == 0
+                    used[ent] = 1
+                    acc += blocks[ent // nne, ent % nne]
                 assert not np.isnan(acc).any()
                 Jn = pat.blk_indices[bp + pcol].item()
                 assert t["cl_tn_node"][tn0 + int((rec[s] >> 16) & 0xFF)] == Jn
@@ -134,7 +138,6 @@ def emulate_iso(plan, pat, nodes, elements, lam, mu, allow_unwritten=False):
                         dst = cc * nv * blk_nnz + nv * bp + aa * deg + pcol
                         K[dst] = Kb[cc, aa]
                         written[dst] += 1
-            # the gap entry after the row is never staged
-            assert np.isnan(stage[int(off[sb0 + deg]) - 1, 0, 0])
+        assert used.sum() == n_inc * nne  # every block is gathered exactly once
     assert (written <= 1).all() and (allow_unwritten or (written == 1).all()), "every CSR value must be written exactly once"
     return K
