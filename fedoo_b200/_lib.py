@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_fdk.so")
+LIB_PATH = os.environ.get("FDK_LIB") or os.path.join(HERE, "_fdk.so")  # FDK_LIB: diagnostic builds (scripts/)
 
 HEX8, TET4, TET10, QUAD4 = 0, 1, 2, 3
 ELEM_IDS = {"hex8": HEX8, "tet4": TET4, "tet10": TET10, "quad4": QUAD4}
@@ -15,7 +15,7 @@ MATRIX, VECTOR, ALL = 1, 2, 3
 COMPUTE_FLAGS = {"matrix": MATRIX, "vector": VECTOR, "all": ALL}
 
 EXPORTS = [
-    "fdk_last_error_string", "fdk_version", "fdk_set_option", "fdk_get_option", "fdk_element_info", "fdk_element_table",
+    "fdk_last_error_string", "fdk_version", "fdk_set_option", "fdk_get_option", "fdk_debug_phase_clocks", "fdk_element_info", "fdk_element_table",
     "fdk_sym_block_keys", "fdk_sym_block_csr", "fdk_sym_expand_csr",
     "fdk_assemble_elastic_iso", "fdk_assemble_elastic_general", "fdk_assemble_heat",
     "fdk_gp_strain_stress", "fdk_gp_temperature", "fdk_j2_update",
@@ -90,6 +90,7 @@ def load():
     lib.fdk_version.restype = i32
     lib.fdk_set_option.argtypes = [C.c_char_p, i32]
     lib.fdk_get_option.argtypes = [C.c_char_p, C.POINTER(i32)]
+    lib.fdk_debug_phase_clocks.argtypes = [C.POINTER(C.c_ulonglong), i32, i32]
     lib.fdk_element_info.argtypes = [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.fdk_element_table.argtypes = [i32, vp, vp, vp]
     lib.fdk_sym_block_keys.argtypes = [i32, i64, i32, vp, vp, C.POINTER(i64), vp]

@@ -66,6 +66,25 @@ int fdk_get_option(const char* key, int* value) {
   return FDK_EINVAL;
 }
 
+int fdk_debug_phase_clocks(unsigned long long* out_h, int n, int reset) {
+#ifdef FDK_PHASE_CLOCKS
+  FDK_REQUIRE(out_h != nullptr && n >= 0 && n <= 16, FDK_EINVAL, "bad arguments");
+  unsigned long long tmp[16];
+  FDK_CUDA(cudaDeviceSynchronize());
+  FDK_CUDA(cudaMemcpyFromSymbol(tmp, g_phase_clk, sizeof(tmp)));
+  for (int i = 0; i < n; ++i) out_h[i] = tmp[i];
+  if (reset) {
+    for (int i = 0; i < 16; ++i) tmp[i] = 0;
+    FDK_CUDA(cudaMemcpyToSymbol(g_phase_clk, tmp, sizeof(tmp)));
+  }
+  return 0;
+#else
+  (void)out_h; (void)n; (void)reset;
+  set_error("libfdk was built without -DFDK_PHASE_CLOCKS");
+  return FDK_EINVAL;
+#endif
+}
+
 int fdk_element_info(int elem_type, int* nne, int* ngp, int* dim) { return elem_dims(elem_type, nne, ngp, dim); }
 
 int fdk_element_table(int elem_type, double* w, double* N, double* dN) {

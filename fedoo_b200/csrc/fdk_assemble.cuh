@@ -214,6 +214,19 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Optional phase clocks (-DFDK_PHASE_CLOCKS): SM cycles spent by each CTA between its barriers, summed over
+// all CTAs; read back by fdk_debug_phase_clocks.  Compiled out of the production library.
+#ifdef FDK_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[16];
+#define FDK_CLK_DECL long long _clk_t = clock64(); unsigned long long _clk_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define FDK_CLK(i) { const long long _n = clock64(); _clk_acc[i] += (unsigned long long)(_n - _clk_t); _clk_t = _n; }
+#define FDK_CLK_FLUSH if (threadIdx.x == 0) { for (int _i = 0; _i < 10; ++_i) atomicAdd(&g_phase_clk[_i], _clk_acc[_i]); }
+#else
+#define FDK_CLK_DECL
+#define FDK_CLK(i)
+#define FDK_CLK_FLUSH
+#endif
+
 // Per-cluster header (fdk_plan::cl_hdr, 16 int32 per cluster): one 64-byte load instead of a chain of
 // dependent loads through the individual range arrays.
 struct ClusterHdr {
@@ -367,6 +380,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   fetch_inputs(cur, 0);
 
   int buf = 0;
+  FDK_CLK_DECL
   for (int c = blockIdx.x; c < p.n_clusters; c += gridDim.x, buf ^= 1) {
   const int q0 = cur.q0, n_owned = cur.n_owned, te0 = cur.te0, n_te = cur.n_te, n_inc = cur.n_inc;
   const int inc0 = cur.inc0, h0 = cur.h0, n_heavy = cur.n_heavy, n_slots = cur.n_slots;
@@ -410,6 +424,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   }
   cp_async_wait_group<1>();  // the phase-1 inputs of this cluster (issued one cluster ago) have landed
   __syncthreads();
+  FDK_CLK(1)  // phase 0 wait
 
   if constexpr (!MMA) {
     // ---------------- phase 1: geometry (+ w*sigma) per (touched element, gp) ----------------
@@ -513,6 +528,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
     if (has_next) load_node_ids(nxt);  // consumed after phase 2
     cp_async_wait_group<0>();          // this cluster's descriptors
     __syncthreads();
+    FDK_CLK(2)  // phase 1
 
     // ---------------- phase 2: per-incidence half rows in registers ----------------
     double acc[NH][BLK];
@@ -656,6 +672,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
       }
     }
     __syncthreads();  // everyone is done reading the geometry region; it becomes the staging region
+    FDK_CLK(3)  // phase 2
     if (it < n_inc) {
       if (do_mat) {
   #pragma unroll
@@ -709,6 +726,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
     if (has_next) load_node_ids(nxt);  // consumed after phase 2m
     cp_async_wait_group<0>();          // this cluster's descriptors
     __syncthreads();
+    FDK_CLK(2)  // phase 1m
 
     // ---------------- phase 2m: one warp per touched element, S^e by DMMA ----------------
     {
@@ -772,6 +790,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   if (has_next) fetch_inputs(nxt, buf ^ 1);  // lands during phase 3 and the next cluster's phase 0
   else cp_async_commit();
   __syncthreads();
+  FDK_CLK(4)  // staging stores / next fetch issue
 
   // slot record: first staging entry | local touched-node index of the column node << 16 | owner << 24;
   // the run of a slot ends where the next one starts (minus the gap entry that closes a block row)
@@ -793,6 +812,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
         sBlk[(src0 / NNE) * ISTR + (src0 % NNE) * BLK + b] = v;
       }
       __syncthreads();
+      FDK_CLK(5)  // phase 3a (heavy)
     }
     // ---------------- phase 3b: slot gather, constitutive closed form, final stores ----------------
     for (int s = tid; s < n_slots; s += THREADS) {
@@ -862,6 +882,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
     }
   }
   if (fuse_ku) __syncthreads();  // sR complete (uniform)
+  FDK_CLK(6)  // phase 3b
   if (do_vec) {
     for (int n = tid; n < n_owned; n += THREADS) {
       double s[NV];
@@ -878,8 +899,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
     }
   }
   __syncthreads();  // staging, descriptors and row buffers are free for the next cluster
+  FDK_CLK(7)  // D tail + end barrier
   cur = nxt;
   }  // cluster loop
+  FDK_CLK_FLUSH
 }
 
 // ---- host launcher -----------------------------------------------------------------------

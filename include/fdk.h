@@ -52,6 +52,10 @@ int fdk_version(void);
 int fdk_set_option(const char* key, int value);
 int fdk_get_option(const char* key, int* value);
 
+/* Diagnostic (builds with -DFDK_PHASE_CLOCKS only, FDK_EINVAL otherwise): SM cycles spent between the barriers
+ * of the cluster kernel, summed over all CTAs since the last reset; out_h receives the first n (<= 16) counters. */
+int fdk_debug_phase_clocks(unsigned long long* out_h, int n, int reset);
+
 /* element table accessors (host): what the kernels integrate with.
  * Replaces fedoo/lib_elements/{hexahedron,tetrahedron,quadrangle}.py tables
  * (hexahedron.py:22-27,134-135,178-248; tetrahedron.py:21-61,72-97,106-208;
