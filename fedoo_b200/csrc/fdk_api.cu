@@ -3,6 +3,7 @@
 #include <cstdlib>
 
 #include "fdk_assemble.cuh"
+#include "fdk_assemble_iso.cuh"
 #include "fdk_gp.cuh"
 #include "fdk_symbolic.cuh"
 
@@ -21,6 +22,9 @@ int env_flag(const char* name, int dflt) {
 }
 int g_opt_fuse = env_flag("FDK_NO_FUSE_KU", 0) ? 0 : 1;
 int g_opt_mma = env_flag("FDK_MMA", 1);
+//   iso4    : hex8 + isotropic law + matrix requested (residual fused): the balanced 1024-thread kernel of
+//             fdk_assemble_iso.cuh (default 1; FDK_ISO4=0 -> 0: k_assemble, with or without mma)
+int g_opt_iso4 = env_flag("FDK_ISO4", 1);
 
 int check_plan(const fdk_plan* p) {
   FDK_REQUIRE(p != nullptr, FDK_EINVAL, "plan is NULL");
@@ -54,7 +58,8 @@ int fdk_set_option(const char* key, int value) {
   FDK_REQUIRE(key != nullptr, FDK_EINVAL, "option key is NULL");
   if (strcmp(key, "fuse_ku") == 0) { g_opt_fuse = value != 0; return 0; }
   if (strcmp(key, "mma") == 0) { g_opt_mma = value != 0; return 0; }
-  set_error("unknown option '%s' (known: fuse_ku, mma)", key);
+  if (strcmp(key, "iso4") == 0) { g_opt_iso4 = value != 0; return 0; }
+  set_error("unknown option '%s' (known: fuse_ku, mma, iso4)", key);
   return FDK_EINVAL;
 }
 
@@ -62,7 +67,8 @@ int fdk_get_option(const char* key, int* value) {
   FDK_REQUIRE(key != nullptr && value != nullptr, FDK_EINVAL, "NULL argument");
   if (strcmp(key, "fuse_ku") == 0) { *value = g_opt_fuse; return 0; }
   if (strcmp(key, "mma") == 0) { *value = g_opt_mma; return 0; }
-  set_error("unknown option '%s' (known: fuse_ku, mma)", key);
+  if (strcmp(key, "iso4") == 0) { *value = g_opt_iso4; return 0; }
+  set_error("unknown option '%s' (known: fuse_ku, mma, iso4)", key);
   return FDK_EINVAL;
 }
 
@@ -138,6 +144,10 @@ int fdk_assemble_elastic_iso(const fdk_plan* plan, int compute, const double* co
   // so it is taken from the assembled rows in the gather phase instead of a second B^T sigma pass
   a.fuse_ku = (compute == FDK_ALL && U != nullptr && stress_gp == nullptr && g_opt_fuse) ? 1 : 0;
   a.no_mma = g_opt_mma ? 0 : 1;
+  // headline case: matrix requested and no B^T sigma pass -> balanced kernel (fdk_assemble_iso.cuh)
+  const bool bts = (compute & FDK_VECTOR) && !a.fuse_ku;
+  if (g_opt_iso4 && (compute & FDK_MATRIX) && !bts && plan->elem_type == FDK_HEX8 && plan->threads == Hex8::THREADS)
+    return launch_assemble_iso<Hex8, 1024, 4>(a, (cudaStream_t)stream);
   return dispatch_assemble<PHYS_ISO>(a, (cudaStream_t)stream);
 }
 

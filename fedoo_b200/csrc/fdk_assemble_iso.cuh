@@ -1,0 +1,453 @@
+// fdk_assemble_iso.cuh -- balanced cluster kernel for the headline case: isotropic elasticity, matrix
+// requested, residual (if any) taken from the assembled rows (D = -K_row . U).
+//
+// Same owner-computes algorithm and the same plan as k_assemble (fdk_assemble.cuh); what differs is how the
+// work is laid on the SM.  Measured on B200 (profiles/r1_pipe_overlap.txt, r1_phase_clocks.txt): FP64 FMAs and
+// shared-memory instructions largely SERIALISE (a DFMA warp-instruction costs 0.5 SM-cycles, an LDS ~1, an
+// STS.64 2, and a mix costs ~0.85 x the sum), and one third of the stall samples of k_assemble were warps
+// waiting at barriers because every phase ran 1.2-1.7 "rounds" over 512 threads.  Hence:
+//   * THREADS = TPI x (max incidences): TPI = 4 threads per incidence (two column blocks each, 18
+//     accumulators, <= 64 registers) -> 1024 threads, 32 warps per SM; for a 32-node hex8 cluster the
+//     geometry phase (600 tasks), the block phase (256 incidences x 4) and the gather (864 slots) are ONE
+//     round each, so every warp carries the same load between two barriers;
+//   * sqrt(w_g |det J|) is folded into dN/dx in the geometry phase (S_IJ = sum_g (sqrt(w) G_I) (x) (sqrt(w) G_J)
+//     exactly as before up to one rounding): no weight load and no weight multiply in the block phase;
+//   * the geometry task streams over the element nodes twice (Jacobian, then dN/dx) instead of holding
+//     the coordinates and the 24 derivatives in registers;
+//   * four barriers per cluster: the prefetched inputs of the next cluster are waited for BEFORE the
+//     barrier that closes the gather, so that barrier also publishes them; the per-node reduction of the
+//     residual is spread over 8 lanes per (node, component) and overlaps the next cluster's geometry phase;
+//   * heavy slots (the diagonal) are pre-reduced with all source lookups and all block loads in flight
+//     together (two shared-memory latencies instead of two per contribution).
+//
+// Reference: same as k_assemble -- fedoo/core/assembly.py:143-470, 776-928; fedoo/core/_sparsematrix.py:55-174,
+// 256-315; fedoo/constitutivelaw/elastic_isotrop.py:35-68.
+#pragma once
+#include "fdk_assemble.cuh"
+
+namespace fdk {
+
+template <class El, int TPI>
+struct IsoLayout {
+  using L = Layout<El, PHYS_ISO>;
+  static constexpr int NNE = El::NNE, NGP = El::NGP, DIM = El::DIM, NV = DIM, BLK = NV * NV;
+  static constexpr int GROW = L::GROW, GSTR = L::GSTR;
+  static constexpr int NH = NNE / TPI;  // column blocks per thread: j = part, part + TPI, ...
+  static_assert(NNE % TPI == 0, "threads per incidence must divide the element nodes");
+  // Bank-conflict-free strides (8-byte banks, 16 per half-warp; lanes = 8 incidences x TPI parts):
+  //  * staging: lane (it, part) stores block j = part (+ TPI) at it*ISTR + j*BLK + b.  With BLK = 9 and TPI = 4 the
+  //    part offsets are {0,9,2,11} mod 16, so ISTR = 4 or 12 mod 16 makes the 16 lanes of a half-warp hit 16
+  //    different banks (hex8: 76);
+  //  * geometry: the own-row loads of the incidences of elements le and le+1 differ by ESTR + 3 (i - i'); with
+  //    ESTR = 8 mod 16 they never collide (3 d = 8 mod 16 has no solution with |d| <= 7) (hex8: 216).
+  static constexpr int ISTR = (NNE == 8 && DIM == 3 && TPI == 4) ? 76 : L::ISTR;
+  static constexpr int ESTR = (NNE == 8 && DIM == 3) ? 216 : L::ESTR;
+  static constexpr int TSTR = (GROW + 2) & ~1;  // even: the reference gradients are read as 128-bit node pairs
+  static_assert(NNE % 2 == 0, "node pairs");
+  static constexpr int XSTR = 4;  // padded coordinates of a touched node: one 128-bit + one 64-bit load
+  static constexpr int TAB_DOUBLES = (NGP * TSTR + NGP + 1) & ~1;
+  static_assert(ISTR >= NNE * BLK && ESTR >= NGP * GSTR, "strides cover the rows");
+
+  __host__ __device__ static int xu_doubles(const fdk_plan& p) { return (p.cap_tn * (XSTR + NV) + 1) & ~1; }
+  // staging of the blocks; the per-slot K.u products live BEHIND both views of the big region so that the
+  // residual reduction of cluster c may overlap the geometry phase of cluster c+1
+  __host__ __device__ static long sr_offset(const fdk_plan& p) {
+    const long g = (long)p.cap_te * ESTR, s = (long)p.cap_inc * ISTR;
+    return ((g > s ? g : s) + 1) & ~1L;
+  }
+  static size_t smem_bytes(const fdk_plan& p) {
+    long doubles = TAB_DOUBLES + 2L * xu_doubles(p) + sr_offset(p) + (((long)p.cap_slots * NV + 1) & ~1L) + p.cap_owned;
+    size_t bytes = (size_t)doubles * 8;
+    bytes += (size_t)(p.cap_owned + 1) * 4;            // sSlotBase
+    bytes += (size_t)(p.cap_slots + 1) * 4;            // sRec
+    bytes += (size_t)p.cap_heavy * 4;                  // sHeavy
+    bytes += 2 * (size_t)((p.cap_te * NNE + 3) & ~3);  // sLconn (double-buffered)
+    bytes += (size_t)((p.cap_ent + 3) & ~3) * 2;       // sEnt
+    return bytes;
+  }
+};
+
+template <class El, int THREADS, int TPI>
+__global__ void __launch_bounds__(THREADS, 1) k_assemble_iso(const __grid_constant__ AsmArgs a) {
+  using IL = IsoLayout<El, TPI>;
+  constexpr int NNE = IL::NNE, NGP = IL::NGP, DIM = IL::DIM, NV = IL::NV, BLK = IL::BLK, ISTR = IL::ISTR;
+  constexpr int GROW = IL::GROW, GSTR = IL::GSTR, ESTR = IL::ESTR, TSTR = IL::TSTR, NH = IL::NH, XSTR = IL::XSTR;
+  constexpr int INC = THREADS / TPI;  // incidences per cluster <= INC
+  const fdk_plan& p = a.p;
+  const int tid = threadIdx.x;
+  const bool fuse_ku = a.fuse_ku != 0;
+  // the TPI threads of an incidence sit in adjacent lanes: a warp covers 32 / TPI incidences of 2-3 elements
+  // (element-major order), so its own-row loads touch 32 / TPI addresses and its column loads ~10
+  const int it = tid / TPI;         // incidence of this thread (phase 2)
+  const int part = tid - it * TPI;  // its column blocks: part, part + TPI, ...
+
+  extern __shared__ __align__(16) double smem[];
+  double* sdN = smem;              // [NGP][TSTR] reference gradients, [g][d][k]
+  double* sW = sdN + NGP * TSTR;   // [NGP]
+  const int xu_doubles = IL::xu_doubles(p);
+  double* sXbuf = smem + IL::TAB_DOUBLES;  // [2][xu_doubles]: padded coordinates, then dofs
+  double* sBig = sXbuf + 2 * xu_doubles;
+  double* sG = sBig;                       // geometry view  [n_te][ESTR]: sqrt(w) dN/dx, [g][k][d]
+  double* sBlk = sBig;                     // staging view   [cap_inc][ISTR]
+  double* sR = sBig + IL::sr_offset(p);    // [cap_slots][NV] per-slot K.u products
+  long long* sBptr = reinterpret_cast<long long*>(sR + (((long)p.cap_slots * NV + 1) & ~1L));  // [cap_owned]
+  int* sSlotBase = reinterpret_cast<int*>(sBptr + p.cap_owned);                                 // [cap_owned+1]
+  unsigned* sRec = reinterpret_cast<unsigned*>(sSlotBase + (p.cap_owned + 1));                  // [cap_slots+1]
+  unsigned* sHeavy = sRec + (p.cap_slots + 1);                                                  // [cap_heavy]
+  unsigned char* sLbuf = reinterpret_cast<unsigned char*>(sHeavy + p.cap_heavy);                // [2][lc_bytes]
+  const int lc_bytes = (p.cap_te * NNE + 3) & ~3;
+  unsigned short* sEnt = reinterpret_cast<unsigned short*>(sLbuf + 2 * lc_bytes);               // [cap_ent]
+
+  // ---------------- prologue: tables (once per CTA), the first cluster's inputs ----------------
+  {
+    const ElemTable& tab = c_tab[El::ID];
+    for (int t = tid; t < NGP * GROW; t += THREADS) {
+      const int g = t / GROW, r = t - g * GROW;
+      sdN[g * TSTR + r] = tab.dN[t];
+    }
+    if (tid < NGP) sW[tid] = tab.w[tid];
+  }
+  constexpr int RT = (256 + THREADS - 1) / THREADS;  // cap_tn <= 256
+  int node_r[RT];
+  auto load_node_ids = [&](const ClusterHdr& h) {
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const int t = tid + r * THREADS;
+      node_r[r] = (t < h.n_tn) ? p.cl_tn_node[h.tn0 + t] : -1;
+    }
+  };
+  // coordinates, dofs and local connectivity of one cluster -> buffer b (one cp.async group)
+  auto fetch_inputs = [&](const ClusterHdr& h, int b) {
+    double* dX = sXbuf + b * xu_doubles;
+    double* dU = dX + p.cap_tn * XSTR;
+    unsigned char* dL = sLbuf + b * lc_bytes;
+    const unsigned char* lc = p.cl_lconn + (int64_t)h.te0 * NNE;
+    if constexpr (NNE % 4 == 0) {
+      for (int t = tid; t < h.n_te * NNE / 4; t += THREADS) cp_async<4>(dL + 4 * t, lc + 4 * t);
+    } else {
+      for (int t = tid; t < h.n_te * NNE; t += THREADS) dL[t] = lc[t];
+    }
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const int t = tid + r * THREADS;
+      const int node = node_r[r];
+      if (node >= 0) {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) cp_async<8>(dX + t * XSTR + d, a.coords + (int64_t)node * DIM + d);
+        if (fuse_ku) {
+#pragma unroll
+          for (int v = 0; v < DIM; ++v) cp_async<8>(dU + t * DIM + v, a.U + (int64_t)v * p.n_nodes + node);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  ClusterHdr cur = load_hdr(p.cl_hdr, blockIdx.x);
+  load_node_ids(cur);
+  fetch_inputs(cur, 0);
+  cp_async_wait_group<0>();
+  __syncthreads();  // tables and the first inputs are visible
+
+  FDK_CLK_DECL
+  int buf = 0;
+  for (int c = blockIdx.x; c < p.n_clusters; c += gridDim.x, buf ^= 1) {
+    const int q0 = cur.q0, n_owned = cur.n_owned, n_te = cur.n_te, n_inc = cur.n_inc;
+    const int inc0 = cur.inc0, h0 = cur.h0, n_heavy = cur.n_heavy, n_slots = cur.n_slots;
+    const int64_t slot0 = cur.slot0;
+    const double* sX = sXbuf + buf * xu_doubles;
+    const double* sU = sX + p.cap_tn * XSTR;
+    const unsigned char* sLconn = sLbuf + buf * lc_bytes;
+    const int c_next = c + gridDim.x;
+    const bool has_next = c_next < p.n_clusters;
+    ClusterHdr nxt = cur;
+    if (has_next) nxt = load_hdr(p.cl_hdr, c_next);  // consumed after phase 1
+    unsigned my_desc = 0;
+    if (it < n_inc) my_desc = p.inc_desc[inc0 + it];  // consumed in phase 2
+    int my_node = 0;  // row node of this thread's share of the residual reduction (consumed at the very end)
+    if (fuse_ku && (tid >> 3) < n_owned * NV) my_node = p.cl_node[q0 + (tid >> 3) / NV];
+
+    // ---------------- phase 1: sqrt(w) dN/dx per (touched element, Gauss point) ----------------
+    for (int task = tid; task < n_te * NGP; task += THREADS) {
+      const int le = task / NGP, g = task - le * NGP;
+      const unsigned char* lc = sLconn + le * NNE;
+      const double* dN = sdN + g * TSTR;
+      int ln[NNE];
+      if constexpr (NNE % 4 == 0) {
+        const unsigned* lc4 = reinterpret_cast<const unsigned*>(lc);
+#pragma unroll
+        for (int q = 0; q < NNE / 4; ++q) {
+          const unsigned w4 = lc4[q];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ln[4 * q + k] = (w4 >> (8 * k)) & 0xFF;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < NNE; ++k) ln[k] = lc[k];
+      }
+      double J[DIM][DIM];
+#pragma unroll
+      for (int r = 0; r < DIM; ++r)
+#pragma unroll
+        for (int x = 0; x < DIM; ++x) J[r][x] = 0.0;
+#pragma unroll
+      for (int k = 0; k < NNE; k += 2) {
+        double X[2][DIM];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double* xk = sX + ln[k + h] * XSTR;
+          const double2 x01 = *reinterpret_cast<const double2*>(xk);
+          X[h][0] = x01.x;
+          X[h][1] = x01.y;
+          if constexpr (DIM == 3) X[h][2] = xk[2];
+        }
+#pragma unroll
+        for (int r = 0; r < DIM; ++r) {
+          const double2 dn = *reinterpret_cast<const double2*>(dN + r * NNE + k);  // nodes k, k+1
+#pragma unroll
+          for (int x = 0; x < DIM; ++x) J[r][x] = fma(dn.y, X[1][x], fma(dn.x, X[0][x], J[r][x]));
+        }
+      }
+      double iJ[DIM][DIM];
+      const double det = invert<DIM>(J, iJ);
+      const double s = sqrt(sW[g] * fabs(det));
+#pragma unroll
+      for (int x = 0; x < DIM; ++x)
+#pragma unroll
+        for (int r = 0; r < DIM; ++r) iJ[x][r] *= s;
+      // G[k][x] = sum_r iJ[x][r] dN[r][k], stored [k][x] as 128-bit pairs
+      double2* out = reinterpret_cast<double2*>(sG + le * ESTR + g * GSTR);
+#pragma unroll
+      for (int k = 0; k < NNE; k += 2) {
+        double2 dn[DIM];
+#pragma unroll
+        for (int r = 0; r < DIM; ++r) dn[r] = *reinterpret_cast<const double2*>(dN + r * NNE + k);
+        double v[2 * DIM];  // [h][x]
+#pragma unroll
+        for (int x = 0; x < DIM; ++x) {
+          double v0 = iJ[x][0] * dn[0].x, v1 = iJ[x][0] * dn[0].y;
+#pragma unroll
+          for (int r = 1; r < DIM; ++r) {
+            v0 = fma(iJ[x][r], dn[r].x, v0);
+            v1 = fma(iJ[x][r], dn[r].y, v1);
+          }
+          v[x] = v0;
+          v[DIM + x] = v1;
+        }
+#pragma unroll
+        for (int t = 0; t < DIM; ++t) out[(k * DIM) / 2 + t] = make_double2(v[2 * t], v[2 * t + 1]);
+      }
+    }
+    if (has_next) load_node_ids(nxt);  // consumed after phase 2
+    __syncthreads();                   // B2: geometry complete
+    FDK_CLK(2)
+
+    // ---------------- descriptors of this cluster's gather (land during phase 2) ----------------
+    {
+      const unsigned* rec = p.slot_rec + slot0 + c;
+      for (int t = tid; t <= n_slots; t += THREADS) cp_async<4>(sRec + t, rec + t);
+      for (int t = tid; t < n_owned; t += THREADS) {
+        cp_async<8>(sBptr + t, p.cl_bptr + q0 + t);
+        cp_async<4>(sSlotBase + t, p.cl_slot_loc + q0 + t);
+      }
+      const unsigned short* esrc = p.ent_src + cur.ent0;  // even offset: 4-byte aligned
+      const int n_ent = n_inc * NNE + n_owned;
+      for (int t = tid; t < (n_ent + 1) / 2; t += THREADS) cp_async<4>(sEnt + 2 * t, esrc + 2 * t);
+      for (int t = tid; t < n_heavy; t += THREADS) cp_async<4>(sHeavy + t, p.heavy_slot + h0 + t);
+      cp_async_commit();
+      if (tid == 0) sSlotBase[n_owned] = n_slots;
+    }
+
+    // ---------------- phase 2: NH column blocks of one incidence per thread ----------------
+    double acc[NH][BLK];
+#pragma unroll
+    for (int j = 0; j < NH; ++j)
+#pragma unroll
+      for (int b = 0; b < BLK; ++b) acc[j][b] = 0.0;
+    if (it < n_inc) {
+      const int le = my_desc & 0xFFF, i = my_desc >> 12;
+      const double* gi_p = sG + le * ESTR + i * DIM;
+      const double* gj_p = sG + le * ESTR + part * DIM;
+#pragma unroll 2
+      for (int g = 0; g < NGP; ++g) {
+        double gi[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) gi[d] = gi_p[g * GSTR + d];
+#pragma unroll
+        for (int j = 0; j < NH; ++j) {
+          double gj[DIM];
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) gj[d] = gj_p[g * GSTR + j * TPI * DIM + d];
+#pragma unroll
+          for (int cc = 0; cc < DIM; ++cc)
+#pragma unroll
+            for (int aa = 0; aa < DIM; ++aa) acc[j][cc * DIM + aa] = fma(gi[cc], gj[aa], acc[j][cc * DIM + aa]);
+        }
+      }
+    }
+    if (has_next) fetch_inputs(nxt, buf ^ 1);  // lands during the gather
+    else cp_async_commit();
+    __syncthreads();  // B3: everyone is done reading the geometry; the region becomes the staging array
+    FDK_CLK(3)
+    if (it < n_inc) {
+#pragma unroll
+      for (int j = 0; j < NH; ++j) {
+        double* sp = sBlk + it * ISTR + (part + j * TPI) * BLK;
+#pragma unroll
+        for (int b = 0; b < BLK; ++b) sp[b] = acc[j][b];
+      }
+    }
+    cp_async_wait_group<1>();  // this cluster's descriptors (the next cluster's inputs may still be in flight)
+    __syncthreads();           // B4: staging and descriptors complete
+    FDK_CLK(4)
+
+    // ---------------- phase 3a: heavy slots, all loads of a slot entry in flight together ----------------
+    if (n_heavy > 0) {  // uniform over the CTA
+      for (int t = tid; t < n_heavy * BLK; t += THREADS) {
+        const int h = t / BLK, b = t - h * BLK;
+        const int s = sHeavy[h];
+        const unsigned r0 = sRec[s], r1 = sRec[s + 1];
+        const int e0 = r0 & 0xFFFF;
+        const int e1 = (int)(r1 & 0xFFFF) - (((r0 ^ r1) >> 24) ? 1 : 0);
+        double v = 0.0;
+        for (int eb = e0; eb < e1; eb += 8) {
+          int src[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) src[k] = sEnt[eb + k < e1 ? eb + k : e0];
+          double x[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) x[k] = sBlk[(src[k] / NNE) * ISTR + (src[k] % NNE) * BLK + b];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (eb + k < e1) v += x[k];
+        }
+        // in place: only this thread touches column b of the entries of slot h
+        const int src0 = sEnt[e0];
+        sBlk[(src0 / NNE) * ISTR + (src0 % NNE) * BLK + b] = v;
+      }
+      __syncthreads();
+      FDK_CLK(5)
+    }
+
+    // ---------------- phase 3b: slot gather, constitutive closed form, final stores ----------------
+    for (int s = tid; s < n_slots; s += THREADS) {
+      const unsigned r0 = sRec[s], r1 = sRec[s + 1];
+      const int e0 = r0 & 0xFFFF;
+      const int n = r0 >> 24;
+      int cnt = (int)(r1 & 0xFFFF) - e0 - (((r0 ^ r1) >> 24) ? 1 : 0);  // one gap entry after each row
+      if (cnt > HEAVY_T) cnt = 1;                                       // pre-reduced in 3a
+      const int sb = sSlotBase[n];
+      const int deg = sSlotBase[n + 1] - sb;
+      const int pcol = s - sb;
+      const int64_t bp = sBptr[n];
+      const double* bp_[HEAVY_T];
+#pragma unroll
+      for (int t = 0; t < HEAVY_T; ++t) {
+        const int src = sEnt[e0 + (t < cnt ? t : 0)];
+        bp_[t] = sBlk + (src / NNE) * ISTR + (src % NNE) * BLK;
+      }
+      double S[BLK];
+#pragma unroll
+      for (int b = 0; b < BLK; ++b) S[b] = bp_[0][b];
+#pragma unroll
+      for (int t = 1; t < HEAVY_T; ++t) {
+        if (t < cnt) {
+#pragma unroll
+          for (int b = 0; b < BLK; ++b) S[b] += bp_[t][b];
+        }
+      }
+      // K_IJ = lambda S + mu S^T + mu tr(S) 1
+      double Kb[BLK];
+      double tr = 0.0;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) tr += S[d * DIM + d];
+#pragma unroll
+      for (int cc = 0; cc < DIM; ++cc)
+#pragma unroll
+        for (int aa = 0; aa < DIM; ++aa) {
+          double v = fma(a.lam, S[cc * DIM + aa], a.mu * S[aa * DIM + cc]);
+          if (cc == aa) v = fma(a.mu, tr, v);
+          Kb[cc * DIM + aa] = v;
+        }
+#pragma unroll
+      for (int cc = 0; cc < NV; ++cc) {
+        double* row = a.K + ((int64_t)cc * NV * p.blk_nnz + (int64_t)NV * bp);
+#pragma unroll
+        for (int aa = 0; aa < NV; ++aa) __stcs(row + (int64_t)aa * deg + pcol, Kb[cc * NV + aa]);
+      }
+      if (fuse_ku) {  // this slot's share of (K U)_I
+        const double* uj = sU + (int)((r0 >> 16) & 0xFF) * DIM;
+#pragma unroll
+        for (int cc = 0; cc < NV; ++cc) {
+          double r = 0.0;
+#pragma unroll
+          for (int aa = 0; aa < NV; ++aa) r = fma(Kb[cc * NV + aa], uj[aa], r);
+          sR[s * NV + cc] = r;
+        }
+      }
+    }
+    cp_async_wait_group<0>();  // the next cluster's inputs: published by the barrier below
+    __syncthreads();           // B6: gather done (staging free), sR complete, next inputs visible
+    FDK_CLK(6)
+
+    // ---------------- residual: D_I = -sum over the slots of row I, 8 lanes per (node, component) ----------------
+    if (fuse_ku) {
+      const int n_out = n_owned * NV * 8;
+      for (int t0 = 0; t0 < n_out; t0 += THREADS) {  // whole warps take part in the shuffles
+        const int t = t0 + tid;
+        const int sub = t & 7, o = t >> 3;
+        const int n = o / NV, v = o - n * NV;
+        double sum = 0.0;
+        if (t < n_out) {
+          const int k1 = sSlotBase[n + 1];
+          for (int k = sSlotBase[n] + sub; k < k1; k += 8) sum += sR[k * NV + v];
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        if (t < n_out && sub == 0) {
+          const int node = (t0 == 0) ? my_node : p.cl_node[q0 + n];
+          a.D[(int64_t)v * p.n_nodes + node] = -sum;
+        }
+      }
+    }
+    FDK_CLK(7)
+    // no closing barrier: the next cluster's phase 1 writes only the geometry view (below sR), its
+    // descriptor copies are issued after its B2, which every warp reaches after finishing this reduction
+    cur = nxt;
+  }  // cluster loop
+  FDK_CLK_FLUSH
+}
+
+template <class El, int THREADS, int TPI>
+int launch_assemble_iso(AsmArgs& a, cudaStream_t stream) {
+  using IL = IsoLayout<El, TPI>;
+  const fdk_plan& p = a.p;
+  FDK_REQUIRE(TPI * p.cap_inc <= THREADS, FDK_ECAP, "cluster with %d incidences exceeds %d threads / %d", p.cap_inc,
+              THREADS, TPI);
+  FDK_REQUIRE(p.cap_te < 4096 && p.cap_tn <= 256 && p.cap_owned < 255 && p.cap_ent < 65536 && p.cap_slots < 65535,
+              FDK_ECAP, "cluster capacity overflow (te=%d tn=%d owned=%d ent=%d slots=%d)", p.cap_te, p.cap_tn,
+              p.cap_owned, p.cap_ent, p.cap_slots);
+  FDK_REQUIRE(p.nvar == IL::NV, FDK_EINVAL, "plan nvar %d does not match the operator (%d)", p.nvar, IL::NV);
+  const size_t smem = IL::smem_bytes(p);
+  FDK_REQUIRE(smem <= 227 * 1024, FDK_ECAP, "cluster needs %zu bytes of shared memory (> 227 KB)", smem);
+  if (p.n_clusters == 0) return 0;
+  if (int rc = ensure_device_tables()) return rc;
+  auto kern = k_assemble_iso<El, THREADS, TPI>;
+  static thread_local size_t smem_set = 0;
+  if (smem > smem_set) {
+    FDK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  static thread_local int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    FDK_CUDA(cudaGetDevice(&dev));
+    FDK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = p.n_clusters < sms ? p.n_clusters : sms;  // persistent: one CTA per SM
+  kern<<<grid, THREADS, smem, stream>>>(a);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fdk

@@ -309,7 +309,8 @@ def test_hex8_properties_large(fd, n):
     assert K.has_sorted_indices
     scale = np.abs(K.data).max()
     assert nrm(D, -(K @ U)) <= 1e-11
-    assert np.abs((K - K.T).data).max() <= 1e-11 * scale
+    asym = (K - K.T).data  # empty when K is exactly symmetric (scipy drops the zeros)
+    assert asym.size == 0 or np.abs(asym).max() <= 1e-11 * scale
     nn = n**3
     for v in range(3):
         t = np.zeros(3 * nn)
