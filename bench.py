@@ -307,6 +307,10 @@ def run_b200(args):
         except Exception:
             traffic = None
 
+    from fedoo_b200 import _lib as _fdk_lib
+
+    kernel_name = ("fdk::k_assemble_iso<Hex8, 1024 threads, 4 per incidence>" if _fdk_lib.get_option("iso4")
+                   else "fdk::k_assemble<Hex8, PHYS_ISO>")  # fmt: skip
     checks = None
     if args.check and world == 1:
         checks = property_checks(asm, pb, U_host, n)
@@ -346,7 +350,9 @@ def run_b200(args):
                 "frac": achieved / peak,
                 "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s",
-                "kernel": "fdk::k_assemble<Hex8, PHYS_ISO>",
+                "kernel": kernel_name,
+                "binding_resource": "shared FP64 / shared-memory issue path of the SM (ncu: LSU data pipe + FP64 pipe "
+                "~ 98 % busy, DRAM ~ 11 %); see DESIGN.md section 7",
                 "kernel_ms": ms_kernel_max,
                 "algorithmic_bytes_per_launch": algo_bytes,
             },

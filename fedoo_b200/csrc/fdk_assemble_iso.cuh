@@ -25,7 +25,20 @@
 #pragma once
 #include "fdk_assemble.cuh"
 
+#ifndef FDK_P2_UNROLL
+#define FDK_P2_UNROLL 2  // Gauss points in flight per thread in the block phase (register budget: 64)
+#endif
+
 namespace fdk {
+
+constexpr int P2_UNROLL = FDK_P2_UNROLL;
+#ifndef FDK_ISO_PART_UNIFORM
+#define FDK_ISO_PART_UNIFORM 0
+#endif
+// 1: the threads of a warp work on 32 incidences and the same column part (columns part*NH ..., 128-bit column
+// loads shared by the lanes of an element); 0: the TPI threads of an incidence sit in adjacent lanes (columns
+// part, part + TPI, ...: own-row loads shared by TPI lanes)
+constexpr bool PART_UNIFORM = FDK_ISO_PART_UNIFORM != 0;
 
 template <class El, int TPI>
 struct IsoLayout {
@@ -40,7 +53,7 @@ struct IsoLayout {
   //    different banks (hex8: 76);
   //  * geometry: the own-row loads of the incidences of elements le and le+1 differ by ESTR + 3 (i - i'); with
   //    ESTR = 8 mod 16 they never collide (3 d = 8 mod 16 has no solution with |d| <= 7) (hex8: 216).
-  static constexpr int ISTR = (NNE == 8 && DIM == 3 && TPI == 4) ? 76 : L::ISTR;
+  static constexpr int ISTR = (NNE == 8 && DIM == 3 && TPI == 4 && !PART_UNIFORM) ? 76 : L::ISTR;
   static constexpr int ESTR = (NNE == 8 && DIM == 3) ? 216 : L::ESTR;
   static constexpr int TSTR = (GROW + 2) & ~1;  // even: the reference gradients are read as 128-bit node pairs
   static_assert(NNE % 2 == 0, "node pairs");
@@ -78,8 +91,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_assemble_iso(const __grid_consta
   const bool fuse_ku = a.fuse_ku != 0;
   // the TPI threads of an incidence sit in adjacent lanes: a warp covers 32 / TPI incidences of 2-3 elements
   // (element-major order), so its own-row loads touch 32 / TPI addresses and its column loads ~10
-  const int it = tid / TPI;         // incidence of this thread (phase 2)
-  const int part = tid - it * TPI;  // its column blocks: part, part + TPI, ...
+  const int it = PART_UNIFORM ? tid % INC : tid / TPI;    // incidence of this thread (phase 2)
+  const int part = PART_UNIFORM ? tid / INC : tid % TPI;  // its column blocks
+  // column block jj of this thread: part*NH + jj (contiguous) or part + jj*TPI (interleaved)
+  auto col = [&](int jj) { return PART_UNIFORM ? part * NH + jj : part + jj * TPI; };
 
   extern __shared__ __align__(16) double smem[];
   double* sdN = smem;              // [NGP][TSTR] reference gradients, [g][d][k]
@@ -266,22 +281,33 @@ __global__ void __launch_bounds__(THREADS, 1) k_assemble_iso(const __grid_consta
     if (it < n_inc) {
       const int le = my_desc & 0xFFF, i = my_desc >> 12;
       const double* gi_p = sG + le * ESTR + i * DIM;
-      const double* gj_p = sG + le * ESTR + part * DIM;
-#pragma unroll 2
+      const double* gj_p = sG + le * ESTR + col(0) * DIM;
+#pragma unroll P2_UNROLL
       for (int g = 0; g < NGP; ++g) {
         double gi[DIM];
 #pragma unroll
         for (int d = 0; d < DIM; ++d) gi[d] = gi_p[g * GSTR + d];
+        double gj[NH][DIM];
+        if constexpr (PART_UNIFORM && (NH * DIM) % 2 == 0) {  // contiguous columns: 128-bit loads
+          const double2* g2 = reinterpret_cast<const double2*>(gj_p + g * GSTR);
 #pragma unroll
-        for (int j = 0; j < NH; ++j) {
-          double gj[DIM];
+          for (int t = 0; t < NH * DIM / 2; ++t) {
+            const double2 v = g2[t];
+            gj[(2 * t) / DIM][(2 * t) % DIM] = v.x;
+            gj[(2 * t + 1) / DIM][(2 * t + 1) % DIM] = v.y;
+          }
+        } else {
 #pragma unroll
-          for (int d = 0; d < DIM; ++d) gj[d] = gj_p[g * GSTR + j * TPI * DIM + d];
+          for (int j = 0; j < NH; ++j)
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) gj[j][d] = gj_p[g * GSTR + (col(j) - col(0)) * DIM + d];
+        }
+#pragma unroll
+        for (int j = 0; j < NH; ++j)
 #pragma unroll
           for (int cc = 0; cc < DIM; ++cc)
 #pragma unroll
-            for (int aa = 0; aa < DIM; ++aa) acc[j][cc * DIM + aa] = fma(gi[cc], gj[aa], acc[j][cc * DIM + aa]);
-        }
+            for (int aa = 0; aa < DIM; ++aa) acc[j][cc * DIM + aa] = fma(gi[cc], gj[j][aa], acc[j][cc * DIM + aa]);
       }
     }
     if (has_next) fetch_inputs(nxt, buf ^ 1);  // lands during the gather
@@ -291,7 +317,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_assemble_iso(const __grid_consta
     if (it < n_inc) {
 #pragma unroll
       for (int j = 0; j < NH; ++j) {
-        double* sp = sBlk + it * ISTR + (part + j * TPI) * BLK;
+        double* sp = sBlk + it * ISTR + col(j) * BLK;
 #pragma unroll
         for (int b = 0; b < BLK; ++b) sp[b] = acc[j][b];
       }

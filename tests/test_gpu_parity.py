@@ -99,15 +99,18 @@ def test_elastic_against_reference(fd, golden_dir, name, elm, space):
 
 @pytest.mark.parametrize("name", ["hex8_cantilever", "hex8_jitter"])
 @pytest.mark.parametrize("small", [True, False])
-def test_hex8_tensor_core_producer(fd, golden_dir, name, small, monkeypatch):
-    """hex8 + isotropic law with the DMMA.8x8x4 producer (option 'mma') and with both cluster sizes:
-    same CSR values and residual as the reference; the CUDA-core producer agrees to rounding."""
+def test_hex8_kernel_variants(fd, golden_dir, name, small, monkeypatch):
+    """hex8 + isotropic law through every kernel variant -- the balanced 1024-thread kernel (option 'iso4',
+    the default for 32-node clusters), the DMMA.8x8x4 producer ('mma') and the CUDA-core producer of
+    k_assemble -- and with both cluster sizes: same CSR values and residual as the reference; the variants
+    agree with each other to rounding."""
     from fedoo_b200 import _lib
 
     monkeypatch.setenv("FDK_SMALL_CTA", "1" if small else "0")
     g = load(golden_dir, name)
     out = {}
-    for mma in (1, 0):
+    for variant, (iso4, mma) in {"iso4": (1, 1), "mma": (0, 1), "cuda_core": (0, 0)}.items():
+        _lib.set_option("iso4", iso4)
         _lib.set_option("mma", mma)
         try:
             law = fd.constitutivelaw.ElasticIsotrop(float(g["E"]), float(g["nu"]), name="law")
@@ -115,14 +118,16 @@ def test_hex8_tensor_core_producer(fd, golden_dir, name, small, monkeypatch):
             pb.set_X(g["U"])
             a.update(pb, compute="all")
             K = a.get_global_matrix().tocsr()
-            out[mma] = (K.data.copy(), np.array(a.get_global_vector()))
+            out[variant] = (K.data.copy(), np.array(a.get_global_vector()))
             assert np.array_equal(K.indptr, g["K_indptr"]) and np.array_equal(K.indices, g["K_indices"])
-            assert nrm(K.data, g["K_data"]) <= TOL and nrm(out[mma][1], g["D"]) <= TOL
+            assert nrm(K.data, g["K_data"]) <= TOL and nrm(out[variant][1], g["D"]) <= TOL
             a.assemble_global_mat("matrix")
             assert np.array_equal(a.get_global_matrix().tocsr().data, K.data)  # deterministic
         finally:
+            _lib.set_option("iso4", 1)
             _lib.set_option("mma", 1)
-    assert nrm(out[1][0], out[0][0]) <= 1e-14 and nrm(out[1][1], out[0][1]) <= 1e-13
+    for v in ("mma", "cuda_core"):
+        assert nrm(out["iso4"][0], out[v][0]) <= 1e-14 and nrm(out["iso4"][1], out[v][1]) <= 1e-13
 
 
 def test_zero_displacement_vector_is_scalar_zero(fd, golden_dir):
