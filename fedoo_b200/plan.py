@@ -79,24 +79,41 @@ def _part1by1(x):
 
 
 def morton_order(coords):
-    """Locality-preserving node order: per-axis rank buckets -> Morton key -> stable sort.
+    """Locality-preserving node order: per-axis buckets -> Morton key -> stable sort.
 
-    For a structured (even jittered) box the buckets are the lattice indices, so Morton
-    blocks are compact bricks of nodes."""
+    The number of buckets of an axis follows the bounding box (extent / mean node spacing), so a slab
+    that is half as thick as it is wide gets half as many buckets across: Morton blocks stay compact
+    bricks of nodes.  An axis whose sorted coordinates fall into well separated planes is bucketed by plane
+    (the lattice planes of a structured, even jittered, box), any other axis by equal-count rank buckets."""
     n, dim = coords.shape
-    nb = max(1, int(round(n ** (1.0 / dim))))
+    if n == 0:
+        e = torch.zeros(0, dtype=torch.int64, device=coords.device)
+        return e, e
+    lo, hi = coords.min(0).values, coords.max(0).values
+    ext = (hi - lo).to(torch.float64)
+    live = ext > 0
+    n_live = max(1, int(live.sum()))
+    vol = float(torch.prod(torch.where(live, ext, torch.ones_like(ext))))
+    h = (vol / n) ** (1.0 / n_live)  # mean node spacing
     comps = []
     for d in range(dim):
         x = coords[:, d]
-        n_unique = int(torch.unique(x).numel())
-        nbd = min(n_unique, nb)
-        if n_unique <= nb:  # structured axis: bucket = index of the coordinate value
-            _, inv = torch.unique(x, sorted=True, return_inverse=True)
-            comps.append(inv.to(torch.int64))
-        else:
-            rank = torch.empty(n, dtype=torch.int64, device=coords.device)
-            rank[torch.argsort(x, stable=True)] = torch.arange(n, device=coords.device)
-            comps.append(rank * nbd // n)
+        nbd = max(1, int(round(float(ext[d]) / h))) if bool(live[d]) else 1
+        # lattice planes: runs of the sorted coordinates separated by gaps of a good fraction of the mean
+        # spacing (exact for a structured axis, robust to a jitter of +-0.2 h)
+        xs, perm = torch.sort(x, stable=True)
+        big = torch.zeros(n, dtype=torch.int64, device=coords.device)
+        if n > 1:
+            big[1:] = ((xs[1:] - xs[:-1]) > 0.25 * h).to(torch.int64)
+        plane = torch.cumsum(big, 0)
+        n_planes = int(plane[-1]) + 1
+        if nbd // 2 <= n_planes <= 2 * nbd + 1:
+            comp = torch.empty(n, dtype=torch.int64, device=coords.device)
+            comp[perm] = plane
+        else:  # no plane structure: equal-count buckets by rank
+            comp = torch.empty(n, dtype=torch.int64, device=coords.device)
+            comp[perm] = torch.arange(n, device=coords.device) * nbd // n
+        comps.append(comp)
     if dim == 3:
         key = _part1by2(comps[0]) | (_part1by2(comps[1]) << 1) | (_part1by2(comps[2]) << 2)
     else:
@@ -164,10 +181,14 @@ class Plan:
         deg = pattern.blk_indptr[1:] - pattern.blk_indptr[:-1]
 
         # ---- Morton order with unique keys ----
-        order, mk = morton_order(coords)
         if owned is not None:
-            keep = owned.to(dev)[order]
-            order, mk = order[keep], mk[keep]
+            # only owned nodes get clusters: build the curve on THEIR lattice, so that the Morton blocks are
+            # aligned with the owned region (a z-slab starts one halo layer into the local mesh)
+            own_idx = torch.nonzero(owned.to(dev)).reshape(-1)
+            sub_order, mk = morton_order(coords[own_idx])
+            order = own_idx[sub_order]
+        else:
+            order, mk = morton_order(coords)
         n_mesh_nodes = n_nodes
         n_nodes = int(order.numel())  # from here on: number of OWNED nodes (cluster order)
         if n_nodes > 0:
