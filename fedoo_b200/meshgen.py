@@ -107,3 +107,39 @@ def jitter_nodes_2d(nodes, nx, ny, amplitude=0.2, seed=1):
     h = ext / np.array([nx - 1, ny - 1])
     nodes[interior] += rng.uniform(-amplitude, amplitude, size=(interior.size, 2)) * h
     return nodes
+
+
+def hole_plate_quad4(nr=11, nt=11, length=100.0, height=100.0, radius=20.0):
+    """Plate [-length/2, length/2] x [-height/2, height/2] with a central circular hole, as a ring of
+    8 (nr-1)(nt-1) quad4 (same counts as fd.mesh.hole_plate_mesh, fedoo/mesh/structured_mesh.py:247: nr
+    nodes from the hole to the outer edge, nt nodes on each half of an outer edge).  Nodes (t, r) with t
+    around the hole (periodic, 8 (nt-1) columns) and r outwards: a straight blend of the circle point at
+    the angle of the outer-edge point and that point."""
+    L, H = 0.5 * length, 0.5 * height
+    s = np.linspace(0.0, 1.0, nt)[:-1]  # along one half edge
+    # outer boundary, counter-clockwise from (L, 0): 8 half edges
+    corners = np.array([[L, 0], [L, H], [0, H], [-L, H], [-L, 0], [-L, -H], [0, -H], [L, -H], [L, 0]], dtype=float)
+    outer = np.concatenate([corners[k] + s[:, None] * (corners[k + 1] - corners[k]) for k in range(8)])
+    theta = np.arctan2(outer[:, 1], outer[:, 0])
+    inner = radius * np.stack([np.cos(theta), np.sin(theta)], axis=1)
+    r = np.linspace(0.0, 1.0, nr)
+    nodes = (inner[:, None, :] + r[None, :, None] * (outer - inner)[:, None, :]).reshape(-1, 2)  # index t*nr + r
+    n_t = len(outer)
+    t = np.arange(n_t, dtype=np.int64)[:, None]
+    k = np.arange(nr - 1, dtype=np.int64)[None, :]
+    tn = (t + 1) % n_t
+    elements = np.stack([t * nr + k, t * nr + k + 1, tn * nr + k + 1, tn * nr + k], axis=2).reshape(-1, 4)
+    return nodes, elements
+
+
+def extrude_quad4_to_hex8(nodes2d, quads, thickness, n_layers):
+    """Extrude a quad4 mesh along z into n_layers element layers of hex8 (node layer k at z = k thickness / n_layers;
+    hex8 local order = the quad at the lower layer, then at the upper one, fedoo/mesh/functions.py:272)."""
+    nodes2d = np.asarray(nodes2d, dtype=float)
+    quads = np.asarray(quads, dtype=np.int64)
+    n2 = len(nodes2d)
+    z = np.linspace(0.0, thickness, n_layers + 1)
+    nodes = np.concatenate([np.tile(nodes2d, (n_layers + 1, 1)), np.repeat(z, n2)[:, None]], axis=1)
+    lay = np.arange(n_layers, dtype=np.int64)[:, None, None] * n2
+    elements = np.concatenate([quads[None] + lay, quads[None] + lay + n2], axis=2).reshape(-1, 8)
+    return nodes, elements
