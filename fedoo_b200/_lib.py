@@ -113,7 +113,7 @@ def load():
 
 
 def set_option(key, value):
-    """Process-wide kernel option (include/fdk.h: fdk_set_option): 'fuse_ku', 'mma'."""
+    """Process-wide kernel option (include/fdk.h: fdk_set_option): 'fuse_ku', 'mma', 'iso4'."""
     check(load().fdk_set_option(key.encode(), int(value)), "fdk_set_option")
 
 

@@ -48,7 +48,9 @@ int fdk_version(void);
 
 /* Runtime options (process-wide): "fuse_ku" (default 1): for a linear law with K and D both requested the
  * residual is taken from the assembled rows, D = -K_row . U, instead of a second B^T sigma integration;
- * "mma" (default 1): hex8 + isotropic law, element matrices by FP64 tensor-core DMMA.m8n8k4. */
+ * "mma" (default 1): hex8 + isotropic law in the generic cluster kernel: element matrices by FP64 tensor-core
+ * DMMA.m8n8k4; "iso4" (default 1): hex8 + isotropic law + matrix requested (residual fused): the balanced
+ * 1024-thread kernel (4 threads per incidence) instead of the generic one. */
 int fdk_set_option(const char* key, int value);
 int fdk_get_option(const char* key, int* value);
 
