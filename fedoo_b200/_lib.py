@@ -20,6 +20,7 @@ EXPORTS = [
     "fdk_assemble_elastic_iso", "fdk_assemble_elastic_general", "fdk_assemble_heat",
     "fdk_gp_strain_stress", "fdk_gp_temperature", "fdk_j2_update",
     "fdk_gather_f64", "fdk_scatter_add_f64",
+    "fdk_csr_spmv", "fdk_csr_diagonal", "fdk_pcg_work_doubles", "fdk_pcg_jacobi",
 ]  # fmt: skip
 
 
@@ -103,11 +104,17 @@ def load():
     lib.fdk_gp_strain_stress.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.fdk_gp_temperature.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, vp]
     lib.fdk_j2_update.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp]
+    lib.fdk_csr_spmv.argtypes = [i64, i64, vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.fdk_csr_diagonal.argtypes = [i64, vp, vp, i32, vp, vp, vp]
+    lib.fdk_pcg_work_doubles.argtypes = [i64]
+    lib.fdk_pcg_jacobi.argtypes = [i64, i64, vp, vp, i32, vp, vp, vp, vp, dbl, i32, i32, vp, C.POINTER(i32),
+                                   C.POINTER(dbl), vp]
     lib.fdk_gather_f64.argtypes = [i64, vp, vp, vp, vp]
     lib.fdk_scatter_add_f64.argtypes = [i64, vp, vp, vp, vp]
     for name in EXPORTS:
-        if name not in ("fdk_last_error_string",):
+        if name not in ("fdk_last_error_string", "fdk_pcg_work_doubles"):
             getattr(lib, name).restype = i32
+    lib.fdk_pcg_work_doubles.restype = i64
     _lib = lib
     return lib
 

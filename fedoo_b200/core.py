@@ -191,7 +191,67 @@ class DeviceCSR:
             self.shape = (n, n)
             self._host = None
 
+    def _index_bytes(self):
+        assert self.indptr.dtype == self.indices.dtype, "indptr and indices share one integer type (scipy convention)"
+        return self.indptr.element_size()
+
+    def matvec(self, x, free_mask=None, out=None):
+        """y = A x on the device (csrc/fdk_solve.cuh); with ``free_mask`` (uint8 per dof, 0 = imposed) rows and
+        columns of imposed dofs are left out: the Dirichlet elimination of fedoo/core/problem.py:277-298
+        without forming MatCB^T A MatCB."""
+        from . import _lib
+
+        x = as_device_f64(x, self.data.device)
+        assert x.numel() == self.shape[1]
+        y = torch.empty(self.shape[0], dtype=torch.float64, device=self.data.device) if out is None else out
+        _lib.check(
+            _lib.load().fdk_csr_spmv(
+                self.shape[0], self.nnz, _lib.ptr(self.indptr), _lib.ptr(self.indices), self._index_bytes(),
+                _lib.ptr(self.data), _lib.ptr(x), _lib.ptr(free_mask), _lib.ptr(y), _lib.current_stream(),
+            ),
+            "fdk_csr_spmv",
+        )
+        return y
+
+    def diagonal_device(self):
+        from . import _lib
+
+        d = torch.empty(self.shape[0], dtype=torch.float64, device=self.data.device)
+        _lib.check(
+            _lib.load().fdk_csr_diagonal(
+                self.shape[0], _lib.ptr(self.indptr), _lib.ptr(self.indices), self._index_bytes(), _lib.ptr(self.data),
+                _lib.ptr(d), _lib.current_stream(),
+            ),
+            "fdk_csr_diagonal",
+        )
+        return d
+
+    def pcg(self, b, free_mask=None, rtol=1e-8, maxiter=None, check_every=10):
+        """Jacobi-preconditioned CG on the device (scipy.sparse.linalg.cg with M = diag(1 / A.diagonal()),
+        fedoo/core/base.py:521-537).  Returns (x, iterations, ||r|| / ||b||), x a device tensor."""
+        import ctypes as C
+
+        from . import _lib
+
+        lib = _lib.load()
+        n = self.shape[0]
+        b = as_device_f64(b, self.data.device)
+        x = torch.empty(n, dtype=torch.float64, device=self.data.device)
+        work = torch.empty(int(lib.fdk_pcg_work_doubles(n)), dtype=torch.float64, device=self.data.device)
+        it, rel = C.c_int(0), C.c_double(0.0)
+        _lib.check(
+            lib.fdk_pcg_jacobi(
+                n, self.nnz, _lib.ptr(self.indptr), _lib.ptr(self.indices), self._index_bytes(), _lib.ptr(self.data),
+                _lib.ptr(b), _lib.ptr(x), _lib.ptr(free_mask), float(rtol), int(10 * n if maxiter is None else maxiter),
+                int(check_every), _lib.ptr(work), C.byref(it), C.byref(rel), _lib.current_stream(),
+            ),
+            "fdk_pcg_jacobi",
+        )
+        return x, it.value, rel.value
+
     def __matmul__(self, x):
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            return self.matvec(x)
         return self.tocsr() @ x
 
     def __rmatmul__(self, x):

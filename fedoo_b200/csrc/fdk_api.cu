@@ -5,6 +5,7 @@
 #include "fdk_assemble.cuh"
 #include "fdk_assemble_iso.cuh"
 #include "fdk_gp.cuh"
+#include "fdk_solve.cuh"
 #include "fdk_symbolic.cuh"
 
 using namespace fdk;
@@ -262,6 +263,56 @@ int fdk_j2_update(int64_t n_gp, const double* props_h, const double* strain_gp, 
   k_j2_update<<<(unsigned)((n_gp + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
   FDK_CUDA(cudaGetLastError());
   return 0;
+}
+
+int fdk_csr_spmv(int64_t n_rows, int64_t nnz, const void* indptr, const void* indices, int index_bytes,
+                 const double* data, const double* x, const uint8_t* free_mask, double* y, fdk_stream_t stream) {
+  FDK_REQUIRE(n_rows >= 0 && nnz >= 0, FDK_EINVAL, "negative size");
+  if (n_rows == 0) return 0;
+  FDK_REQUIRE(indptr && x && y && (nnz == 0 || (indices && data)), FDK_EINVAL, "NULL argument");
+  FDK_REQUIRE(index_bytes == 4 || index_bytes == 8, FDK_EINVAL, "index_bytes must be 4 or 8");
+  const int lanes = pick_lanes(n_rows, nnz);
+  if (index_bytes == 4)
+    return launch_spmv<int32_t>(n_rows, (const int32_t*)indptr, (const int32_t*)indices, data, x, free_mask, y, lanes,
+                                (cudaStream_t)stream);
+  return launch_spmv<int64_t>(n_rows, (const int64_t*)indptr, (const int64_t*)indices, data, x, free_mask, y, lanes,
+                              (cudaStream_t)stream);
+}
+
+int fdk_csr_diagonal(int64_t n_rows, const void* indptr, const void* indices, int index_bytes, const double* data,
+                     double* diag, fdk_stream_t stream) {
+  FDK_REQUIRE(n_rows >= 0, FDK_EINVAL, "negative size");
+  if (n_rows == 0) return 0;
+  FDK_REQUIRE(indptr && indices && data && diag, FDK_EINVAL, "NULL argument");
+  FDK_REQUIRE(index_bytes == 4 || index_bytes == 8, FDK_EINVAL, "index_bytes must be 4 or 8");
+  const unsigned grid = (unsigned)((n_rows + 255) / 256);
+  if (index_bytes == 4)
+    k_csr_diagonal<int32_t><<<grid, 256, 0, (cudaStream_t)stream>>>(n_rows, (const int32_t*)indptr,
+                                                                      (const int32_t*)indices, data, diag);
+  else
+    k_csr_diagonal<int64_t><<<grid, 256, 0, (cudaStream_t)stream>>>(n_rows, (const int64_t*)indptr,
+                                                                      (const int64_t*)indices, data, diag);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int64_t fdk_pcg_work_doubles(int64_t n) { return 5 * n + 2 * RED_BLOCKS + S_COUNT; }
+
+int fdk_pcg_jacobi(int64_t n, int64_t nnz, const void* indptr, const void* indices, int index_bytes, const double* data,
+                   const double* b, double* x, const uint8_t* free_mask, double rtol, int max_iter, int check_every,
+                   double* work, int* iters_h, double* relres_h, fdk_stream_t stream) {
+  FDK_REQUIRE(n >= 0 && nnz >= 0 && max_iter >= 0 && rtol >= 0.0, FDK_EINVAL, "bad size or tolerance");
+  if (iters_h) *iters_h = 0;
+  if (relres_h) *relres_h = 0.0;
+  if (n == 0) return 0;
+  FDK_REQUIRE(indptr && indices && data && b && x && work, FDK_EINVAL, "NULL argument");
+  FDK_REQUIRE(index_bytes == 4 || index_bytes == 8, FDK_EINVAL, "index_bytes must be 4 or 8");
+  if (check_every < 1) check_every = 1;
+  if (index_bytes == 4)
+    return pcg_jacobi<int32_t>(n, nnz, (const int32_t*)indptr, (const int32_t*)indices, data, b, x, free_mask, rtol,
+                               max_iter, check_every, work, iters_h, relres_h, (cudaStream_t)stream);
+  return pcg_jacobi<int64_t>(n, nnz, (const int64_t*)indptr, (const int64_t*)indices, data, b, x, free_mask, rtol,
+                             max_iter, check_every, work, iters_h, relres_h, (cudaStream_t)stream);
 }
 
 int fdk_gather_f64(int64_t n, const int64_t* index, const double* src, double* dst, fdk_stream_t stream) {

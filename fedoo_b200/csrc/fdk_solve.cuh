@@ -1,0 +1,249 @@
+// fdk_solve.cuh -- what the callers of the assembly path do with K on the device:
+// CSR sparse matrix-vector product with Dirichlet masking, diagonal extraction and a Jacobi-preconditioned
+// conjugate gradient, so that Problem.solve() never has to bring the 23 GB matrix to the host.
+//
+// Reference: fedoo/core/problem.py:277-298 (elimination of the imposed dofs: MatCB^T A MatCB x = MatCB^T (B - A Xbc);
+// for pure Dirichlet conditions MatCB selects the free dofs, which is what the mask does here without forming
+// the product), fedoo/core/base.py:521-537 (scipy.sparse.linalg.cg with M = diag(1 / A.diagonal())).
+//
+// All kernels are HBM-bound streaming kernels: the SpMV reads 8 + index_bytes bytes per stored entry once
+// (values and column indices with ld.global.nc, coalesced: one sub-warp per row) and gathers x through L2;
+// the vector updates are fused so that every CG iteration reads / writes each vector once.  Reductions are
+// two-stage with a fixed block order (no floating-point atomics): results are bit-reproducible.
+#pragma once
+#include "fdk_common.cuh"
+
+namespace fdk {
+
+constexpr int RED_BLOCKS = 1184;  // 8 x 148: partial sums of the dot products
+constexpr int RED_THREADS = 256;
+
+template <class Idx, int LPR>  // LPR lanes per row (power of two <= 32)
+__global__ void __launch_bounds__(256) k_csr_spmv(int64_t n_rows, const Idx* __restrict__ indptr,
+                                                   const Idx* __restrict__ indices, const double* __restrict__ data,
+                                                   const double* __restrict__ x, const unsigned char* __restrict__ mask,
+                                                   double* __restrict__ y) {
+  constexpr int RPW = 32 / LPR;  // rows per warp
+  const int lane = threadIdx.x & (LPR - 1);
+  const int sub = (threadIdx.x & 31) / LPR;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t rb = warp * RPW; rb < n_rows; rb += n_warps * RPW) {  // warp-uniform trip count (shuffles below)
+    const int64_t r = rb + sub;
+    double s = 0.0;
+    const bool live = r < n_rows && (mask == nullptr || mask[r]);
+    if (live) {
+      const int64_t e0 = indptr[r], e1 = indptr[r + 1];
+      for (int64_t e = e0 + lane; e < e1; e += LPR) {
+        const int64_t c = indices[e];
+        if (mask == nullptr || mask[c]) s = fma(__ldg(data + e), x[c], s);
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, LPR);
+    if (lane == 0 && r < n_rows) y[r] = s;
+  }
+}
+
+template <class Idx>
+__global__ void k_csr_diagonal(int64_t n_rows, const Idx* __restrict__ indptr, const Idx* __restrict__ indices,
+                               const double* __restrict__ data, double* __restrict__ diag) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  // sorted columns (scipy canonical form): binary search of the diagonal entry
+  int64_t lo = indptr[r], hi = indptr[r + 1];
+  double d = 0.0;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const int64_t c = indices[mid];
+    if (c == r) {
+      d = data[mid];
+      break;
+    }
+    if (c < r) lo = mid + 1;
+    else hi = mid;
+  }
+  diag[r] = d;
+}
+
+// block-level sum in a fixed order; the result is valid in thread 0
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double sh[RED_THREADS / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < RED_THREADS / 32; ++w) s += sh[w];
+  }
+  __syncthreads();
+  return s;
+}
+
+// scal[k] = sum of the RED_BLOCKS partials part[k][*], k < n_sums (one block)
+__global__ void __launch_bounds__(RED_THREADS) k_reduce_final(const double* __restrict__ part, int n_sums,
+                                                              double* __restrict__ scal) {
+  for (int k = 0; k < n_sums; ++k) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < RED_BLOCKS; i += RED_THREADS) v += part[k * RED_BLOCKS + i];
+    const double s = block_sum(v);
+    if (threadIdx.x == 0) scal[k] = s;
+  }
+}
+
+// scalars on the device: 0 rz, 1 pq, 2 rz_new, 3 rr, 4 bb
+enum { S_RZ = 0, S_PQ = 1, S_RZN = 2, S_RR = 3, S_BB = 4, S_COUNT = 8 };
+
+// r = b (masked), z = dinv r, p = z; partials of rz, rr
+__global__ void __launch_bounds__(RED_THREADS) k_pcg_init(int64_t n, const double* __restrict__ b,
+                                                          const double* __restrict__ diag,
+                                                          const unsigned char* __restrict__ mask, double* __restrict__ x,
+                                                          double* __restrict__ r, double* __restrict__ z,
+                                                          double* __restrict__ p, double* __restrict__ part) {
+  double rz = 0.0, rr = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool live = mask == nullptr || mask[i];
+    const double ri = live ? b[i] : 0.0;
+    const double di = diag[i];
+    const double zi = (live && di != 0.0) ? ri / di : 0.0;
+    x[i] = 0.0;
+    r[i] = ri;
+    z[i] = zi;
+    p[i] = zi;
+    rz = fma(ri, zi, rz);
+    rr = fma(ri, ri, rr);
+  }
+  const double a = block_sum(rz), c = block_sum(rr);
+  if (threadIdx.x == 0) {
+    part[0 * RED_BLOCKS + blockIdx.x] = a;
+    part[1 * RED_BLOCKS + blockIdx.x] = c;
+  }
+}
+
+__global__ void __launch_bounds__(RED_THREADS) k_dot(int64_t n, const double* __restrict__ a,
+                                                     const double* __restrict__ b, double* __restrict__ part) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s = fma(a[i], b[i], s);
+  const double v = block_sum(s);
+  if (threadIdx.x == 0) part[blockIdx.x] = v;
+}
+
+// alpha = rz / pq; x += alpha p; r -= alpha q; z = dinv r; partials of rz_new, rr
+__global__ void __launch_bounds__(RED_THREADS) k_pcg_update(int64_t n, const double* __restrict__ scal,
+                                                            const double* __restrict__ diag,
+                                                            const unsigned char* __restrict__ mask,
+                                                            const double* __restrict__ p, const double* __restrict__ q,
+                                                            double* __restrict__ x, double* __restrict__ r,
+                                                            double* __restrict__ z, double* __restrict__ part) {
+  const double pq = scal[S_PQ];
+  const double alpha = pq != 0.0 ? scal[S_RZ] / pq : 0.0;
+  double rz = 0.0, rr = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool live = mask == nullptr || mask[i];
+    const double ri = live ? fma(-alpha, q[i], r[i]) : 0.0;
+    const double di = diag[i];
+    const double zi = (live && di != 0.0) ? ri / di : 0.0;
+    x[i] = fma(alpha, p[i], x[i]);
+    r[i] = ri;
+    z[i] = zi;
+    rz = fma(ri, zi, rz);
+    rr = fma(ri, ri, rr);
+  }
+  const double a = block_sum(rz), c = block_sum(rr);
+  if (threadIdx.x == 0) {
+    part[0 * RED_BLOCKS + blockIdx.x] = a;
+    part[1 * RED_BLOCKS + blockIdx.x] = c;
+  }
+}
+
+// beta = rz_new / rz; p = z + beta p; then rz <- rz_new (thread 0 of block 0, after everyone has read it:
+// the swap is done by the NEXT launch reading S_RZN, see pcg_jacobi)
+__global__ void __launch_bounds__(RED_THREADS) k_pcg_direction(int64_t n, const double* __restrict__ scal,
+                                                               const double* __restrict__ z, double* __restrict__ p) {
+  const double rz = scal[S_RZ];
+  const double beta = rz != 0.0 ? scal[S_RZN] / rz : 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = fma(beta, p[i], z[i]);
+}
+
+__global__ void k_copy_scalar(double* scal, int dst, int src) { scal[dst] = scal[src]; }
+
+template <class Idx>
+int launch_spmv(int64_t n_rows, const Idx* indptr, const Idx* indices, const double* data, const double* x,
+                const unsigned char* mask, double* y, int lanes_per_row, cudaStream_t stream) {
+  if (n_rows == 0) return 0;
+  const int threads = 256;
+  auto grid_for = [&](int lpr) {
+    const int64_t need = (n_rows * lpr + threads - 1) / threads;
+    const int64_t cap = 148 * 16;  // grid-stride beyond a few waves
+    return (unsigned)(need < cap ? need : cap);
+  };
+  switch (lanes_per_row) {
+    case 32: k_csr_spmv<Idx, 32><<<grid_for(32), threads, 0, stream>>>(n_rows, indptr, indices, data, x, mask, y); break;
+    case 16: k_csr_spmv<Idx, 16><<<grid_for(16), threads, 0, stream>>>(n_rows, indptr, indices, data, x, mask, y); break;
+    case 8: k_csr_spmv<Idx, 8><<<grid_for(8), threads, 0, stream>>>(n_rows, indptr, indices, data, x, mask, y); break;
+    default: k_csr_spmv<Idx, 4><<<grid_for(4), threads, 0, stream>>>(n_rows, indptr, indices, data, x, mask, y); break;
+  }
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+inline int pick_lanes(int64_t n_rows, int64_t nnz) {
+  const double avg = n_rows > 0 ? (double)nnz / (double)n_rows : 0.0;
+  return avg >= 48 ? 32 : avg >= 24 ? 16 : avg >= 10 ? 8 : 4;
+}
+
+// Jacobi-PCG on the free dofs.  work: 5 n doubles (r, z, p, q, diag) + (2 RED_BLOCKS + S_COUNT) doubles.
+template <class Idx>
+int pcg_jacobi(int64_t n, int64_t nnz, const Idx* indptr, const Idx* indices, const double* data, const double* b,
+               double* x, const unsigned char* mask, double rtol, int max_iter, int check_every, double* work,
+               int* iters_h, double* relres_h, cudaStream_t stream) {
+  double* r = work;
+  double* z = r + n;
+  double* p = z + n;
+  double* q = p + n;
+  double* diag = q + n;
+  double* part = diag + n;
+  double* scal = part + 2 * RED_BLOCKS;
+  const int lanes = pick_lanes(n, nnz);
+  k_csr_diagonal<Idx><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, indptr, indices, data, diag);
+  k_pcg_init<<<RED_BLOCKS, RED_THREADS, 0, stream>>>(n, b, diag, mask, x, r, z, p, part);
+  k_reduce_final<<<1, RED_THREADS, 0, stream>>>(part, 2, scal + S_RZN);  // S_RZN = rz, S_RR = rr
+  k_copy_scalar<<<1, 1, 0, stream>>>(scal, S_RZ, S_RZN);
+  k_copy_scalar<<<1, 1, 0, stream>>>(scal, S_BB, S_RR);
+  FDK_CUDA(cudaGetLastError());
+  double h[S_COUNT];
+  FDK_CUDA(cudaMemcpyAsync(h, scal, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  FDK_CUDA(cudaStreamSynchronize(stream));
+  const double bb = h[S_BB];
+  int it = 0;
+  double rr = bb;
+  if (bb > 0.0) {
+    const double target = rtol * rtol * bb;
+    while (it < max_iter) {
+      if (int rc = launch_spmv<Idx>(n, indptr, indices, data, p, mask, q, lanes, stream)) return rc;
+      k_dot<<<RED_BLOCKS, RED_THREADS, 0, stream>>>(n, p, q, part);
+      k_reduce_final<<<1, RED_THREADS, 0, stream>>>(part, 1, scal + S_PQ);
+      k_pcg_update<<<RED_BLOCKS, RED_THREADS, 0, stream>>>(n, scal, diag, mask, p, q, x, r, z, part);
+      k_reduce_final<<<1, RED_THREADS, 0, stream>>>(part, 2, scal + S_RZN);
+      k_pcg_direction<<<RED_BLOCKS, RED_THREADS, 0, stream>>>(n, scal, z, p);
+      k_copy_scalar<<<1, 1, 0, stream>>>(scal, S_RZ, S_RZN);
+      ++it;
+      if (it % check_every == 0 || it == max_iter) {
+        FDK_CUDA(cudaMemcpyAsync(h, scal, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        FDK_CUDA(cudaStreamSynchronize(stream));
+        rr = h[S_RR];
+        if (!(rr > target)) break;  // also leaves on NaN
+      }
+    }
+    FDK_CUDA(cudaGetLastError());
+  }
+  if (iters_h) *iters_h = it;
+  if (relres_h) *relres_h = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+  return 0;
+}
+
+}  // namespace fdk

@@ -2,9 +2,11 @@
 assembly path (fedoo/problem/linear.py:7-100, fedoo/problem/non_linear.py:13-224,
 fedoo/core/problem.py:18-120).  They hold the dof vector, drive the assembly lifecycle and
 expose Dirichlet conditions.  The sparse solve is out of scope of the accelerated path
-(BASELINE.json north_star); ``solve()`` eliminates Dirichlet dofs and calls SciPy on the host
-exactly like the reference's fallback solver (fedoo/core/base.py:521-537), so that the
-reference's known-answer tests can be replayed end to end.
+(BASELINE.json north_star); by default ``solve()`` eliminates Dirichlet dofs and calls SciPy on the
+host like the reference's direct solver, so that the reference's known-answer tests can be
+replayed end to end.  ``set_solver("cg")`` (fedoo/core/base.py:444-519: the reference's iterative
+option, scipy cg with a Jacobi preconditioner :521-537) runs the elimination and the Krylov loop on
+the DEVICE instead (csrc/fdk_solve.cuh): K never leaves HBM.
 """
 
 from __future__ import annotations
@@ -43,7 +45,53 @@ class _ProblemBase(_Named):
         self.nlgeom = False
         self.time = 0
         self.dtime = 0
+        self._solver = ("direct", True, {})
+        self.solver_info = None
         self._register(name)
+
+    def set_solver(self, solver="direct", precond=True, **kargs):
+        """fedoo/core/base.py:444-519.  "direct" / "direct_scipy": host spsolve; "cg": Jacobi-preconditioned CG on
+        the device (kargs: rtol / tol, maxiter)."""
+        solver = solver.lower()
+        if solver in ("direct", "direct_scipy"):
+            solver = "direct"
+        elif solver != "cg":
+            raise NameError("Choosen solver not available")
+        self._solver = (solver, bool(precond), dict(kargs))
+
+    def _solve(self, A, D, X0=None):
+        if self._solver[0] == "cg":
+            return self._solve_device(A, D, X0)
+        return self._solve_host(A, D, X0)
+
+    def _solve_device(self, A, D, X0=None):
+        """A dX = D with the imposed dofs eliminated, on the device: rhs = (D - A Xbc) on the free dofs, then
+        Jacobi-PCG restricted to them (fedoo/core/problem.py:277-298, fedoo/core/base.py:521-537)."""
+        import torch
+
+        from .core import as_device_f64
+
+        if self._dirichlet is None:
+            self.apply_boundary_conditions()
+        dofs, vals = self._dirichlet
+        n = A.shape[0]
+        dev = A.data.device
+        Xbc = torch.zeros(n, dtype=torch.float64, device=dev)
+        free = torch.ones(n, dtype=torch.uint8, device=dev)
+        if len(dofs):
+            d_dofs = torch.from_numpy(dofs).to(dev)
+            imposed = vals if X0 is None else vals - np.asarray(X0)[dofs]
+            Xbc[d_dofs] = torch.from_numpy(np.ascontiguousarray(imposed, dtype=float)).to(dev)
+            free[d_dofs] = 0
+        rhs = torch.zeros(n, dtype=torch.float64, device=dev) if np.isscalar(D) else as_device_f64(D, dev).clone()
+        rhs -= A.matvec(Xbc)
+        kargs = self._solver[2]
+        rtol = kargs.get("rtol", kargs.get("tol", 1e-8))
+        x, it, rel = A.pcg(rhs, free_mask=free, rtol=rtol, maxiter=kargs.get("maxiter"))
+        self.solver_info = {"iterations": it, "relative_residual": rel}
+        if rel > rtol:
+            print(f"Warning: cg solver convergence to tolerance not achieved ({rel:.2e} after {it} iterations)")
+        return (x + Xbc).cpu().numpy()
 
     @property
     def n_dof(self):
@@ -120,7 +168,7 @@ class Linear(_ProblemBase):
         A = self.assembly.get_global_matrix()
         D = self.assembly.get_global_vector()
         X0 = None if np.isscalar(self._X) else np.asarray(self._X)
-        dX = self._solve_host(A, D, X0)
+        dX = self._solve(A, D, X0)
         self._X = dX if X0 is None else X0 + dX
         if kargs.pop("updateWF", True):
             self.update(compute="none")
@@ -172,7 +220,7 @@ class NonLinear(_ProblemBase):
             self.set_start()
             A, D = self.assembly.get_global_matrix(), self.assembly.get_global_vector()
             X0 = np.zeros(self.n_dof) if np.isscalar(self._U) else np.asarray(self._U)
-            self._dU = self._solve_host(A, D, X0)  # elastic prediction with the imposed values
+            self._dU = self._solve(A, D, X0)  # elastic prediction with the imposed values
             for _ in range(max_subiter):
                 self.update(compute="all")
                 D = self.assembly.get_global_vector()
@@ -181,7 +229,7 @@ class NonLinear(_ProblemBase):
                 res[dofs] = 0.0
                 if np.linalg.norm(res) <= tol * max(np.linalg.norm(D), 1e-300):
                     break
-                corr = self._solve_host(self.assembly.get_global_matrix(), D, X0 + self._dU)
+                corr = self._solve(self.assembly.get_global_matrix(), D, X0 + self._dU)
                 self._dU = self._dU + corr
             self._U = X0 + self._dU
             self._dU = 0

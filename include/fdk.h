@@ -204,6 +204,31 @@ int fdk_j2_update(int64_t n_gp, const double* props_h, const double* strain_gp, 
                   double* stress_gp, double* statev, double* tangent_gp, fdk_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
+ * What the callers of the assembly do with K, on the device.  Replaces the
+ * host-side elimination + solve of Problem.solve (fedoo/core/problem.py:277-298: MatCB^T A MatCB,
+ * B - A Xbc; fedoo/core/base.py:521-537: scipy cg with M = diag(1 / A.diagonal())) for pure
+ * Dirichlet conditions.  CSR with float64 values; index_bytes = 4 (int32) or 8 (int64) for BOTH
+ * indptr and indices (scipy's convention); free_mask: one byte per dof, 0 = imposed, or NULL.
+ * ------------------------------------------------------------------------- */
+
+/* y = A x restricted to the free dofs: y[r] = sum over free columns c of A[r,c] x[c] for free rows, 0 otherwise. */
+int fdk_csr_spmv(int64_t n_rows, int64_t nnz, const void* indptr, const void* indices, int index_bytes,
+                 const double* data, const double* x, const uint8_t* free_mask, double* y, fdk_stream_t stream);
+
+/* diag[r] = A[r,r] (0 if not stored); columns sorted within a row (the pattern of fdk_sym_expand_csr is). */
+int fdk_csr_diagonal(int64_t n_rows, const void* indptr, const void* indices, int index_bytes, const double* data,
+                     double* diag, fdk_stream_t stream);
+
+/* Jacobi-preconditioned conjugate gradient for A x = b on the free dofs, x = 0 initially and on the imposed
+ * dofs; stops when ||r|| <= rtol ||b|| (checked every check_every iterations) or after max_iter iterations.
+ * work: fdk_pcg_work_doubles(n) doubles of device scratch.  iters_h / relres_h (host, may be NULL) receive the
+ * iteration count and ||r|| / ||b||.  Synchronises the stream (it reads the residual norm back). */
+int64_t fdk_pcg_work_doubles(int64_t n);
+int fdk_pcg_jacobi(int64_t n, int64_t nnz, const void* indptr, const void* indices, int index_bytes, const double* data,
+                   const double* b, double* x, const uint8_t* free_mask, double rtol, int max_iter, int check_every,
+                   double* work, int* iters_h, double* relres_h, fdk_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
  * Multi-GPU helpers: pack / unpack-add of owned or halo entries around an NCCL
  * exchange of the global vector (no reference counterpart: the reference is
  * single-process).

@@ -340,3 +340,80 @@ def test_c_abi_error_paths(fd):
         m = fd.Mesh(np.zeros((4, 3)), np.zeros((1, 3), dtype=int), "tri3", name="bad")
         law = fd.constitutivelaw.ElasticIsotrop(1.0, 0.3, name="law")
         fd.Assembly.create(fd.weakform.StressEquilibrium(law, name="wfbad"), m)
+
+
+# ----------------------------------------------------------------------------------------------
+# what Problem.solve does with K, on the device (csrc/fdk_solve.cuh)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("index_dtype", ["int32", "int64"])
+def test_csr_spmv_and_diagonal_against_scipy(fd, golden_dir, index_dtype):
+    """Device SpMV (plain and with the Dirichlet mask) and diagonal vs scipy on the reference's own K."""
+    import torch
+    from scipy import sparse
+
+    from fedoo_b200.core import DeviceCSR
+
+    g = load(golden_dir, "hex8_jitter")
+    K = sparse.csr_matrix((g["K_data"], g["K_indices"], g["K_indptr"]))
+    n = K.shape[0]
+    idt = getattr(torch, index_dtype)
+    A = DeviceCSR(torch.from_numpy(K.indptr).cuda().to(idt), torch.from_numpy(K.indices).cuda().to(idt),
+                  torch.from_numpy(K.data).cuda(), K.shape)  # fmt: skip
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(n)
+    assert nrm(A.matvec(x).cpu().numpy(), K @ x) <= 1e-14
+    assert np.array_equal(A.diagonal_device().cpu().numpy(), K.diagonal())
+    free = np.ones(n, dtype=np.uint8)
+    free[rng.choice(n, n // 7, replace=False)] = 0
+    ref = (K @ (x * free)) * free  # rows and columns of the imposed dofs left out
+    got = A.matvec(x, free_mask=torch.from_numpy(free).cuda()).cpu().numpy()
+    assert nrm(got, ref) <= 1e-14
+    assert (A @ torch.from_numpy(x).cuda()).is_cuda  # device operand -> device product
+
+
+def test_cantilever_known_answer_device_cg(fd, golden_dir):
+    """The reference's cantilever test again, with the elimination and the Krylov solve on the device
+    (pb.set_solver("cg"), fedoo/core/base.py:444-537): same solution as the reference's direct solve."""
+    g = load(golden_dir, "hex8_cantilever")
+    fd.Assembly.delete_memory()
+    fd.ModelingSpace("3D")
+    mesh = fd.mesh.box_mesh(nx=11, ny=5, nz=5, x_min=0, x_max=1000, y_min=0, y_max=100, z_min=0, z_max=100,
+                            elm_type="hex8", name="Domain")  # fmt: skip
+    fd.constitutivelaw.ElasticIsotrop(200e3, 0.3, name="ElasticLaw")
+    fd.weakform.StressEquilibrium("ElasticLaw", name="weakform")
+    fd.Assembly.create("weakform", "Domain", "hex8", name="Assembling")
+    pb = fd.problem.Linear("Assembling")
+    pb.set_solver("cg", rtol=1e-13)
+    for var, val in (("DispX", 0), ("DispY", 0), ("DispZ", 0)):
+        pb.bc.add("Dirichlet", mesh.node_sets["left"], var, val)
+    pb.bc.add("Dirichlet", mesh.node_sets["right"], "DispY", -10)
+    pb.apply_boundary_conditions()
+    pb.solve()
+    assert pb.solver_info["relative_residual"] <= 1e-13 and 0 < pb.solver_info["iterations"] < 5000
+    assert nrm(pb.get_dof_solution("all"), g["U_sol"]) <= 1e-9
+    assert nrm(fd.Assembly["Assembling"].sv["Stress"].asarray(), g["stress_gp_sol"]) <= 1e-8
+
+
+def test_device_cg_matches_host_direct(fd):
+    """A jittered 14^3-node box pulled at one end: device PCG == host spsolve; deterministic (bitwise) reruns."""
+    fd.Assembly.delete_memory()
+    fd.ModelingSpace("3D")
+    n = 14
+    nodes, elements = fd.meshgen.box_hex8(n, n, n)
+    nodes = fd.meshgen.jitter_nodes(nodes, n, n, n)
+    mesh = fd.Mesh(nodes, elements, "hex8", node_sets=fd.meshgen.box_node_sets(n, n, n), name="Domain")
+    fd.constitutivelaw.ElasticIsotrop(200e3, 0.3, name="law")
+    fd.weakform.StressEquilibrium("law", name="wf")
+    fd.Assembly.create("wf", "Domain", "hex8", name="A")
+    sols = []
+    for solver in ("direct", "cg", "cg"):
+        pb = fd.problem.Linear("A", name=f"pb_{solver}_{len(sols)}")
+        pb.set_solver(solver, rtol=1e-12)
+        for var in ("DispX", "DispY", "DispZ"):
+            pb.bc.add("Dirichlet", mesh.node_sets["left"], var, 0)
+        pb.bc.add("Dirichlet", mesh.node_sets["right"], "DispX", 0.01)
+        pb.apply_boundary_conditions()
+        pb.solve()
+        sols.append(np.array(pb.get_dof_solution("all")))
+    assert nrm(sols[1], sols[0]) <= 1e-9
+    assert np.array_equal(sols[1], sols[2])
