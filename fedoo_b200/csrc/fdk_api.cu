@@ -273,9 +273,9 @@ int fdk_csr_spmv(int64_t n_rows, int64_t nnz, const void* indptr, const void* in
   FDK_REQUIRE(index_bytes == 4 || index_bytes == 8, FDK_EINVAL, "index_bytes must be 4 or 8");
   const int lanes = pick_lanes(n_rows, nnz);
   if (index_bytes == 4)
-    return launch_spmv<int32_t>(n_rows, (const int32_t*)indptr, (const int32_t*)indices, data, x, free_mask, y, lanes,
+    return launch_spmv<int32_t, true>(n_rows, (const int32_t*)indptr, (const int32_t*)indices, data, x, free_mask, y, lanes,
                                 (cudaStream_t)stream);
-  return launch_spmv<int64_t>(n_rows, (const int64_t*)indptr, (const int64_t*)indices, data, x, free_mask, y, lanes,
+  return launch_spmv<int64_t, true>(n_rows, (const int64_t*)indptr, (const int64_t*)indices, data, x, free_mask, y, lanes,
                               (cudaStream_t)stream);
 }
 

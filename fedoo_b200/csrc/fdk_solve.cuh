@@ -18,12 +18,14 @@ namespace fdk {
 constexpr int RED_BLOCKS = 1184;  // 8 x 148: partial sums of the dot products
 constexpr int RED_THREADS = 256;
 
-template <class Idx, int LPR>  // LPR lanes per row (power of two <= 32)
+// MASK_COLS = false: the caller guarantees x == 0 on the imposed dofs (the CG direction is), only rows are masked.
+template <class Idx, int LPR, bool MASK_COLS>  // LPR lanes per row (power of two <= 32)
 __global__ void __launch_bounds__(256) k_csr_spmv(int64_t n_rows, const Idx* __restrict__ indptr,
                                                    const Idx* __restrict__ indices, const double* __restrict__ data,
                                                    const double* __restrict__ x, const unsigned char* __restrict__ mask,
                                                    double* __restrict__ y) {
   constexpr int RPW = 32 / LPR;  // rows per warp
+  constexpr int UN = 4;          // entries per lane in flight: all index / value loads, then all gathers
   const int lane = threadIdx.x & (LPR - 1);
   const int sub = (threadIdx.x & 31) / LPR;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -33,10 +35,26 @@ __global__ void __launch_bounds__(256) k_csr_spmv(int64_t n_rows, const Idx* __r
     double s = 0.0;
     const bool live = r < n_rows && (mask == nullptr || mask[r]);
     if (live) {
-      const int64_t e0 = indptr[r], e1 = indptr[r + 1];
-      for (int64_t e = e0 + lane; e < e1; e += LPR) {
-        const int64_t c = indices[e];
-        if (mask == nullptr || mask[c]) s = fma(__ldg(data + e), x[c], s);
+      const int64_t e0 = __ldg(indptr + r), e1 = __ldg(indptr + r + 1);
+      for (int64_t eb = e0 + lane; eb < e1; eb += UN * LPR) {
+        int64_t c[UN];
+        double v[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const int64_t e = eb + u * LPR;
+          const bool in = e < e1;
+          c[u] = in ? (int64_t)__ldg(indices + e) : -1;
+          v[u] = in ? __ldg(data + e) : 0.0;
+        }
+        double xv[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          bool take = c[u] >= 0;
+          if (MASK_COLS) take = take && (mask == nullptr || mask[c[u]]);
+          xv[u] = take ? __ldg(x + c[u]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) s = fma(v[u], xv[u], s);
       }
     }
 #pragma unroll
@@ -171,21 +189,21 @@ __global__ void __launch_bounds__(RED_THREADS) k_pcg_direction(int64_t n, const 
 
 __global__ void k_copy_scalar(double* scal, int dst, int src) { scal[dst] = scal[src]; }
 
-template <class Idx>
+template <class Idx, bool MASK_COLS>
 int launch_spmv(int64_t n_rows, const Idx* indptr, const Idx* indices, const double* data, const double* x,
                 const unsigned char* mask, double* y, int lanes_per_row, cudaStream_t stream) {
   if (n_rows == 0) return 0;
   const int threads = 256;
   auto grid_for = [&](int lpr) {
     const int64_t need = (n_rows * lpr + threads - 1) / threads;
-    const int64_t cap = 148 * 16;  // grid-stride beyond a few waves
+    const int64_t cap = 148 * 32;  // grid-stride beyond a few waves
     return (unsigned)(need < cap ? need : cap);
   };
   switch (lanes_per_row) {
-    case 32: k_csr_spmv<Idx, 32><<<grid_for(32), threads, 0, stream>>>(n_rows, indptr, indices, data, x, mask, y); break;
-    case 16: k_csr_spmv<Idx, 16><<<grid_for(16), threads, 0, stream>>>(n_rows, indptr, indices, data, x, mask, y); break;
-    case 8: k_csr_spmv<Idx, 8><<<grid_for(8), threads, 0, stream>>>(n_rows, indptr, indices, data, x, mask, y); break;
-    default: k_csr_spmv<Idx, 4><<<grid_for(4), threads, 0, stream>>>(n_rows, indptr, indices, data, x, mask, y); break;
+    case 32: k_csr_spmv<Idx, 32, MASK_COLS><<<grid_for(32), threads, 0, stream>>>(n_rows, indptr, indices, data, x, mask, y); break;
+    case 16: k_csr_spmv<Idx, 16, MASK_COLS><<<grid_for(16), threads, 0, stream>>>(n_rows, indptr, indices, data, x, mask, y); break;
+    case 8: k_csr_spmv<Idx, 8, MASK_COLS><<<grid_for(8), threads, 0, stream>>>(n_rows, indptr, indices, data, x, mask, y); break;
+    default: k_csr_spmv<Idx, 4, MASK_COLS><<<grid_for(4), threads, 0, stream>>>(n_rows, indptr, indices, data, x, mask, y); break;
   }
   FDK_CUDA(cudaGetLastError());
   return 0;
@@ -193,7 +211,8 @@ int launch_spmv(int64_t n_rows, const Idx* indptr, const Idx* indices, const dou
 
 inline int pick_lanes(int64_t n_rows, int64_t nnz) {
   const double avg = n_rows > 0 ? (double)nnz / (double)n_rows : 0.0;
-  return avg >= 48 ? 32 : avg >= 24 ? 16 : avg >= 10 ? 8 : 4;
+  // a lane keeps 4 entries in flight: 81-entry elasticity rows fit one pass of 32 lanes, 27-entry rows one of 8
+  return avg >= 64 ? 32 : avg >= 32 ? 16 : avg >= 16 ? 8 : 4;
 }
 
 // Jacobi-PCG on the free dofs.  work: 5 n doubles (r, z, p, q, diag) + (2 RED_BLOCKS + S_COUNT) doubles.
@@ -224,7 +243,8 @@ int pcg_jacobi(int64_t n, int64_t nnz, const Idx* indptr, const Idx* indices, co
   if (bb > 0.0) {
     const double target = rtol * rtol * bb;
     while (it < max_iter) {
-      if (int rc = launch_spmv<Idx>(n, indptr, indices, data, p, mask, q, lanes, stream)) return rc;
+      // p vanishes on the imposed dofs by construction: only the rows need the mask
+      if (int rc = launch_spmv<Idx, false>(n, indptr, indices, data, p, mask, q, lanes, stream)) return rc;
       k_dot<<<RED_BLOCKS, RED_THREADS, 0, stream>>>(n, p, q, part);
       k_reduce_final<<<1, RED_THREADS, 0, stream>>>(part, 1, scal + S_PQ);
       k_pcg_update<<<RED_BLOCKS, RED_THREADS, 0, stream>>>(n, scal, diag, mask, p, q, x, r, z, part);
