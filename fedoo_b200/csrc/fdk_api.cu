@@ -147,6 +147,8 @@ int fdk_assemble_elastic_iso(const fdk_plan* plan, int compute, const double* co
   a.no_mma = g_opt_mma ? 0 : 1;
   // headline case: matrix requested and no B^T sigma pass -> balanced kernel (fdk_assemble_iso.cuh)
   const bool bts = (compute & FDK_VECTOR) && !a.fuse_ku;
+  // (the template also compiles and passes parity for tet4 / tet10 / quad4 and for 16-node hex8 clusters, but was
+  // measured slower than k_assemble on tet10 -- 64 vs 55 ms at 5 M elements -- and is unmeasured on the others)
   if (g_opt_iso4 && (compute & FDK_MATRIX) && !bts && plan->elem_type == FDK_HEX8 && plan->threads == Hex8::THREADS)
     return launch_assemble_iso<Hex8, 1024, 4>(a, (cudaStream_t)stream);
   return dispatch_assemble<PHYS_ISO>(a, (cudaStream_t)stream);

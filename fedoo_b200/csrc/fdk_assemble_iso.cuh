@@ -81,7 +81,7 @@ struct IsoLayout {
 };
 
 template <class El, int THREADS, int TPI>
-__global__ void __launch_bounds__(THREADS, 1) k_assemble_iso(const __grid_constant__ AsmArgs a) {
+__global__ void __launch_bounds__(THREADS, (1024 / THREADS > 0 ? 1024 / THREADS : 1)) k_assemble_iso(const __grid_constant__ AsmArgs a) {
   using IL = IsoLayout<El, TPI>;
   constexpr int NNE = IL::NNE, NGP = IL::NGP, DIM = IL::DIM, NV = IL::NV, BLK = IL::BLK, ISTR = IL::ISTR;
   constexpr int GROW = IL::GROW, GSTR = IL::GSTR, ESTR = IL::ESTR, TSTR = IL::TSTR, NH = IL::NH, XSTR = IL::XSTR;
@@ -464,13 +464,16 @@ int launch_assemble_iso(AsmArgs& a, cudaStream_t stream) {
     FDK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  static thread_local int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
+  // persistent CTAs: as many as are resident at once (one per SM for the 1024-thread variants)
+  static thread_local int resident = 0;
+  if (resident == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
     FDK_CUDA(cudaGetDevice(&dev));
     FDK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+    resident = sms * (per_sm > 0 ? per_sm : 1);
   }
-  const int grid = p.n_clusters < sms ? p.n_clusters : sms;  // persistent: one CTA per SM
+  const int grid = p.n_clusters < resident ? p.n_clusters : resident;
   kern<<<grid, THREADS, smem, stream>>>(a);
   FDK_CUDA(cudaGetLastError());
   return 0;

@@ -251,6 +251,15 @@ def main():
             line = fn(args.scale if name != "thermal" else args.scale ** (1 / 3))
         except Exception as e:  # report and go on with the next configuration
             line = dict(config=name, error=f"{type(e).__name__}: {e}")
+        if "clk" in os.environ.get("FDK_LIB", ""):  # diagnostic build: SM cycles per phase of the cluster kernel
+            import ctypes as C
+
+            from fedoo_b200 import _lib
+
+            out = (C.c_ulonglong * 16)()
+            _lib.check(_lib.load().fdk_debug_phase_clocks(out, 16, 1), "phase clocks")
+            tot = max(1, sum(out[:10]))
+            line["phase_clock_shares"] = {str(i): round(out[i] / tot, 3) for i in range(10) if out[i]}
         line["wall_s"] = time.perf_counter() - t0
         line["scale"] = args.scale
         print(json.dumps(line), flush=True)
