@@ -314,6 +314,24 @@ class Assembly(_Named):
         )  # fmt: skip
         return grad, strain, stress
 
+    def convert_data(self, data, convert_from="GaussPoint", convert_to="Node"):
+        """Mesh.convert_data for Gauss-point fields (fedoo/core/mesh.py:1267-1308), on the device; returns NumPy."""
+        if convert_from != "GaussPoint":
+            raise NotImplementedError("only Gauss-point fields are converted on the accelerated path")
+        from .results import convert_gp
+
+        return convert_gp(self, data, convert_to).cpu().numpy()
+
+    def get_strain(self, U, type_output="Node", nlgeom=False):
+        """Legacy accessor used by the reference's cantilever test (fedoo/core/assembly.py get_strain): the small
+        strain of the dof vector U at the nodes / elements / Gauss points, six arrays in Voigt order."""
+        if nlgeom:
+            raise NotImplementedError("nlgeom is outside the accelerated path")
+        from .results import NodeTensor, convert_gp
+
+        strain = self._gp_strain_stress(as_device_f64(U), want_strain=True)[1]  # (N, 6)
+        return NodeTensor(convert_gp(self, GaussPointTensor(strain, "strain"), type_output).cpu().numpy())
+
     def get_grad_disp(self, U, type_output="GaussPoint"):
         """fedoo/core/assembly.py:1285-1336: 3x3 list of (N,) arrays, gp-major."""
         if type_output != "GaussPoint":

@@ -81,6 +81,17 @@ class ElasticAnisotropic(ConstitutiveLaw):
             assembly.sv["TangentMatrix"] = self.get_tangent_matrix(assembly)
         assembly._elastic_stress_update(self)
 
+    def get_stress_from_strain(self, assembly, strain_tensor, dimension=None):
+        """sigma_i = sum_j H_ij eps_j on whatever support the strain lives (nodes, elements, Gauss points):
+        fedoo/constitutivelaw/elastic_anisotropic.py:58-77."""
+        from .results import NodeTensor
+
+        H = self.get_tangent_matrix(assembly, dimension)
+        if np.ndim(H) != 2:
+            raise NotImplementedError("per-Gauss-point tangent: use sv['Stress']")
+        eps = [np.asarray(strain_tensor[j]) for j in range(6)]
+        return NodeTensor([sum(eps[j] * H[i][j] for j in range(6)) for i in range(6)])
+
     def tangent_device(self, assembly):
         """Per-GP tangent as a CUDA tensor in (6,6,N) Fortran layout, or None if uniform."""
         H = assembly.sv["TangentMatrix"]

@@ -84,6 +84,10 @@ class ModelingSpace(_Named):
     def list_variables(self):
         return list(self._variable)
 
+    def list_vectors(self):
+        """fedoo/core/modelingspace.py: the displacement vector registered by StressEquilibrium."""
+        return ["Disp"] if "DispX" in self._variable else []
+
 
 class BoundingBox:
     def __init__(self, nodes):

@@ -5,6 +5,7 @@
 #include "fdk_assemble.cuh"
 #include "fdk_assemble_iso.cuh"
 #include "fdk_gp.cuh"
+#include "fdk_results.cuh"
 #include "fdk_solve.cuh"
 #include "fdk_symbolic.cuh"
 
@@ -315,6 +316,47 @@ int fdk_pcg_jacobi(int64_t n, int64_t nnz, const void* indptr, const void* indic
                                max_iter, check_every, work, iters_h, relres_h, (cudaStream_t)stream);
   return pcg_jacobi<int64_t>(n, nnz, (const int64_t*)indptr, (const int64_t*)indices, data, b, x, free_mask, rtol,
                              max_iter, check_every, work, iters_h, relres_h, (cudaStream_t)stream);
+}
+
+int fdk_gp_to_node(int nne, int ngp, int n_nodes, int64_t n_elems, const int64_t* node_ptr, const int32_t* node_inc,
+                   const double* P_h, const double* field, int ncomp, int64_t comp_stride, int64_t gp_stride,
+                   int von_mises, double* out, fdk_stream_t stream) {
+  FDK_REQUIRE(nne > 0 && nne <= MAX_NNE && ngp > 0 && ngp <= MAX_NGP && n_nodes >= 0 && n_elems >= 0, FDK_EINVAL, "bad sizes");
+  FDK_REQUIRE(von_mises ? ncomp == 6 : (ncomp >= 1 && ncomp <= 6), FDK_EINVAL, "ncomp must be 1..6 (6 for von Mises)");
+  if (n_nodes == 0) return 0;
+  FDK_REQUIRE(node_ptr && node_inc && P_h && field && out, FDK_EINVAL, "NULL argument");
+  ConvArgs a{};
+  a.nne = nne; a.ngp = ngp; a.n_nodes = n_nodes; a.ncomp = ncomp; a.von_mises = von_mises; a.n_elems = n_elems;
+  a.comp_stride = comp_stride; a.gp_stride = gp_stride; a.node_ptr = node_ptr; a.node_inc = node_inc;
+  a.field = field; a.out = out;
+  for (int i = 0; i < nne * ngp; ++i) a.P[i] = P_h[i];
+  k_gp_to_node<6><<<(unsigned)((n_nodes + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int fdk_gp_to_element(int ngp, int64_t n_elems, const double* field, int ncomp, int64_t comp_stride, int64_t gp_stride,
+                      int von_mises, double* out, fdk_stream_t stream) {
+  FDK_REQUIRE(ngp > 0 && ngp <= MAX_NGP && n_elems >= 0, FDK_EINVAL, "bad sizes");
+  FDK_REQUIRE(von_mises ? ncomp == 6 : (ncomp >= 1 && ncomp <= 6), FDK_EINVAL, "ncomp must be 1..6 (6 for von Mises)");
+  if (n_elems == 0) return 0;
+  FDK_REQUIRE(field && out, FDK_EINVAL, "NULL argument");
+  ConvArgs a{};
+  a.ngp = ngp; a.ncomp = ncomp; a.von_mises = von_mises; a.n_elems = n_elems;
+  a.comp_stride = comp_stride; a.gp_stride = gp_stride; a.field = field; a.out = out;
+  k_gp_to_element<6><<<(unsigned)((n_elems + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int fdk_gp_von_mises(int64_t n_gp, const double* field, int64_t comp_stride, int64_t gp_stride, double* out,
+                     fdk_stream_t stream) {
+  FDK_REQUIRE(n_gp >= 0, FDK_EINVAL, "negative n_gp");
+  if (n_gp == 0) return 0;
+  FDK_REQUIRE(field && out, FDK_EINVAL, "NULL argument");
+  k_gp_von_mises<<<(unsigned)((n_gp + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_gp, field, comp_stride, gp_stride, out);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int fdk_gather_f64(int64_t n, const int64_t* index, const double* src, double* dst, fdk_stream_t stream) {

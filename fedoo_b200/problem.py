@@ -109,6 +109,22 @@ class _ProblemBase(_Named):
         r = self._var_rank(name)
         return X[r * n : (r + 1) * n]
 
+    def get_results(self, *args, **kargs):
+        """fedoo/core/problem.py:207-265: get_results(assemb, output_list, output_type) or
+        get_results(output_list, output_type)."""
+        from .results import get_results
+
+        args = list(args)
+        if args and (isinstance(args[0], Assembly) or (isinstance(args[0], str) and args[0] in Assembly.get_all())):
+            assemb = args.pop(0)
+            if isinstance(assemb, str):
+                assemb = Assembly.get_all()[assemb]
+        else:
+            assemb = kargs.pop("assemb", self.assembly)
+        output_list = args.pop(0) if args else kargs.pop("output_list")
+        output_type = args.pop(0) if args else kargs.pop("output_type", None)
+        return get_results(self, assemb, output_list, output_type)
+
     def apply_boundary_conditions(self):
         """Dirichlet part of fedoo/core/problem.py:335-432."""
         n = self.mesh.n_nodes

@@ -229,6 +229,31 @@ int fdk_pcg_jacobi(int64_t n, int64_t nnz, const void* indptr, const void* indic
                    double* work, int* iters_h, double* relres_h, fdk_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
+ * Results extraction.  Replaces Mesh.convert_data GaussPoint -> Node / Element
+ * (fedoo/core/mesh.py:1149-1160,1267-1308) and StressTensorList.von_mises (fedoo/util/voigt_tensors.py:270-283)
+ * as used by Problem.get_results (fedoo/core/output.py:120-330).
+ * field: value of component c at Gauss point n (gp-major, n = g * n_elems + e) at field[n * gp_stride + c * comp_stride]
+ * (a (ncomp, N) column-major array has gp_stride = ncomp, comp_stride = 1; a row-major one gp_stride = 1,
+ * comp_stride = N); ncomp <= 6.  von_mises != 0: the field has 6 Voigt stress components and the ONE converted
+ * quantity is their von Mises norm, taken at the Gauss points first (output.py:190-197).
+ * ------------------------------------------------------------------------- */
+
+/* node value = (1 / #elements around the node) sum over those elements and their Gauss points of P[i][g] * value,
+ * P_h = pinv(shape functions at the Gauss points), host, [nne][ngp] row-major.  node_ptr [n_nodes+1] / node_inc
+ * (element * nne + local node) list the incidences of every node.  out: [ncomp_out][n_nodes] row-major. */
+int fdk_gp_to_node(int nne, int ngp, int n_nodes, int64_t n_elems, const int64_t* node_ptr, const int32_t* node_inc,
+                   const double* P_h, const double* field, int ncomp, int64_t comp_stride, int64_t gp_stride,
+                   int von_mises, double* out, fdk_stream_t stream);
+
+/* element value = mean over the element's Gauss points.  out: [ncomp_out][n_elems] row-major. */
+int fdk_gp_to_element(int ngp, int64_t n_elems, const double* field, int ncomp, int64_t comp_stride, int64_t gp_stride,
+                      int von_mises, double* out, fdk_stream_t stream);
+
+/* out[n] = von Mises norm of the 6 Voigt stress components at Gauss point n. */
+int fdk_gp_von_mises(int64_t n_gp, const double* field, int64_t comp_stride, int64_t gp_stride, double* out,
+                     fdk_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
  * Multi-GPU helpers: pack / unpack-add of owned or halo entries around an NCCL
  * exchange of the global vector (no reference counterpart: the reference is
  * single-process).

@@ -417,3 +417,74 @@ def test_device_cg_matches_host_direct(fd):
         sols.append(np.array(pb.get_dof_solution("all")))
     assert nrm(sols[1], sols[0]) <= 1e-9
     assert np.array_equal(sols[1], sols[2])
+
+
+# ----------------------------------------------------------------------------------------------
+# results extraction (csrc/fdk_results.cuh), pinned on pb.get_results of the reference
+# (oracle/gen_golden_results.py)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,elm", [("results_hex8", "hex8"), ("results_tet10", "tet10")])
+def test_results_conversion_against_reference(fd, golden_dir, name, elm):
+    """Strain / Stress_vm at nodes, elements and Gauss points == the reference's pb.get_results."""
+    g = load(golden_dir, name)
+    law = fd.constitutivelaw.ElasticIsotrop(1e5, 0.3, name="law")
+    mesh, a, pb = _elastic_setup(fd, "3D", g["nodes"], g["elements"], elm, law)
+    pb.set_X(g["U"])
+    a.update(pb, compute="none")
+    for typ, attr in (("Node", "node_data"), ("Element", "element_data"), ("GaussPoint", "gausspoint_data")):
+        res = pb.get_results("A", ["Stress_vm", "Strain", "Stress"], typ)
+        d = getattr(res, attr)
+        assert nrm(d["Strain"], g[f"Strain_{typ}"]) <= 1e-12, typ
+        assert nrm(d["Stress_vm"], g[f"Stress_vm_{typ}"]) <= 1e-12, typ
+    assert nrm(pb.get_results(["Stress"], "GaussPoint").gausspoint_data["Stress"], g["Stress_GaussPoint"]) <= 1e-12
+    assert np.array_equal(pb.get_results(["Disp"]).node_data["Disp"], g["U"].reshape(3, -1))
+
+
+def test_plate_with_hole_known_answers(fd, golden_dir):
+    """tests/test_platewithhol.py of the reference replayed on the device path (mesh and node sets taken from the
+    reference's generator, whose numbering the asserts depend on): U[1, 40] and the nodal von Mises stress at 282."""
+    g = load(golden_dir, "results_plate")
+    fd.Assembly.delete_memory()
+    fd.ModelingSpace("2Dstress")
+    fd.Mesh(g["nodes"], g["elements"], "quad4", name="Domain")
+    fd.constitutivelaw.ElasticIsotrop(2e5, 0.3, name="ElasticLaw")
+    fd.weakform.StressEquilibrium("ElasticLaw", name="WeakForm")
+    fd.Assembly.create("WeakForm", "Domain", name="Assembly", MeshChange=True)
+    pb = fd.problem.Linear("Assembly")
+    pb.bc.add("Dirichlet", g["left"], "DispX", 0)
+    pb.bc.add("Dirichlet", g["bottom"], "DispY", 0)
+    pb.bc.add("Dirichlet", g["right"], "DispX", 0.1)
+    pb.apply_boundary_conditions()
+    pb.solve()
+    res = pb.get_results("Assembly", ["Stress_vm", "Strain"], "Node")
+    U = pb.get_disp()
+    assert U[0, 40] == 0.1
+    assert np.abs(U[1, 40] + 0.01962855744173) < 1e-10
+    assert np.abs(res.node_data["Stress_vm"][282] - 175.50126302014) < 1e-9
+    assert nrm(res.node_data["Stress_vm"], g["Stress_vm_Node"]) <= 1e-10
+    assert nrm(res.node_data["Strain"], g["Strain_Node"]) <= 1e-10
+
+
+def test_cantilever_node_stress_known_answer(fd, golden_dir):
+    """The assert of tests/test_cantilever_beam_3D_model.py:60-72: node strain through the legacy accessor, stress
+    from the law, TensorStress[5][-1] == -0.9007983467254552."""
+    g = load(golden_dir, "results_cantilever")
+    fd.Assembly.delete_memory()
+    fd.ModelingSpace("3D")
+    mesh = fd.mesh.box_mesh(nx=11, ny=5, nz=5, x_min=0, x_max=1000, y_min=0, y_max=100, z_min=0, z_max=100,
+                            elm_type="hex8", name="Domain")  # fmt: skip
+    fd.constitutivelaw.ElasticIsotrop(200e3, 0.3, name="ElasticLaw")
+    fd.weakform.StressEquilibrium("ElasticLaw", name="weakform")
+    fd.Assembly.create("weakform", "Domain", "hex8", name="Assembling")
+    pb = fd.problem.Linear("Assembling")
+    for var in ("DispX", "DispY", "DispZ"):
+        pb.bc.add("Dirichlet", mesh.node_sets["left"], var, 0)
+    pb.bc.add("Dirichlet", mesh.node_sets["right"], "DispY", -10)
+    pb.apply_boundary_conditions()
+    pb.solve()
+    asm = fd.Assembly["Assembling"]
+    TensorStrain = asm.get_strain(pb.get_dof_solution(), "Node", nlgeom=False)
+    TensorStress = fd.ConstitutiveLaw["ElasticLaw"].get_stress_from_strain(asm, TensorStrain)
+    assert np.abs(TensorStress[5][-1] + 0.9007983467254552) < 1e-9
+    assert nrm(TensorStrain.asarray(), g["strain_node_legacy"]) <= 1e-9
+    assert nrm(TensorStress.asarray(), g["stress_node_legacy"]) <= 1e-9
