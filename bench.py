@@ -314,6 +314,19 @@ def run_b200(args):
     checks = None
     if args.check and world == 1:
         checks = property_checks(asm, pb, U_host, n)
+    elif args.check:
+        # the gathered residual: identical on every rank, and self-equilibrated (sum over the nodes = 0 per component),
+        # which fails if any rank's run of owned entries did not land
+        asm.vector_on_device = True
+        step_device()
+        s3 = torch.stack([D_global[v * n_nodes_global : (v + 1) * n_nodes_global].sum() for v in range(3)])
+        spread = torch.stack([D_global.sum(), -D_global.sum()])
+        dist.all_reduce(spread, op=dist.ReduceOp.MAX)
+        checks = {
+            "D_sum_rel": float(s3.abs().max() / D_global.abs().max()),
+            "D_identical_on_all_ranks": bool(float(spread[0] + spread[1]) == 0.0),
+            "D_nonzero_fraction": float((D_global != 0).double().mean()),
+        }
 
     if rank == 0:
         cb = None
@@ -365,7 +378,8 @@ def run_b200(args):
                 "note": "pinned host U -> HBM, fused K+R kernel, residual -> pinned host; K stays in HBM "
                 "(DeviceCSR, materialised to scipy only on demand)",
             },
-            "gpu_launches": args.steps * (1 if world == 1 else 1 + 3 + 2),
+            # the assembly kernel, plus pack / unpack of the residual exchange (NCCL's own kernels not counted)
+            "gpu_launches": args.steps * (1 if world == 1 else (3 if exch.seg_pack is not None else 6)),
             "clocks": clk.summary(),
         }
         if checks is not None:

@@ -19,7 +19,7 @@ EXPORTS = [
     "fdk_sym_block_keys", "fdk_sym_block_csr", "fdk_sym_expand_csr",
     "fdk_assemble_elastic_iso", "fdk_assemble_elastic_general", "fdk_assemble_heat",
     "fdk_gp_strain_stress", "fdk_gp_temperature", "fdk_j2_update",
-    "fdk_gather_f64", "fdk_scatter_add_f64",
+    "fdk_gather_f64", "fdk_scatter_add_f64", "fdk_copy_segments",
     "fdk_csr_spmv", "fdk_csr_diagonal", "fdk_pcg_work_doubles", "fdk_pcg_jacobi",
     "fdk_gp_to_node", "fdk_gp_to_element", "fdk_gp_von_mises",
 ]  # fmt: skip
@@ -113,6 +113,7 @@ def load():
     lib.fdk_gp_to_node.argtypes = [i32, i32, i32, i64, vp, vp, vp, vp, i32, i64, i64, i32, vp, vp]
     lib.fdk_gp_to_element.argtypes = [i32, i64, vp, i32, i64, i64, i32, vp, vp]
     lib.fdk_gp_von_mises.argtypes = [i64, vp, i64, i64, vp, vp]
+    lib.fdk_copy_segments.argtypes = [i32, vp, vp, vp, i64, vp, vp, vp]
     lib.fdk_gather_f64.argtypes = [i64, vp, vp, vp, vp]
     lib.fdk_scatter_add_f64.argtypes = [i64, vp, vp, vp, vp]
     for name in EXPORTS:

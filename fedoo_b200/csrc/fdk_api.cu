@@ -367,6 +367,20 @@ int fdk_gather_f64(int64_t n, const int64_t* index, const double* src, double* d
   return 0;
 }
 
+int fdk_copy_segments(int n_seg, const int64_t* seg_src, const int64_t* seg_dst, const int64_t* seg_len,
+                      int64_t max_len, const double* src, double* dst, fdk_stream_t stream) {
+  FDK_REQUIRE(n_seg >= 0 && max_len >= 0, FDK_EINVAL, "negative size");
+  if (n_seg == 0 || max_len == 0) return 0;
+  FDK_REQUIRE(seg_src && seg_dst && seg_len && src && dst, FDK_EINVAL, "NULL argument");
+  FDK_REQUIRE(n_seg <= 65535, FDK_EINVAL, "too many segments");
+  int64_t bx = (max_len + 255) / 256;
+  if (bx > 1024) bx = 1024;
+  k_copy_segments<<<dim3((unsigned)bx, (unsigned)n_seg), 256, 0, (cudaStream_t)stream>>>(n_seg, seg_src, seg_dst, seg_len,
+                                                                                      src, dst);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int fdk_scatter_add_f64(int64_t n, const int64_t* index, const double* src, double* dst, fdk_stream_t stream) {
   if (n <= 0) return 0;
   FDK_REQUIRE(index && src && dst, FDK_EINVAL, "NULL argument");

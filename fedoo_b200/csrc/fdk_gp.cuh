@@ -292,4 +292,18 @@ __global__ void k_scatter_add_f64(int64_t n, const int64_t* __restrict__ index, 
   if (i < n) dst[index[i]] += src[i];  // indices are unique within one call (owner rows)
 }
 
+// dst[seg_dst[s] + k] = src[seg_src[s] + k], k < seg_len[s]: the pack / unpack of the residual exchange when the owned
+// dofs of a rank are contiguous runs (slab partitions): one launch, no index arrays, no zero-fill
+__global__ void __launch_bounds__(256) k_copy_segments(int n_seg, const int64_t* __restrict__ seg_src,
+                                                       const int64_t* __restrict__ seg_dst,
+                                                       const int64_t* __restrict__ seg_len, const double* __restrict__ src,
+                                                       double* __restrict__ dst) {
+  const int s = blockIdx.y;
+  if (s >= n_seg) return;
+  const int64_t len = seg_len[s];
+  const double* a = src + seg_src[s];
+  double* b = dst + seg_dst[s];
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < len; k += (int64_t)gridDim.x * blockDim.x) b[k] = a[k];
+}
+
 }  // namespace fdk

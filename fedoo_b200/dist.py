@@ -182,12 +182,34 @@ class VectorExchange:
         self.recv_pos = torch.cat(pos).contiguous()
         self.dst_index = torch.cat(dst).contiguous()
         self.n_own = len(own_l)
+        # contiguous runs (slab partitions: the owned nodes of a rank are one range of local AND of global ids):
+        # pack and unpack become one segment-copy launch each, without index arrays or zero-fill
+        self.seg_pack = self.seg_unpack = None
+        gid_all = self.all_gid.cpu().numpy()
+        runs_ok = len(own_l) > 0 and np.array_equal(own_l, np.arange(own_l[0], own_l[0] + len(own_l)))
+        for r in range(self.world):
+            c = self.counts[r]
+            runs_ok = runs_ok and c > 0 and np.array_equal(gid_all[r, :c], np.arange(gid_all[r, 0], gid_all[r, 0] + c))
+        if runs_ok and dev.type == "cuda":
+            def seg(rows):
+                a = np.asarray(rows, dtype=np.int64).reshape(-1, 3)
+                return tuple(torch.from_numpy(np.ascontiguousarray(a[:, k])).to(dev) for k in range(3)) + (int(a[:, 2].max()),)
+
+            self.seg_pack = seg([(v * n_loc + own_l[0], v * self.max_own, len(own_l)) for v in range(nvar)])
+            self.seg_unpack = seg([(r * self.n_send + v * self.max_own, v * self.n_global + gid_all[r, 0], self.counts[r])
+                                   for r in range(self.world) for v in range(nvar)])  # fmt: skip
 
     def allgather(self, D_local: torch.Tensor, D_global: torch.Tensor | None = None) -> torch.Tensor:
         if D_global is None:
             D_global = torch.zeros(self.nvar * self.n_global, dtype=torch.float64, device=self.dev)
-        n = self.nvar * self.n_own
-        if D_local.is_cuda:
+        segs = D_local.is_cuda and self.seg_pack is not None
+        if segs:
+            lib = _lib.load()
+            stream = _lib.current_stream()
+            ss, sd, sl, mx = self.seg_pack
+            _lib.check(lib.fdk_copy_segments(len(ss), _lib.ptr(ss), _lib.ptr(sd), _lib.ptr(sl), mx, _lib.ptr(D_local),
+                                             _lib.ptr(self.send), stream), "fdk_copy_segments")  # fmt: skip
+        elif D_local.is_cuda:
             lib = _lib.load()
             stream = _lib.current_stream()
             # pack: send[v * max_own + k] = D_local[v * n_loc + own_l[k]]
@@ -208,7 +230,11 @@ class VectorExchange:
             self.dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
         else:
             self.recv.copy_(self.send)
-        if D_local.is_cuda:
+        if segs:  # the runs tile the whole global vector: nothing to zero
+            ss, sd, sl, mx = self.seg_unpack
+            _lib.check(lib.fdk_copy_segments(len(ss), _lib.ptr(ss), _lib.ptr(sd), _lib.ptr(sl), mx, _lib.ptr(self.recv),
+                                             _lib.ptr(D_global), _lib.current_stream()), "fdk_copy_segments")  # fmt: skip
+        elif D_local.is_cuda:
             lib = _lib.load()
             tmp = torch.empty(self.recv_pos.numel(), dtype=torch.float64, device=self.dev)
             _lib.check(lib.fdk_gather_f64(self.recv_pos.numel(), _lib.ptr(self.recv_pos), _lib.ptr(self.recv), _lib.ptr(tmp),

@@ -259,6 +259,10 @@ int fdk_gp_von_mises(int64_t n_gp, const double* field, int64_t comp_stride, int
  * single-process).
  * ------------------------------------------------------------------------- */
 int fdk_gather_f64(int64_t n, const int64_t* index, const double* src, double* dst, fdk_stream_t stream);
+/* dst[seg_dst[s] + k] = src[seg_src[s] + k] for k < seg_len[s], s < n_seg (device arrays; max_len = max seg_len):
+ * pack / unpack when the owned dofs of every rank are contiguous runs (slab partitions). */
+int fdk_copy_segments(int n_seg, const int64_t* seg_src, const int64_t* seg_dst, const int64_t* seg_len,
+                      int64_t max_len, const double* src, double* dst, fdk_stream_t stream);
 int fdk_scatter_add_f64(int64_t n, const int64_t* index, const double* src, double* dst, fdk_stream_t stream);
 
 #ifdef __cplusplus
