@@ -119,6 +119,14 @@ class Assembly(_Named):
         self._saved_bloc_structure = entry
         return entry, entry["csr"][(nvar, n_glob)], n_glob
 
+    def _small_plan(self, entry):
+        """Second cluster plan of the same pattern with half-size (16-node hex8) clusters, built on first use."""
+        if "plan_small" not in entry:
+            coords, conn = self.mesh.device_arrays()
+            owned = None if self.owned_nodes is None else torch.from_numpy(np.asarray(self.owned_nodes, dtype=bool))
+            entry["plan_small"] = symbolic.build_plan(self.elm_type, coords, conn, entry["pattern"], owned=owned, small=True)
+        return entry["plan_small"]
+
     def _coords(self):
         if self.meshChange:
             self.mesh.invalidate_device()
@@ -168,6 +176,10 @@ class Assembly(_Named):
                 else:
                     H = self.sv["TangentMatrix"]
                     C_h = None if tangent_dev is not None else np.ascontiguousarray(H, dtype=np.float64)
+                    if self.elm_type == "hex8" and nvar == 3 and want_mat:
+                        # general tangent on hex8: 16-node clusters, so that the 36 tangent entries of every (touched
+                        # element, Gauss point) fit in shared memory next to the geometry (csrc/fdk_assemble_iso.cuh)
+                        plan = self._small_plan(entry)
                     rc = lib.fdk_assemble_elastic_general(
                         C.byref(plan.struct(nvar)), flags, _lib.ptr(coords), _lib.ptr(C_h), _lib.ptr(tangent_dev),
                         _lib.ptr(U_dev), _lib.ptr(stress_dev), _lib.ptr(K), _lib.ptr(D), stream,

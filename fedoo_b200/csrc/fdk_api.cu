@@ -150,7 +150,8 @@ int fdk_assemble_elastic_iso(const fdk_plan* plan, int compute, const double* co
   const bool bts = (compute & FDK_VECTOR) && !a.fuse_ku;
   // (the template also compiles and passes parity for tet4 / tet10 / quad4 and for 16-node hex8 clusters, but was
   // measured slower than k_assemble on tet10 -- 64 vs 55 ms at 5 M elements -- and is unmeasured on the others)
-  if (g_opt_iso4 && (compute & FDK_MATRIX) && !bts && plan->elem_type == FDK_HEX8 && plan->threads == Hex8::THREADS)
+  if (g_opt_iso4 && (compute & FDK_MATRIX) && !bts && plan->elem_type == FDK_HEX8 && plan->threads == Hex8::THREADS &&
+      assemble_iso_fits<Hex8, 1024, 4>(a))
     return launch_assemble_iso<Hex8, 1024, 4>(a, (cudaStream_t)stream);
   return dispatch_assemble<PHYS_ISO>(a, (cudaStream_t)stream);
 }
@@ -175,6 +176,12 @@ int fdk_assemble_elastic_general(const fdk_plan* plan, int compute, const double
   a.compute = compute;
   a.fuse_ku =
       (compute == FDK_ALL && U != nullptr && stress_gp == nullptr && tangent_gp == nullptr && g_opt_fuse) ? 1 : 0;
+  // 3D hex8 on 16-node clusters (plans built with small = True), matrix requested, residual fused or integrated from
+  // a given stress: balanced kernel with the tangent staged in shared memory (fdk_assemble_iso.cuh)
+  const bool vec_ok = !(compute & FDK_VECTOR) || a.fuse_ku || stress_gp != nullptr;
+  if (g_opt_iso4 && (compute & FDK_MATRIX) && vec_ok && plan->elem_type == FDK_HEX8 &&
+      plan->threads == Hex8::THREADS / 2 && assemble_iso_fits<Hex8, 512, 4, PHYS_GENERAL>(a))
+    return launch_assemble_iso<Hex8, 512, 4, PHYS_GENERAL>(a, (cudaStream_t)stream);
   return dispatch_assemble<PHYS_GENERAL>(a, (cudaStream_t)stream);
 }
 

@@ -20,6 +20,14 @@
 //   * heavy slots (the diagonal) are pre-reduced with all source lookups and all block loads in flight
 //     together (two shared-memory latencies instead of two per contribution).
 //
+// PHYS = PHYS_GENERAL (3D): the same organisation for a general tangent -- uniform 6x6 or per Gauss point (6,6,N), the
+// consistent tangent of the J2 update -- with the residual either fused (uniform tangent, D = -K_row . U) or
+// integrated as B^T sigma from a given stress (the Newton iteration of a plastic step).  Per (touched element,
+// Gauss point) the geometry phase also parks the 36 tangent entries (cp.async, issued one cluster ahead) and
+// sqrt(w) sigma in shared memory, so the block phase reads them as broadcasts instead of 36 global loads per
+// thread and Gauss point (k_assemble: 63 % of its time, with 650 bytes of register spills).  Sized for 16-node
+// clusters (plans built with small = True): 512 threads, 4 per incidence, <= 128 registers.
+//
 // Reference: same as k_assemble -- fedoo/core/assembly.py:143-470, 776-928; fedoo/core/_sparsematrix.py:55-174,
 // 256-315; fedoo/constitutivelaw/elastic_isotrop.py:35-68.
 #pragma once
@@ -43,6 +51,8 @@ constexpr bool PART_UNIFORM = FDK_ISO_PART_UNIFORM != 0;
 template <class El, int TPI>
 struct IsoLayout {
   using L = Layout<El, PHYS_ISO>;
+  static constexpr int CSTR = 36;  // tangent entries per (touched element, Gauss point), Fortran order i + 6 j
+  static constexpr int SGS = 6;    // sqrt(w) sigma per (touched element, Gauss point)
   static constexpr int NNE = El::NNE, NGP = El::NGP, DIM = El::DIM, NV = DIM, BLK = NV * NV;
   static constexpr int GROW = L::GROW, GSTR = L::GSTR;
   static constexpr int NH = NNE / TPI;  // column blocks per thread: j = part, part + TPI, ...
@@ -68,10 +78,24 @@ struct IsoLayout {
     const long g = (long)p.cap_te * ESTR, s = (long)p.cap_inc * ISTR;
     return ((g > s ? g : s) + 1) & ~1L;
   }
-  static size_t smem_bytes(const fdk_plan& p) {
-    long doubles = TAB_DOUBLES + 2L * xu_doubles(p) + sr_offset(p) + (((long)p.cap_slots * NV + 1) & ~1L) + p.cap_owned;
+  // per-slot K.u products or per-incidence nodal forces (never both)
+  __host__ __device__ static long sr_doubles(const fdk_plan& p) {
+    const long n = p.cap_slots > p.cap_inc ? p.cap_slots : p.cap_inc;
+    return (n * NV + 1) & ~1L;
+  }
+  // sqrt(w) sigma is dead once the block phase is over and the nodal forces are parked after it: they share one
+  // region (the price: a closing barrier per cluster on the B^T sigma path, see the kernel)
+  __host__ __device__ static long rs_doubles(const fdk_plan& p, bool bts) {
+    const long r = sr_doubles(p), g = bts ? (((long)p.cap_te * NGP * SGS + 1) & ~1L) : 0;
+    return r > g ? r : g;
+  }
+  __host__ __device__ static long extra_doubles(const fdk_plan& p, bool tangent_gp) {
+    return tangent_gp ? (long)p.cap_te * NGP * CSTR : 0;
+  }
+  static size_t smem_bytes(const fdk_plan& p, bool tangent_gp = false, bool bts = false) {
+    long doubles = TAB_DOUBLES + 2L * xu_doubles(p) + sr_offset(p) + rs_doubles(p, bts) + extra_doubles(p, tangent_gp) + p.cap_owned;
     size_t bytes = (size_t)doubles * 8;
-    bytes += (size_t)(p.cap_owned + 1) * 4;            // sSlotBase
+    bytes += (size_t)(2 * (p.cap_owned + 1)) * 4;      // sSlotBase, sFinc
     bytes += (size_t)(p.cap_slots + 1) * 4;            // sRec
     bytes += (size_t)p.cap_heavy * 4;                  // sHeavy
     bytes += 2 * (size_t)((p.cap_te * NNE + 3) & ~3);  // sLconn (double-buffered)
@@ -80,15 +104,21 @@ struct IsoLayout {
   }
 };
 
-template <class El, int THREADS, int TPI>
-__global__ void __launch_bounds__(THREADS, (1024 / THREADS > 0 ? 1024 / THREADS : 1)) k_assemble_iso(const __grid_constant__ AsmArgs a) {
+template <class El, int THREADS, int TPI, int PHYS = PHYS_ISO>
+__global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS > 0 ? 1024 / THREADS : 1))
+    k_assemble_iso(const __grid_constant__ AsmArgs a) {
   using IL = IsoLayout<El, TPI>;
+  constexpr bool GEN = PHYS == PHYS_GENERAL;
+  static_assert(PHYS == PHYS_ISO || (GEN && El::DIM == 3), "balanced kernel: isotropic, or general tangent in 3D");
+  constexpr int CSTR = IL::CSTR, SGS = IL::SGS;
   constexpr int NNE = IL::NNE, NGP = IL::NGP, DIM = IL::DIM, NV = IL::NV, BLK = IL::BLK, ISTR = IL::ISTR;
   constexpr int GROW = IL::GROW, GSTR = IL::GSTR, ESTR = IL::ESTR, TSTR = IL::TSTR, NH = IL::NH, XSTR = IL::XSTR;
   constexpr int INC = THREADS / TPI;  // incidences per cluster <= INC
   const fdk_plan& p = a.p;
   const int tid = threadIdx.x;
   const bool fuse_ku = a.fuse_ku != 0;
+  const bool do_bts = GEN && (a.compute & FDK_VECTOR) && !fuse_ku;  // residual as B^T sigma from a given stress
+  const bool per_gp = GEN && a.tangent_gp != nullptr;
   // the TPI threads of an incidence sit in adjacent lanes: a warp covers 32 / TPI incidences of 2-3 elements
   // (element-major order), so its own-row loads touch 32 / TPI addresses and its column loads ~10
   const int it = PART_UNIFORM ? tid % INC : tid / TPI;    // incidence of this thread (phase 2)
@@ -104,10 +134,14 @@ __global__ void __launch_bounds__(THREADS, (1024 / THREADS > 0 ? 1024 / THREADS 
   double* sBig = sXbuf + 2 * xu_doubles;
   double* sG = sBig;                       // geometry view  [n_te][ESTR]: sqrt(w) dN/dx, [g][k][d]
   double* sBlk = sBig;                     // staging view   [cap_inc][ISTR]
-  double* sR = sBig + IL::sr_offset(p);    // [cap_slots][NV] per-slot K.u products
-  long long* sBptr = reinterpret_cast<long long*>(sR + (((long)p.cap_slots * NV + 1) & ~1L));  // [cap_owned]
+  double* sR = sBig + IL::sr_offset(p);    // [cap_slots][NV] per-slot K.u products / [cap_inc][NV] nodal forces
+  double* sF = sR;
+  double* sSig = sR;                       // [cap_te][NGP][6] sqrt(w) sigma (do_bts): shares the space of sF
+  double* sC = sR + IL::rs_doubles(p, do_bts);  // [cap_te][NGP][36] tangent of every (touched element, gp) (per_gp)
+  long long* sBptr = reinterpret_cast<long long*>(sC + IL::extra_doubles(p, per_gp));  // [cap_owned]
   int* sSlotBase = reinterpret_cast<int*>(sBptr + p.cap_owned);                                 // [cap_owned+1]
-  unsigned* sRec = reinterpret_cast<unsigned*>(sSlotBase + (p.cap_owned + 1));                  // [cap_slots+1]
+  int* sFinc = sSlotBase + (p.cap_owned + 1);                                                   // [cap_owned+1]
+  unsigned* sRec = reinterpret_cast<unsigned*>(sFinc + (p.cap_owned + 1));                      // [cap_slots+1]
   unsigned* sHeavy = sRec + (p.cap_slots + 1);                                                  // [cap_heavy]
   unsigned char* sLbuf = reinterpret_cast<unsigned char*>(sHeavy + p.cap_heavy);                // [2][lc_bytes]
   const int lc_bytes = (p.cap_te * NNE + 3) & ~3;
@@ -157,9 +191,31 @@ __global__ void __launch_bounds__(THREADS, (1024 / THREADS > 0 ? 1024 / THREADS 
     }
     cp_async_commit();
   };
+  // general tangent: global element of "this thread's" geometry task (task = tid) and the copy of its 36 tangent
+  // entries into shared memory; issued one cluster ahead, once the block phase is done with the previous ones
+  [[maybe_unused]] int my_te_elem = -1, nxt_te_elem = -1;
+  [[maybe_unused]] auto load_te_elem = [&](const ClusterHdr& h) {
+    return (tid < h.n_te * NGP) ? p.cl_te_elem[h.te0 + tid / NGP] : -1;
+  };
+  [[maybe_unused]] auto fetch_tangent = [&](const ClusterHdr& h) {
+    // consecutive lanes copy consecutive 16-byte pieces of one (element, gp) tangent: 288 contiguous bytes per task
+    // (the element ids are L1 hits: load_te_elem read them a phase ago)
+    constexpr int PIECES = CSTR / 2;
+    for (int idx = tid; idx < h.n_te * NGP * PIECES; idx += THREADS) {
+      const int task = idx / PIECES, k = idx - task * PIECES;
+      const int le = task / NGP, g = task - le * NGP;
+      const int64_t e = p.cl_te_elem[h.te0 + le];
+      cp_async<16>(sC + (long)task * CSTR + 2 * k, a.tangent_gp + CSTR * ((int64_t)g * p.n_elems + e) + 2 * k);
+    }
+  };
   ClusterHdr cur = load_hdr(p.cl_hdr, blockIdx.x);
   load_node_ids(cur);
   fetch_inputs(cur, 0);
+  if constexpr (GEN) {
+    if (per_gp || do_bts) my_te_elem = load_te_elem(cur);  // (also warms L1 for fetch_tangent)
+    if (per_gp) fetch_tangent(cur);
+    cp_async_commit();
+  }
   cp_async_wait_group<0>();
   __syncthreads();  // tables and the first inputs are visible
 
@@ -179,7 +235,9 @@ __global__ void __launch_bounds__(THREADS, (1024 / THREADS > 0 ? 1024 / THREADS 
     unsigned my_desc = 0;
     if (it < n_inc) my_desc = p.inc_desc[inc0 + it];  // consumed in phase 2
     int my_node = 0;  // row node of this thread's share of the residual reduction (consumed at the very end)
-    if (fuse_ku && (tid >> 3) < n_owned * NV) my_node = p.cl_node[q0 + (tid >> 3) / NV];
+    if ((fuse_ku || do_bts) && (tid >> 3) < n_owned * NV) my_node = p.cl_node[q0 + (tid >> 3) / NV];
+    [[maybe_unused]] unsigned my_fdst = 0;  // node-major rank of the incidence: where its nodal force is parked
+    if (do_bts && part == 0 && it < n_inc) my_fdst = p.inc_fdst[inc0 + it];
 
     // ---------------- phase 1: sqrt(w) dN/dx per (touched element, Gauss point) ----------------
     for (int task = tid; task < n_te * NGP; task += THREADS) {
@@ -229,6 +287,15 @@ __global__ void __launch_bounds__(THREADS, (1024 / THREADS > 0 ? 1024 / THREADS 
       for (int x = 0; x < DIM; ++x)
 #pragma unroll
         for (int r = 0; r < DIM; ++r) iJ[x][r] *= s;
+      if constexpr (GEN) {
+        if (do_bts) {  // sqrt(w) sigma of this Gauss point: with sqrt(w) dN/dx it gives w B^T sigma
+          const int64_t e = task == tid ? my_te_elem : p.cl_te_elem[cur.te0 + le];
+          const double* sp = a.stress_gp + 6 * ((int64_t)g * p.n_elems + e);
+          double* so = sSig + (long)task * SGS;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) so[k] = s * sp[k];
+        }
+      }
       // G[k][x] = sum_r iJ[x][r] dN[r][k], stored [k][x] as 128-bit pairs
       double2* out = reinterpret_cast<double2*>(sG + le * ESTR + g * GSTR);
 #pragma unroll
@@ -253,6 +320,9 @@ __global__ void __launch_bounds__(THREADS, (1024 / THREADS > 0 ? 1024 / THREADS 
       }
     }
     if (has_next) load_node_ids(nxt);  // consumed after phase 2
+    if constexpr (GEN) {
+      if (has_next && (per_gp || do_bts)) nxt_te_elem = load_te_elem(nxt);
+    }
     __syncthreads();                   // B2: geometry complete
     FDK_CLK(2)
 
@@ -268,8 +338,13 @@ __global__ void __launch_bounds__(THREADS, (1024 / THREADS > 0 ? 1024 / THREADS 
       const int n_ent = n_inc * NNE + n_owned;
       for (int t = tid; t < (n_ent + 1) / 2; t += THREADS) cp_async<4>(sEnt + 2 * t, esrc + 2 * t);
       for (int t = tid; t < n_heavy; t += THREADS) cp_async<4>(sHeavy + t, p.heavy_slot + h0 + t);
+      if (do_bts)
+        for (int t = tid; t < n_owned; t += THREADS) cp_async<4>(sFinc + t, p.cl_finc_loc + q0 + t);
       cp_async_commit();
-      if (tid == 0) sSlotBase[n_owned] = n_slots;
+      if (tid == 0) {
+        sSlotBase[n_owned] = n_slots;
+        sFinc[n_owned] = n_inc;
+      }
     }
 
     // ---------------- phase 2: NH column blocks of one incidence per thread ----------------
@@ -278,36 +353,87 @@ __global__ void __launch_bounds__(THREADS, (1024 / THREADS > 0 ? 1024 / THREADS 
     for (int j = 0; j < NH; ++j)
 #pragma unroll
       for (int b = 0; b < BLK; ++b) acc[j][b] = 0.0;
+    [[maybe_unused]] double f[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) f[v] = 0.0;
     if (it < n_inc) {
       const int le = my_desc & 0xFFF, i = my_desc >> 12;
       const double* gi_p = sG + le * ESTR + i * DIM;
       const double* gj_p = sG + le * ESTR + col(0) * DIM;
+      if constexpr (!GEN) {
 #pragma unroll P2_UNROLL
-      for (int g = 0; g < NGP; ++g) {
-        double gi[DIM];
+        for (int g = 0; g < NGP; ++g) {
+          double gi[DIM];
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) gi[d] = gi_p[g * GSTR + d];
-        double gj[NH][DIM];
-        if constexpr (PART_UNIFORM && (NH * DIM) % 2 == 0) {  // contiguous columns: 128-bit loads
-          const double2* g2 = reinterpret_cast<const double2*>(gj_p + g * GSTR);
+          for (int d = 0; d < DIM; ++d) gi[d] = gi_p[g * GSTR + d];
+          double gj[NH][DIM];
+          if constexpr (PART_UNIFORM && (NH * DIM) % 2 == 0) {  // contiguous columns: 128-bit loads
+            const double2* g2 = reinterpret_cast<const double2*>(gj_p + g * GSTR);
 #pragma unroll
-          for (int t = 0; t < NH * DIM / 2; ++t) {
-            const double2 v = g2[t];
-            gj[(2 * t) / DIM][(2 * t) % DIM] = v.x;
-            gj[(2 * t + 1) / DIM][(2 * t + 1) % DIM] = v.y;
+            for (int t = 0; t < NH * DIM / 2; ++t) {
+              const double2 v = g2[t];
+              gj[(2 * t) / DIM][(2 * t) % DIM] = v.x;
+              gj[(2 * t + 1) / DIM][(2 * t + 1) % DIM] = v.y;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < NH; ++j)
+#pragma unroll
+              for (int d = 0; d < DIM; ++d) gj[j][d] = gj_p[g * GSTR + (col(j) - col(0)) * DIM + d];
           }
-        } else {
 #pragma unroll
           for (int j = 0; j < NH; ++j)
 #pragma unroll
-            for (int d = 0; d < DIM; ++d) gj[j][d] = gj_p[g * GSTR + (col(j) - col(0)) * DIM + d];
+            for (int cc = 0; cc < DIM; ++cc)
+#pragma unroll
+              for (int aa = 0; aa < DIM; ++aa) acc[j][cc * DIM + aa] = fma(gi[cc], gj[j][aa], acc[j][cc * DIM + aa]);
         }
+      } else {
+        // K_ij += B_i^T C_g B_j with B of Voigt order [xx, yy, zz, xy, xz, yz] (engineering shears): first
+        // t = B_i^T C_g (3 x 6), one tangent column (6 contiguous entries, Fortran order) at a time, then
+        // acc_j += t B_j.  sqrt(w) sits in both gradients.
+        const double* c_p = per_gp ? sC + (long)le * NGP * CSTR : nullptr;
+        const double* s_p = sSig + (long)le * NGP * SGS;
+#pragma unroll 1
+        for (int g = 0; g < NGP; ++g) {
+          double gi[3];
 #pragma unroll
-        for (int j = 0; j < NH; ++j)
+          for (int d = 0; d < 3; ++d) gi[d] = gi_p[g * GSTR + d];
+          if (do_bts && part == 0) {  // nodal force of this incidence: B_i^T (w sigma)
+            const double* ws = s_p + g * SGS;
+            f[0] += ws[0] * gi[0] + ws[3] * gi[1] + ws[4] * gi[2];
+            f[1] += ws[1] * gi[1] + ws[3] * gi[0] + ws[5] * gi[2];
+            f[2] += ws[2] * gi[2] + ws[4] * gi[0] + ws[5] * gi[1];
+          }
+          double t[3][6];
 #pragma unroll
-          for (int cc = 0; cc < DIM; ++cc)
+          for (int sc = 0; sc < 6; ++sc) {
+            double c0, c1, c2, c3, c4, c5;  // C[0..5][sc]
+            if (per_gp) {
+              const double2* cc2 = reinterpret_cast<const double2*>(c_p + g * CSTR + 6 * sc);
+              const double2 u0 = cc2[0], u1 = cc2[1], u2 = cc2[2];
+              c0 = u0.x; c1 = u0.y; c2 = u1.x; c3 = u1.y; c4 = u2.x; c5 = u2.y;
+            } else {
+              c0 = a.C[0 * 6 + sc]; c1 = a.C[1 * 6 + sc]; c2 = a.C[2 * 6 + sc];
+              c3 = a.C[3 * 6 + sc]; c4 = a.C[4 * 6 + sc]; c5 = a.C[5 * 6 + sc];
+            }
+            t[0][sc] = gi[0] * c0 + gi[1] * c3 + gi[2] * c4;
+            t[1][sc] = gi[1] * c1 + gi[0] * c3 + gi[2] * c5;
+            t[2][sc] = gi[2] * c2 + gi[0] * c4 + gi[1] * c5;
+          }
 #pragma unroll
-            for (int aa = 0; aa < DIM; ++aa) acc[j][cc * DIM + aa] = fma(gi[cc], gj[j][aa], acc[j][cc * DIM + aa]);
+          for (int j = 0; j < NH; ++j) {
+            double gj[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) gj[d] = gj_p[g * GSTR + (col(j) - col(0)) * 3 + d];
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+              acc[j][cc * 3 + 0] += t[cc][0] * gj[0] + t[cc][3] * gj[1] + t[cc][4] * gj[2];
+              acc[j][cc * 3 + 1] += t[cc][1] * gj[1] + t[cc][3] * gj[0] + t[cc][5] * gj[2];
+              acc[j][cc * 3 + 2] += t[cc][2] * gj[2] + t[cc][4] * gj[0] + t[cc][5] * gj[1];
+            }
+          }
+        }
       }
     }
     if (has_next) fetch_inputs(nxt, buf ^ 1);  // lands during the gather
@@ -321,8 +447,20 @@ __global__ void __launch_bounds__(THREADS, (1024 / THREADS > 0 ? 1024 / THREADS 
 #pragma unroll
         for (int b = 0; b < BLK; ++b) sp[b] = acc[j][b];
       }
+      if constexpr (GEN) {
+        if (do_bts && part == 0) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) sF[my_fdst * NV + v] = f[v];
+        }
+      }
     }
-    cp_async_wait_group<1>();  // this cluster's descriptors (the next cluster's inputs may still be in flight)
+    if constexpr (GEN) {  // every warp is past the block phase: the tangent buffer may take the next cluster's entries
+      if (per_gp && has_next) fetch_tangent(nxt);
+      cp_async_commit();
+      cp_async_wait_group<2>();  // this cluster's descriptors (two younger groups may still be in flight)
+    } else {
+      cp_async_wait_group<1>();  // this cluster's descriptors (the next cluster's inputs may still be in flight)
+    }
     __syncthreads();           // B4: staging and descriptors complete
     FDK_CLK(4)
 
@@ -381,19 +519,23 @@ __global__ void __launch_bounds__(THREADS, (1024 / THREADS > 0 ? 1024 / THREADS 
           for (int b = 0; b < BLK; ++b) S[b] += bp_[t][b];
         }
       }
-      // K_IJ = lambda S + mu S^T + mu tr(S) 1
       double Kb[BLK];
-      double tr = 0.0;
+      if constexpr (GEN) {
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) tr += S[d * DIM + d];
+        for (int b = 0; b < BLK; ++b) Kb[b] = S[b];
+      } else {  // K_IJ = lambda S + mu S^T + mu tr(S) 1
+        double tr = 0.0;
 #pragma unroll
-      for (int cc = 0; cc < DIM; ++cc)
+        for (int d = 0; d < DIM; ++d) tr += S[d * DIM + d];
 #pragma unroll
-        for (int aa = 0; aa < DIM; ++aa) {
-          double v = fma(a.lam, S[cc * DIM + aa], a.mu * S[aa * DIM + cc]);
-          if (cc == aa) v = fma(a.mu, tr, v);
-          Kb[cc * DIM + aa] = v;
-        }
+        for (int cc = 0; cc < DIM; ++cc)
+#pragma unroll
+          for (int aa = 0; aa < DIM; ++aa) {
+            double v = fma(a.lam, S[cc * DIM + aa], a.mu * S[aa * DIM + cc]);
+            if (cc == aa) v = fma(a.mu, tr, v);
+            Kb[cc * DIM + aa] = v;
+          }
+      }
 #pragma unroll
       for (int cc = 0; cc < NV; ++cc) {
         double* row = a.K + ((int64_t)cc * NV * p.blk_nnz + (int64_t)NV * bp);
@@ -416,7 +558,8 @@ __global__ void __launch_bounds__(THREADS, (1024 / THREADS > 0 ? 1024 / THREADS 
     FDK_CLK(6)
 
     // ---------------- residual: D_I = -sum over the slots of row I, 8 lanes per (node, component) ----------------
-    if (fuse_ku) {
+    if (fuse_ku || do_bts) {
+      const int* sBase = fuse_ku ? sSlotBase : sFinc;  // per-slot K.u products or per-incidence nodal forces
       const int n_out = n_owned * NV * 8;
       for (int t0 = 0; t0 < n_out; t0 += THREADS) {  // whole warps take part in the shuffles
         const int t = t0 + tid;
@@ -424,8 +567,8 @@ __global__ void __launch_bounds__(THREADS, (1024 / THREADS > 0 ? 1024 / THREADS 
         const int n = o / NV, v = o - n * NV;
         double sum = 0.0;
         if (t < n_out) {
-          const int k1 = sSlotBase[n + 1];
-          for (int k = sSlotBase[n] + sub; k < k1; k += 8) sum += sR[k * NV + v];
+          const int k1 = sBase[n + 1];
+          for (int k = sBase[n] + sub; k < k1; k += 8) sum += sR[k * NV + v];
         }
         sum += __shfl_xor_sync(0xffffffffu, sum, 4);
         sum += __shfl_xor_sync(0xffffffffu, sum, 2);
@@ -437,14 +580,27 @@ __global__ void __launch_bounds__(THREADS, (1024 / THREADS > 0 ? 1024 / THREADS 
       }
     }
     FDK_CLK(7)
-    // no closing barrier: the next cluster's phase 1 writes only the geometry view (below sR), its
+    if constexpr (GEN) {
+      if (do_bts) __syncthreads();  // the next geometry phase overwrites the parked forces with sqrt(w) sigma
+    }
+    // no closing barrier (otherwise): the next cluster's phase 1 writes only the geometry view (below sR), its
     // descriptor copies are issued after its B2, which every warp reaches after finishing this reduction
     cur = nxt;
+    if constexpr (GEN) my_te_elem = nxt_te_elem;
   }  // cluster loop
   FDK_CLK_FLUSH
 }
 
-template <class El, int THREADS, int TPI>
+// does the balanced kernel fit this plan (threads per cluster, shared memory)?  Otherwise the caller uses k_assemble.
+template <class El, int THREADS, int TPI, int PHYS = PHYS_ISO>
+bool assemble_iso_fits(const AsmArgs& a) {
+  using IL = IsoLayout<El, TPI>;
+  const bool bts = PHYS == PHYS_GENERAL && (a.compute & FDK_VECTOR) && !a.fuse_ku;
+  return TPI * a.p.cap_inc <= THREADS &&
+         IL::smem_bytes(a.p, PHYS == PHYS_GENERAL && a.tangent_gp != nullptr, bts) <= 227 * 1024;
+}
+
+template <class El, int THREADS, int TPI, int PHYS = PHYS_ISO>
 int launch_assemble_iso(AsmArgs& a, cudaStream_t stream) {
   using IL = IsoLayout<El, TPI>;
   const fdk_plan& p = a.p;
@@ -454,11 +610,12 @@ int launch_assemble_iso(AsmArgs& a, cudaStream_t stream) {
               FDK_ECAP, "cluster capacity overflow (te=%d tn=%d owned=%d ent=%d slots=%d)", p.cap_te, p.cap_tn,
               p.cap_owned, p.cap_ent, p.cap_slots);
   FDK_REQUIRE(p.nvar == IL::NV, FDK_EINVAL, "plan nvar %d does not match the operator (%d)", p.nvar, IL::NV);
-  const size_t smem = IL::smem_bytes(p);
+  const bool bts = PHYS == PHYS_GENERAL && (a.compute & FDK_VECTOR) && !a.fuse_ku;
+  const size_t smem = IL::smem_bytes(p, PHYS == PHYS_GENERAL && a.tangent_gp != nullptr, bts);
   FDK_REQUIRE(smem <= 227 * 1024, FDK_ECAP, "cluster needs %zu bytes of shared memory (> 227 KB)", smem);
   if (p.n_clusters == 0) return 0;
   if (int rc = ensure_device_tables()) return rc;
-  auto kern = k_assemble_iso<El, THREADS, TPI>;
+  auto kern = k_assemble_iso<El, THREADS, TPI, PHYS>;
   static thread_local size_t smem_set = 0;
   if (smem > smem_set) {
     FDK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
