@@ -144,7 +144,7 @@ def plastic(scale):
     e0 = 2.5e-3 * (0.5 + nodes[:, 1] / 100.0)
     U = np.concatenate([e0 * nodes[:, 0], -0.3 * e0 * nodes[:, 1], -0.3 * e0 * nodes[:, 2]])
     U += np.random.default_rng(0).standard_normal(3 * nn) * 1e-5
-    pb.set_X(U)
+    pb.set_X(torch.from_numpy(U).cuda())  # the iterate lives in HBM between Newton iterations (no 100 MB pageable H2D per update)
     a.vector_on_device = True
     t0 = time.perf_counter()
     a.update(pb, compute="all")
