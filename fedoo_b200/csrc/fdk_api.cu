@@ -4,6 +4,7 @@
 
 #include "fdk_assemble.cuh"
 #include "fdk_assemble_iso.cuh"
+#include "fdk_color.cuh"
 #include "fdk_gp.cuh"
 #include "fdk_results.cuh"
 #include "fdk_solve.cuh"
@@ -126,6 +127,18 @@ int fdk_sym_expand_csr(int n_nodes, int nvar, int n_global_dof, int64_t blk_nnz,
                         (cudaStream_t)stream);
 }
 
+int fdk_plan_color_blocks(const fdk_plan* plan, uint8_t* blk_slot, uint16_t* ent_pos, fdk_stream_t stream) {
+  if (int rc = check_plan(plan)) return rc;
+  FDK_REQUIRE(plan->elem_type == FDK_HEX8, FDK_EINVAL, "block colouring is defined for hex8 plans");
+  FDK_REQUIRE(plan->cap_inc * 8 <= COLOR_MAX_BLOCKS, FDK_ECAP, "cluster with %d incidences exceeds the colouring capacity",
+              plan->cap_inc);
+  if (plan->n_clusters == 0) return 0;
+  FDK_REQUIRE(blk_slot && ent_pos, FDK_EINVAL, "NULL output");
+  k_color_blocks<<<plan->n_clusters, 32, 0, (cudaStream_t)stream>>>(*plan, blk_slot, ent_pos);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int fdk_assemble_elastic_iso(const fdk_plan* plan, int compute, const double* coords, double lambda, double mu,
                              const double* U, const double* stress_gp, double* K_values, double* D,
                              fdk_stream_t stream) {
@@ -151,7 +164,7 @@ int fdk_assemble_elastic_iso(const fdk_plan* plan, int compute, const double* co
   // (the template also compiles and passes parity for tet4 / tet10 / quad4 and for 16-node hex8 clusters, but was
   // measured slower than k_assemble on tet10 -- 64 vs 55 ms at 5 M elements -- and is unmeasured on the others)
   if (g_opt_iso4 && (compute & FDK_MATRIX) && !bts && plan->elem_type == FDK_HEX8 && plan->threads == Hex8::THREADS &&
-      assemble_iso_fits<Hex8, 1024, 4>(a))
+      plan->blk_slot && plan->ent_pos && assemble_iso_fits<Hex8, 1024, 4>(a))
     return launch_assemble_iso<Hex8, 1024, 4>(a, (cudaStream_t)stream);
   return dispatch_assemble<PHYS_ISO>(a, (cudaStream_t)stream);
 }
@@ -180,7 +193,8 @@ int fdk_assemble_elastic_general(const fdk_plan* plan, int compute, const double
   // a given stress: balanced kernel with the tangent staged in shared memory (fdk_assemble_iso.cuh)
   const bool vec_ok = !(compute & FDK_VECTOR) || a.fuse_ku || stress_gp != nullptr;
   if (g_opt_iso4 && (compute & FDK_MATRIX) && vec_ok && plan->elem_type == FDK_HEX8 &&
-      plan->threads == Hex8::THREADS / 2 && assemble_iso_fits<Hex8, 512, 4, PHYS_GENERAL>(a))
+      plan->threads == Hex8::THREADS / 2 && plan->blk_slot && plan->ent_pos &&
+      assemble_iso_fits<Hex8, 512, 4, PHYS_GENERAL>(a))
     return launch_assemble_iso<Hex8, 512, 4, PHYS_GENERAL>(a, (cudaStream_t)stream);
   return dispatch_assemble<PHYS_GENERAL>(a, (cudaStream_t)stream);
 }

@@ -64,6 +64,12 @@ struct IsoLayout {
   //  * geometry: the own-row loads of the incidences of elements le and le+1 differ by ESTR + 3 (i - i'); with
   //    ESTR = 8 mod 16 they never collide (3 d = 8 mod 16 has no solution with |d| <= 7) (hex8: 216).
   static constexpr int ISTR = (NNE == 8 && DIM == 3 && TPI == 4 && !PART_UNIFORM) ? 76 : L::ISTR;
+  // hex8, 4 threads per incidence: block positions come from the plan (csrc/fdk_color.cuh): the 16 blocks a half-warp
+  // stores together share a window of 16 positions, permuted so that the gather is conflict-free as well
+  static constexpr bool COLORED = NNE == 8 && TPI == 4 && !PART_UNIFORM;
+  __host__ __device__ static long stage_doubles(const fdk_plan& p) {
+    return COLORED ? (long)((p.cap_inc + 3) / 4) * 32 * BLK : (long)p.cap_inc * ISTR;
+  }
   static constexpr int ESTR = (NNE == 8 && DIM == 3) ? 216 : L::ESTR;
   static constexpr int TSTR = (GROW + 2) & ~1;  // even: the reference gradients are read as 128-bit node pairs
   static_assert(NNE % 2 == 0, "node pairs");
@@ -75,7 +81,7 @@ struct IsoLayout {
   // staging of the blocks; the per-slot K.u products live BEHIND both views of the big region so that the
   // residual reduction of cluster c may overlap the geometry phase of cluster c+1
   __host__ __device__ static long sr_offset(const fdk_plan& p) {
-    const long g = (long)p.cap_te * ESTR, s = (long)p.cap_inc * ISTR;
+    const long g = (long)p.cap_te * ESTR, s = stage_doubles(p);
     return ((g > s ? g : s) + 1) & ~1L;
   }
   // per-slot K.u products or per-incidence nodal forces (never both)
@@ -109,6 +115,7 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
     k_assemble_iso(const __grid_constant__ AsmArgs a) {
   using IL = IsoLayout<El, TPI>;
   constexpr bool GEN = PHYS == PHYS_GENERAL;
+  constexpr bool COLORED = IL::COLORED;
   static_assert(PHYS == PHYS_ISO || (GEN && El::DIM == 3), "balanced kernel: isotropic, or general tangent in 3D");
   constexpr int CSTR = IL::CSTR, SGS = IL::SGS;
   constexpr int NNE = IL::NNE, NGP = IL::NGP, DIM = IL::DIM, NV = IL::NV, BLK = IL::BLK, ISTR = IL::ISTR;
@@ -146,6 +153,9 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
   unsigned char* sLbuf = reinterpret_cast<unsigned char*>(sHeavy + p.cap_heavy);                // [2][lc_bytes]
   const int lc_bytes = (p.cap_te * NNE + 3) & ~3;
   unsigned short* sEnt = reinterpret_cast<unsigned short*>(sLbuf + 2 * lc_bytes);               // [cap_ent]
+
+  // offset of a staged block from its gather-list entry
+  auto blk_off = [&](int src) { return COLORED ? src * BLK : (src / NNE) * ISTR + (src % NNE) * BLK; };
 
   // ---------------- prologue: tables (once per CTA), the first cluster's inputs ----------------
   {
@@ -234,6 +244,14 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
     if (has_next) nxt = load_hdr(p.cl_hdr, c_next);  // consumed after phase 1
     unsigned my_desc = 0;
     if (it < n_inc) my_desc = p.inc_desc[inc0 + it];  // consumed in phase 2
+    [[maybe_unused]] int my_pos[NH];                   // staging positions of this thread's blocks (after phase 2)
+    if constexpr (COLORED) {
+      if (it < n_inc) {
+#pragma unroll
+        for (int j = 0; j < NH; ++j)
+          my_pos[j] = ((((it >> 2) * 2 + j) << 4) + (int)p.blk_slot[(int64_t)(inc0 + it) * NNE + col(j)]);
+      }
+    }
     int my_node = 0;  // row node of this thread's share of the residual reduction (consumed at the very end)
     if ((fuse_ku || do_bts) && (tid >> 3) < n_owned * NV) my_node = p.cl_node[q0 + (tid >> 3) / NV];
     [[maybe_unused]] unsigned my_fdst = 0;  // node-major rank of the incidence: where its nodal force is parked
@@ -334,7 +352,8 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
         cp_async<8>(sBptr + t, p.cl_bptr + q0 + t);
         cp_async<4>(sSlotBase + t, p.cl_slot_loc + q0 + t);
       }
-      const unsigned short* esrc = p.ent_src + cur.ent0;  // even offset: 4-byte aligned
+      // gather lists: staging positions (coloured layout) or block ids it * nne + j; even offset: 4-byte aligned
+      const unsigned short* esrc = (COLORED ? p.ent_pos : p.ent_src) + cur.ent0;
       const int n_ent = n_inc * NNE + n_owned;
       for (int t = tid; t < (n_ent + 1) / 2; t += THREADS) cp_async<4>(sEnt + 2 * t, esrc + 2 * t);
       for (int t = tid; t < n_heavy; t += THREADS) cp_async<4>(sHeavy + t, p.heavy_slot + h0 + t);
@@ -443,7 +462,7 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
     if (it < n_inc) {
 #pragma unroll
       for (int j = 0; j < NH; ++j) {
-        double* sp = sBlk + it * ISTR + col(j) * BLK;
+        double* sp = COLORED ? sBlk + my_pos[j] * BLK : sBlk + it * ISTR + col(j) * BLK;
 #pragma unroll
         for (int b = 0; b < BLK; ++b) sp[b] = acc[j][b];
       }
@@ -479,14 +498,14 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
           for (int k = 0; k < 8; ++k) src[k] = sEnt[eb + k < e1 ? eb + k : e0];
           double x[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) x[k] = sBlk[(src[k] / NNE) * ISTR + (src[k] % NNE) * BLK + b];
+          for (int k = 0; k < 8; ++k) x[k] = sBlk[blk_off(src[k]) + b];
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             if (eb + k < e1) v += x[k];
         }
         // in place: only this thread touches column b of the entries of slot h
         const int src0 = sEnt[e0];
-        sBlk[(src0 / NNE) * ISTR + (src0 % NNE) * BLK + b] = v;
+        sBlk[blk_off(src0) + b] = v;
       }
       __syncthreads();
       FDK_CLK(5)
@@ -507,7 +526,7 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
 #pragma unroll
       for (int t = 0; t < HEAVY_T; ++t) {
         const int src = sEnt[e0 + (t < cnt ? t : 0)];
-        bp_[t] = sBlk + (src / NNE) * ISTR + (src % NNE) * BLK;
+        bp_[t] = sBlk + blk_off(src);
       }
       double S[BLK];
 #pragma unroll
@@ -610,6 +629,8 @@ int launch_assemble_iso(AsmArgs& a, cudaStream_t stream) {
               FDK_ECAP, "cluster capacity overflow (te=%d tn=%d owned=%d ent=%d slots=%d)", p.cap_te, p.cap_tn,
               p.cap_owned, p.cap_ent, p.cap_slots);
   FDK_REQUIRE(p.nvar == IL::NV, FDK_EINVAL, "plan nvar %d does not match the operator (%d)", p.nvar, IL::NV);
+  FDK_REQUIRE(!IL::COLORED || (p.blk_slot && p.ent_pos), FDK_EINVAL,
+              "the plan carries no block colouring (fdk_plan_color_blocks)");
   const bool bts = PHYS == PHYS_GENERAL && (a.compute & FDK_VECTOR) && !a.fuse_ku;
   const size_t smem = IL::smem_bytes(p, PHYS == PHYS_GENERAL && a.tangent_gp != nullptr, bts);
   FDK_REQUIRE(smem <= 227 * 1024, FDK_ECAP, "cluster needs %zu bytes of shared memory (> 227 KB)", smem);

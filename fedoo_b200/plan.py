@@ -434,6 +434,20 @@ class Plan:
             heavy_slot=heavy_slot.to(torch.uint32),
         )
         self._structs = {}
+        # hex8: conflict-free staging layout of the balanced kernel, computed by the library (csrc/fdk_color.cuh);
+        # device plans only (the CPU emulator of the tests follows the generic kernel's layout)
+        if elem_type == "hex8" and dev.type == "cuda" and n_cl > 0:
+            import ctypes as C
+
+            blk_slot = torch.zeros(max(n_inc_tot * nne, 1), dtype=torch.uint8, device=dev)
+            ent_pos = torch.zeros(max(int(ent0_pad[-1]), 1), dtype=torch.uint16, device=dev)
+            _lib.check(
+                _lib.load().fdk_plan_color_blocks(C.byref(self.struct(3)), _lib.ptr(blk_slot), _lib.ptr(ent_pos),
+                                                  _lib.current_stream()),
+                "fdk_plan_color_blocks",
+            )  # fmt: skip
+            self.t["blk_slot"], self.t["ent_pos"] = blk_slot, ent_pos
+            self._structs = {}
 
     @staticmethod
     def _cluster_stats(cl_of_pos, n_cl, order, inc_count_o, deg_o, inc_ptr_node, inc_e_by_node, conn64):

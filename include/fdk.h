@@ -133,7 +133,16 @@ typedef struct fdk_plan {
                                   the last record of a cluster is an end sentinel with owner 0xFF          */
   const int32_t* cl_heavy_ptr; /* [n_clusters+1] range of heavy slots (more than 4 contributions)         */
   const uint32_t* heavy_slot;  /* cluster-local slot index of each heavy slot                             */
+  const uint8_t* blk_slot;     /* hex8 balanced kernel (fdk_plan_color_blocks), may be NULL: [n_inc][nne]
+                                  slot (0..15) of block (incidence, j) inside the 16-block staging window of
+                                  its producer group (incidence / 4) * 2 + j / 4                          */
+  const uint16_t* ent_pos;     /* same indexing as ent_src: staging POSITION of the entry's block         */
 } fdk_plan;
+
+/* Fills blk_slot / ent_pos (device arrays sized like inc_desc * nne and ent_src) for a hex8 plan: a bank-conflict-free
+ * layout of the staging array of the balanced kernel (csrc/fdk_color.cuh).  One-time, per plan; the two pointers of
+ * *plan are ignored on input. */
+int fdk_plan_color_blocks(const fdk_plan* plan, uint8_t* blk_slot, uint16_t* ent_pos, fdk_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
  * Numeric assembly (per step).  Replaces Assembly.assemble_global_mat
