@@ -39,17 +39,17 @@ __global__ void __launch_bounds__(32) k_color_blocks(const fdk_plan p, unsigned 
   }
   for (int i = lane; i < COLOR_MAX_CG * W; i += 32) (&s_use[0][0])[i] = 0;
   __syncwarp();
-  // consumer group of every block: (half-warp of its slot, rank among the slot's contributions); the contributions
-  // of a heavy slot are read one after the other by a single thread and stay unconstrained
+  // consumer group of every block: (half-warp of its slot, rank among the slot's contributions); the other
+  // contributions of a heavy slot are read one after the other by a single thread and stay unconstrained
   for (int s = lane; s < n_slots; s += 32) {
     const unsigned r0 = rec[s], r1 = rec[s + 1];
     const int e0 = r0 & 0xFFFF;
     const int cnt = (int)(r1 & 0xFFFF) - e0 - (((r0 ^ r1) >> 24) ? 1 : 0);
-    if (cnt <= HEAVY_T) {
-      for (int t = 0; t < cnt; ++t) {
-        const int cg = (s >> 4) * HEAVY_T + t;
-        s_cg[ent[e0 + t]] = cg < COLOR_MAX_CG ? (unsigned short)cg : 0xFFFF;
-      }
+    // (a heavy slot is pre-reduced into its FIRST entry, which the gather then reads at step 0 like any other slot)
+    const int n_con = cnt <= HEAVY_T ? cnt : 1;
+    for (int t = 0; t < n_con; ++t) {
+      const int cg = (s >> 4) * HEAVY_T + t;
+      s_cg[ent[e0 + t]] = cg < COLOR_MAX_CG ? (unsigned short)cg : 0xFFFF;
     }
   }
   __syncwarp();
