@@ -20,7 +20,7 @@ EXPORTS = [
     "fdk_assemble_elastic_iso", "fdk_assemble_elastic_general", "fdk_assemble_heat",
     "fdk_gp_strain_stress", "fdk_gp_temperature", "fdk_j2_update",
     "fdk_gather_f64", "fdk_scatter_add_f64", "fdk_copy_segments",
-    "fdk_csr_spmv", "fdk_csr_diagonal", "fdk_pcg_work_doubles", "fdk_pcg_jacobi",
+    "fdk_csr_spmv", "fdk_csr_diagonal", "fdk_pcg_work_doubles", "fdk_pcg_jacobi", "fdk_bcsr_spmv", "fdk_bcsr_pcg_jacobi",
     "fdk_gp_to_node", "fdk_gp_to_element", "fdk_gp_von_mises",
 ]  # fmt: skip
 
@@ -110,6 +110,9 @@ def load():
     lib.fdk_j2_update.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp]
     lib.fdk_csr_spmv.argtypes = [i64, i64, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.fdk_csr_diagonal.argtypes = [i64, vp, vp, i32, vp, vp, vp]
+    lib.fdk_bcsr_spmv.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp]
+    lib.fdk_bcsr_pcg_jacobi.argtypes = [i32, i32, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, dbl, i32, i32, vp,
+                                        C.POINTER(i32), C.POINTER(dbl), vp]
     lib.fdk_pcg_work_doubles.argtypes = [i64]
     lib.fdk_pcg_jacobi.argtypes = [i64, i64, vp, vp, i32, vp, vp, vp, vp, dbl, i32, i32, vp, C.POINTER(i32),
                                    C.POINTER(dbl), vp]

@@ -206,7 +206,8 @@ class Assembly(_Named):
 
         if want_mat:
             n_rows = nvar * n_nodes + n_glob
-            self.global_matrix = DeviceCSR(indptr, indices, K, (n_rows, n_rows))
+            block = (pattern.blk_indptr, pattern.blk_indices, nvar, n_nodes) if n_glob == 0 else None
+            self.global_matrix = DeviceCSR(indptr, indices, K, (n_rows, n_rows), block=block)
         if want_vec:
             if has_vec:
                 self.global_vector_device = D

@@ -162,10 +162,13 @@ class DeviceCSR:
     and the scipy object is materialised on first host access (``tocsr()`` or any scipy-like
     attribute); ``indptr`` / ``indices`` / ``data`` are the device tensors."""
 
-    def __init__(self, indptr, indices, data, shape):
+    def __init__(self, indptr, indices, data, shape, block=None):
         self.indptr, self.indices, self.data = indptr, indices, data
         self.shape = tuple(shape)
         self._host = None
+        # (blk_indptr int64, blk_indices int32, nvar, n_nodes) of the tiled pattern when the matrix comes from the
+        # assembly and has no global dofs: matvec / pcg then read every block row's column list once
+        self.block = block
 
     @property
     def nnz(self):
@@ -194,6 +197,7 @@ class DeviceCSR:
             self.indptr = torch.cat([self.indptr, self.indptr[-1:].expand(extra)])
             self.shape = (n, n)
             self._host = None
+            self.block = None  # trailing global dofs: back to the generic CSR kernels
 
     def _index_bytes(self):
         assert self.indptr.dtype == self.indices.dtype, "indptr and indices share one integer type (scipy convention)"
@@ -208,6 +212,14 @@ class DeviceCSR:
         x = as_device_f64(x, self.data.device)
         assert x.numel() == self.shape[1]
         y = torch.empty(self.shape[0], dtype=torch.float64, device=self.data.device) if out is None else out
+        if self.block is not None:
+            bp, bi, nvar, n_nodes = self.block
+            _lib.check(
+                _lib.load().fdk_bcsr_spmv(n_nodes, nvar, int(bi.numel()), _lib.ptr(bp), _lib.ptr(bi), _lib.ptr(self.data),
+                                          _lib.ptr(x), _lib.ptr(free_mask), _lib.ptr(y), _lib.current_stream()),
+                "fdk_bcsr_spmv",
+            )  # fmt: skip
+            return y
         _lib.check(
             _lib.load().fdk_csr_spmv(
                 self.shape[0], self.nnz, _lib.ptr(self.indptr), _lib.ptr(self.indices), self._index_bytes(),
@@ -243,6 +255,18 @@ class DeviceCSR:
         x = torch.empty(n, dtype=torch.float64, device=self.data.device)
         work = torch.empty(int(lib.fdk_pcg_work_doubles(n)), dtype=torch.float64, device=self.data.device)
         it, rel = C.c_int(0), C.c_double(0.0)
+        if self.block is not None:
+            bp, bi, nvar, n_nodes = self.block
+            _lib.check(
+                lib.fdk_bcsr_pcg_jacobi(
+                    n_nodes, nvar, int(bi.numel()), _lib.ptr(bp), _lib.ptr(bi), _lib.ptr(self.indptr), _lib.ptr(self.indices),
+                    self._index_bytes(), _lib.ptr(self.data), _lib.ptr(b), _lib.ptr(x), _lib.ptr(free_mask), float(rtol),
+                    int(10 * n if maxiter is None else maxiter), int(check_every), _lib.ptr(work), C.byref(it), C.byref(rel),
+                    _lib.current_stream(),
+                ),
+                "fdk_bcsr_pcg_jacobi",
+            )  # fmt: skip
+            return x, it.value, rel.value
         _lib.check(
             lib.fdk_pcg_jacobi(
                 n, self.nnz, _lib.ptr(self.indptr), _lib.ptr(self.indices), self._index_bytes(), _lib.ptr(self.data),

@@ -303,6 +303,38 @@ int fdk_csr_spmv(int64_t n_rows, int64_t nnz, const void* indptr, const void* in
                               (cudaStream_t)stream);
 }
 
+int fdk_bcsr_spmv(int n_nodes, int nvar, int64_t blk_nnz, const int64_t* blk_indptr, const int32_t* blk_indices,
+                  const double* data, const double* x, const uint8_t* free_mask, double* y, fdk_stream_t stream) {
+  FDK_REQUIRE(n_nodes >= 0 && blk_nnz >= 0, FDK_EINVAL, "negative size");
+  if (n_nodes == 0) return 0;
+  FDK_REQUIRE(blk_indptr && blk_indices && data && x && y, FDK_EINVAL, "NULL argument");
+  BlockPattern b;
+  b.n_nodes = n_nodes; b.nvar = nvar; b.blk_nnz = blk_nnz; b.blk_indptr = blk_indptr; b.blk_indices = blk_indices;
+  return launch_bspmv<true>(b, data, x, free_mask, y, (cudaStream_t)stream);
+}
+
+int fdk_bcsr_pcg_jacobi(int n_nodes, int nvar, int64_t blk_nnz, const int64_t* blk_indptr, const int32_t* blk_indices,
+                        const void* indptr, const void* indices, int index_bytes, const double* data, const double* b,
+                        double* x, const uint8_t* free_mask, double rtol, int max_iter, int check_every, double* work,
+                        int* iters_h, double* relres_h, fdk_stream_t stream) {
+  FDK_REQUIRE(n_nodes >= 0 && blk_nnz >= 0 && nvar >= 1 && nvar <= 3 && max_iter >= 0 && rtol >= 0.0, FDK_EINVAL,
+              "bad size or tolerance");
+  if (iters_h) *iters_h = 0;
+  if (relres_h) *relres_h = 0.0;
+  if (n_nodes == 0) return 0;
+  FDK_REQUIRE(blk_indptr && blk_indices && indptr && indices && data && b && x && work, FDK_EINVAL, "NULL argument");
+  FDK_REQUIRE(index_bytes == 4 || index_bytes == 8, FDK_EINVAL, "index_bytes must be 4 or 8");
+  if (check_every < 1) check_every = 1;
+  BlockPattern bp;
+  bp.n_nodes = n_nodes; bp.nvar = nvar; bp.blk_nnz = blk_nnz; bp.blk_indptr = blk_indptr; bp.blk_indices = blk_indices;
+  const int64_t n = (int64_t)nvar * n_nodes, nnz = (int64_t)nvar * nvar * blk_nnz;
+  if (index_bytes == 4)
+    return pcg_jacobi<int32_t>(n, nnz, (const int32_t*)indptr, (const int32_t*)indices, data, b, x, free_mask, rtol,
+                               max_iter, check_every, work, iters_h, relres_h, (cudaStream_t)stream, &bp);
+  return pcg_jacobi<int64_t>(n, nnz, (const int64_t*)indptr, (const int64_t*)indices, data, b, x, free_mask, rtol,
+                             max_iter, check_every, work, iters_h, relres_h, (cudaStream_t)stream, &bp);
+}
+
 int fdk_csr_diagonal(int64_t n_rows, const void* indptr, const void* indices, int index_bytes, const double* data,
                      double* diag, fdk_stream_t stream) {
   FDK_REQUIRE(n_rows >= 0, FDK_EINVAL, "negative size");

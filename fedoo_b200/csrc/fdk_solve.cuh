@@ -11,6 +11,8 @@
 // the vector updates are fused so that every CG iteration reads / writes each vector once.  Reductions are
 // two-stage with a fixed block order (no floating-point atomics): results are bit-reproducible.
 #pragma once
+#include <cstdlib>
+
 #include "fdk_common.cuh"
 
 namespace fdk {
@@ -61,6 +63,93 @@ __global__ void __launch_bounds__(256) k_csr_spmv(int64_t n_rows, const Idx* __r
     for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, LPR);
     if (lane == 0 && r < n_rows) y[r] = s;
   }
+}
+
+// The same product for the TILED pattern of the assembly (scipy.sparse.bmat layout: row v n + I = concat over v' of
+// v' n + blockrow(I), values at v NV blk_nnz + NV bp(I) + v' deg(I) + pcol): one sub-warp per NODE row reads the block
+// row's column list once for its NV x NV scalar rows -- the generic kernel reads each column index NV x NV times, a
+// third of its traffic -- and gathers the NV dofs of every column node once instead of NV times.
+template <int NV, int LPR, bool MASK_COLS>
+__global__ void __launch_bounds__(256) k_bcsr_spmv(int n_nodes, int64_t blk_nnz, const int64_t* __restrict__ blk_indptr,
+                                                    const int32_t* __restrict__ blk_indices,
+                                                    const double* __restrict__ data, const double* __restrict__ x,
+                                                    const unsigned char* __restrict__ mask, double* __restrict__ y) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & (LPR - 1);
+  const int sub = (threadIdx.x & 31) / LPR;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t rb = warp * RPW; rb < n_nodes; rb += n_warps * RPW) {
+    const int64_t I = rb + sub;
+    double acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+    if (I < n_nodes) {
+      const int64_t e0 = __ldg(blk_indptr + I), e1 = __ldg(blk_indptr + I + 1);
+      const int64_t deg = e1 - e0;
+      for (int64_t pc = lane; pc < deg; pc += LPR) {
+        const int64_t J = __ldg(blk_indices + e0 + pc);
+        double xj[NV];
+#pragma unroll
+        for (int w = 0; w < NV; ++w) {
+          const int64_t c = (int64_t)w * n_nodes + J;
+          const bool take = !MASK_COLS || mask == nullptr || mask[c];
+          xj[w] = take ? __ldg(x + c) : 0.0;
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const double* row = data + ((int64_t)v * NV * blk_nnz + (int64_t)NV * e0 + pc);
+#pragma unroll
+          for (int w = 0; w < NV; ++w) acc[v] = fma(__ldg(row + (int64_t)w * deg), xj[w], acc[v]);
+        }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      double s = acc[v];
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, LPR);
+      if (lane == 0 && I < n_nodes) {
+        const int64_t r = (int64_t)v * n_nodes + I;
+        y[r] = (mask == nullptr || mask[r]) ? s : 0.0;
+      }
+    }
+  }
+}
+
+struct BlockPattern {  // optional tiled-pattern description of a CSR matrix assembled by this library
+  int n_nodes = 0, nvar = 0;
+  int64_t blk_nnz = 0;
+  const int64_t* blk_indptr = nullptr;
+  const int32_t* blk_indices = nullptr;
+};
+
+template <bool MASK_COLS>
+int launch_bspmv(const BlockPattern& b, const double* data, const double* x, const unsigned char* mask, double* y,
+                 cudaStream_t stream) {
+  if (b.n_nodes == 0) return 0;
+  const int threads = 256;
+  const double avg = (double)b.blk_nnz / (double)b.n_nodes;
+  int lpr = avg >= 160 ? 32 : avg >= 80 ? 16 : avg >= 40 ? 8 : 4;  // measured at 27 blocks per row: 4.1 ms with 8 lanes,
+  if (const char* e = getenv("FDK_BSPMV_LANES")) lpr = atoi(e);      // 4.7 with 16, 6.3 with 32 (more rows in flight)
+  const int64_t need = ((int64_t)b.n_nodes * lpr + threads - 1) / threads;
+  const unsigned grid = (unsigned)(need < 148 * 32 ? need : 148 * 32);
+#define FDK_BSPMV(NV_, LPR_)                                                                                       \
+  k_bcsr_spmv<NV_, LPR_, MASK_COLS><<<grid, threads, 0, stream>>>(b.n_nodes, b.blk_nnz, b.blk_indptr, b.blk_indices, \
+                                                                   data, x, mask, y)
+  if (b.nvar == 3) {
+    if (lpr == 32) FDK_BSPMV(3, 32); else if (lpr == 16) FDK_BSPMV(3, 16); else if (lpr == 8) FDK_BSPMV(3, 8); else FDK_BSPMV(3, 4);
+  } else if (b.nvar == 2) {
+    if (lpr == 32) FDK_BSPMV(2, 32); else if (lpr == 16) FDK_BSPMV(2, 16); else if (lpr == 8) FDK_BSPMV(2, 8); else FDK_BSPMV(2, 4);
+  } else if (b.nvar == 1) {
+    if (lpr == 32) FDK_BSPMV(1, 32); else if (lpr == 16) FDK_BSPMV(1, 16); else if (lpr == 8) FDK_BSPMV(1, 8); else FDK_BSPMV(1, 4);
+  } else {
+    set_error("tiled SpMV: nvar must be 1, 2 or 3 (got %d)", b.nvar);
+    return FDK_EINVAL;
+  }
+#undef FDK_BSPMV
+  FDK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 template <class Idx>
@@ -219,7 +308,7 @@ inline int pick_lanes(int64_t n_rows, int64_t nnz) {
 template <class Idx>
 int pcg_jacobi(int64_t n, int64_t nnz, const Idx* indptr, const Idx* indices, const double* data, const double* b,
                double* x, const unsigned char* mask, double rtol, int max_iter, int check_every, double* work,
-               int* iters_h, double* relres_h, cudaStream_t stream) {
+               int* iters_h, double* relres_h, cudaStream_t stream, const BlockPattern* blk = nullptr) {
   double* r = work;
   double* z = r + n;
   double* p = z + n;
@@ -244,7 +333,11 @@ int pcg_jacobi(int64_t n, int64_t nnz, const Idx* indptr, const Idx* indices, co
     const double target = rtol * rtol * bb;
     while (it < max_iter) {
       // p vanishes on the imposed dofs by construction: only the rows need the mask
-      if (int rc = launch_spmv<Idx, false>(n, indptr, indices, data, p, mask, q, lanes, stream)) return rc;
+      if (blk != nullptr) {
+        if (int rc = launch_bspmv<false>(*blk, data, p, mask, q, stream)) return rc;
+      } else if (int rc = launch_spmv<Idx, false>(n, indptr, indices, data, p, mask, q, lanes, stream)) {
+        return rc;
+      }
       k_dot<<<RED_BLOCKS, RED_THREADS, 0, stream>>>(n, p, q, part);
       k_reduce_final<<<1, RED_THREADS, 0, stream>>>(part, 1, scal + S_PQ);
       k_pcg_update<<<RED_BLOCKS, RED_THREADS, 0, stream>>>(n, scal, diag, mask, p, q, x, r, z, part);

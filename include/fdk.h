@@ -224,6 +224,16 @@ int fdk_j2_update(int64_t n_gp, const double* props_h, const double* strain_gp, 
 int fdk_csr_spmv(int64_t n_rows, int64_t nnz, const void* indptr, const void* indices, int index_bytes,
                  const double* data, const double* x, const uint8_t* free_mask, double* y, fdk_stream_t stream);
 
+/* The same product and solve for a matrix in the TILED pattern of fdk_sym_expand_csr without global dofs, given its
+ * block pattern (blk_indptr int64 [n_nodes+1], blk_indices int32 [blk_nnz]): the column list of a block row is read
+ * once for its nvar x nvar scalar rows (nvar = 1, 2, 3).  Results are identical up to summation order. */
+int fdk_bcsr_spmv(int n_nodes, int nvar, int64_t blk_nnz, const int64_t* blk_indptr, const int32_t* blk_indices,
+                  const double* data, const double* x, const uint8_t* free_mask, double* y, fdk_stream_t stream);
+int fdk_bcsr_pcg_jacobi(int n_nodes, int nvar, int64_t blk_nnz, const int64_t* blk_indptr, const int32_t* blk_indices,
+                        const void* indptr, const void* indices, int index_bytes, const double* data, const double* b,
+                        double* x, const uint8_t* free_mask, double rtol, int max_iter, int check_every, double* work,
+                        int* iters_h, double* relres_h, fdk_stream_t stream);
+
 /* diag[r] = A[r,r] (0 if not stored); columns sorted within a row (the pattern of fdk_sym_expand_csr is). */
 int fdk_csr_diagonal(int64_t n_rows, const void* indptr, const void* indices, int index_bytes, const double* data,
                      double* diag, fdk_stream_t stream);
