@@ -37,6 +37,16 @@ enum Physics { PHYS_ISO = 0, PHYS_GENERAL = 1, PHYS_HEAT = 2 };
 
 constexpr int HEAVY_T = 4;  // slots with more contributions are pre-reduced (must match plan.py)
 
+// Balanced hex8 kernel (fdk_assemble_iso.cuh), 4 threads per incidence: which two column blocks thread `part` takes.
+// ADJ = 1: j = 2 part + jj (6 contiguous doubles of dN/dx: three 128-bit loads per Gauss point);
+// ADJ = 0: j = part + 4 jj (six 64-bit loads).  The staging colouring (fdk_color.cuh) follows the same rule.
+#ifndef FDK_ISO_COLS_ADJ
+#define FDK_ISO_COLS_ADJ 1
+#endif
+constexpr bool ISO_COLS_ADJ = FDK_ISO_COLS_ADJ != 0;
+__host__ __device__ constexpr int iso_col(int part, int jj) { return ISO_COLS_ADJ ? 2 * part + jj : part + 4 * jj; }
+__host__ __device__ constexpr int iso_jj(int j) { return ISO_COLS_ADJ ? (j & 1) : (j >> 2); }
+
 struct AsmArgs {
   fdk_plan p;
   const double* coords;

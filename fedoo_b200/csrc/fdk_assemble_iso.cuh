@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
   const int it = PART_UNIFORM ? tid % INC : tid / TPI;    // incidence of this thread (phase 2)
   const int part = PART_UNIFORM ? tid / INC : tid % TPI;  // its column blocks
   // column block jj of this thread: part*NH + jj (contiguous) or part + jj*TPI (interleaved)
-  auto col = [&](int jj) { return PART_UNIFORM ? part * NH + jj : part + jj * TPI; };
+  auto col = [&](int jj) { return PART_UNIFORM ? part * NH + jj : (COLORED ? iso_col(part, jj) : part + jj * TPI); };
+  constexpr bool ADJ = COLORED && ISO_COLS_ADJ;  // the thread's two columns are adjacent: 6 contiguous doubles
 
   extern __shared__ __align__(16) double smem[];
   double* sdN = smem;              // [NGP][TSTR] reference gradients, [g][d][k]
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
 #pragma unroll
           for (int d = 0; d < DIM; ++d) gi[d] = gi_p[g * GSTR + d];
           double gj[NH][DIM];
-          if constexpr (PART_UNIFORM && (NH * DIM) % 2 == 0) {  // contiguous columns: 128-bit loads
+          if constexpr ((PART_UNIFORM || ADJ) && (NH * DIM) % 2 == 0) {  // contiguous columns: 128-bit loads
             const double2* g2 = reinterpret_cast<const double2*>(gj_p + g * GSTR);
 #pragma unroll
             for (int t = 0; t < NH * DIM / 2; ++t) {
@@ -440,11 +441,21 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
             t[1][sc] = gi[1] * c1 + gi[0] * c3 + gi[2] * c5;
             t[2][sc] = gi[2] * c2 + gi[0] * c4 + gi[1] * c5;
           }
+          [[maybe_unused]] double gjv[NH * 3];
+          if constexpr (ADJ) {
+            const double2* g2 = reinterpret_cast<const double2*>(gj_p + g * GSTR);
+#pragma unroll
+            for (int q = 0; q < NH * 3 / 2; ++q) {
+              const double2 v = g2[q];
+              gjv[2 * q] = v.x;
+              gjv[2 * q + 1] = v.y;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < NH; ++j) {
             double gj[3];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) gj[d] = gj_p[g * GSTR + (col(j) - col(0)) * 3 + d];
+            for (int d = 0; d < 3; ++d) gj[d] = ADJ ? gjv[j * 3 + d] : gj_p[g * GSTR + (col(j) - col(0)) * 3 + d];
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) {
               acc[j][cc * 3 + 0] += t[cc][0] * gj[0] + t[cc][3] * gj[1] + t[cc][4] * gj[2];

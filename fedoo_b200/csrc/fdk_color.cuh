@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(32) k_color_blocks(const fdk_plan p, unsigned 
     const int n_groups = ((n_inc + TPI - 1) / TPI) * 2;
     auto block_of = [&](int G, int l) {  // lane l of producer group G -> block id, or -1 past the last incidence
       const int it = (G >> 1) * TPI + (l >> 2);
-      return it < n_inc ? it * NNE + (l & 3) + 4 * (G & 1) : -1;
+      return it < n_inc ? it * NNE + iso_col(l & 3, G & 1) : -1;
     };
     for (int G = 0; G < n_groups; ++G) {  // greedy
       unsigned pmask = 0;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(32) k_color_blocks(const fdk_plan p, unsigned 
   for (int e = lane; e < n_ent; e += 32) {
     const int b = ent[e];  // gap entries hold 0: harmless, never read
     const int it = b / NNE, j = b - it * NNE;
-    out_pos[e] = b < n_blocks ? (unsigned short)((((it >> 2) * 2 + (j >> 2)) << 4) + s_slot[b]) : 0;
+    out_pos[e] = b < n_blocks ? (unsigned short)((((it >> 2) * 2 + iso_jj(j)) << 4) + s_slot[b]) : 0;
   }
 }
 
