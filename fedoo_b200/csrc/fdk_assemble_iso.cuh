@@ -258,6 +258,22 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
     [[maybe_unused]] unsigned my_fdst = 0;  // node-major rank of the incidence: where its nodal force is parked
     if (do_bts && part == 0 && it < n_inc) my_fdst = p.inc_fdst[inc0 + it];
 
+    // gather descriptors nobody reads between the closing barrier of the previous cluster and this cluster's gather:
+    // issued by the threads that have no geometry task (600 tasks on 1024 threads), so they cost the others nothing
+    auto fetch_desc = [&](int first, int stride) {
+      const unsigned* rec = p.slot_rec + slot0 + c;
+      for (int t = first; t <= n_slots; t += stride) cp_async<4>(sRec + t, rec + t);
+      for (int t = first; t < n_owned; t += stride) cp_async<8>(sBptr + t, p.cl_bptr + q0 + t);
+      // gather lists: staging positions (coloured layout) or block ids it * nne + j; even offset: 4-byte aligned
+      const unsigned short* esrc = (COLORED ? p.ent_pos : p.ent_src) + cur.ent0;
+      const int n_ent = n_inc * NNE + n_owned;
+      for (int t = first; t < (n_ent + 1) / 2; t += stride) cp_async<4>(sEnt + 2 * t, esrc + 2 * t);
+      for (int t = first; t < n_heavy; t += stride) cp_async<4>(sHeavy + t, p.heavy_slot + h0 + t);
+    };
+    const int n_task = n_te * NGP;
+    const bool desc_early = n_task + 128 <= THREADS;  // uniform over the CTA
+    if (desc_early && tid >= n_task) fetch_desc(tid - n_task, THREADS - n_task);
+
     // ---------------- phase 1: sqrt(w) dN/dx per (touched element, Gauss point) ----------------
     for (int task = tid; task < n_te * NGP; task += THREADS) {
       const int le = task / NGP, g = task - le * NGP;
@@ -345,21 +361,13 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
     __syncthreads();                   // B2: geometry complete
     FDK_CLK(2)
 
-    // ---------------- descriptors of this cluster's gather (land during phase 2) ----------------
+    // ---------------- the rest of the gather descriptors (land during phase 2) ----------------
     {
-      const unsigned* rec = p.slot_rec + slot0 + c;
-      for (int t = tid; t <= n_slots; t += THREADS) cp_async<4>(sRec + t, rec + t);
-      for (int t = tid; t < n_owned; t += THREADS) {
-        cp_async<8>(sBptr + t, p.cl_bptr + q0 + t);
-        cp_async<4>(sSlotBase + t, p.cl_slot_loc + q0 + t);
+      if (!desc_early) fetch_desc(tid, THREADS);
+      for (int t = tid; t < n_owned; t += THREADS) {  // read by the residual reduction of the previous cluster:
+        cp_async<4>(sSlotBase + t, p.cl_slot_loc + q0 + t);  // only now, after every warp has passed it
+        if (do_bts) cp_async<4>(sFinc + t, p.cl_finc_loc + q0 + t);
       }
-      // gather lists: staging positions (coloured layout) or block ids it * nne + j; even offset: 4-byte aligned
-      const unsigned short* esrc = (COLORED ? p.ent_pos : p.ent_src) + cur.ent0;
-      const int n_ent = n_inc * NNE + n_owned;
-      for (int t = tid; t < (n_ent + 1) / 2; t += THREADS) cp_async<4>(sEnt + 2 * t, esrc + 2 * t);
-      for (int t = tid; t < n_heavy; t += THREADS) cp_async<4>(sHeavy + t, p.heavy_slot + h0 + t);
-      if (do_bts)
-        for (int t = tid; t < n_owned; t += THREADS) cp_async<4>(sFinc + t, p.cl_finc_loc + q0 + t);
       cp_async_commit();
       if (tid == 0) {
         sSlotBase[n_owned] = n_slots;
