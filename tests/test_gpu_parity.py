@@ -518,3 +518,55 @@ def test_tiled_spmv_matches_generic(fd, golden_dir):
     x1, it1, r1 = K.pcg(b, free_mask=fm, rtol=1e-12)
     x2, it2, r2 = generic.pcg(b, free_mask=fm, rtol=1e-12)
     assert r1 <= 1e-12 and r2 <= 1e-12 and nrm(x1.cpu().numpy(), x2.cpu().numpy()) <= 1e-9
+
+
+def test_block_colouring_of_the_plan(fd):
+    """fdk_plan_color_blocks (csrc/fdk_color.cuh): inside every 16-block producer window the slots are a permutation
+    (two blocks never share a staging position), the gather lists point at the blocks' positions, and the 16 blocks a
+    half-warp of the gather loads at one step sit in (nearly always) 16 different slots."""
+    import torch
+
+    from fedoo_b200 import symbolic
+
+    n = 13
+    nodes, elements = fd.meshgen.box_hex8(n, n, n)
+    nodes = fd.meshgen.jitter_nodes(nodes, n, n, n)
+    coords = torch.from_numpy(nodes).cuda()
+    conn = torch.from_numpy(elements.astype(np.int32)).cuda()
+    plan = symbolic.build_plan("hex8", coords, conn, small=False)
+
+    def host(v):
+        a = v.cpu()
+        if a.dtype == torch.uint16:
+            return a.view(torch.int16).numpy().astype(np.int64) & 0xFFFF
+        if a.dtype == torch.uint32:
+            return a.view(torch.int32).numpy().astype(np.int64) & 0xFFFFFFFF
+        return a.numpy().astype(np.int64)
+
+    t = {k: host(plan.t[k]) for k in ("cl_hdr", "slot_rec", "ent_src", "ent_pos", "blk_slot", "cl_slot_ptr")}
+    waves = ideal = 0
+    for c in range(plan.n_clusters):
+        hdr = t["cl_hdr"][c]
+        q0, n_owned, n_inc, n_slots, ent0 = hdr[0], hdr[1], hdr[7], hdr[12], hdr[13]
+        inc0 = hdr[6]
+        slot0 = t["cl_slot_ptr"][q0]
+        slots = t["blk_slot"][inc0 * 8 : (inc0 + n_inc) * 8].reshape(n_inc, 8)
+        it = np.arange(n_inc)[:, None]
+        j = np.arange(8)[None, :]
+        pos = (((it >> 2) * 2 + (j & 1)) << 4) + slots  # column blocks 2 part + jj: jj = j & 1 (ISO_COLS_ADJ)
+        assert slots.max() < 16 and len(np.unique(pos)) == n_inc * 8  # a permutation inside every window
+        rec = t["slot_rec"][slot0 + c : slot0 + c + n_slots + 1]
+        off, own = rec & 0xFFFF, rec >> 24
+        cnt = off[1:] - off[:-1] - (own[1:] != own[:-1])
+        ent_src = t["ent_src"][ent0 : ent0 + n_inc * 8 + n_owned]
+        ent_pos = t["ent_pos"][ent0 : ent0 + n_inc * 8 + n_owned]
+        for s in range(n_slots):
+            e = np.arange(off[s], off[s] + cnt[s])
+            assert np.array_equal(ent_pos[e], pos.reshape(-1)[ent_src[e]])
+        for h in range(0, n_slots, 16):  # wavefronts of the gather per half-warp and step
+            for step in range(4):
+                p = [ent_pos[off[s] + step] & 15 for s in range(h, min(h + 16, n_slots)) if step < min(cnt[s], 4 if cnt[s] <= 4 else 1)]
+                if p:
+                    waves += np.bincount(p, minlength=16).max()
+                    ideal += 1
+    assert waves <= 1.15 * ideal, (waves, ideal)
