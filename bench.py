@@ -364,8 +364,8 @@ def run_b200(args):
                 "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s",
                 "kernel": kernel_name,
-                "binding_resource": "shared FP64 / shared-memory issue path of the SM (ncu: LSU data pipe + FP64 pipe "
-                "~ 98 % busy, DRAM ~ 11 %); see DESIGN.md section 7",
+                "binding_resource": "shared FP64 / shared-memory issue path of the SM (ncu: LSU data pipe 75 % + FP64 pipe "
+                "24 % busy, DRAM 13 %); see DESIGN.md section 7",
                 "kernel_ms": ms_kernel_max,
                 "algorithmic_bytes_per_launch": algo_bytes,
             },
