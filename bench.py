@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-n", type=int, default=40, help="edge of the bounded CPU-baseline sample (40 -> 64 k hex8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: residual exchange fused into the kernel over NVLink peer memory, or NCCL all-gather")
     ap.add_argument("--check", action="store_true", help="verify size-independent properties of the assembled K, D")
     return ap.parse_args()
 
@@ -121,7 +123,8 @@ def workload_config(args, **extra):
         "K + residual assembly (configs[1])",
         "jitter": bool(args.jitter),
         "l2": "working set (>= 16 GB written per step at n=200) far exceeds the 126 MB L2; no flush needed",
-        "partition": f"z-slabs of nodes over {args.gpus} GPU(s), owner-computes rows, NCCL all-gather of D",
+        "partition": f"z-slabs of nodes over {args.gpus} GPU(s), owner-computes rows, residual exchange: "
+        + ("none (1 GPU)" if args.gpus == 1 else extra.pop("exchange", "NCCL all-gather of D")),
     }
     cfg.update(extra)
     return cfg
@@ -222,8 +225,23 @@ def run_b200(args):
     t_first = time.perf_counter() - t0
     entry = asm._saved_bloc_structure
     plan, pattern = entry["plan"], entry["pattern"]
-    exch = fdist.VectorExchange(loc, 3) if world > 1 else None
-    D_global = torch.zeros(3 * n_nodes_global, dtype=torch.float64, device="cuda") if world > 1 else None
+    # N > 1: the exchange of the residual.  Default: fused into the assembly kernel (stores over NVLink into a
+    # symmetric, multicast-mapped global vector, fedoo_b200.dist.PeerVector); --exchange nccl, or a failed
+    # symmetric-memory rendezvous: pack + NCCL all-gather + unpack (fedoo_b200.dist.VectorExchange)
+    exch = peer = D_global = None
+    if world > 1:
+        if args.exchange == "peer":
+            try:
+                peer = fdist.PeerVector(loc, 3)
+                asm.peer_vector = peer
+                D_global = peer.tensor
+            except Exception as e:  # noqa: BLE001
+                if rank == 0:
+                    print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); NCCL all-gather", file=sys.stderr)
+                peer = None
+        if peer is None:
+            exch = fdist.VectorExchange(loc, 3)
+            D_global = torch.zeros(3 * n_nodes_global, dtype=torch.float64, device="cuda")
 
     def barrier():
         if world > 1:
@@ -348,6 +366,9 @@ def run_b200(args):
             "data": "synthetic",
             "config": workload_config(
                 args,
+                exchange=("fused into the assembly kernel: stores over NVLink into a symmetric global vector ("
+                          + ("NVSwitch multicast" if peer is not None and peer.multicast else "peer addresses") + ") + device barrier"
+                          if peer is not None else "pack + NCCL all-gather of D + unpack"),
                 nnz=9 * pattern.blk_nnz if world == 1 else None,
                 nnz_per_s=(9 * (3 * n + 1) ** 3) / (ms_step * 1e-3),
                 clusters=plan.n_clusters,
@@ -379,7 +400,7 @@ def run_b200(args):
                 "(DeviceCSR, materialised to scipy only on demand)",
             },
             # the assembly kernel, plus pack / unpack of the residual exchange (NCCL's own kernels not counted)
-            "gpu_launches": args.steps * (1 if world == 1 else (3 if exch.seg_pack is not None else 6)),
+            "gpu_launches": args.steps * (1 if exch is None else (3 if exch.seg_pack is not None else 6)),
             "clocks": clk.summary(),
         }
         if checks is not None:

@@ -63,6 +63,8 @@ class Assembly(_Named):
         self.reuse_buffers = kargs.pop("reuse_buffers", False)
         # leave the global vector in HBM (``global_vector`` is then the CUDA tensor): no D2H copy
         self.vector_on_device = kargs.pop("vector_on_device", False)
+        # multi-GPU: a fedoo_b200.dist.PeerVector -> the residual exchange is fused into the assembly kernel
+        self.peer_vector = kargs.pop("peer_vector", None)
         self._bufs = {}
         self.mesh = mesh
         if elm_type == "":
@@ -166,7 +168,18 @@ class Assembly(_Named):
                     stress_dev = stress.device_tensor
             if flags:
                 tangent_dev = law.tangent_device(self) if hasattr(law, "tangent_device") else None
-                if isinstance(law, ElasticIsotrop) and tangent_dev is None:
+                peer = self.peer_vector
+                if (isinstance(law, ElasticIsotrop) and tangent_dev is None and peer is not None and flags == _lib.ALL
+                        and U_dev is not None and stress_dev is None):
+                    # multi-GPU: the kernel stores the owned residual entries straight into every rank's global vector
+                    lam, mu = law.lame(dimension)
+                    rc = lib.fdk_assemble_elastic_iso_dist(
+                        C.byref(plan.struct(nvar)), flags, _lib.ptr(coords), lam, mu, _lib.ptr(U_dev), _lib.ptr(K),
+                        _lib.ptr(D), peer._ptr_array, len(peer.dst_ptrs), _lib.ptr(peer.node_gid), peer.n_global, stream,
+                    )  # fmt: skip
+                    _lib.check(rc, "fdk_assemble_elastic_iso_dist")
+                    peer.barrier()
+                elif isinstance(law, ElasticIsotrop) and tangent_dev is None:
                     lam, mu = law.lame(dimension)
                     rc = lib.fdk_assemble_elastic_iso(
                         C.byref(plan.struct(nvar)), flags, _lib.ptr(coords), lam, mu, _lib.ptr(U_dev),

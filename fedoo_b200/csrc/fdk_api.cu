@@ -169,6 +169,36 @@ int fdk_assemble_elastic_iso(const fdk_plan* plan, int compute, const double* co
   return dispatch_assemble<PHYS_ISO>(a, (cudaStream_t)stream);
 }
 
+int fdk_assemble_elastic_iso_dist(const fdk_plan* plan, int compute, const double* coords, double lambda, double mu,
+                                  const double* U, double* K_values, double* D, double* const* D_dst_h, int n_dst,
+                                  const int64_t* node_gid, int64_t n_global_nodes, fdk_stream_t stream) {
+  if (int rc = check_plan(plan)) return rc;
+  if (int rc = check_io(compute, coords, K_values, D)) return rc;
+  FDK_REQUIRE(compute == FDK_ALL && U != nullptr, FDK_EINVAL, "the fused exchange needs compute = all and U");
+  FDK_REQUIRE(n_dst >= 1 && n_dst <= 8 && D_dst_h && node_gid && n_global_nodes > 0, FDK_EINVAL, "bad destinations");
+  AsmArgs a{};
+  a.p = *plan;
+  a.coords = coords;
+  a.U = U;
+  a.K = K_values;
+  a.D = D;
+  a.lam = lambda;
+  a.mu = mu;
+  a.compute = compute;
+  a.fuse_ku = 1;
+  for (int r = 0; r < n_dst; ++r) {
+    FDK_REQUIRE(D_dst_h[r] != nullptr, FDK_EINVAL, "NULL destination");
+    a.D_dst[r] = D_dst_h[r];
+  }
+  a.n_dst = n_dst;
+  a.node_gid = node_gid;
+  a.n_dst_nodes = n_global_nodes;
+  const bool served = plan->elem_type == FDK_HEX8 && plan->threads == Hex8::THREADS && plan->blk_slot &&
+                      plan->ent_pos && (assemble_iso_fits<Hex8, 1024, 4>(a));
+  FDK_REQUIRE(served, FDK_EINVAL, "the fused exchange is served by the balanced hex8 kernel (32-node clusters) only");
+  return launch_assemble_iso<Hex8, 1024, 4>(a, (cudaStream_t)stream);
+}
+
 int fdk_assemble_elastic_general(const fdk_plan* plan, int compute, const double* coords, const double* C_h,
                                  const double* tangent_gp, const double* U, const double* stress_gp,
                                  double* K_values, double* D, fdk_stream_t stream) {

@@ -64,6 +64,13 @@ struct AsmArgs {
   int big_doubles;  // size of the aliased geometry / staging region
   int fuse_ku;      // linear law, K and D both requested: D = -(assembled rows) . U in the gather phase
   int no_mma;       // FDK_NO_MMA=1: keep the CUDA-core producer even where the tensor-core one applies
+  // fused residual exchange (balanced kernel, multi-GPU): besides D (rank-local numbering) every owned entry is
+  // stored at var * n_dst_nodes + node_gid[node] of n_dst destination vectors -- ONE NVLink multicast address
+  // (NVSwitch replicates the store into every GPU's copy of the global vector) or the peers' own addresses
+  double* D_dst[8];
+  int n_dst;
+  const int64_t* node_gid;  // rank-local node -> global node
+  int64_t n_dst_nodes;
 };
 
 template <class El, int PHYS>

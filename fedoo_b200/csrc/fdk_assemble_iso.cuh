@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
     }
     int my_node = 0;  // row node of this thread's share of the residual reduction (consumed at the very end)
     if ((fuse_ku || do_bts) && (tid >> 3) < n_owned * NV) my_node = p.cl_node[q0 + (tid >> 3) / NV];
+    [[maybe_unused]] int64_t my_gid = 0;  // its global id, for the fused exchange (a second dependent load, hidden by phase 1)
+    if (a.n_dst > 0 && (fuse_ku || do_bts) && (tid >> 3) < n_owned * NV) my_gid = a.node_gid[my_node];
     [[maybe_unused]] unsigned my_fdst = 0;  // node-major rank of the incidence: where its nodal force is parked
     if (do_bts && part == 0 && it < n_inc) my_fdst = p.inc_fdst[inc0 + it];
 
@@ -614,6 +616,13 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
         if (t < n_out && sub == 0) {
           const int node = (t0 == 0) ? my_node : p.cl_node[q0 + n];
           a.D[(int64_t)v * p.n_nodes + node] = -sum;
+          if (a.n_dst > 0) {  // fused exchange: straight into every rank's global vector over NVLink
+            const int64_t gid = (t0 == 0) ? my_gid : a.node_gid[node];
+            for (int r = 0; r < a.n_dst; ++r) {
+              double* dst = a.D_dst[r] + (int64_t)v * a.n_dst_nodes + gid;
+              *dst = -sum;  // weak store: visible to the peers once the kernel and the barrier behind it are through
+            }
+          }
         }
       }
     }

@@ -246,3 +246,34 @@ class VectorExchange:
             D_global.zero_()
             D_global[self.dst_index] = self.recv[self.recv_pos]
         return D_global
+
+
+class PeerVector:
+    """The global vector replicated on every rank in SYMMETRIC memory (torch.distributed._symmetric_memory), so that
+    the assembly kernel itself can deliver the owned entries of the residual into every rank's copy over NVLink --
+    one store to the allocation's multicast address, which NVSwitch replicates to all GPUs, or stores to the peers'
+    own addresses when no multicast object could be created.  Replaces pack + NCCL all-gather + unpack
+    (``VectorExchange``) by ``fdk_assemble_elastic_iso_dist`` + a device-side barrier."""
+
+    def __init__(self, local: LocalMesh, nvar: int, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group or dist.group.WORLD
+        self.nvar, self.n_global = nvar, local.n_global_nodes
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.tensor = symm_mem.empty(nvar * self.n_global, dtype=torch.float64, device=dev)
+        self.tensor.zero_()
+        self.handle = symm_mem.rendezvous(self.tensor, self.group)
+        mc = int(self.handle.multicast_ptr or 0)
+        self.dst_ptrs = [mc] if mc else [int(x) for x in self.handle.buffer_ptrs]
+        assert len(self.dst_ptrs) <= 8, "peer-address fallback is limited to 8 ranks"
+        self.multicast = bool(mc)
+        self.node_gid = torch.from_numpy(np.ascontiguousarray(local.node_gid, dtype=np.int64)).to(dev)
+        self._ptr_array = (C.c_void_p * len(self.dst_ptrs))(*self.dst_ptrs)
+        torch.cuda.synchronize()
+        self.handle.barrier()
+
+    def barrier(self):
+        """Device-side barrier on the current stream: after it every rank's stores have landed everywhere."""
+        self.handle.barrier()

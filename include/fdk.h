@@ -169,6 +169,17 @@ int fdk_assemble_elastic_iso(const fdk_plan* plan, int compute, const double* co
                              const double* U, const double* stress_gp, double* K_values, double* D,
                              fdk_stream_t stream);
 
+/* The same with the exchange of the residual FUSED into the kernel (multi-GPU, one process per GPU): every owned
+ * entry of D is also stored at var * n_global_nodes + node_gid[node] of n_dst destination vectors -- one NVLink
+ * multicast address of a symmetric allocation (NVSwitch replicates each store into all GPUs' copies) or the peers'
+ * own addresses (n_dst <= 8, host array of device pointers).  node_gid: int64 [plan->n_nodes] rank-local node ->
+ * global node.  The caller synchronises the ranks afterwards (a device-side barrier on the same stream).  Served by
+ * the balanced hex8 kernel only (matrix requested, residual from U): FDK_EINVAL otherwise.  No reference
+ * counterpart (the reference is single-process). */
+int fdk_assemble_elastic_iso_dist(const fdk_plan* plan, int compute, const double* coords, double lambda, double mu,
+                                  const double* U, double* K_values, double* D, double* const* D_dst_h, int n_dst,
+                                  const int64_t* node_gid, int64_t n_global_nodes, fdk_stream_t stream);
+
 /* General tangent: C is 6x6 row-major uniform (tangent_gp == NULL) or per Gauss point
  * tangent_gp [(6,6,N) Fortran order: C_ij of GP n at i + 6 j + 36 n] = sv["TangentMatrix"]
  * (fedoo/constitutivelaw/simcoon_umat.py:556-580, elastic_anisotropic.py:19-31).
