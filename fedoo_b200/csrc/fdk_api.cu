@@ -196,7 +196,7 @@ int fdk_assemble_elastic_iso_dist(const fdk_plan* plan, int compute, const doubl
   const bool served = plan->elem_type == FDK_HEX8 && plan->threads == Hex8::THREADS && plan->blk_slot &&
                       plan->ent_pos && (assemble_iso_fits<Hex8, 1024, 4>(a));
   FDK_REQUIRE(served, FDK_EINVAL, "the fused exchange is served by the balanced hex8 kernel (32-node clusters) only");
-  return launch_assemble_iso<Hex8, 1024, 4>(a, (cudaStream_t)stream);
+  return launch_assemble_iso<Hex8, 1024, 4, PHYS_ISO, true>(a, (cudaStream_t)stream);
 }
 
 int fdk_assemble_elastic_general(const fdk_plan* plan, int compute, const double* coords, const double* C_h,

@@ -110,7 +110,8 @@ struct IsoLayout {
   }
 };
 
-template <class El, int THREADS, int TPI, int PHYS = PHYS_ISO>
+// DIST: the fused multi-GPU exchange of the residual (a separate instantiation: the single-GPU kernel pays nothing)
+template <class El, int THREADS, int TPI, int PHYS = PHYS_ISO, bool DIST = false>
 __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS > 0 ? 1024 / THREADS : 1))
     k_assemble_iso(const __grid_constant__ AsmArgs a) {
   using IL = IsoLayout<El, TPI>;
@@ -256,7 +257,9 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
     int my_node = 0;  // row node of this thread's share of the residual reduction (consumed at the very end)
     if ((fuse_ku || do_bts) && (tid >> 3) < n_owned * NV) my_node = p.cl_node[q0 + (tid >> 3) / NV];
     [[maybe_unused]] int64_t my_gid = 0;  // its global id, for the fused exchange (a second dependent load, hidden by phase 1)
-    if (a.n_dst > 0 && (fuse_ku || do_bts) && (tid >> 3) < n_owned * NV) my_gid = a.node_gid[my_node];
+    if constexpr (DIST) {
+      if ((fuse_ku || do_bts) && (tid >> 3) < n_owned * NV) my_gid = a.node_gid[my_node];
+    }
     [[maybe_unused]] unsigned my_fdst = 0;  // node-major rank of the incidence: where its nodal force is parked
     if (do_bts && part == 0 && it < n_inc) my_fdst = p.inc_fdst[inc0 + it];
 
@@ -616,7 +619,7 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
         if (t < n_out && sub == 0) {
           const int node = (t0 == 0) ? my_node : p.cl_node[q0 + n];
           a.D[(int64_t)v * p.n_nodes + node] = -sum;
-          if (a.n_dst > 0) {  // fused exchange: straight into every rank's global vector over NVLink
+          if constexpr (DIST) {  // fused exchange: straight into every rank's global vector over NVLink
             const int64_t gid = (t0 == 0) ? my_gid : a.node_gid[node];
             for (int r = 0; r < a.n_dst; ++r) {
               double* dst = a.D_dst[r] + (int64_t)v * a.n_dst_nodes + gid;
@@ -647,7 +650,7 @@ bool assemble_iso_fits(const AsmArgs& a) {
          IL::smem_bytes(a.p, PHYS == PHYS_GENERAL && a.tangent_gp != nullptr, bts) <= 227 * 1024;
 }
 
-template <class El, int THREADS, int TPI, int PHYS = PHYS_ISO>
+template <class El, int THREADS, int TPI, int PHYS = PHYS_ISO, bool DIST = false>
 int launch_assemble_iso(AsmArgs& a, cudaStream_t stream) {
   using IL = IsoLayout<El, TPI>;
   const fdk_plan& p = a.p;
@@ -664,7 +667,7 @@ int launch_assemble_iso(AsmArgs& a, cudaStream_t stream) {
   FDK_REQUIRE(smem <= 227 * 1024, FDK_ECAP, "cluster needs %zu bytes of shared memory (> 227 KB)", smem);
   if (p.n_clusters == 0) return 0;
   if (int rc = ensure_device_tables()) return rc;
-  auto kern = k_assemble_iso<El, THREADS, TPI, PHYS>;
+  auto kern = DIST ? k_assemble_iso<El, THREADS, TPI, PHYS, true> : k_assemble_iso<El, THREADS, TPI, PHYS, false>;
   static thread_local size_t smem_set = 0;
   if (smem > smem_set) {
     FDK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
