@@ -84,3 +84,26 @@ def test_plan_unreferenced_nodes_and_single_node_overflow():
 
     with pytest.raises(FdkError):
         make_plan("hex8", nodes, el, caps=dict(inc_max=4, te_max=80))  # interior nodes have 8 incidences
+
+
+def test_slab_ranks_get_the_same_bricks_as_one_gpu():
+    """The Morton curve is built on the lattice of the OWNED nodes with per-axis bucket counts following the bounding
+    box: the z-slabs of a multi-GPU partition (structured or jittered) are cut into the same 4x4x2-node bricks as the
+    whole box, so the total number of clusters does not grow with the number of ranks."""
+    from fedoo_b200 import dist as fdist
+
+    n = 24  # 25^3 nodes
+    totals = {}
+    for jitter in (False, True):
+        for world in (1, 2, 4):
+            tot = 0
+            for rank in range(world):
+                loc = fdist.box_local_slab(n, rank, world, jitter=jitter)
+                owned = torch.from_numpy(loc.owned) if world > 1 else None
+                plan, _ = make_plan("hex8", loc.nodes, loc.elements, owned=owned, small=False)
+                tot += plan.n_clusters
+            totals[(jitter, world)] = tot
+    one = totals[(False, 1)]
+    assert totals[(True, 1)] == one
+    for key, tot in totals.items():
+        assert tot <= 1.08 * one, (key, tot, one)  # slab faces may add a layer of partial bricks, nothing more
