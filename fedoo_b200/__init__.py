@@ -8,11 +8,12 @@ All numeric work happens in hand-written CUDA kernels behind the C ABI of ``incl
 (``fedoo_b200/_fdk.so``); there is no CPU fallback.
 """
 
-from . import constitutivelaw, mesh, meshgen, problem, weakform
+from . import constitutivelaw, constraint, homogen, mesh, meshgen, problem, weakform
 from ._lib import FdkError
 from .assembly import Assembly
 from .constitutivelaw import ConstitutiveLaw
 from .core import DeviceCSR, GaussPointTensor, Mesh, ModelingSpace
+from .problem import Problem
 from .weakform import WeakFormBase
 
 WeakForm = WeakFormBase
@@ -20,6 +21,6 @@ WeakForm = WeakFormBase
 __version__ = "0.1.0"
 
 __all__ = [
-    "Assembly", "ConstitutiveLaw", "DeviceCSR", "FdkError", "GaussPointTensor", "Mesh", "ModelingSpace",
-    "WeakForm", "WeakFormBase", "constitutivelaw", "mesh", "meshgen", "problem", "weakform",
+    "Assembly", "ConstitutiveLaw", "DeviceCSR", "FdkError", "GaussPointTensor", "Mesh", "ModelingSpace", "Problem",
+    "WeakForm", "WeakFormBase", "constitutivelaw", "constraint", "homogen", "mesh", "meshgen", "problem", "weakform",
 ]  # fmt: skip

@@ -21,12 +21,30 @@ EXPORTS = [
     "fdk_gp_strain_stress", "fdk_gp_temperature", "fdk_j2_update",
     "fdk_gather_f64", "fdk_scatter_add_f64", "fdk_copy_segments",
     "fdk_csr_spmv", "fdk_csr_diagonal", "fdk_pcg_work_doubles", "fdk_pcg_jacobi", "fdk_bcsr_spmv", "fdk_bcsr_pcg_jacobi",
+    "fdk_mpc_expand", "fdk_mpc_fold", "fdk_bcsr_pcg_jacobi_mpc",
     "fdk_gp_to_node", "fdk_gp_to_element", "fdk_gp_von_mises",
 ]  # fmt: skip
 
 
 class FdkError(RuntimeError):
     pass
+
+
+class MpcStruct(C.Structure):
+    """Mirror of ``struct fdk_mpc`` (include/fdk.h)."""
+
+    _fields_ = [
+        ("n_nodal", C.c_int64),
+        ("n_glob", C.c_int32),
+        ("n_slave", C.c_int64),
+        ("slave", C.c_void_p),
+        ("master", C.c_void_p),
+        ("coef", C.c_void_p),
+        ("n_master", C.c_int64),
+        ("mst_dof", C.c_void_p),
+        ("mst_ptr", C.c_void_p),
+        ("mst_slv", C.c_void_p),
+    ]
 
 
 class PlanStruct(C.Structure):
@@ -115,6 +133,11 @@ def load():
     lib.fdk_bcsr_pcg_jacobi.argtypes = [i32, i32, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, dbl, i32, i32, vp,
                                         C.POINTER(i32), C.POINTER(dbl), vp]
     lib.fdk_pcg_work_doubles.argtypes = [i64]
+    mp = C.POINTER(MpcStruct)
+    lib.fdk_mpc_expand.argtypes = [mp, vp, vp]
+    lib.fdk_mpc_fold.argtypes = [mp, vp, vp]
+    lib.fdk_bcsr_pcg_jacobi_mpc.argtypes = [i32, i32, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, dbl, i32, i32, vp, mp,
+                                            C.POINTER(i32), C.POINTER(dbl), vp]
     lib.fdk_pcg_jacobi.argtypes = [i64, i64, vp, vp, i32, vp, vp, vp, vp, dbl, i32, i32, vp, C.POINTER(i32),
                                    C.POINTER(dbl), vp]
     lib.fdk_gp_to_node.argtypes = [i32, i32, i32, i64, vp, vp, vp, vp, i32, i64, i64, i32, vp, vp]

@@ -100,6 +100,18 @@ class BoundingBox:
     def __iter__(self):
         return iter((self.mins, self.maxs))
 
+    @property
+    def center(self):
+        return (self.mins + self.maxs) / 2
+
+    @property
+    def size(self):
+        return self.maxs - self.mins
+
+    @property
+    def volume(self):
+        return float(np.prod(self.size))
+
 
 class Mesh(_Named):
     """fedoo/core/mesh.py:70: nodes (n, dim) float64, elements (n_el, nne) ints, elm_type."""
@@ -242,14 +254,37 @@ class DeviceCSR:
         )
         return d
 
-    def pcg(self, b, free_mask=None, rtol=1e-8, maxiter=None, check_every=10):
+    def pcg(self, b, free_mask=None, rtol=1e-8, maxiter=None, check_every=10, mpc=None):
         """Jacobi-preconditioned CG on the device (scipy.sparse.linalg.cg with M = diag(1 / A.diagonal()),
-        fedoo/core/base.py:521-537).  Returns (x, iterations, ||r|| / ||b||), x a device tensor."""
+        fedoo/core/base.py:521-537).  Returns (x, iterations, ||r|| / ||b||), x a device tensor.
+        With ``mpc`` (constraint.MpcMap) the system is T^T A T on n_nodal + n_glob entries: b already folded,
+        free_mask 0 on imposed dofs and slaves, x = the independent dofs."""
         import ctypes as C
 
         from . import _lib
 
         lib = _lib.load()
+        if mpc is not None:
+            if self.block is None:
+                raise NotImplementedError("the constrained solve runs on the tiled pattern of the assembly (nodal size)")
+            bp, bi, nvar, n_nodes = self.block
+            n = mpc.n_total
+            assert self.shape[0] == mpc.n_nodal and free_mask is not None and free_mask.numel() == n
+            b = as_device_f64(b, self.data.device)
+            assert b.numel() == n
+            x = torch.empty(n, dtype=torch.float64, device=self.data.device)
+            work = torch.empty(int(lib.fdk_pcg_work_doubles(n)), dtype=torch.float64, device=self.data.device)
+            it, rel = C.c_int(0), C.c_double(0.0)
+            _lib.check(
+                lib.fdk_bcsr_pcg_jacobi_mpc(
+                    n_nodes, nvar, int(bi.numel()), _lib.ptr(bp), _lib.ptr(bi), _lib.ptr(self.indptr), _lib.ptr(self.indices),
+                    self._index_bytes(), _lib.ptr(self.data), _lib.ptr(b), _lib.ptr(x), _lib.ptr(free_mask), float(rtol),
+                    int(10 * n if maxiter is None else maxiter), int(check_every), _lib.ptr(work), mpc.struct(),
+                    C.byref(it), C.byref(rel), _lib.current_stream(),
+                ),
+                "fdk_bcsr_pcg_jacobi_mpc",
+            )  # fmt: skip
+            return x, it.value, rel.value
         n = self.shape[0]
         b = as_device_f64(b, self.data.device)
         x = torch.empty(n, dtype=torch.float64, device=self.data.device)

@@ -365,6 +365,60 @@ int fdk_bcsr_pcg_jacobi(int n_nodes, int nvar, int64_t blk_nnz, const int64_t* b
                              max_iter, check_every, work, iters_h, relres_h, (cudaStream_t)stream, &bp);
 }
 
+static int mpc_from_abi(const fdk_mpc* m, MpcMap* out) {
+  FDK_REQUIRE(m != nullptr, FDK_EINVAL, "NULL constraint map");
+  FDK_REQUIRE(m->n_nodal >= 0 && m->n_glob >= 0 && m->n_slave >= 0 && m->n_master >= 0, FDK_EINVAL, "negative size");
+  FDK_REQUIRE(m->n_nodal + m->n_glob <= 0x7fffffffLL, FDK_EOVERFLOW, "constraint map indices are int32");
+  if (m->n_slave > 0)
+    FDK_REQUIRE(m->slave && m->master && (m->n_glob == 0 || m->coef) && m->mst_dof && m->mst_ptr && m->mst_slv, FDK_EINVAL,
+                "NULL constraint array");
+  out->n_nodal = m->n_nodal; out->n_glob = m->n_glob; out->n_slave = m->n_slave; out->slave = m->slave;
+  out->master = m->master; out->coef = m->coef; out->n_master = m->n_master; out->mst_dof = m->mst_dof;
+  out->mst_ptr = m->mst_ptr; out->mst_slv = m->mst_slv;
+  return 0;
+}
+
+int fdk_mpc_expand(const fdk_mpc* mpc, double* x, fdk_stream_t stream) {
+  MpcMap m;
+  if (int rc = mpc_from_abi(mpc, &m)) return rc;
+  FDK_REQUIRE(x != nullptr || m.n_slave == 0, FDK_EINVAL, "NULL argument");
+  return mpc_expand(m, x, (cudaStream_t)stream);
+}
+
+int fdk_mpc_fold(const fdk_mpc* mpc, double* q, fdk_stream_t stream) {
+  MpcMap m;
+  if (int rc = mpc_from_abi(mpc, &m)) return rc;
+  FDK_REQUIRE(q != nullptr || (m.n_slave == 0 && m.n_glob == 0), FDK_EINVAL, "NULL argument");
+  return mpc_fold(m, q, nullptr, false, (cudaStream_t)stream);
+}
+
+int fdk_bcsr_pcg_jacobi_mpc(int n_nodes, int nvar, int64_t blk_nnz, const int64_t* blk_indptr,
+                            const int32_t* blk_indices, const void* indptr, const void* indices, int index_bytes,
+                            const double* data, const double* b, double* x, const uint8_t* free_mask, double rtol,
+                            int max_iter, int check_every, double* work, const fdk_mpc* mpc, int* iters_h,
+                            double* relres_h, fdk_stream_t stream) {
+  FDK_REQUIRE(n_nodes >= 0 && blk_nnz >= 0 && nvar >= 1 && nvar <= 3 && max_iter >= 0 && rtol >= 0.0, FDK_EINVAL,
+              "bad size or tolerance");
+  if (iters_h) *iters_h = 0;
+  if (relres_h) *relres_h = 0.0;
+  if (n_nodes == 0) return 0;
+  MpcMap m;
+  if (int rc = mpc_from_abi(mpc, &m)) return rc;
+  FDK_REQUIRE(m.n_nodal == (int64_t)nvar * n_nodes, FDK_EINVAL, "constraint map / matrix size mismatch");
+  FDK_REQUIRE(blk_indptr && blk_indices && indptr && indices && data && b && x && work && free_mask, FDK_EINVAL,
+              "NULL argument");
+  FDK_REQUIRE(index_bytes == 4 || index_bytes == 8, FDK_EINVAL, "index_bytes must be 4 or 8");
+  if (check_every < 1) check_every = 1;
+  BlockPattern bp;
+  bp.n_nodes = n_nodes; bp.nvar = nvar; bp.blk_nnz = blk_nnz; bp.blk_indptr = blk_indptr; bp.blk_indices = blk_indices;
+  const int64_t n = (int64_t)nvar * n_nodes, nnz = (int64_t)nvar * nvar * blk_nnz;
+  if (index_bytes == 4)
+    return pcg_jacobi<int32_t>(n, nnz, (const int32_t*)indptr, (const int32_t*)indices, data, b, x, free_mask, rtol,
+                               max_iter, check_every, work, iters_h, relres_h, (cudaStream_t)stream, &bp, &m);
+  return pcg_jacobi<int64_t>(n, nnz, (const int64_t*)indptr, (const int64_t*)indices, data, b, x, free_mask, rtol,
+                             max_iter, check_every, work, iters_h, relres_h, (cudaStream_t)stream, &bp, &m);
+}
+
 int fdk_csr_diagonal(int64_t n_rows, const void* indptr, const void* indices, int index_bytes, const double* data,
                      double* diag, fdk_stream_t stream) {
   FDK_REQUIRE(n_rows >= 0, FDK_EINVAL, "negative size");

@@ -304,11 +304,96 @@ inline int pick_lanes(int64_t n_rows, int64_t nnz) {
   return avg >= 64 ? 32 : avg >= 32 ? 16 : avg >= 16 ? 8 : 4;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-point constraints of the periodic boundary conditions (fedoo/constraint/periodic_bc.py:910-1800 builds them as
+// MPC objects, fedoo/core/problem.py:277-298 eliminates them through MatCB^T A MatCB):
+//   x[slave_s] = x[master_s] + sum_k coef[s][k] * x[n_nodal + k]          (k < n_glob trailing global dofs)
+// The reduced operator T^T A T is applied matrix-free on full-length vectors whose slave entries are kept at zero:
+// expand (x_s from masters and globals), SpMV, reduce (rows of the slaves folded into their master and into the
+// global dofs), zero the slaves.  Reductions run in a fixed order (slaves grouped by master, one block per global dof).
+struct MpcMap {
+  int64_t n_nodal;
+  int n_glob;
+  int64_t n_slave;
+  const int* slave;     // (n_slave) dof index < n_nodal
+  const int* master;    // (n_slave) dof index < n_nodal
+  const double* coef;   // (n_slave, n_glob) row-major
+  int64_t n_master;     // distinct master dofs
+  const int* mst_dof;   // (n_master)
+  const int* mst_ptr;   // (n_master + 1) into mst_slv
+  const int* mst_slv;   // slave ordinals grouped by master
+};
+
+__global__ void k_mpc_expand(MpcMap m, double* __restrict__ x) {
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < m.n_slave; s += (int64_t)gridDim.x * blockDim.x) {
+    double v = x[m.master[s]];
+    for (int k = 0; k < m.n_glob; ++k) v = fma(m.coef[s * m.n_glob + k], x[m.n_nodal + k], v);
+    x[m.slave[s]] = v;
+  }
+}
+
+__global__ void k_mpc_fold_master(MpcMap m, double* __restrict__ q) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m.n_master; i += (int64_t)gridDim.x * blockDim.x) {
+    double acc = q[m.mst_dof[i]];
+    for (int t = m.mst_ptr[i]; t < m.mst_ptr[i + 1]; ++t) acc += q[m.slave[m.mst_slv[t]]];
+    q[m.mst_dof[i]] = acc;
+  }
+}
+
+// q[n_nodal + k] = sum_s coef[s][k]^(1|2) q[slave_s]: one block per global dof
+template <bool SQUARE>
+__global__ void __launch_bounds__(RED_THREADS) k_mpc_fold_glob(MpcMap m, double* __restrict__ q) {
+  const int k = blockIdx.x;
+  double acc = 0.0;
+  for (int64_t s = threadIdx.x; s < m.n_slave; s += RED_THREADS) {
+    const double c = m.coef[s * m.n_glob + k];
+    acc = fma(SQUARE ? c * c : c, q[m.slave[s]], acc);
+  }
+  const double v = block_sum(acc);
+  if (threadIdx.x == 0) q[m.n_nodal + k] = v;
+}
+
+__global__ void k_mpc_zero_slaves(MpcMap m, double* __restrict__ a, double* __restrict__ b) {
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < m.n_slave; s += (int64_t)gridDim.x * blockDim.x) {
+    a[m.slave[s]] = 0.0;
+    if (b != nullptr) b[m.slave[s]] = 0.0;
+  }
+}
+
+inline unsigned mpc_grid(int64_t n) {
+  const int64_t need = (n + 255) / 256;
+  return (unsigned)(need < 1 ? 1 : need > 148 * 8 ? 148 * 8 : need);
+}
+
+// q <- T^T q (q holds A x on the nodal rows; the global rows are overwritten), then the slave entries of q (and of
+// ``also``: the search direction that k_mpc_expand filled) are cleared
+inline int mpc_fold(const MpcMap& m, double* q, double* also, bool square, cudaStream_t stream) {
+  if (m.n_slave > 0) k_mpc_fold_master<<<mpc_grid(m.n_master), 256, 0, stream>>>(m, q);
+  if (m.n_glob > 0) {
+    if (square) k_mpc_fold_glob<true><<<m.n_glob, RED_THREADS, 0, stream>>>(m, q);
+    else k_mpc_fold_glob<false><<<m.n_glob, RED_THREADS, 0, stream>>>(m, q);
+  }
+  if (m.n_slave > 0) k_mpc_zero_slaves<<<mpc_grid(m.n_slave), 256, 0, stream>>>(m, q, also);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+inline int mpc_expand(const MpcMap& m, double* x, cudaStream_t stream) {
+  if (m.n_slave > 0) k_mpc_expand<<<mpc_grid(m.n_slave), 256, 0, stream>>>(m, x);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // Jacobi-PCG on the free dofs.  work: 5 n doubles (r, z, p, q, diag) + (2 RED_BLOCKS + S_COUNT) doubles.
+// With ``mpc`` the vectors carry n + n_glob entries, ``mask`` marks the independent free dofs (0 on imposed dofs AND on
+// slaves), b must already be folded (T^T b) and x returns the independent dofs (expand it afterwards).
 template <class Idx>
-int pcg_jacobi(int64_t n, int64_t nnz, const Idx* indptr, const Idx* indices, const double* data, const double* b,
+int pcg_jacobi(int64_t n_rows, int64_t nnz, const Idx* indptr, const Idx* indices, const double* data, const double* b,
                double* x, const unsigned char* mask, double rtol, int max_iter, int check_every, double* work,
-               int* iters_h, double* relres_h, cudaStream_t stream, const BlockPattern* blk = nullptr) {
+               int* iters_h, double* relres_h, cudaStream_t stream, const BlockPattern* blk = nullptr,
+               const MpcMap* mpc = nullptr) {
+  const int64_t n = n_rows + (mpc != nullptr ? mpc->n_glob : 0);
+  const unsigned char* row_mask = mpc != nullptr ? nullptr : mask;  // slave rows are needed, the vector kernels mask
   double* r = work;
   double* z = r + n;
   double* p = z + n;
@@ -316,8 +401,11 @@ int pcg_jacobi(int64_t n, int64_t nnz, const Idx* indptr, const Idx* indices, co
   double* diag = q + n;
   double* part = diag + n;
   double* scal = part + 2 * RED_BLOCKS;
-  const int lanes = pick_lanes(n, nnz);
-  k_csr_diagonal<Idx><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, indptr, indices, data, diag);
+  const int lanes = pick_lanes(n_rows, nnz);
+  k_csr_diagonal<Idx><<<(unsigned)((n_rows + 255) / 256), 256, 0, stream>>>(n_rows, indptr, indices, data, diag);
+  if (mpc != nullptr) {  // diag(T^T A T) without the cross terms A_ms (a preconditioner only needs an SPD diagonal)
+    if (int rc = mpc_fold(*mpc, diag, nullptr, true, stream)) return rc;
+  }
   k_pcg_init<<<RED_BLOCKS, RED_THREADS, 0, stream>>>(n, b, diag, mask, x, r, z, p, part);
   k_reduce_final<<<1, RED_THREADS, 0, stream>>>(part, 2, scal + S_RZN);  // S_RZN = rz, S_RR = rr
   k_copy_scalar<<<1, 1, 0, stream>>>(scal, S_RZ, S_RZN);
@@ -333,10 +421,16 @@ int pcg_jacobi(int64_t n, int64_t nnz, const Idx* indptr, const Idx* indices, co
     const double target = rtol * rtol * bb;
     while (it < max_iter) {
       // p vanishes on the imposed dofs by construction: only the rows need the mask
+      if (mpc != nullptr) {
+        if (int rc = mpc_expand(*mpc, p, stream)) return rc;
+      }
       if (blk != nullptr) {
-        if (int rc = launch_bspmv<false>(*blk, data, p, mask, q, stream)) return rc;
-      } else if (int rc = launch_spmv<Idx, false>(n, indptr, indices, data, p, mask, q, lanes, stream)) {
+        if (int rc = launch_bspmv<false>(*blk, data, p, row_mask, q, stream)) return rc;
+      } else if (int rc = launch_spmv<Idx, false>(n_rows, indptr, indices, data, p, row_mask, q, lanes, stream)) {
         return rc;
+      }
+      if (mpc != nullptr) {
+        if (int rc = mpc_fold(*mpc, q, p, false, stream)) return rc;
       }
       k_dot<<<RED_BLOCKS, RED_THREADS, 0, stream>>>(n, p, q, part);
       k_reduce_final<<<1, RED_THREADS, 0, stream>>>(part, 1, scal + S_PQ);

@@ -18,36 +18,131 @@ from .core import _Named
 
 
 class _BC:
+    """Boundary-condition list (fedoo/core/boundary_conditions.py:90-260): ``add("Dirichlet" | "Neumann", node_set,
+    variable(s), value, name=...)``, ``add("Neumann", "E_xx", value)`` on a global dof, ``add(PeriodicBC(...))``,
+    ``remove(name)``."""
+
     def __init__(self, pb):
         self._pb = pb
-        self.list = []
+        self.list = []  # (nodes, variable, value, type, name)
+        self.constraints = []
 
-    def add(self, bc_type, node_set, variable, value=0, **kargs):
-        if bc_type != "Dirichlet":
-            raise NotImplementedError("only Dirichlet conditions are mirrored")
-        if isinstance(node_set, str):
-            node_set = self._pb.mesh.node_sets[node_set]
-        self.list.append((np.asarray(node_set, dtype=np.int64), variable, value))
+    def add(self, *args, **kargs):
+        pb = self._pb
+        if not isinstance(args[0], str):  # a constraint object: initialised when added (boundary_conditions.py:116-118)
+            bc = args[0]
+            bc.initialize(pb)
+            self.constraints.append(bc)
+            pb._dirichlet = None
+            return bc
+        bc_type = args[0]
+        if bc_type not in ("Dirichlet", "Neumann"):
+            raise NotImplementedError("only Dirichlet / Neumann conditions and PeriodicBC are mirrored")
+        rest = list(args[1:])
+        if rest and isinstance(rest[0], str) and rest[0] in pb._global_dof:  # global dof: no node set
+            node_set, variable = np.zeros(1, dtype=np.int64), rest.pop(0)
+        else:
+            node_set = rest.pop(0) if rest else kargs.pop("node_set")
+            variable = rest.pop(0) if rest else kargs.pop("variable")
+            if isinstance(node_set, str):
+                node_set = pb.mesh.node_sets[node_set]
+            node_set = np.atleast_1d(np.asarray(node_set, dtype=np.int64))
+        value = rest.pop(0) if rest else kargs.pop("value", 0)
+        name = kargs.get("name", "")
+        variables = [variable] if isinstance(variable, str) else list(variable)
+        for var in variables:
+            for v in pb._expand_vector(var):
+                self.list.append((node_set, v, value, bc_type, name))
+        pb._dirichlet = None
+
+    def remove(self, name):
+        self.list = [bc for bc in self.list if bc[4] != name]
+        self._pb._dirichlet = None
 
 
 class _ProblemBase(_Named):
     _dict = {}
+    _active = None
 
-    def __init__(self, assembly, name="MainProblem"):
+    def __init__(self, assembly, name="MainProblem", mesh=None, space=None):
         if isinstance(assembly, str):
             assembly = Assembly.get_all()[assembly]
         self.assembly = assembly
-        self.mesh = assembly.mesh
-        self.space = assembly.space
+        self.mesh = assembly.mesh if assembly is not None else mesh
+        if isinstance(self.mesh, str):
+            from .core import Mesh
+
+            self.mesh = Mesh[self.mesh]
+        if space is None:
+            from .core import ModelingSpace
+
+            space = assembly.space if assembly is not None else ModelingSpace.get_active()
+        self.space = space
         self.n_global_dof = 0
+        self._global_dof = {}  # variable name -> index among the global dofs
+        self._global_vector = {}  # vector name -> list of variable names
         self.bc = _BC(self)
         self._dirichlet = None
+        self._neumann = 0
         self.nlgeom = False
         self.time = 0
         self.dtime = 0
         self._solver = ("direct", True, {})
         self.solver_info = None
         self._register(name)
+        _ProblemBase._active = self
+
+    def make_active(self):
+        _ProblemBase._active = self
+
+    @staticmethod
+    def get_active():
+        return _ProblemBase._active
+
+    def add_global_dof(self, variable_names, n_dof=1, vector_name=None):
+        """fedoo/core/base.py:336-366: dofs that belong to no node, stored after the nodal ones."""
+        if isinstance(variable_names, str):
+            variable_names = [variable_names]
+        if n_dof != 1:
+            raise NotImplementedError("one dof per global variable")
+        for v in variable_names:
+            if v not in self._global_dof:
+                self._global_dof[v] = self.n_global_dof
+                self.n_global_dof += 1
+        if vector_name is not None:
+            self._global_vector[vector_name] = list(variable_names)
+        self._dirichlet = None
+        return np.array([self._global_dof[v] for v in variable_names])
+
+    def _expand_vector(self, var):
+        if var in self._global_vector:
+            return self._global_vector[var]
+        if var == "Disp" and "Disp" not in self.space._variable:
+            return ["DispX", "DispY", "DispZ"][: self.space.ndim]
+        return [var]
+
+    def _dof_of(self, var, nodes):
+        if var in self._global_dof:
+            return np.full(len(nodes), self.space.nvar * self.mesh.n_nodes + self._global_dof[var], dtype=np.int64)
+        return self._var_rank(var) * self.mesh.n_nodes + nodes
+
+    def _get_vect_component(self, X, name):
+        """fedoo/core/problem.py:100-130."""
+        n = self.mesh.n_nodes
+        if name in self._global_dof:
+            i = self.space.nvar * n + self._global_dof[name]
+            return X[i : i + 1]
+        if name in self._global_vector:
+            i = self.space.nvar * n + self._global_dof[self._global_vector[name][0]]
+            return X[i : i + len(self._global_vector[name])]
+        return self._slice(X, name)
+
+    @property
+    def _mpc(self):
+        maps = [c.mpc for c in self.bc.constraints if getattr(c, "mpc", None) is not None]
+        if len(maps) > 1:
+            raise NotImplementedError("one constraint map per problem")
+        return maps[0] if maps else None
 
     def set_solver(self, solver="direct", precond=True, **kargs):
         """fedoo/core/base.py:444-519.  "direct" / "direct_scipy": host spsolve; "cg": Jacobi-preconditioned CG on
@@ -60,21 +155,29 @@ class _ProblemBase(_Named):
         self._solver = (solver, bool(precond), dict(kargs))
 
     def _solve(self, A, D, X0=None):
+        if self._dirichlet is None:
+            self.apply_boundary_conditions()
+        if not np.isscalar(self._neumann):  # external forces B (fedoo/core/problem.py:288-296: A X = B + D)
+            D = self._neumann + (0 if np.isscalar(D) else self._pad(np.asarray(D)))
         if self._solver[0] == "cg":
             return self._solve_device(A, D, X0)
         return self._solve_host(A, D, X0)
 
+    def _pad(self, v):
+        return v if v.shape[0] == self.n_dof else np.concatenate([v, np.zeros(self.n_dof - v.shape[0])])
+
     def _solve_device(self, A, D, X0=None):
         """A dX = D with the imposed dofs eliminated, on the device: rhs = (D - A Xbc) on the free dofs, then
-        Jacobi-PCG restricted to them (fedoo/core/problem.py:277-298, fedoo/core/base.py:521-537)."""
+        Jacobi-PCG restricted to them (fedoo/core/problem.py:277-298, fedoo/core/base.py:521-537).  With a
+        PeriodicBC the constraint map T is applied matrix-free: T^T A T y = T^T (D - A Xbc), X = T y + Xbc."""
         import torch
 
         from .core import as_device_f64
 
-        if self._dirichlet is None:
-            self.apply_boundary_conditions()
         dofs, vals = self._dirichlet
-        n = A.shape[0]
+        mpc = self._mpc
+        n = self.n_dof if mpc is not None else A.shape[0]
+        n_mat = A.shape[0]
         dev = A.data.device
         Xbc = torch.zeros(n, dtype=torch.float64, device=dev)
         free = torch.ones(n, dtype=torch.uint8, device=dev)
@@ -83,11 +186,26 @@ class _ProblemBase(_Named):
             imposed = vals if X0 is None else vals - np.asarray(X0)[dofs]
             Xbc[d_dofs] = torch.from_numpy(np.ascontiguousarray(imposed, dtype=float)).to(dev)
             free[d_dofs] = 0
-        rhs = torch.zeros(n, dtype=torch.float64, device=dev) if np.isscalar(D) else as_device_f64(D, dev).clone()
-        rhs -= A.matvec(Xbc)
+        rhs = torch.zeros(n, dtype=torch.float64, device=dev)
+        if not np.isscalar(D):
+            d = as_device_f64(D, dev)
+            rhs[: d.numel()] += d
         kargs = self._solver[2]
         rtol = kargs.get("rtol", kargs.get("tol", 1e-8))
-        x, it, rel = A.pcg(rhs, free_mask=free, rtol=rtol, maxiter=kargs.get("maxiter"))
+        if mpc is None:
+            rhs -= A.matvec(Xbc)
+            x, it, rel = A.pcg(rhs, free_mask=free, rtol=rtol, maxiter=kargs.get("maxiter"))
+        else:
+            if np.intersect1d(dofs, mpc.slave_h).size:
+                raise NotImplementedError("a Dirichlet condition on an eliminated (slave) dof")
+            mpc.expand(Xbc)
+            rhs[:n_mat] -= A.matvec(Xbc[:n_mat] if n_mat < n else Xbc)[:n_mat]
+            load = rhs[mpc.n_nodal :].clone()  # loads on the global dofs (fold overwrites those rows)
+            mpc.fold(rhs)
+            rhs[mpc.n_nodal :] += load
+            free[torch.from_numpy(mpc.slave_h).to(dev)] = 0
+            x, it, rel = A.pcg(rhs, free_mask=free, rtol=rtol, maxiter=kargs.get("maxiter"), mpc=mpc)
+            mpc.expand(x)
         self.solver_info = {"iterations": it, "relative_residual": rel}
         if rel > rtol:
             print(f"Warning: cg solver convergence to tolerance not achieved ({rel:.2e} after {it} iterations)")
@@ -95,7 +213,7 @@ class _ProblemBase(_Named):
 
     @property
     def n_dof(self):
-        return self.assembly.nvar * self.mesh.n_nodes + self.n_global_dof
+        return self.space.nvar * self.mesh.n_nodes + self.n_global_dof
 
     def _var_rank(self, name):
         return self.space.variable_rank(name)
@@ -126,13 +244,20 @@ class _ProblemBase(_Named):
         return get_results(self, assemb, output_list, output_type)
 
     def apply_boundary_conditions(self):
-        """Dirichlet part of fedoo/core/problem.py:335-432."""
-        n = self.mesh.n_nodes
+        """Dirichlet and Neumann part of fedoo/core/problem.py:335-432."""
         dofs, vals = [], []
-        for nodes, var, value in self.bc.list:
-            r = self._var_rank(var)
-            dofs.append(r * n + nodes)
-            vals.append(np.broadcast_to(np.asarray(value, dtype=float), nodes.shape))
+        B = None
+        for nodes, var, value, bc_type, _name in self.bc.list:
+            d = self._dof_of(var, nodes)
+            v = np.broadcast_to(np.asarray(value, dtype=float), nodes.shape)
+            if bc_type == "Dirichlet":
+                dofs.append(d)
+                vals.append(v)
+            else:
+                if B is None:
+                    B = np.zeros(self.n_dof)
+                np.add.at(B, d, v)
+        self._neumann = 0 if B is None else B
         if dofs:
             dofs, vals = np.concatenate(dofs), np.concatenate(vals)
             dofs, first = np.unique(dofs, return_index=True)
@@ -141,20 +266,66 @@ class _ProblemBase(_Named):
             self._dirichlet = (np.zeros(0, dtype=np.int64), np.zeros(0))
 
     def _solve_host(self, A, D, X0=None):
-        """Solve A dX = D with Dirichlet elimination on the host (out of the accelerated scope)."""
+        """Solve A dX = D with Dirichlet (and periodic MPC) elimination on the host like the reference
+        (fedoo/core/problem.py:277-298; out of the accelerated scope, kept for cross-checks)."""
+        from scipy import sparse
         from scipy.sparse.linalg import spsolve
 
         A = A.tocsr()
-        n = A.shape[0]
-        if self._dirichlet is None:
-            self.apply_boundary_conditions()
+        mpc = self._mpc
+        n = self.n_dof if mpc is not None else A.shape[0]
+        if A.shape[0] < n:
+            A = sparse.csr_matrix((A.data, A.indices, np.concatenate([A.indptr, np.full(n - A.shape[0], A.indptr[-1])])), shape=(n, n))
         dofs, vals = self._dirichlet
         X = np.zeros(n)
         X[dofs] = vals if X0 is None else vals - X0[dofs]
-        free = np.setdiff1d(np.arange(n), dofs)
-        rhs = (D if not np.isscalar(D) else np.zeros(n))[free] - (A @ X)[free]
-        X[free] = spsolve(A[free][:, free].tocsc(), rhs)
-        return X
+        keep = np.ones(n, dtype=bool)
+        keep[dofs] = False
+        rhs = np.zeros(n) if np.isscalar(D) else self._pad(np.asarray(D, dtype=float)).copy() if mpc is not None else np.asarray(D, dtype=float)
+        if mpc is None:
+            free = np.nonzero(keep)[0]
+            rhs = rhs[free] - (A @ X)[free]
+            X[free] = spsolve(A[free][:, free].tocsc(), rhs)
+            return X
+        T = mpc.to_scipy()
+        X = T @ X
+        keep[mpc.slave_h] = False
+        free = np.nonzero(keep)[0]
+        Tf = T[:, free]
+        y = spsolve((Tf.T @ A @ Tf).tocsc(), Tf.T @ (rhs - A @ X))
+        return Tf @ y + X
+
+
+class Problem(_ProblemBase):
+    """``fd.Problem(A, B, D, mesh, name)``: the generic linear problem A X = B + D (fedoo/core/problem.py:18-98) that
+    ``fd.homogen`` builds around an already assembled stiffness matrix."""
+
+    def __init__(self, A=0, B=0, D=0, mesh=None, name="MainProblem", space=None):
+        super().__init__(None, name, mesh=mesh, space=space)
+        self._A, self._B, self._D = A, B, D
+        self._X = 0
+
+    def set_A(self, A):
+        self._A = A
+
+    def get_A(self):
+        return self._A
+
+    def set_B(self, B):
+        self._B = B
+
+    def set_D(self, D):
+        self._D = D
+
+    def get_X(self):
+        return self._X
+
+    def get_dof_solution(self, name="all"):
+        return self._X if np.isscalar(self._X) else self._get_vect_component(self._X, name)
+
+    def solve(self, **kargs):
+        rhs = self._B + self._D
+        self._X = self._solve(self._A, rhs)
 
 
 class Linear(_ProblemBase):
@@ -165,6 +336,14 @@ class Linear(_ProblemBase):
 
     def set_X(self, X):
         self._X = X
+
+    def set_A(self, A):
+        """fedoo/problem/linear.py: the matrix is the assembly's; kept for API parity with fd.homogen."""
+        self._A = A
+
+    def get_A(self):
+        A = getattr(self, "_A", None)
+        return A if A is not None else self.assembly.get_global_matrix()
 
     def get_X(self):
         return self._X

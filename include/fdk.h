@@ -245,6 +245,37 @@ int fdk_bcsr_pcg_jacobi(int n_nodes, int nvar, int64_t blk_nnz, const int64_t* b
                         double* x, const uint8_t* free_mask, double rtol, int max_iter, int check_every, double* work,
                         int* iters_h, double* relres_h, fdk_stream_t stream);
 
+/* Periodic boundary conditions with global (non-nodal) dofs, on the device.  Replaces the MPC
+ * elimination of Problem.solve (fedoo/core/problem.py:277-298, MatCB built by fedoo/core/boundary_conditions.py:560-700)
+ * for the constraints PeriodicBC generates (fedoo/constraint/periodic_bc.py:910-1800):
+ *     x[slave_s] = x[master_s] + sum_k coef[s][k] * x[n_nodal + k],   k < n_glob ("MeanStrain" dofs E_xx..E_yz)
+ * Vectors carry n_nodal + n_glob entries.  The matrix keeps its nodal size: the global rows/columns that
+ * Assembly.assemble_global_mat appends by resize (fedoo/core/assembly.py:192-197,459-460) are empty. */
+typedef struct fdk_mpc {
+  int64_t n_nodal;         /* nvar * n_nodes */
+  int32_t n_glob;          /* trailing global dofs */
+  int64_t n_slave;
+  const int32_t* slave;    /* (n_slave) eliminated dof */
+  const int32_t* master;   /* (n_slave) dof it follows; never itself a slave */
+  const double* coef;      /* (n_slave, n_glob) row-major */
+  int64_t n_master;        /* distinct masters */
+  const int32_t* mst_dof;  /* (n_master) */
+  const int32_t* mst_ptr;  /* (n_master + 1) into mst_slv */
+  const int32_t* mst_slv;  /* slave ordinals grouped by master (fixed summation order) */
+} fdk_mpc;
+
+/* x <- T x: fills the slave entries from their masters and the global dofs. */
+int fdk_mpc_expand(const fdk_mpc* mpc, double* x, fdk_stream_t stream);
+/* q <- T^T q: slave rows folded into their masters and into the global rows (overwritten), slave entries cleared. */
+int fdk_mpc_fold(const fdk_mpc* mpc, double* q, fdk_stream_t stream);
+/* Jacobi-PCG on T^T A T: b already folded, free_mask (n_nodal + n_glob bytes) = 0 on imposed dofs AND on slaves,
+ * x returns the independent dofs (call fdk_mpc_expand on it); work = fdk_pcg_work_doubles(n_nodal + n_glob). */
+int fdk_bcsr_pcg_jacobi_mpc(int n_nodes, int nvar, int64_t blk_nnz, const int64_t* blk_indptr,
+                            const int32_t* blk_indices, const void* indptr, const void* indices, int index_bytes,
+                            const double* data, const double* b, double* x, const uint8_t* free_mask, double rtol,
+                            int max_iter, int check_every, double* work, const fdk_mpc* mpc, int* iters_h,
+                            double* relres_h, fdk_stream_t stream);
+
 /* diag[r] = A[r,r] (0 if not stored); columns sorted within a row (the pattern of fdk_sym_expand_csr is). */
 int fdk_csr_diagonal(int64_t n_rows, const void* indptr, const void* indices, int index_bytes, const double* data,
                      double* diag, fdk_stream_t stream);

@@ -570,3 +570,79 @@ def test_block_colouring_of_the_plan(fd):
                     waves += np.bincount(p, minlength=16).max()
                     ideal += 1
     assert waves <= 1.15 * ideal, (waves, ideal)
+
+
+# ----------------------------------------------------------------------------------------------
+# PeriodicBC + homogen.get_homogenized_stiffness on the device (csrc/fdk_solve.cuh: constraint
+# map kernels around the tiled SpMV), pinned on the reference's own result (oracle/gen_golden_homogen.py)
+# ----------------------------------------------------------------------------------------------
+def _iso_H_gp(E_gp, nu):
+    H = np.zeros((6, 6, len(E_gp)))
+    lam = E_gp * nu / ((1 + nu) * (1 - 2 * nu))
+    mu = 0.5 * E_gp / (1 + nu)
+    for i in range(3):
+        for j in range(3):
+            H[i, j] = lam
+        H[i, i] = lam + 2 * mu
+        H[3 + i, 3 + i] = mu
+    return H
+
+
+def test_mpc_expand_fold_match_the_constraint_matrix(fd, golden_dir):
+    """fdk_mpc_expand / fdk_mpc_fold == T x / T^T q with T the scipy change-of-basis matrix."""
+    import torch
+
+    from fedoo_b200.constraint import PeriodicBC
+
+    g = load(golden_dir, "homogen_hex8_inclusion")
+    fd.Assembly.delete_memory()
+    space = fd.ModelingSpace("3D")
+    for v in ("DispX", "DispY", "DispZ"):
+        space.new_variable(v)
+    mesh = fd.Mesh(g["nodes"], g["elements"], "hex8", name="Domain")
+    pb = fd.Problem(0, 0, 0, mesh, name="pb_mpc")
+    bc = pb.bc.add(PeriodicBC("small_strain"))
+    assert pb.n_global_dof == 6 and pb.n_dof == 3 * mesh.n_nodes + 6
+    m = bc.mpc
+    T = m.to_scipy()
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(pb.n_dof)
+    xi = x.copy()
+    xi[m.slave_h] = 0.0
+    out = m.expand(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert nrm(out, T @ xi) <= 1e-15
+    q = rng.standard_normal(pb.n_dof)
+    q0 = q.copy()
+    q0[3 * mesh.n_nodes :] = 0.0  # the global rows are overwritten by the fold
+    out = m.fold(torch.from_numpy(q).cuda()).cpu().numpy()
+    assert nrm(out, T.T @ q0) <= 1e-14
+    assert np.all(out[m.slave_h] == 0.0)
+
+
+def test_homogenized_stiffness_against_reference(fd, golden_dir):
+    """Periodic hex8 cell with a stiff inclusion (per-Gauss-point tangent): C_hom and the full solution of the E_xx
+    load case == the reference's fd.homogen.get_homogenized_stiffness; device CG == host elimination + direct solve;
+    homogeneous cell -> the elastic matrix itself."""
+    g = load(golden_dir, "homogen_hex8_inclusion")
+    law = fd.constitutivelaw.ElasticAnisotropic(_iso_H_gp(np.tile(g["E_el"], 8), float(g["nu"])), name="law")
+    mesh, a, _ = _elastic_setup(fd, "3D", g["nodes"], g["elements"], "hex8", law)
+    C = fd.homogen.get_homogenized_stiffness(a, rtol=1e-12)
+    assert nrm(C, g["C"]) <= 1e-9
+    pert = fd.Problem["_perturbation"]
+    assert all(i["relative_residual"] <= 1e-12 and 0 < i["iterations"] < 3000 for i in pert.load_case_info)
+    assert a.get_global_matrix().shape == (3 * mesh.n_nodes,) * 2  # K keeps its nodal size: the map carries the E dofs
+    # one load case in full
+    for k, name in enumerate(["E_xx", "E_yy", "E_zz", "E_xy", "E_xz", "E_yz"]):
+        pert.bc.add("Neumann", name, 1.0 if k == 0 else 0.0, name="_Strain")
+    pert.solve()
+    assert nrm(pert.get_X(), g["X_exx"]) <= 1e-9
+    assert nrm(pert.get_dof_solution("MeanStrain"), g["X_exx"][-6:]) <= 1e-9
+    pert.bc.remove("_Strain")
+    C_host = fd.homogen.get_homogenized_stiffness(a, solver="direct")
+    assert nrm(C_host, g["C"]) <= 1e-10
+
+    law_h = fd.constitutivelaw.ElasticIsotrop(1.0e5, 0.3, name="law_h")
+    mesh, a, _ = _elastic_setup(fd, "3D", g["nodes"], g["elements"], "hex8", law_h)
+    C_h = fd.homogen.get_homogenized_stiffness(a, rtol=1e-12)
+    assert nrm(C_h, g["C_homogeneous"]) <= 1e-9
+    assert nrm(C_h, law_h.get_tangent_matrix(dimension="3D")) <= 1e-9
