@@ -44,7 +44,11 @@ class MpcStruct(C.Structure):
         ("mst_dof", C.c_void_p),
         ("mst_ptr", C.c_void_p),
         ("mst_slv", C.c_void_p),
+        ("scratch", C.c_void_p),
     ]
+
+
+MPC_SCRATCH_DOUBLES = 9 * 148
 
 
 class PlanStruct(C.Structure):

@@ -55,9 +55,10 @@ class MpcMap:
         self.slave, self.master = i32(self.slave_h), i32(self.master_h)
         self.coef = torch.from_numpy(self.coef_h).to(dev)
         self.mst_dof, self.mst_ptr, self.mst_slv = i32(mst_dof), i32(mst_ptr), i32(order)
+        self.scratch = torch.zeros(_lib.MPC_SCRATCH_DOUBLES, dtype=torch.float64, device=dev)
         self._struct = _lib.MpcStruct(
             self.n_nodal, self.n_glob, len(self.slave_h), _lib.ptr(self.slave), _lib.ptr(self.master), _lib.ptr(self.coef),
-            len(mst_dof), _lib.ptr(self.mst_dof), _lib.ptr(self.mst_ptr), _lib.ptr(self.mst_slv),
+            len(mst_dof), _lib.ptr(self.mst_dof), _lib.ptr(self.mst_ptr), _lib.ptr(self.mst_slv), _lib.ptr(self.scratch),
         )  # fmt: skip
 
     @property

@@ -369,12 +369,14 @@ static int mpc_from_abi(const fdk_mpc* m, MpcMap* out) {
   FDK_REQUIRE(m != nullptr, FDK_EINVAL, "NULL constraint map");
   FDK_REQUIRE(m->n_nodal >= 0 && m->n_glob >= 0 && m->n_slave >= 0 && m->n_master >= 0, FDK_EINVAL, "negative size");
   FDK_REQUIRE(m->n_nodal + m->n_glob <= 0x7fffffffLL, FDK_EOVERFLOW, "constraint map indices are int32");
+  FDK_REQUIRE(m->n_glob <= MPC_MAX_GLOB, FDK_ECAP, "at most 9 global dofs");
+  FDK_REQUIRE(m->n_glob == 0 || m->scratch != nullptr, FDK_EINVAL, "NULL scratch (FDK_MPC_SCRATCH_DOUBLES doubles)");
   if (m->n_slave > 0)
     FDK_REQUIRE(m->slave && m->master && (m->n_glob == 0 || m->coef) && m->mst_dof && m->mst_ptr && m->mst_slv, FDK_EINVAL,
                 "NULL constraint array");
   out->n_nodal = m->n_nodal; out->n_glob = m->n_glob; out->n_slave = m->n_slave; out->slave = m->slave;
   out->master = m->master; out->coef = m->coef; out->n_master = m->n_master; out->mst_dof = m->mst_dof;
-  out->mst_ptr = m->mst_ptr; out->mst_slv = m->mst_slv;
+  out->mst_ptr = m->mst_ptr; out->mst_slv = m->mst_slv; out->scratch = m->scratch;
   return 0;
 }
 

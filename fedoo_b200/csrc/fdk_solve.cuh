@@ -322,6 +322,7 @@ struct MpcMap {
   const int* mst_dof;   // (n_master)
   const int* mst_ptr;   // (n_master + 1) into mst_slv
   const int* mst_slv;   // slave ordinals grouped by master
+  double* scratch;      // (MPC_MAX_GLOB * MPC_FOLD_BLOCKS) partial sums of the fold
 };
 
 __global__ void k_mpc_expand(MpcMap m, double* __restrict__ x) {
@@ -340,17 +341,39 @@ __global__ void k_mpc_fold_master(MpcMap m, double* __restrict__ q) {
   }
 }
 
-// q[n_nodal + k] = sum_s coef[s][k]^(1|2) q[slave_s]: one block per global dof
+// q[n_nodal + k] = sum_s coef[s][k]^(1|2) q[slave_s], two stages in a fixed order: MPC_FOLD_BLOCKS partial sums per
+// global dof in the caller's scratch, then one block adds them up
+constexpr int MPC_FOLD_BLOCKS = 148;
+constexpr int MPC_MAX_GLOB = 9;
+
 template <bool SQUARE>
-__global__ void __launch_bounds__(RED_THREADS) k_mpc_fold_glob(MpcMap m, double* __restrict__ q) {
-  const int k = blockIdx.x;
-  double acc = 0.0;
-  for (int64_t s = threadIdx.x; s < m.n_slave; s += RED_THREADS) {
-    const double c = m.coef[s * m.n_glob + k];
-    acc = fma(SQUARE ? c * c : c, q[m.slave[s]], acc);
+__global__ void __launch_bounds__(RED_THREADS) k_mpc_fold_glob_part(MpcMap m, const double* __restrict__ q,
+                                                                    double* __restrict__ scratch) {
+  double acc[MPC_MAX_GLOB];
+#pragma unroll
+  for (int k = 0; k < MPC_MAX_GLOB; ++k) acc[k] = 0.0;
+  for (int64_t s = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x; s < m.n_slave; s += (int64_t)gridDim.x * RED_THREADS) {
+    const double v = q[m.slave[s]];
+    const double* c = m.coef + s * m.n_glob;
+#pragma unroll
+    for (int k = 0; k < MPC_MAX_GLOB; ++k)
+      if (k < m.n_glob) acc[k] = fma(SQUARE ? c[k] * c[k] : c[k], v, acc[k]);
   }
-  const double v = block_sum(acc);
-  if (threadIdx.x == 0) q[m.n_nodal + k] = v;
+#pragma unroll
+  for (int k = 0; k < MPC_MAX_GLOB; ++k) {
+    if (k < m.n_glob) {
+      const double v = block_sum(acc[k]);
+      if (threadIdx.x == 0) scratch[k * MPC_FOLD_BLOCKS + blockIdx.x] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RED_THREADS) k_mpc_fold_glob_final(MpcMap m, const double* __restrict__ scratch,
+                                                                     double* __restrict__ q) {
+  for (int k = 0; k < m.n_glob; ++k) {
+    const double v = block_sum(threadIdx.x < MPC_FOLD_BLOCKS ? scratch[k * MPC_FOLD_BLOCKS + threadIdx.x] : 0.0);
+    if (threadIdx.x == 0) q[m.n_nodal + k] = v;
+  }
 }
 
 __global__ void k_mpc_zero_slaves(MpcMap m, double* __restrict__ a, double* __restrict__ b) {
@@ -370,8 +393,9 @@ inline unsigned mpc_grid(int64_t n) {
 inline int mpc_fold(const MpcMap& m, double* q, double* also, bool square, cudaStream_t stream) {
   if (m.n_slave > 0) k_mpc_fold_master<<<mpc_grid(m.n_master), 256, 0, stream>>>(m, q);
   if (m.n_glob > 0) {
-    if (square) k_mpc_fold_glob<true><<<m.n_glob, RED_THREADS, 0, stream>>>(m, q);
-    else k_mpc_fold_glob<false><<<m.n_glob, RED_THREADS, 0, stream>>>(m, q);
+    if (square) k_mpc_fold_glob_part<true><<<MPC_FOLD_BLOCKS, RED_THREADS, 0, stream>>>(m, q, m.scratch);
+    else k_mpc_fold_glob_part<false><<<MPC_FOLD_BLOCKS, RED_THREADS, 0, stream>>>(m, q, m.scratch);
+    k_mpc_fold_glob_final<<<1, RED_THREADS, 0, stream>>>(m, m.scratch, q);
   }
   if (m.n_slave > 0) k_mpc_zero_slaves<<<mpc_grid(m.n_slave), 256, 0, stream>>>(m, q, also);
   FDK_CUDA(cudaGetLastError());

@@ -262,7 +262,10 @@ typedef struct fdk_mpc {
   const int32_t* mst_dof;  /* (n_master) */
   const int32_t* mst_ptr;  /* (n_master + 1) into mst_slv */
   const int32_t* mst_slv;  /* slave ordinals grouped by master (fixed summation order) */
+  double* scratch;         /* FDK_MPC_SCRATCH_DOUBLES doubles of device scratch (partial sums of the fold; one map per
+                              stream at a time) */
 } fdk_mpc;
+#define FDK_MPC_SCRATCH_DOUBLES (9 * 148) /* n_glob <= 9 */
 
 /* x <- T x: fills the slave entries from their masters and the global dofs. */
 int fdk_mpc_expand(const fdk_mpc* mpc, double* x, fdk_stream_t stream);
