@@ -130,9 +130,34 @@ class Assembly(_Named):
         return entry["plan_small"]
 
     def _coords(self):
+        if getattr(self, "_coords_override", None) is not None:
+            return self._coords_override
         if self.meshChange:
             self.mesh.invalidate_device()
         return self.mesh.device_arrays()[0]
+
+    def set_disp(self, disp):
+        """Updated-Lagrangian geometry refresh (fedoo/core/assembly.py:1207-1229): ``self.current`` becomes an assembly
+        on the node positions ``mesh.nodes + disp.T``.  The reference has to rebuild the Jacobians and the elementary
+        operators of the moved mesh; here J, det J and grad N are recomputed inside the assembly kernel from the
+        coordinates at every launch, so the refresh is one axpy on the coordinate array -- pattern, cluster plan and
+        CSR structure (topology only) are shared with the undeformed assembly."""
+        if np.isscalar(disp) and disp == 0:
+            self.current = self
+            return
+        from copy import copy
+
+        from .core import as_device_f64
+
+        base = self.mesh.device_arrays()[0]
+        d = as_device_f64(disp, base.device).reshape(-1, self.mesh.n_nodes)[: base.shape[1]]
+        if self.current is self:
+            cur = copy(self)
+            cur.global_matrix = cur.global_vector = cur.global_vector_device = None
+            cur._bufs = {}
+            cur.current = cur
+            self.current = cur
+        self.current._coords_override = (base + d.T).contiguous()
 
     # ------------------------------------------------------------------ the hot path
     def assemble_global_mat(self, compute="all"):

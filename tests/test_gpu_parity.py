@@ -646,3 +646,34 @@ def test_homogenized_stiffness_against_reference(fd, golden_dir):
     C_h = fd.homogen.get_homogenized_stiffness(a, rtol=1e-12)
     assert nrm(C_h, g["C_homogeneous"]) <= 1e-9
     assert nrm(C_h, law_h.get_tangent_matrix(dimension="3D")) <= 1e-9
+
+
+def test_set_disp_geometry_refresh(fd, golden_dir):
+    """SURVEY 8f rank 4 (geometry part): Assembly.set_disp(U) -> ``assembly.current`` assembles on nodes + U^T
+    (fedoo/core/assembly.py:1207-1229); same pattern and plan, values == the oracle on the moved mesh; the undeformed
+    assembly is untouched and set_disp(0) goes back to it."""
+    from oracle import fedoo_oracle as fo
+
+    g = load(golden_dir, "hex8_jitter")
+    law = fd.constitutivelaw.ElasticIsotrop(200e3, 0.3, name="law")
+    mesh, a, pb = _elastic_setup(fd, "3D", g["nodes"], g["elements"], "hex8", law)
+    a.assemble_global_mat("matrix")
+    K0 = a.get_global_matrix().tocsr().copy()
+    h = np.ptp(g["nodes"], axis=0).max() / round(len(g["nodes"]) ** (1 / 3))
+    disp = 0.05 * h * np.random.default_rng(7).standard_normal((3, mesh.n_nodes))
+    a.set_disp(disp)
+    assert a.current is not a and a.current.mesh is a.mesh
+    a.current.assemble_global_mat("matrix")
+    K1 = a.current.get_global_matrix().tocsr()
+    Kref = fo.assemble_stiffness(g["nodes"] + disp.T, g["elements"].astype(np.int64), "hex8", fo.elastic_isotropic_H(200e3, 0.3), 3).tocsr()
+    assert np.array_equal(K1.indptr, Kref.indptr) and np.array_equal(K1.indices, Kref.indices)
+    assert nrm(K1.data, Kref.data) <= TOL
+    assert nrm(K1.data, K0.data) > 1e-3  # the geometry did move
+    a.set_disp(2 * disp)  # a second refresh reuses the same current assembly
+    a.current.assemble_global_mat("matrix")
+    Kref2 = fo.assemble_stiffness(g["nodes"] + 2 * disp.T, g["elements"].astype(np.int64), "hex8", fo.elastic_isotropic_H(200e3, 0.3), 3).tocsr()
+    assert nrm(a.current.get_global_matrix().tocsr().data, Kref2.data) <= TOL
+    a.assemble_global_mat("matrix")
+    assert np.array_equal(a.get_global_matrix().tocsr().data, K0.data)
+    a.set_disp(0)
+    assert a.current is a
