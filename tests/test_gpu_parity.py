@@ -677,3 +677,22 @@ def test_set_disp_geometry_refresh(fd, golden_dir):
     assert np.array_equal(a.get_global_matrix().tocsr().data, K0.data)
     a.set_disp(0)
     assert a.current is a
+
+
+def test_homogenized_stiffness_2d_and_tet10_against_reference(fd, golden_dir):
+    """The same helper on a quad4 plate with a hole (plane strain, isotropic closed-form kernel, three mean-strain dofs)
+    and on a tet10 cell with a stiff inclusion (general-tangent kernel, 15 Gauss points): C == the reference's."""
+    g = load(golden_dir, "homogen_quad4_hole")
+    law = fd.constitutivelaw.ElasticIsotrop(float(g["E"]), float(g["nu"]), name="law2d")
+    mesh, a, _ = _elastic_setup(fd, "2Dplane", g["nodes"], g["elements"], "quad4", law)
+    C = fd.homogen.get_homogenized_stiffness(a, rtol=1e-12)
+    assert C.shape == (3, 3) and nrm(C, g["C"]) <= 1e-9
+    assert fd.Problem["_perturbation"].n_global_dof == 3
+
+    g = load(golden_dir, "homogen_tet10_inclusion")
+    law = fd.constitutivelaw.ElasticAnisotropic(_iso_H_gp(np.tile(g["E_el"], 15), float(g["nu"])), name="law_t")
+    mesh, a, _ = _elastic_setup(fd, "3D", g["nodes"], g["elements"], "tet10", law)
+    C = fd.homogen.get_homogenized_stiffness(a, rtol=1e-12)
+    assert nrm(C, g["C"]) <= 1e-9
+    C_host = fd.homogen.get_homogenized_stiffness(a, solver="direct")
+    assert nrm(C_host, g["C"]) <= 1e-10
