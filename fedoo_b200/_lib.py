@@ -21,7 +21,7 @@ EXPORTS = [
     "fdk_gp_strain_stress", "fdk_gp_temperature", "fdk_j2_update",
     "fdk_gather_f64", "fdk_scatter_add_f64", "fdk_copy_segments",
     "fdk_csr_spmv", "fdk_csr_diagonal", "fdk_pcg_work_doubles", "fdk_pcg_jacobi", "fdk_bcsr_spmv", "fdk_bcsr_pcg_jacobi",
-    "fdk_mpc_expand", "fdk_mpc_fold", "fdk_bcsr_pcg_jacobi_mpc",
+    "fdk_mpc_expand", "fdk_mpc_fold", "fdk_bcsr_pcg_jacobi_mpc", "fdk_pcg_multi_work_doubles", "fdk_bcsr_pcg_jacobi_multi",
     "fdk_gp_to_node", "fdk_gp_to_element", "fdk_gp_von_mises",
 ]  # fmt: skip
 
@@ -48,7 +48,7 @@ class MpcStruct(C.Structure):
     ]
 
 
-MPC_SCRATCH_DOUBLES = 9 * 148
+MPC_SCRATCH_DOUBLES = 9 * 9 * 148
 
 
 class PlanStruct(C.Structure):
@@ -139,6 +139,10 @@ def load():
     lib.fdk_pcg_work_doubles.argtypes = [i64]
     mp = C.POINTER(MpcStruct)
     lib.fdk_mpc_expand.argtypes = [mp, vp, vp]
+    lib.fdk_pcg_multi_work_doubles.argtypes = [i64, i32]
+    lib.fdk_pcg_multi_work_doubles.restype = i64
+    lib.fdk_bcsr_pcg_jacobi_multi.argtypes = [i32, i32, i64, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, dbl, i32, i32, vp, mp,
+                                              C.POINTER(i32), C.POINTER(dbl), vp]
     lib.fdk_mpc_fold.argtypes = [mp, vp, vp]
     lib.fdk_bcsr_pcg_jacobi_mpc.argtypes = [i32, i32, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, dbl, i32, i32, vp, mp,
                                             C.POINTER(i32), C.POINTER(dbl), vp]

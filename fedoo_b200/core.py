@@ -312,6 +312,36 @@ class DeviceCSR:
         )
         return x, it.value, rel.value
 
+    def pcg_multi(self, B, free_mask=None, rtol=1e-8, maxiter=None, check_every=10, mpc=None):
+        """R right-hand sides in lockstep (R = 3 or 6): B, X are (n, R) device tensors, K is read once per iteration
+        for all of them (csrc/fdk_solve.cuh: k_bcsr_spmm + per-column CG recurrences).  With ``mpc`` B must be folded
+        and X comes back expanded.  Returns (X, iterations, [||r_k|| / ||b_k||])."""
+        import ctypes as C
+
+        from . import _lib
+
+        if self.block is None:
+            raise NotImplementedError("the multi-right-hand-side solve runs on the tiled pattern of the assembly")
+        lib = _lib.load()
+        bp, bi, nvar, n_nodes = self.block
+        n = self.shape[0] if mpc is None else mpc.n_total
+        B = as_device_f64(B, self.data.device)
+        R = int(B.shape[1])
+        assert B.shape[0] == n and B.is_contiguous()
+        X = torch.empty((n, R), dtype=torch.float64, device=self.data.device)
+        work = torch.empty(int(lib.fdk_pcg_multi_work_doubles(n, R)), dtype=torch.float64, device=self.data.device)
+        it, rel = C.c_int(0), (C.c_double * R)()
+        _lib.check(
+            lib.fdk_bcsr_pcg_jacobi_multi(
+                n_nodes, nvar, int(bi.numel()), _lib.ptr(bp), _lib.ptr(bi), _lib.ptr(self.indptr), _lib.ptr(self.indices),
+                self._index_bytes(), _lib.ptr(self.data), R, _lib.ptr(B), _lib.ptr(X), _lib.ptr(free_mask), float(rtol),
+                int(10 * n if maxiter is None else maxiter), int(check_every), _lib.ptr(work),
+                None if mpc is None else mpc.struct(), C.byref(it), rel, _lib.current_stream(),
+            ),
+            "fdk_bcsr_pcg_jacobi_multi",
+        )  # fmt: skip
+        return X, it.value, list(rel)
+
     def __matmul__(self, x):
         if isinstance(x, torch.Tensor) and x.is_cuda:
             return self.matvec(x)

@@ -421,6 +421,45 @@ int fdk_bcsr_pcg_jacobi_mpc(int n_nodes, int nvar, int64_t blk_nnz, const int64_
                              max_iter, check_every, work, iters_h, relres_h, (cudaStream_t)stream, &bp, &m);
 }
 
+int64_t fdk_pcg_multi_work_doubles(int64_t n, int n_rhs) { return pcg_multi_work_doubles(n, n_rhs); }
+
+int fdk_bcsr_pcg_jacobi_multi(int n_nodes, int nvar, int64_t blk_nnz, const int64_t* blk_indptr,
+                              const int32_t* blk_indices, const void* indptr, const void* indices, int index_bytes,
+                              const double* data, int n_rhs, const double* b, double* x, const uint8_t* free_mask,
+                              double rtol, int max_iter, int check_every, double* work, const fdk_mpc* mpc, int* iters_h,
+                              double* relres_h, fdk_stream_t stream) {
+  FDK_REQUIRE(n_nodes >= 0 && blk_nnz >= 0 && nvar >= 1 && nvar <= 3 && max_iter >= 0 && rtol >= 0.0, FDK_EINVAL,
+              "bad size or tolerance");
+  FDK_REQUIRE(n_rhs == 3 || n_rhs == 6, FDK_EINVAL, "n_rhs must be 3 or 6");
+  if (iters_h) *iters_h = 0;
+  if (relres_h)
+    for (int k = 0; k < n_rhs; ++k) relres_h[k] = 0.0;
+  if (n_nodes == 0) return 0;
+  MpcMap m;
+  if (mpc != nullptr) {
+    if (int rc = mpc_from_abi(mpc, &m)) return rc;
+    FDK_REQUIRE(m.n_nodal == (int64_t)nvar * n_nodes, FDK_EINVAL, "constraint map / matrix size mismatch");
+    FDK_REQUIRE(free_mask != nullptr, FDK_EINVAL, "the constrained solve needs the mask of the independent dofs");
+  }
+  FDK_REQUIRE(blk_indptr && blk_indices && indptr && indices && data && b && x && work, FDK_EINVAL, "NULL argument");
+  FDK_REQUIRE(index_bytes == 4 || index_bytes == 8, FDK_EINVAL, "index_bytes must be 4 or 8");
+  if (check_every < 1) check_every = 1;
+  BlockPattern bp;
+  bp.n_nodes = n_nodes; bp.nvar = nvar; bp.blk_nnz = blk_nnz; bp.blk_indptr = blk_indptr; bp.blk_indices = blk_indices;
+  const int64_t n = (int64_t)nvar * n_nodes;
+  const MpcMap* mp = mpc != nullptr ? &m : nullptr;
+#define FDK_MULTI(IDX_, R_)                                                                                          \
+  return pcg_jacobi_multi<IDX_, R_>(n, (const IDX_*)indptr, (const IDX_*)indices, data, b, x, free_mask, rtol, max_iter, \
+                                    check_every, work, iters_h, relres_h, (cudaStream_t)stream, bp, mp)
+  if (index_bytes == 4) {
+    if (n_rhs == 3) FDK_MULTI(int32_t, 3);
+    FDK_MULTI(int32_t, 6);
+  }
+  if (n_rhs == 3) FDK_MULTI(int64_t, 3);
+  FDK_MULTI(int64_t, 6);
+#undef FDK_MULTI
+}
+
 int fdk_csr_diagonal(int64_t n_rows, const void* indptr, const void* indices, int index_bytes, const double* data,
                      double* diag, fdk_stream_t stream) {
   FDK_REQUIRE(n_rows >= 0, FDK_EINVAL, "negative size");

@@ -322,7 +322,7 @@ struct MpcMap {
   const int* mst_dof;   // (n_master)
   const int* mst_ptr;   // (n_master + 1) into mst_slv
   const int* mst_slv;   // slave ordinals grouped by master
-  double* scratch;      // (MPC_MAX_GLOB * MPC_FOLD_BLOCKS) partial sums of the fold
+  double* scratch;      // (MPC_MAX_GLOB * MPC_MAX_GLOB * MPC_FOLD_BLOCKS) partial sums of the fold
 };
 
 __global__ void k_mpc_expand(MpcMap m, double* __restrict__ x) {
@@ -476,5 +476,376 @@ int pcg_jacobi(int64_t n_rows, int64_t nnz, const Idx* indptr, const Idx* indice
   if (relres_h) *relres_h = bb > 0.0 ? sqrt(rr / bb) : 0.0;
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// R right-hand sides in lockstep (the six load cases of fd.homogen.get_tangent_stiffness share one K,
+// fedoo/homogen/tangent_stiffness.py:97-153): vectors are interleaved [n][R], every iteration reads K ONCE for the R
+// products (the SpMV is the HBM-bound part of the loop) and runs R independent CG recurrences with per-column scalars.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NV, int LPR, int R>
+__global__ void __launch_bounds__(256) k_bcsr_spmm(int n_nodes, int64_t blk_nnz, const int64_t* __restrict__ blk_indptr,
+                                                    const int32_t* __restrict__ blk_indices,
+                                                    const double* __restrict__ data, const double* __restrict__ x,
+                                                    double* __restrict__ y) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & (LPR - 1);
+  const int sub = (threadIdx.x & 31) / LPR;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t rb = warp * RPW; rb < n_nodes; rb += n_warps * RPW) {
+    const int64_t I = rb + sub;
+    double acc[NV][R];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int k = 0; k < R; ++k) acc[v][k] = 0.0;
+    if (I < n_nodes) {
+      const int64_t e0 = __ldg(blk_indptr + I), e1 = __ldg(blk_indptr + I + 1);
+      const int64_t deg = e1 - e0;
+      for (int64_t pc = lane; pc < deg; pc += LPR) {
+        const int64_t J = __ldg(blk_indices + e0 + pc);
+#pragma unroll
+        for (int w = 0; w < NV; ++w) {
+          const double* xr = x + ((int64_t)w * n_nodes + J) * R;
+          double xj[R];
+          if constexpr (R % 2 == 0) {  // rows of R doubles are 16-byte aligned
+#pragma unroll
+            for (int k = 0; k < R; k += 2) {
+              const double2 t = __ldg(reinterpret_cast<const double2*>(xr + k));
+              xj[k] = t.x;
+              xj[k + 1] = t.y;
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) xj[k] = __ldg(xr + k);
+          }
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const double a = __ldg(data + ((int64_t)v * NV * blk_nnz + (int64_t)NV * e0 + pc) + (int64_t)w * deg);
+#pragma unroll
+            for (int k = 0; k < R; ++k) acc[v][k] = fma(a, xj[k], acc[v][k]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        double s = acc[v][k];
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, LPR);
+        if (lane == 0 && I < n_nodes) y[((int64_t)v * n_nodes + I) * R + k] = s;
+      }
+    }
+  }
+}
+
+template <int R>
+int launch_bspmm(const BlockPattern& b, const double* data, const double* x, double* y, cudaStream_t stream) {
+  if (b.n_nodes == 0) return 0;
+  const int threads = 256;
+  const double avg = (double)b.blk_nnz / (double)b.n_nodes;
+  const int lpr = avg >= 80 ? 16 : avg >= 40 ? 8 : 4;
+  const int64_t need = ((int64_t)b.n_nodes * lpr + threads - 1) / threads;
+  const unsigned grid = (unsigned)(need < 148 * 32 ? need : 148 * 32);
+#define FDK_BSPMM(NV_, LPR_) \
+  k_bcsr_spmm<NV_, LPR_, R><<<grid, threads, 0, stream>>>(b.n_nodes, b.blk_nnz, b.blk_indptr, b.blk_indices, data, x, y)
+  if (b.nvar == 3) {
+    if (lpr == 16) FDK_BSPMM(3, 16); else if (lpr == 8) FDK_BSPMM(3, 8); else FDK_BSPMM(3, 4);
+  } else if (b.nvar == 2) {
+    if (lpr == 16) FDK_BSPMM(2, 16); else if (lpr == 8) FDK_BSPMM(2, 8); else FDK_BSPMM(2, 4);
+  } else if (b.nvar == 1) {
+    if (lpr == 16) FDK_BSPMM(1, 16); else if (lpr == 8) FDK_BSPMM(1, 8); else FDK_BSPMM(1, 4);
+  } else {
+    set_error("tiled SpMM: nvar must be 1, 2 or 3 (got %d)", b.nvar);
+    return FDK_EINVAL;
+  }
+#undef FDK_BSPMM
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// constraint map on interleaved vectors
+template <int R>
+__global__ void k_mpc_expand_multi(MpcMap m, double* __restrict__ x) {
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < m.n_slave; s += (int64_t)gridDim.x * blockDim.x) {
+    double v[R];
+    const double* xm = x + (int64_t)m.master[s] * R;
+#pragma unroll
+    for (int k = 0; k < R; ++k) v[k] = xm[k];
+    for (int g = 0; g < m.n_glob; ++g) {
+      const double c = m.coef[s * m.n_glob + g];
+      const double* xg = x + (m.n_nodal + g) * R;
+#pragma unroll
+      for (int k = 0; k < R; ++k) v[k] = fma(c, xg[k], v[k]);
+    }
+    double* xs = x + (int64_t)m.slave[s] * R;
+#pragma unroll
+    for (int k = 0; k < R; ++k) xs[k] = v[k];
+  }
+}
+
+template <int R>
+__global__ void k_mpc_fold_master_multi(MpcMap m, double* __restrict__ q) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m.n_master; i += (int64_t)gridDim.x * blockDim.x) {
+    double acc[R];
+    double* qm = q + (int64_t)m.mst_dof[i] * R;
+#pragma unroll
+    for (int k = 0; k < R; ++k) acc[k] = qm[k];
+    for (int t = m.mst_ptr[i]; t < m.mst_ptr[i + 1]; ++t) {
+      const double* qs = q + (int64_t)m.slave[m.mst_slv[t]] * R;
+#pragma unroll
+      for (int k = 0; k < R; ++k) acc[k] += qs[k];
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) qm[k] = acc[k];
+  }
+}
+
+// one global dof g per blockIdx.y: scratch[(g R + k) MPC_FOLD_BLOCKS + blockIdx.x]
+template <int R>
+__global__ void __launch_bounds__(RED_THREADS) k_mpc_fold_glob_part_multi(MpcMap m, const double* __restrict__ q,
+                                                                          double* __restrict__ scratch) {
+  const int g = blockIdx.y;
+  double acc[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) acc[k] = 0.0;
+  for (int64_t s = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x; s < m.n_slave; s += (int64_t)gridDim.x * RED_THREADS) {
+    const double c = m.coef[s * m.n_glob + g];
+    const double* qs = q + (int64_t)m.slave[s] * R;
+#pragma unroll
+    for (int k = 0; k < R; ++k) acc[k] = fma(c, qs[k], acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const double v = block_sum(acc[k]);
+    if (threadIdx.x == 0) scratch[((int64_t)g * R + k) * MPC_FOLD_BLOCKS + blockIdx.x] = v;
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(RED_THREADS) k_mpc_fold_glob_final_multi(MpcMap m, const double* __restrict__ scratch,
+                                                                           double* __restrict__ q) {
+  const int j = blockIdx.x;  // g R + k
+  const double v = block_sum(threadIdx.x < MPC_FOLD_BLOCKS ? scratch[(int64_t)j * MPC_FOLD_BLOCKS + threadIdx.x] : 0.0);
+  if (threadIdx.x == 0) q[(m.n_nodal + j / R) * R + j % R] = v;
+}
+
+template <int R>
+__global__ void k_mpc_zero_slaves_multi(MpcMap m, double* __restrict__ a, double* __restrict__ b) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < m.n_slave * R; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = (int64_t)m.slave[t / R] * R + t % R;
+    a[i] = 0.0;
+    if (b != nullptr) b[i] = 0.0;
+  }
+}
+
+template <int R>
+int mpc_expand_multi(const MpcMap& m, double* x, cudaStream_t stream) {
+  if (m.n_slave > 0) k_mpc_expand_multi<R><<<mpc_grid(m.n_slave), 256, 0, stream>>>(m, x);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int R>
+int mpc_fold_multi(const MpcMap& m, double* q, double* also, cudaStream_t stream) {
+  if (m.n_slave > 0) k_mpc_fold_master_multi<R><<<mpc_grid(m.n_master), 256, 0, stream>>>(m, q);
+  if (m.n_glob > 0) {
+    k_mpc_fold_glob_part_multi<R><<<dim3(MPC_FOLD_BLOCKS, m.n_glob), RED_THREADS, 0, stream>>>(m, q, m.scratch);
+    k_mpc_fold_glob_final_multi<R><<<m.n_glob * R, RED_THREADS, 0, stream>>>(m, m.scratch, q);
+  }
+  if (m.n_slave > 0) k_mpc_zero_slaves_multi<R><<<mpc_grid(m.n_slave * R), 256, 0, stream>>>(m, q, also);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// per-column scalars: scal[k * S_COUNT + S_xx]; partial sums part[(j R + k) RED_BLOCKS + block], j = which sum.
+// The vector kernels walk the interleaved arrays flat (fully coalesced) with MULTI_BLOCKS x RED_THREADS threads: that
+// count is a multiple of 3 and 6, so a thread keeps its column (flat index % R) along its grid-stride loop.
+constexpr int MULTI_BLOCKS = 1182;
+static_assert((MULTI_BLOCKS * RED_THREADS) % 6 == 0 && MULTI_BLOCKS <= RED_BLOCKS, "column-stable grid");
+
+// sums of v[s] over the threads of the block that share a column -> part[(s R + column) RED_BLOCKS + block]
+template <int R, int NS>
+__device__ __forceinline__ void block_column_sums(const double (&v)[NS], double* __restrict__ part) {
+  __shared__ double sh[NS][RED_THREADS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) sh[s][threadIdx.x] = v[s];
+  __syncthreads();
+  if (threadIdx.x < R) {
+    const int shift = (int)(((int64_t)blockIdx.x * RED_THREADS) % R);
+    const int first = (threadIdx.x - shift + R) % R;  // first thread of the block working on column threadIdx.x
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      double acc = 0.0;
+      for (int t = first; t < RED_THREADS; t += R) acc += sh[s][t];
+      part[((int64_t)s * R + threadIdx.x) * RED_BLOCKS + blockIdx.x] = acc;
+    }
+  }
+  __syncthreads();
+}
+
+// one block per (sum j, column k)
+template <int R>
+__global__ void __launch_bounds__(RED_THREADS) k_reduce_final_multi(const double* __restrict__ part, int first,
+                                                                    double* __restrict__ scal) {
+  const int j = blockIdx.x / R, k = blockIdx.x % R;
+  double v = 0.0;
+  for (int i = threadIdx.x; i < MULTI_BLOCKS; i += RED_THREADS) v += part[((int64_t)j * R + k) * RED_BLOCKS + i];
+  const double s = block_sum(v);
+  if (threadIdx.x == 0) scal[k * S_COUNT + first + j] = s;
+}
+
+template <int R>
+__global__ void __launch_bounds__(RED_THREADS) k_pcg_init_multi(int64_t n, const double* __restrict__ b,
+                                                                const double* __restrict__ diag,
+                                                                const unsigned char* __restrict__ mask,
+                                                                double* __restrict__ x, double* __restrict__ r,
+                                                                double* __restrict__ z, double* __restrict__ p,
+                                                                double* __restrict__ part) {
+  double acc[2] = {0.0, 0.0};
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n * R; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = j / R;
+    const bool live = mask == nullptr || mask[i];
+    const double di = diag[i];
+    const double ri = live ? b[j] : 0.0;
+    const double zi = (live && di != 0.0) ? ri / di : 0.0;
+    x[j] = 0.0;
+    r[j] = ri;
+    z[j] = zi;
+    p[j] = zi;
+    acc[0] = fma(ri, zi, acc[0]);
+    acc[1] = fma(ri, ri, acc[1]);
+  }
+  block_column_sums<R, 2>(acc, part);
+}
+
+template <int R>
+__global__ void __launch_bounds__(RED_THREADS) k_dot_multi(int64_t n, const double* __restrict__ a,
+                                                           const double* __restrict__ b, double* __restrict__ part) {
+  double acc[1] = {0.0};
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n * R; j += (int64_t)gridDim.x * blockDim.x)
+    acc[0] = fma(a[j], b[j], acc[0]);
+  block_column_sums<R, 1>(acc, part);
+}
+
+template <int R>
+__global__ void __launch_bounds__(RED_THREADS) k_pcg_update_multi(int64_t n, const double* __restrict__ scal,
+                                                                  const double* __restrict__ diag,
+                                                                  const unsigned char* __restrict__ mask,
+                                                                  const double* __restrict__ p, const double* __restrict__ q,
+                                                                  double* __restrict__ x, double* __restrict__ r,
+                                                                  double* __restrict__ z, double* __restrict__ part) {
+  const int k = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) % R);
+  const double pq = scal[k * S_COUNT + S_PQ];
+  const double alpha = pq != 0.0 ? scal[k * S_COUNT + S_RZ] / pq : 0.0;
+  double acc[2] = {0.0, 0.0};
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n * R; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = j / R;
+    const bool live = mask == nullptr || mask[i];
+    const double di = diag[i];
+    const double ri = live ? fma(-alpha, q[j], r[j]) : 0.0;
+    const double zi = (live && di != 0.0) ? ri / di : 0.0;
+    x[j] = fma(alpha, p[j], x[j]);
+    r[j] = ri;
+    z[j] = zi;
+    acc[0] = fma(ri, zi, acc[0]);
+    acc[1] = fma(ri, ri, acc[1]);
+  }
+  block_column_sums<R, 2>(acc, part);
+}
+
+template <int R>
+__global__ void __launch_bounds__(RED_THREADS) k_pcg_direction_multi(int64_t n, const double* __restrict__ scal,
+                                                                     const double* __restrict__ z, double* __restrict__ p) {
+  const int k = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) % R);
+  const double rz = scal[k * S_COUNT + S_RZ];
+  const double beta = rz != 0.0 ? scal[k * S_COUNT + S_RZN] / rz : 0.0;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n * R; j += (int64_t)gridDim.x * blockDim.x)
+    p[j] = fma(beta, p[j], z[j]);
+}
+
+template <int R>
+__global__ void k_copy_scalar_multi(double* scal, int dst, int src) {
+  if (threadIdx.x < R) scal[threadIdx.x * S_COUNT + dst] = scal[threadIdx.x * S_COUNT + src];
+}
+
+inline int64_t pcg_multi_work_doubles(int64_t n, int n_rhs) {
+  return 4 * n * n_rhs + n + 2 * (int64_t)n_rhs * RED_BLOCKS + (int64_t)n_rhs * S_COUNT;
+}
+
+// R systems T^T A T y_k = b_k at once on the tiled pattern.  b, x: (n_rows + n_glob, R) row-major; b already folded;
+// x returns the EXPANDED solutions (T y_k).  relres_h: R entries.
+template <class Idx, int R>
+int pcg_jacobi_multi(int64_t n_rows, const Idx* indptr, const Idx* indices, const double* data, const double* b, double* x,
+                     const unsigned char* mask, double rtol, int max_iter, int check_every, double* work, int* iters_h,
+                     double* relres_h, cudaStream_t stream, const BlockPattern& blk, const MpcMap* mpc) {
+  const int64_t n = n_rows + (mpc != nullptr ? mpc->n_glob : 0);
+  double* r = work;
+  double* z = r + n * R;
+  double* p = z + n * R;
+  double* q = p + n * R;
+  double* diag = q + n * R;
+  double* part = diag + n;
+  double* scal = part + 2 * (int64_t)R * RED_BLOCKS;
+  k_csr_diagonal<Idx><<<(unsigned)((n_rows + 255) / 256), 256, 0, stream>>>(n_rows, indptr, indices, data, diag);
+  if (mpc != nullptr) {
+    if (int rc = mpc_fold(*mpc, diag, nullptr, true, stream)) return rc;
+  }
+  FDK_CUDA(cudaMemsetAsync(q, 0, sizeof(double) * n * R, stream));  // the global rows of q are only written by the fold
+  k_pcg_init_multi<R><<<MULTI_BLOCKS, RED_THREADS, 0, stream>>>(n, b, diag, mask, x, r, z, p, part);
+  k_reduce_final_multi<R><<<2 * R, RED_THREADS, 0, stream>>>(part, S_RZN, scal);  // S_RZN = rz, S_RR = rr
+  k_copy_scalar_multi<R><<<1, 32, 0, stream>>>(scal, S_RZ, S_RZN);
+  k_copy_scalar_multi<R><<<1, 32, 0, stream>>>(scal, S_BB, S_RR);
+  FDK_CUDA(cudaGetLastError());
+  double h[R * S_COUNT];
+  FDK_CUDA(cudaMemcpyAsync(h, scal, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  FDK_CUDA(cudaStreamSynchronize(stream));
+  double bb[R], rr[R];
+  bool any = false;
+  for (int k = 0; k < R; ++k) {
+    bb[k] = rr[k] = h[k * S_COUNT + S_BB];
+    any = any || bb[k] > 0.0;
+  }
+  int it = 0;
+  if (any) {
+    while (it < max_iter) {
+      if (mpc != nullptr) {
+        if (int rc = mpc_expand_multi<R>(*mpc, p, stream)) return rc;
+      }
+      if (int rc = launch_bspmm<R>(blk, data, p, q, stream)) return rc;
+      if (mpc != nullptr) {
+        if (int rc = mpc_fold_multi<R>(*mpc, q, p, stream)) return rc;
+      }
+      k_dot_multi<R><<<MULTI_BLOCKS, RED_THREADS, 0, stream>>>(n, p, q, part);
+      k_reduce_final_multi<R><<<R, RED_THREADS, 0, stream>>>(part, S_PQ, scal);
+      k_pcg_update_multi<R><<<MULTI_BLOCKS, RED_THREADS, 0, stream>>>(n, scal, diag, mask, p, q, x, r, z, part);
+      k_reduce_final_multi<R><<<2 * R, RED_THREADS, 0, stream>>>(part, S_RZN, scal);
+      k_pcg_direction_multi<R><<<MULTI_BLOCKS, RED_THREADS, 0, stream>>>(n, scal, z, p);
+      k_copy_scalar_multi<R><<<1, 32, 0, stream>>>(scal, S_RZ, S_RZN);
+      ++it;
+      if (it % check_every == 0 || it == max_iter) {
+        FDK_CUDA(cudaMemcpyAsync(h, scal, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        FDK_CUDA(cudaStreamSynchronize(stream));
+        bool done = true;
+        for (int k = 0; k < R; ++k) {
+          rr[k] = h[k * S_COUNT + S_RR];
+          done = done && !(rr[k] > rtol * rtol * bb[k]);  // a NaN also counts as finished
+        }
+        if (done) break;
+      }
+    }
+    FDK_CUDA(cudaGetLastError());
+  }
+  if (mpc != nullptr) {
+    if (int rc = mpc_expand_multi<R>(*mpc, x, stream)) return rc;
+  }
+  if (iters_h) *iters_h = it;
+  if (relres_h)
+    for (int k = 0; k < R; ++k) relres_h[k] = bb[k] > 0.0 ? sqrt(rr[k] / bb[k]) : 0.0;
+  return 0;
+}
+
 
 }  // namespace fdk

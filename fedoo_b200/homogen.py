@@ -30,7 +30,8 @@ def get_homogenized_stiffness(assemb, meshperio=True, **kargs):
 
 def get_tangent_stiffness(pb=None, meshperio=True, **kargs):
     """fedoo/homogen/tangent_stiffness.py:32-191 (perturbation method, Neumann loads on the mean-strain dofs).
-    kargs: solver ("cg" on the device | "direct" on the host), rtol, maxiter."""
+    kargs: solver ("cg" on the device | "direct" on the host), rtol, maxiter, lockstep (default True: the load cases
+    are solved together, K read once per iteration for all of them; False: one after the other)."""
     solver = kargs.pop("solver", "cg")
     if pb is None:
         pb = _ProblemBase.get_active()
@@ -52,19 +53,35 @@ def get_tangent_stiffness(pb=None, meshperio=True, **kargs):
     else:
         pert = registry["_perturbation"]
     kargs.setdefault("rtol", 1e-10)
+    lockstep_opt = kargs.pop("lockstep", True)
     pert.set_solver(solver, **{k: v for k, v in kargs.items() if v is not None and k not in ("solver_type", "pc_type")})
+    kargs["lockstep"] = lockstep_opt
     pert.set_A(pb.get_A())
 
     d_strain, info = [], []
-    for i in range(len(names)):
+    lockstep = kargs.pop("lockstep", True)
+    if solver == "cg" and lockstep:
+        # the load cases share K: one lockstep solve reads it once per iteration for all of them
         pert.bc.remove("_Strain")
-        for k, name in enumerate(names):
-            pert.bc.add("Neumann", name, 1.0 if k == i else 0.0, start_value=0, name="_Strain")
         pert.apply_boundary_conditions()
-        pert.solve()
-        X = pert.get_X()
-        d_strain.append(np.array([pert._get_vect_component(X, name)[0] for name in names]))
-        info.append(pert.solver_info)
+        loads = np.zeros((pert.n_global_dof, len(names)))
+        for k, name in enumerate(names):
+            loads[pert._global_dof[name], k] = 1.0
+        X = pert.solve_load_cases(pert.get_A(), loads)  # (n_dof, R) on the device
+        pert._X = X[:, -1].cpu().numpy()
+        E = X[X.shape[0] - pert.n_global_dof :].cpu().numpy()  # mean-strain response of every case
+        d_strain = [np.array([E[pert._global_dof[name], i] for name in names]) for i in range(len(names))]
+        info = [pert.solver_info] * len(names)
+    else:
+        for i in range(len(names)):
+            pert.bc.remove("_Strain")
+            for k, name in enumerate(names):
+                pert.bc.add("Neumann", name, 1.0 if k == i else 0.0, start_value=0, name="_Strain")
+            pert.apply_boundary_conditions()
+            pert.solve()
+            X = pert.get_X()
+            d_strain.append(np.array([pert._get_vect_component(X, name)[0] for name in names]))
+            info.append(pert.solver_info)
     pert.bc.remove("_Strain")
     pert.load_case_info = info
     return np.linalg.inv(np.array(d_strain).T) / mesh.bounding_box.volume

@@ -211,6 +211,40 @@ class _ProblemBase(_Named):
             print(f"Warning: cg solver convergence to tolerance not achieved ({rel:.2e} after {it} iterations)")
         return (x + Xbc).cpu().numpy()
 
+    def solve_load_cases(self, A, global_loads):
+        """Several load cases on one matrix at once, on the device (fd.homogen): ``global_loads`` is (n_global_dof, R),
+        the loads on the global dofs of each case (R = 3 or 6); the nodal loads and all imposed values are zero.
+        Returns the (n_dof, R) solutions as a CUDA tensor."""
+        import torch
+
+        if self._dirichlet is None:
+            self.apply_boundary_conditions()
+        dofs, vals = self._dirichlet
+        if np.any(vals != 0):
+            raise NotImplementedError("non-zero imposed values with several load cases")
+        mpc = self._mpc
+        dev = A.data.device
+        global_loads = np.ascontiguousarray(global_loads, dtype=float)
+        n, R = self.n_dof, global_loads.shape[1]
+        assert global_loads.shape[0] == self.n_global_dof and A.shape[0] == n - self.n_global_dof
+        rhs = torch.zeros((n, R), dtype=torch.float64, device=dev)  # T^T of a load on the global rows is itself
+        if self.n_global_dof:
+            rhs[n - self.n_global_dof :] = torch.from_numpy(global_loads).to(dev)
+        free = torch.ones(n, dtype=torch.uint8, device=dev)
+        if len(dofs):
+            free[torch.from_numpy(dofs).to(dev)] = 0
+        if mpc is not None:
+            if np.intersect1d(dofs, mpc.slave_h).size:
+                raise NotImplementedError("a Dirichlet condition on an eliminated (slave) dof")
+            free[torch.from_numpy(mpc.slave_h).to(dev)] = 0
+        kargs = self._solver[2]
+        rtol = kargs.get("rtol", kargs.get("tol", 1e-8))
+        X, it, rel = A.pcg_multi(rhs, free_mask=free, rtol=rtol, maxiter=kargs.get("maxiter"), mpc=mpc)
+        self.solver_info = {"iterations": it, "relative_residual": max(rel), "relative_residuals": rel}
+        if max(rel) > rtol:
+            print(f"Warning: cg solver convergence to tolerance not achieved ({max(rel):.2e} after {it} iterations)")
+        return X
+
     @property
     def n_dof(self):
         return self.space.nvar * self.mesh.n_nodes + self.n_global_dof

@@ -265,7 +265,7 @@ typedef struct fdk_mpc {
   double* scratch;         /* FDK_MPC_SCRATCH_DOUBLES doubles of device scratch (partial sums of the fold; one map per
                               stream at a time) */
 } fdk_mpc;
-#define FDK_MPC_SCRATCH_DOUBLES (9 * 148) /* n_glob <= 9 */
+#define FDK_MPC_SCRATCH_DOUBLES (9 * 9 * 148) /* n_glob <= 9, n_rhs <= 9 */
 
 /* x <- T x: fills the slave entries from their masters and the global dofs. */
 int fdk_mpc_expand(const fdk_mpc* mpc, double* x, fdk_stream_t stream);
@@ -278,6 +278,17 @@ int fdk_bcsr_pcg_jacobi_mpc(int n_nodes, int nvar, int64_t blk_nnz, const int64_
                             const double* data, const double* b, double* x, const uint8_t* free_mask, double rtol,
                             int max_iter, int check_every, double* work, const fdk_mpc* mpc, int* iters_h,
                             double* relres_h, fdk_stream_t stream);
+
+/* n_rhs systems sharing one matrix, solved in lockstep (the load cases of fedoo/homogen/tangent_stiffness.py:97-153):
+ * b, x are (n_nodal + n_glob, n_rhs) row-major; every iteration reads K once for all products.  mpc may be NULL
+ * (Dirichlet conditions only; free_mask then has n_nodal bytes).  b already folded; x returns the EXPANDED solutions;
+ * relres_h has n_rhs entries; work = fdk_pcg_multi_work_doubles(n_nodal + n_glob, n_rhs).  n_rhs = 3 or 6. */
+int64_t fdk_pcg_multi_work_doubles(int64_t n, int n_rhs);
+int fdk_bcsr_pcg_jacobi_multi(int n_nodes, int nvar, int64_t blk_nnz, const int64_t* blk_indptr,
+                              const int32_t* blk_indices, const void* indptr, const void* indices, int index_bytes,
+                              const double* data, int n_rhs, const double* b, double* x, const uint8_t* free_mask,
+                              double rtol, int max_iter, int check_every, double* work, const fdk_mpc* mpc, int* iters_h,
+                              double* relres_h, fdk_stream_t stream);
 
 /* diag[r] = A[r,r] (0 if not stored); columns sorted within a row (the pattern of fdk_sym_expand_csr is). */
 int fdk_csr_diagonal(int64_t n_rows, const void* indptr, const void* indices, int index_bytes, const double* data,

@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--n", type=int, default=100)
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--contrast", type=float, default=20.0)
+    ap.add_argument("--sequential", action="store_true", help="one load case after the other instead of lockstep")
     a = ap.parse_args()
     n = a.n
     fd.ModelingSpace("3D")
@@ -54,9 +55,13 @@ def main():
     torch.cuda.synchronize()
     t_asm = time.perf_counter() - t0
     t0 = time.perf_counter()
-    C = fd.homogen.get_homogenized_stiffness(assemb, rtol=a.rtol)
+    C = fd.homogen.get_homogenized_stiffness(assemb, rtol=a.rtol, lockstep=not a.sequential)
     torch.cuda.synchronize()
     t_hom = time.perf_counter() - t0
+    t0 = time.perf_counter()  # second call: the perturbation problem (node pairing, constraint map) is reused
+    C = fd.homogen.get_homogenized_stiffness(assemb, rtol=a.rtol, lockstep=not a.sequential)
+    torch.cuda.synchronize()
+    t_again = time.perf_counter() - t0
     info = fd.Problem["_perturbation"].load_case_info
     f = float(inside.mean())
     H0, H1 = iso_H_gp(np.array([1.0e5]), 0.3)[:, :, 0], iso_H_gp(np.array([1.0e5 * a.contrast]), 0.3)[:, :, 0]
@@ -74,9 +79,10 @@ def main():
     }
     print(json.dumps({
         "workload": f"periodic hex8 cell {n}^3 elements, inclusion volume fraction {f:.4f}, contrast {a.contrast}",
-        "n_dof": int(3 * mesh.n_nodes + 6), "assemble_ms": round(1e3 * t_asm, 2), "homogenisation_s": round(t_hom, 3),
+        "n_dof": int(3 * mesh.n_nodes + 6), "assemble_ms": round(1e3 * t_asm, 2), "homogenisation_s": round(t_hom, 3), "homogenisation_again_s": round(t_again, 3),
         "iterations": [i["iterations"] for i in info], "relative_residual": [float(f"{i['relative_residual']:.2e}") for i in info],
-        "ms_per_iteration": round(1e3 * t_hom / max(sum(i["iterations"] for i in info), 1), 4),
+        "mode": "sequential" if a.sequential else "lockstep (6 right-hand sides per K read)",
+        "ms_per_iteration": round(1e3 * t_again / max(sum(i["iterations"] for i in info) if a.sequential else info[0]["iterations"], 1), 4),
         "C11_C12_C44": [round(float(C[0, 0]), 3), round(float(C[0, 1]), 3), round(float(C[3, 3]), 3)], "checks": checks,
     }))  # fmt: skip
 

@@ -640,6 +640,10 @@ def test_homogenized_stiffness_against_reference(fd, golden_dir):
     pert.bc.remove("_Strain")
     C_host = fd.homogen.get_homogenized_stiffness(a, solver="direct")
     assert nrm(C_host, g["C"]) <= 1e-10
+    # the default solves the six load cases in lockstep (K read once per iteration); one after the other agrees
+    C_seq = fd.homogen.get_homogenized_stiffness(a, rtol=1e-12, lockstep=False)
+    assert nrm(C_seq, g["C"]) <= 1e-9 and nrm(C_seq, C) <= 1e-10
+    assert fd.Problem["_perturbation"].load_case_info[0] is not fd.Problem["_perturbation"].load_case_info[1]  # six solves
 
     law_h = fd.constitutivelaw.ElasticIsotrop(1.0e5, 0.3, name="law_h")
     mesh, a, _ = _elastic_setup(fd, "3D", g["nodes"], g["elements"], "hex8", law_h)
