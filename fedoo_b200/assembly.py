@@ -331,8 +331,11 @@ class Assembly(_Named):
         """StressEquilibrium.update (fedoo/weakform/stress_equilibrium.py:191-217): record the dof
         vector; sv['Strain'] / sv['DispGradient'] are produced lazily by ``fdk_gp_strain_stress``."""
         self._U_dev = as_device_f64(U)
-        self.sv["Strain"] = _LazyStrain(self, self._U_dev)
-        self.sv["DispGradient"] = _LazyGrad(self, self._U_dev)
+        fbar = bool(getattr(self.weakform, "fbar", False))
+        if fbar and self.space.ndim != 3:
+            raise NotImplementedError("F-bar is available for the 3D modeling space")
+        self.sv["Strain"] = _LazyStrain(self, self._U_dev, fbar)
+        self.sv["DispGradient"] = _LazyGrad(self, self._U_dev, fbar)
 
     def _elastic_stress_update(self, law):
         """ElasticAnisotropic.update (fedoo/constitutivelaw/elastic_anisotropic.py:36-56)."""
@@ -340,9 +343,14 @@ class Assembly(_Named):
         if np.isscalar(strain) and strain == 0:
             self.sv["Stress"] = 0
             return
+        if getattr(strain, "fbar", False):
+            # F-bar: sigma = H eps_bar is not -K U any more -> materialise it, the kernel integrates B^T sigma
+            stress = self._gp_strain_stress(strain.U, want_stress=True, law=law, fbar=True)[2]
+            self.sv["Stress"] = GaussPointTensor(stress, "stress")
+            return
         self.sv["Stress"] = _FusedElasticStress(self, law, strain.U)
 
-    def _gp_strain_stress(self, U_dev, want_grad=False, want_strain=False, want_stress=False, law=None):
+    def _gp_strain_stress(self, U_dev, want_grad=False, want_strain=False, want_stress=False, law=None, fbar=False):
         lib = _lib.load()
         coords, conn = self._coords(), self.mesh.device_arrays()[1]
         N = self.n_gauss_points
@@ -355,6 +363,17 @@ class Assembly(_Named):
             tangent_dev = law.tangent_device(self)
             if tangent_dev is None:
                 C_h = np.ascontiguousarray(self.sv["TangentMatrix"], dtype=np.float64)
+        if fbar:  # small-strain F-bar (fedoo/weakform/stress_equilibrium.py:527-540)
+            center = torch.empty(self.mesh.n_elements, dtype=torch.float64, device=dev)
+            _lib.check(
+                lib.fdk_gp_strain_stress_fbar(
+                    _lib.ELEM_IDS[self.elm_type], self.mesh.n_nodes, self.mesh.n_elements, _lib.ptr(conn), _lib.ptr(coords),
+                    _lib.ptr(U_dev), _lib.ptr(C_h), _lib.ptr(tangent_dev), _lib.ptr(center), _lib.ptr(grad), _lib.ptr(strain),
+                    _lib.ptr(stress), _lib.current_stream(),
+                ),
+                "fdk_gp_strain_stress_fbar",
+            )  # fmt: skip
+            return grad, strain, stress
         _lib.check(
             lib.fdk_gp_strain_stress(
                 _lib.ELEM_IDS[self.elm_type], self.mesh.n_nodes, self.mesh.n_elements, _lib.ptr(conn), _lib.ptr(coords),
@@ -433,13 +452,13 @@ class Assembly(_Named):
 class _LazyStrain(GaussPointTensor):
     """sv['Strain'] of the current dof vector, computed on first access."""
 
-    def __init__(self, assembly, U):
-        self._asm, self.U, self.kind, self._host, self._dev = assembly, U, "strain", None, None
+    def __init__(self, assembly, U, fbar=False):
+        self._asm, self.U, self.kind, self._host, self._dev, self.fbar = assembly, U, "strain", None, None, fbar
 
     @property
     def device_tensor(self):
         if self._dev is None:
-            self._dev = self._asm._gp_strain_stress(self.U, want_strain=True)[1]
+            self._dev = self._asm._gp_strain_stress(self.U, want_strain=True, fbar=self.fbar)[1]
         return self._dev
 
 
@@ -458,12 +477,12 @@ class _FusedElasticStress(GaussPointTensor):
 
 
 class _LazyGrad:
-    def __init__(self, assembly, U):
-        self._asm, self.U, self._host = assembly, U, None
+    def __init__(self, assembly, U, fbar=False):
+        self._asm, self.U, self._host, self.fbar = assembly, U, None, fbar
 
     def _get(self):
         if self._host is None:
-            self._host = self._asm._gp_strain_stress(self.U, want_grad=True)[0].cpu().numpy()
+            self._host = self._asm._gp_strain_stress(self.U, want_grad=True, fbar=self.fbar)[0].cpu().numpy()
         return self._host
 
     def __getitem__(self, a):

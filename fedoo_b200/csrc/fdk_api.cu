@@ -249,9 +249,9 @@ int fdk_assemble_heat(const fdk_plan* plan, int compute, const double* coords, c
   return dispatch_assemble<PHYS_HEAT>(a, (cudaStream_t)stream);
 }
 
-int fdk_gp_strain_stress(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
-                         const double* U, const double* C_h, const double* tangent_gp, double* grad_gp,
-                         double* strain_gp, double* stress_gp, fdk_stream_t stream) {
+static int gp_strain_stress_impl(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                                 const double* U, const double* C_h, const double* tangent_gp, double* fbar_center,
+                                 double* grad_gp, double* strain_gp, double* stress_gp, fdk_stream_t stream) {
   FDK_REQUIRE(conn && coords && U, FDK_EINVAL, "NULL input");
   FDK_REQUIRE(!stress_gp || C_h || tangent_gp, FDK_EINVAL, "stress needs C_h or tangent_gp");
   GpArgs a{};
@@ -264,8 +264,19 @@ int fdk_gp_strain_stress(int elem_type, int n_nodes, int64_t n_elems, const int3
   a.grad_gp = grad_gp;
   a.strain_gp = strain_gp;
   a.stress_gp = stress_gp;
+  a.fbar_center = fbar_center;
   if (C_h)
     for (int i = 0; i < 36; ++i) a.C[i] = C_h[i];
+  if (fbar_center != nullptr) {
+    FDK_REQUIRE(elem_type != FDK_QUAD4, FDK_EINVAL, "F-bar is available for the 3-D elements");
+    int rc = FDK_EINVAL;
+    switch (elem_type) {
+      case FDK_HEX8: rc = launch_gp_fbar_center<Hex8>(a, (cudaStream_t)stream); break;
+      case FDK_TET4: rc = launch_gp_fbar_center<Tet4>(a, (cudaStream_t)stream); break;
+      case FDK_TET10: rc = launch_gp_fbar_center<Tet10>(a, (cudaStream_t)stream); break;
+    }
+    if (rc) return rc;
+  }
   switch (elem_type) {
     case FDK_HEX8: return launch_gp_strain_stress<Hex8>(a, (cudaStream_t)stream);
     case FDK_TET4: return launch_gp_strain_stress<Tet4>(a, (cudaStream_t)stream);
@@ -274,6 +285,21 @@ int fdk_gp_strain_stress(int elem_type, int n_nodes, int64_t n_elems, const int3
   }
   set_error("unknown element type %d", elem_type);
   return FDK_EINVAL;
+}
+
+int fdk_gp_strain_stress(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                         const double* U, const double* C_h, const double* tangent_gp, double* grad_gp,
+                         double* strain_gp, double* stress_gp, fdk_stream_t stream) {
+  return gp_strain_stress_impl(elem_type, n_nodes, n_elems, conn, coords, U, C_h, tangent_gp, nullptr, grad_gp, strain_gp,
+                               stress_gp, stream);
+}
+
+int fdk_gp_strain_stress_fbar(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                              const double* U, const double* C_h, const double* tangent_gp, double* fbar_center,
+                              double* grad_gp, double* strain_gp, double* stress_gp, fdk_stream_t stream) {
+  FDK_REQUIRE(fbar_center != nullptr, FDK_EINVAL, "NULL scratch for the element means");
+  return gp_strain_stress_impl(elem_type, n_nodes, n_elems, conn, coords, U, C_h, tangent_gp, fbar_center, grad_gp,
+                               strain_gp, stress_gp, stream);
 }
 
 int fdk_gp_temperature(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,

@@ -21,6 +21,7 @@ struct GpArgs {
   double* temp_grad_gp;
   double C[36];
   int has_C;
+  double* fbar_center;  // (n_elems) mean over the element's Gauss points of tr(grad u): small-strain F-bar, or NULL
 };
 
 // grad u -> strain -> stress.  Replaces the 9 SpMVs of Assembly.get_grad_disp
@@ -62,6 +63,15 @@ __global__ void __launch_bounds__(256) k_gp_strain_stress(const __grid_constant_
 #pragma unroll
       for (int d = 0; d < DIM; ++d) gu[v][d] = fma(u, G[k][d], gu[v][d]);
     }
+  if (a.fbar_center != nullptr) {
+    // small-strain F-bar (fedoo/weakform/stress_equilibrium.py:527-540): the volumetric part of grad u is replaced by
+    // its mean over the element's Gauss points, grad_ii -= (tr - mean tr) / 3
+    if constexpr (DIM == 3) {
+      const double shift = ((gu[0][0] + gu[1][1] + gu[2][2]) - a.fbar_center[e]) / 3.0;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) gu[d][d] -= shift;
+    }
+  }
   if (a.grad_gp != nullptr) {
 #pragma unroll
     for (int v = 0; v < 3; ++v)
@@ -85,6 +95,53 @@ __global__ void __launch_bounds__(256) k_gp_strain_stress(const __grid_constant_
 #pragma unroll
     for (int s = 0; s < 6; ++s) a.stress_gp[6 * n + s] = sig[s];
   }
+}
+
+// fbar_center[e] = mean over the Gauss points of element e of tr(grad u): one thread per element, Gauss points in
+// order (the reference's np.mean over the gp axis, stress_equilibrium.py:533)
+template <class El>
+__global__ void __launch_bounds__(128) k_gp_fbar_center(const __grid_constant__ GpArgs a) {
+  constexpr int NNE = El::NNE, NGP = El::NGP, DIM = El::DIM;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n_elems) return;
+  const ElemTable& tab = c_tab[El::ID];
+  int nd[NNE];
+  double X[NNE][DIM];
+#pragma unroll
+  for (int k = 0; k < NNE; ++k) {
+    nd[k] = a.conn[e * NNE + k];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) X[k][d] = a.coords[(int64_t)nd[k] * DIM + d];
+  }
+  double sum = 0.0;
+  for (int g = 0; g < NGP; ++g) {
+    double dN[DIM * NNE];
+#pragma unroll
+    for (int t = 0; t < DIM * NNE; ++t) dN[t] = tab.dN[g * DIM * NNE + t];
+    double G[NNE][DIM];
+    gp_geometry<NNE, DIM>(dN, 1.0, X, G);
+    double gd[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) gd[d] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NNE; ++k)
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) gd[d] = fma(a.U[(int64_t)d * a.n_nodes + nd[k]], G[k][d], gd[d]);
+    double tr = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) tr += gd[d];
+    sum += tr;
+  }
+  a.fbar_center[e] = sum / NGP;
+}
+
+template <class El>
+int launch_gp_fbar_center(const GpArgs& a, cudaStream_t stream) {
+  if (a.n_elems == 0) return 0;
+  if (int rc = ensure_device_tables()) return rc;
+  k_gp_fbar_center<El><<<(unsigned)((a.n_elems + 127) / 128), 128, 0, stream>>>(a);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // Temperature and its gradient at the Gauss points (fedoo/weakform/heat_equation.py:64-70,149-152).

@@ -66,7 +66,18 @@ class StressEquilibrium(WeakFormBase):
             self.space.new_variable("DispZ")
         self.constitutivelaw = law
         self.nlgeom = False
+        self._fbar = False  # small-strain F-bar stabilisation (fedoo/weakform/stress_equilibrium.py:84,372-384)
         self.assembly_options["assume_sym"] = True
+
+    @property
+    def fbar(self):
+        return self._fbar
+
+    @fbar.setter
+    def fbar(self, value):
+        if not isinstance(value, bool):
+            raise TypeError("bool expeted for fbar")
+        self._fbar = value
 
     def initialize(self, assembly, pb):
         assembly._nlgeom = False

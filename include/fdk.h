@@ -208,6 +208,14 @@ int fdk_gp_strain_stress(int elem_type, int n_nodes, int64_t n_elems, const int3
                          const double* U, const double* C_h, const double* tangent_gp, double* grad_gp,
                          double* strain_gp, double* stress_gp, fdk_stream_t stream);
 
+/* The same with the small-strain F-bar option of StressEquilibrium (wf.fbar = True,
+ * fedoo/weakform/stress_equilibrium.py:213-214,527-540): the volumetric part of grad u is replaced by its mean over the
+ * element's Gauss points before strain and stress are formed.  fbar_center: n_elems doubles of device scratch (returns
+ * those means).  3-D elements only. */
+int fdk_gp_strain_stress_fbar(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                              const double* U, const double* C_h, const double* tangent_gp, double* fbar_center,
+                              double* grad_gp, double* strain_gp, double* stress_gp, fdk_stream_t stream);
+
 /* Thermal state: temp_gp [n_gp] and temp_gradient_gp [3][n_gp] (row-major)
  * (fedoo/weakform/heat_equation.py:64-70,149-152). */
 int fdk_gp_temperature(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,

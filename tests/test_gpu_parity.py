@@ -700,3 +700,29 @@ def test_homogenized_stiffness_2d_and_tet10_against_reference(fd, golden_dir):
     assert nrm(C, g["C"]) <= 1e-9
     C_host = fd.homogen.get_homogenized_stiffness(a, solver="direct")
     assert nrm(C_host, g["C"]) <= 1e-10
+
+
+def test_fbar_state_and_residual_against_reference(fd, golden_dir):
+    """wf.fbar = True (small-strain F-bar, fedoo/weakform/stress_equilibrium.py:527-540): displacement gradient,
+    strain, stress at the Gauss points and the global vector == the reference's; K is the plain one."""
+    g0, g = load(golden_dir, "hex8_jitter"), load(golden_dir, "hex8_jitter_fbar")
+    law = fd.constitutivelaw.ElasticIsotrop(float(g["E"]), float(g["nu"]), name="law")
+    mesh, a, pb = _elastic_setup(fd, "3D", g0["nodes"], g0["elements"], "hex8", law)
+    a.weakform.fbar = True
+    with pytest.raises(TypeError):
+        a.weakform.fbar = 1
+    pb.set_X(g["U"])
+    a.update(pb, compute="all")
+    grad = a.sv["DispGradient"]
+    for i in range(3):
+        for j in range(3):
+            assert nrm(grad[i][j], g["grad"][i, j]) <= TOL * max(1.0, np.abs(g["grad"]).max() / np.abs(g["grad"][i, j]).max())
+    assert nrm(a.sv["Strain"].asarray(), g["strain"]) <= TOL
+    assert nrm(a.sv["Stress"].asarray(), g["stress"]) <= TOL
+    assert nrm(a.get_global_vector(), g["D"]) <= TOL
+    K_fbar = a.get_global_matrix().tocsr().data.copy()
+    # without F-bar the state differs (the option is live) and K is the same matrix
+    a.weakform.fbar = False
+    a.update(pb, compute="all")
+    assert nrm(a.sv["Stress"].asarray(), g["stress"]) > 1e-3
+    assert np.array_equal(a.get_global_matrix().tocsr().data, K_fbar)
