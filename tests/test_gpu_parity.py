@@ -725,4 +725,4 @@ def test_fbar_state_and_residual_against_reference(fd, golden_dir):
     a.weakform.fbar = False
     a.update(pb, compute="all")
     assert nrm(a.sv["Stress"].asarray(), g["stress"]) > 1e-3
-    assert np.array_equal(a.get_global_matrix().tocsr().data, K_fbar)
+    assert nrm(a.get_global_matrix().tocsr().data, K_fbar) <= 1e-14  # (another kernel variant: summation order)
