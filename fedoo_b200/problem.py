@@ -137,6 +137,24 @@ class _ProblemBase(_Named):
             return X[i : i + len(self._global_vector[name])]
         return self._slice(X, name)
 
+    def get_ext_forces(self, name="all"):
+        """External (reaction) forces A X - D (fedoo/core/problem.py:470-497 without the MPC redistribution): the
+        product runs on the device matrix, only the vector comes back."""
+        import torch
+
+        A = self.get_A()
+        X = self.get_X()
+        if np.isscalar(X):
+            raise ValueError("no solution yet")
+        n = A.shape[0]
+        Xd = torch.from_numpy(np.ascontiguousarray(np.asarray(X)[:n], dtype=float)).to(A.data.device)
+        F = np.zeros(self.n_dof)
+        F[:n] = A.matvec(Xd).cpu().numpy()
+        D = self.get_D() if hasattr(self, "get_D") else 0
+        if not (np.isscalar(D) and D == 0):
+            F[: len(D)] -= np.asarray(D)
+        return self._get_vect_component(F, name)
+
     @property
     def _mpc(self):
         maps = [c.mpc for c in self.bc.constraints if getattr(c, "mpc", None) is not None]
@@ -351,6 +369,9 @@ class Problem(_ProblemBase):
     def set_D(self, D):
         self._D = D
 
+    def get_D(self):
+        return self._D
+
     def get_X(self):
         return self._X
 
@@ -378,6 +399,9 @@ class Linear(_ProblemBase):
     def get_A(self):
         A = getattr(self, "_A", None)
         return A if A is not None else self.assembly.get_global_matrix()
+
+    def get_D(self):
+        return self.assembly.get_global_vector()
 
     def get_X(self):
         return self._X

@@ -726,3 +726,33 @@ def test_fbar_state_and_residual_against_reference(fd, golden_dir):
     a.update(pb, compute="all")
     assert nrm(a.sv["Stress"].asarray(), g["stress"]) > 1e-3
     assert nrm(a.get_global_matrix().tocsr().data, K_fbar) <= 1e-14  # (another kernel variant: summation order)
+
+
+def test_ext_forces_are_the_reactions(fd):
+    """pb.get_ext_forces (fedoo/core/problem.py:470-497): A X - D on the device matrix == scipy's product; zero on the
+    free dofs of a solved problem, reactions in balance on the two loaded faces."""
+    fd.Assembly.delete_memory()
+    fd.ModelingSpace("3D")
+    n = 9
+    nodes, elements = fd.meshgen.box_hex8(n, n, n)
+    nodes = fd.meshgen.jitter_nodes(nodes, n, n, n)
+    mesh = fd.Mesh(nodes, elements, "hex8", node_sets=fd.meshgen.box_node_sets(n, n, n), name="Domain")
+    fd.constitutivelaw.ElasticIsotrop(200e3, 0.3, name="law")
+    fd.weakform.StressEquilibrium("law", name="wf")
+    fd.Assembly.create("wf", "Domain", "hex8", name="A")
+    pb = fd.problem.Linear("A", name="pb_ext")
+    pb.set_solver("cg", rtol=1e-13)
+    pb.bc.add("Dirichlet", mesh.node_sets["left"], "Disp", 0)
+    pb.bc.add("Dirichlet", mesh.node_sets["right"], "DispX", 0.01)
+    pb.apply_boundary_conditions()
+    pb.solve(updateWF=False)
+    F = pb.get_ext_forces()
+    X = np.asarray(pb.get_X())
+    assert nrm(F, pb.get_A().tocsr() @ X) <= 1e-13
+    free = np.ones(F.size, dtype=bool)
+    free[pb._dirichlet[0]] = False
+    assert np.abs(F[free]).max() <= 1e-9 * np.abs(F).max()
+    Fx = pb.get_ext_forces("DispX")
+    assert Fx.shape == (mesh.n_nodes,) and pb.get_ext_forces("Disp").shape == (3, mesh.n_nodes)
+    pull = Fx[mesh.node_sets["right"]].sum()
+    assert pull > 0 and abs(pull + Fx[mesh.node_sets["left"]].sum()) <= 1e-9 * pull
