@@ -482,8 +482,8 @@ int pcg_jacobi(int64_t n_rows, int64_t nnz, const Idx* indptr, const Idx* indice
 // fedoo/homogen/tangent_stiffness.py:97-153): vectors are interleaved [n][R], every iteration reads K ONCE for the R
 // products (the SpMV is the HBM-bound part of the loop) and runs R independent CG recurrences with per-column scalars.
 // ---------------------------------------------------------------------------------------------------------------
-template <int NV, int LPR, int R>
-__global__ void __launch_bounds__(256) k_bcsr_spmm(int n_nodes, int64_t blk_nnz, const int64_t* __restrict__ blk_indptr,
+template <int NV, int LPR, int R, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_bcsr_spmm(int n_nodes, int64_t blk_nnz, const int64_t* __restrict__ blk_indptr,
                                                     const int32_t* __restrict__ blk_indices,
                                                     const double* __restrict__ data, const double* __restrict__ x,
                                                     double* __restrict__ y) {
@@ -546,11 +546,19 @@ int launch_bspmm(const BlockPattern& b, const double* data, const double* x, dou
   if (b.n_nodes == 0) return 0;
   const int threads = 256;
   const double avg = (double)b.blk_nnz / (double)b.n_nodes;
-  const int lpr = avg >= 80 ? 16 : avg >= 40 ? 8 : 4;
+  int lpr = avg >= 80 ? 16 : avg >= 40 ? 8 : 4;
+  if (const char* e = getenv("FDK_SPMM_LANES")) lpr = atoi(e);
+  int minb = 2;
+  if (const char* e = getenv("FDK_SPMM_MINB")) minb = atoi(e);
   const int64_t need = ((int64_t)b.n_nodes * lpr + threads - 1) / threads;
   const unsigned grid = (unsigned)(need < 148 * 32 ? need : 148 * 32);
-#define FDK_BSPMM(NV_, LPR_) \
-  k_bcsr_spmm<NV_, LPR_, R><<<grid, threads, 0, stream>>>(b.n_nodes, b.blk_nnz, b.blk_indptr, b.blk_indices, data, x, y)
+#define FDK_BSPMM_(NV_, LPR_, MB_) \
+  k_bcsr_spmm<NV_, LPR_, R, MB_><<<grid, threads, 0, stream>>>(b.n_nodes, b.blk_nnz, b.blk_indptr, b.blk_indices, data, x, y)
+#define FDK_BSPMM(NV_, LPR_)                 \
+  do {                                       \
+    if (minb >= 3) FDK_BSPMM_(NV_, LPR_, 3); \
+    else FDK_BSPMM_(NV_, LPR_, 2);           \
+  } while (0)
   if (b.nvar == 3) {
     if (lpr == 16) FDK_BSPMM(3, 16); else if (lpr == 8) FDK_BSPMM(3, 8); else FDK_BSPMM(3, 4);
   } else if (b.nvar == 2) {
@@ -561,6 +569,7 @@ int launch_bspmm(const BlockPattern& b, const double* data, const double* x, dou
     set_error("tiled SpMM: nvar must be 1, 2 or 3 (got %d)", b.nvar);
     return FDK_EINVAL;
   }
+#undef FDK_BSPMM_
 #undef FDK_BSPMM
   FDK_CUDA(cudaGetLastError());
   return 0;
