@@ -244,8 +244,8 @@ class Assembly(_Named):
 
         if want_mat:
             n_rows = nvar * n_nodes + n_glob
-            block = (pattern.blk_indptr, pattern.blk_indices, nvar, n_nodes) if n_glob == 0 else None
-            self.global_matrix = DeviceCSR(indptr, indices, K, (n_rows, n_rows), block=block)
+            block = (pattern.blk_indptr, pattern.blk_indices, nvar, n_nodes)
+            self.global_matrix = DeviceCSR(indptr, indices, K, (n_rows, n_rows), block=block, n_glob=n_glob)
         if want_vec:
             if has_vec:
                 self.global_vector_device = D

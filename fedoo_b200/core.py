@@ -174,13 +174,19 @@ class DeviceCSR:
     and the scipy object is materialised on first host access (``tocsr()`` or any scipy-like
     attribute); ``indptr`` / ``indices`` / ``data`` are the device tensors."""
 
-    def __init__(self, indptr, indices, data, shape, block=None):
+    def __init__(self, indptr, indices, data, shape, block=None, n_glob=0):
         self.indptr, self.indices, self.data = indptr, indices, data
         self.shape = tuple(shape)
         self._host = None
         # (blk_indptr int64, blk_indices int32, nvar, n_nodes) of the tiled pattern when the matrix comes from the
-        # assembly and has no global dofs: matvec / pcg then read every block row's column list once
+        # assembly: matvec / pcg then read every block row's column list once.  n_glob: trailing empty rows / columns
+        # of global (non-nodal) dofs (fedoo/core/assembly.py:192-197,459-460)
         self.block = block
+        self.n_glob = int(n_glob)
+
+    @property
+    def n_nodal(self):
+        return self.shape[0] - self.n_glob
 
     @property
     def nnz(self):
@@ -209,7 +215,7 @@ class DeviceCSR:
             self.indptr = torch.cat([self.indptr, self.indptr[-1:].expand(extra)])
             self.shape = (n, n)
             self._host = None
-            self.block = None  # trailing global dofs: back to the generic CSR kernels
+            self.n_glob += extra
 
     def _index_bytes(self):
         assert self.indptr.dtype == self.indices.dtype, "indptr and indices share one integer type (scipy convention)"
@@ -231,6 +237,8 @@ class DeviceCSR:
                                           _lib.ptr(x), _lib.ptr(free_mask), _lib.ptr(y), _lib.current_stream()),
                 "fdk_bcsr_spmv",
             )  # fmt: skip
+            if self.n_glob:
+                y[self.n_nodal :] = 0.0  # the rows of the global dofs are empty
             return y
         _lib.check(
             _lib.load().fdk_csr_spmv(
@@ -269,7 +277,7 @@ class DeviceCSR:
                 raise NotImplementedError("the constrained solve runs on the tiled pattern of the assembly (nodal size)")
             bp, bi, nvar, n_nodes = self.block
             n = mpc.n_total
-            assert self.shape[0] == mpc.n_nodal and free_mask is not None and free_mask.numel() == n
+            assert self.n_nodal == mpc.n_nodal and free_mask is not None and free_mask.numel() == n
             b = as_device_f64(b, self.data.device)
             assert b.numel() == n
             x = torch.empty(n, dtype=torch.float64, device=self.data.device)
@@ -290,7 +298,7 @@ class DeviceCSR:
         x = torch.empty(n, dtype=torch.float64, device=self.data.device)
         work = torch.empty(int(lib.fdk_pcg_work_doubles(n)), dtype=torch.float64, device=self.data.device)
         it, rel = C.c_int(0), C.c_double(0.0)
-        if self.block is not None:
+        if self.block is not None and self.n_glob == 0:
             bp, bi, nvar, n_nodes = self.block
             _lib.check(
                 lib.fdk_bcsr_pcg_jacobi(
@@ -324,6 +332,8 @@ class DeviceCSR:
             raise NotImplementedError("the multi-right-hand-side solve runs on the tiled pattern of the assembly")
         lib = _lib.load()
         bp, bi, nvar, n_nodes = self.block
+        if mpc is None and self.n_glob:
+            raise NotImplementedError("global dofs without a constraint map")
         n = self.shape[0] if mpc is None else mpc.n_total
         B = as_device_f64(B, self.data.device)
         R = int(B.shape[1])

@@ -51,8 +51,10 @@ class _BC:
         name = kargs.get("name", "")
         variables = [variable] if isinstance(variable, str) else list(variable)
         for var in variables:
-            for v in pb._expand_vector(var):
-                self.list.append((node_set, v, value, bc_type, name))
+            comps = pb._expand_vector(var)
+            per_comp = len(comps) > 1 and np.ndim(value) >= 1 and len(value) == len(comps)  # e.g. "MeanStrain", [E...]
+            for i, v in enumerate(comps):
+                self.list.append((node_set, v, value[i] if per_comp else value, bc_type, name))
         pb._dirichlet = None
 
     def remove(self, name):
@@ -195,7 +197,7 @@ class _ProblemBase(_Named):
         dofs, vals = self._dirichlet
         mpc = self._mpc
         n = self.n_dof if mpc is not None else A.shape[0]
-        n_mat = A.shape[0]
+        n_mat = A.shape[0]  # nodal size, or already resized by the global dofs (trailing empty rows)
         dev = A.data.device
         Xbc = torch.zeros(n, dtype=torch.float64, device=dev)
         free = torch.ones(n, dtype=torch.uint8, device=dev)
@@ -244,7 +246,7 @@ class _ProblemBase(_Named):
         dev = A.data.device
         global_loads = np.ascontiguousarray(global_loads, dtype=float)
         n, R = self.n_dof, global_loads.shape[1]
-        assert global_loads.shape[0] == self.n_global_dof and A.shape[0] == n - self.n_global_dof
+        assert global_loads.shape[0] == self.n_global_dof and A.n_nodal == n - self.n_global_dof
         rhs = torch.zeros((n, R), dtype=torch.float64, device=dev)  # T^T of a load on the global rows is itself
         if self.n_global_dof:
             rhs[n - self.n_global_dof :] = torch.from_numpy(global_loads).to(dev)
@@ -295,13 +297,14 @@ class _ProblemBase(_Named):
         output_type = args.pop(0) if args else kargs.pop("output_type", None)
         return get_results(self, assemb, output_list, output_type)
 
-    def apply_boundary_conditions(self):
-        """Dirichlet and Neumann part of fedoo/core/problem.py:335-432."""
+    def apply_boundary_conditions(self, t_fact=1.0):
+        """Dirichlet and Neumann part of fedoo/core/problem.py:335-432; incremental problems pass the time factor:
+        values ramp linearly from 0 (fedoo/core/boundary_conditions.py: start_value + t_fact (value - start_value))."""
         dofs, vals = [], []
         B = None
         for nodes, var, value, bc_type, _name in self.bc.list:
             d = self._dof_of(var, nodes)
-            v = np.broadcast_to(np.asarray(value, dtype=float), nodes.shape)
+            v = np.broadcast_to(np.asarray(value, dtype=float) * t_fact, nodes.shape)
             if bc_type == "Dirichlet":
                 dofs.append(d)
                 vals.append(v)
@@ -428,19 +431,48 @@ class Linear(_ProblemBase):
 
 
 class NonLinear(_ProblemBase):
-    """Holds U (converged) and dU (current increment): dof solution = U + dU
-    (fedoo/problem/non_linear.py:13-131)."""
+    """Holds U (converged) and dU (current increment): dof solution = U + dU.  The increment loop follows the
+    reference step by step (fedoo/problem/non_linear.py:134-165 elastic prediction, :259-338 Newton-Raphson error,
+    :385-432 solve_time_increment, :434-634 nlsolve) so that a script written for it iterates identically: Dirichlet
+    values ramp with the time factor, the prediction uses the matrix of set_start (elastic tangent), every
+    sub-iteration updates the state (compute="vector"), tests the error, reassembles the tangent and corrects."""
 
     def __init__(self, assembly, name="MainProblem"):
         super().__init__(assembly, name)
         self._U = 0
         self._dU = 0
-        self.nr_parameters = {"err0": None, "criterion": "Displacement", "tol": 1e-3, "max_subiter": 5, "norm_type": 2}
+        self._X = 0
+        self._err0 = None
+        self.t0, self.tmax = 0.0, 1.0
+        self.err_num = 1e-8
+        self.print_info = 0
+        self.nr_parameters = {"err0": None, "criterion": "Displacement", "tol": 5e-3, "max_subiter": 10,
+                              "dt_increase_niter": None, "norm_type": 2}  # fmt: skip
+
+    def set_nr_criterion(self, criterion="Displacement", **kargs):
+        """fedoo/problem/non_linear.py:339-383."""
+        if criterion not in ["Displacement", "Force", "Work"]:
+            raise NameError('criterion must be set to "Displacement", "Force" or "Work"')
+        self.nr_parameters["criterion"] = criterion
+        for key in kargs:
+            if key not in ["err0", "tol", "max_subiter", "dt_increase_niter", "norm_type"]:
+                raise NameError("Newton Raphson parameters should be in ['err0', 'tol', 'max_subiter', "
+                                "'dt_increase_niter', 'norm_type']")  # fmt: skip
+            self.nr_parameters[key] = kargs[key]
 
     def get_dof_solution(self, name="all"):
         if np.isscalar(self._U) and np.isscalar(self._dU):
             return self._U + self._dU
-        return self._slice(np.asarray(self._U + self._dU), name)
+        return self._get_vect_component(np.asarray(self._U + self._dU), name)
+
+    def get_X(self):
+        return self._X
+
+    def get_A(self):
+        return self.assembly.current.get_global_matrix()
+
+    def get_D(self):
+        return self.assembly.current.get_global_vector()
 
     def get_temp(self):
         return self.get_dof_solution("Temp")
@@ -452,38 +484,146 @@ class NonLinear(_ProblemBase):
         self.assembly.initialize(self)
 
     def set_start(self):
+        if not (np.isscalar(self._dU) and self._dU == 0):
+            self._U = self._U + self._dU
+            self._dU = 0
+        self._err0 = self.nr_parameters["err0"]
         self.assembly.set_start(self)
 
     def to_start(self):
         self._dU = 0
+        self._err0 = self.nr_parameters["err0"]
         self.assembly.to_start(self)
 
-    def update(self, compute="all"):
-        self.assembly.update(self, compute)
+    def update(self, compute="all", updateWeakForm=True):
+        if updateWeakForm:
+            self.assembly.update(self, compute)
+        else:
+            self.assembly.current.assemble_global_mat(compute)
 
-    def nlsolve(self, dt=0.1, tmax=1.0, max_subiter=5, tol=1e-6):
-        """Fixed-step Newton-Raphson loop (fedoo/problem/non_linear.py:434-634 without automatic
-        time-step control); Dirichlet values are applied at the first iteration of every
-        increment.  Returns the number of increments."""
-        self.initialize()
-        n_inc = int(round(tmax / dt))
-        self.dtime = dt
-        for inc in range(n_inc):
-            self.time = (inc + 1) * dt
-            self.set_start()
-            A, D = self.assembly.get_global_matrix(), self.assembly.get_global_vector()
-            X0 = np.zeros(self.n_dof) if np.isscalar(self._U) else np.asarray(self._U)
-            self._dU = self._solve(A, D, X0)  # elastic prediction with the imposed values
-            for _ in range(max_subiter):
-                self.update(compute="all")
-                D = self.assembly.get_global_vector()
-                dofs = self._dirichlet[0]
-                res = np.array(D, copy=True)
-                res[dofs] = 0.0
-                if np.linalg.norm(res) <= tol * max(np.linalg.norm(D), 1e-300):
-                    break
-                corr = self._solve(self.assembly.get_global_matrix(), D, X0 + self._dU)
-                self._dU = self._dU + corr
-            self._U = X0 + self._dU
-            self._dU = 0
+    @property
+    def t_fact(self):
+        return (self.time + self.dtime - self.t0) / (self.tmax - self.t0)
+
+    def _total(self):
+        U = self._U + self._dU
+        return np.zeros(self.n_dof) if np.isscalar(U) else np.asarray(U)
+
+    def _free_dofs(self):
+        keep = np.ones(self.n_dof, dtype=bool)
+        keep[self._dirichlet[0]] = False
+        if self._mpc is not None:
+            keep[self._mpc.slave_h] = False
+        return np.nonzero(keep)[0]
+
+    def elastic_prediction(self):
+        self.apply_boundary_conditions(self.t_fact)
+        self._X = self._solve(self.get_A(), self.get_D(), self._total())  # imposes the increments of the Dirichlet values
+        self._dU = self._dU + self._X
+
+    def NewtonRaphsonIncrement(self):
+        self._X = self._solve(self.get_A(), self.get_D(), self._total())  # imposed dofs already at their values
+        self._dU = self._dU + self._X
+
+    def NewtonRaphsonError(self):
+        """fedoo/problem/non_linear.py:259-338 (B = 0 beyond what _solve adds: the Neumann vector)."""
+        norm_type = self.nr_parameters["norm_type"]
+        free = self._free_dofs()
+        if len(free) == 0:
+            return 0
+        crit = self.nr_parameters["criterion"]
+        X = np.asarray(self._X)
+        D = self.get_D()
+        R = (0 if np.isscalar(D) else self._pad(np.asarray(D))) + self._neumann  # B + D
+        R = np.zeros(self.n_dof) if np.isscalar(R) else R
+        if self._err0 is None:
+            if crit == "Displacement":
+                err0 = np.linalg.norm(np.asarray(self._dU), norm_type)
+                if err0 == 0:
+                    return 1
+                return np.linalg.norm(X[free], norm_type) / err0
+            if crit == "Force":
+                err0 = np.linalg.norm(self.get_ext_forces(), norm_type)
+                if err0 == 0:
+                    return 1
+                return np.linalg.norm(R[free], norm_type) / err0
+            self._err0 = 1
+            self._err0 = self.NewtonRaphsonError()
+            return 1
+        if crit == "Displacement":
+            return np.linalg.norm(X[free], norm_type) / self._err0
+        if crit == "Force":
+            return np.linalg.norm(R[free], norm_type) / self._err0
+        return np.linalg.norm(X[free] * R[free], norm_type) / self._err0
+
+    def get_ext_forces(self, name="all"):
+        A, X = self.get_A(), self._total()
+        import torch
+
+        n = A.shape[0]
+        F = np.zeros(self.n_dof)
+        F[:n] = A.matvec(torch.from_numpy(np.ascontiguousarray(X[:n])).to(A.data.device)).cpu().numpy()
+        D = self.get_D()
+        if not np.isscalar(D):
+            F[: len(D)] -= np.asarray(D)
+        return self._get_vect_component(F, name)
+
+    def solve_time_increment(self, max_subiter=None, tol_nr=None):
+        """fedoo/problem/non_linear.py:385-432."""
+        max_subiter = self.nr_parameters["max_subiter"] if max_subiter is None else max_subiter
+        tol_nr = self.nr_parameters["tol"] if tol_nr is None else tol_nr
+        self.elastic_prediction()
+        subiter, err = 0, 1.0
+        for subiter in range(max_subiter):
+            self.update(compute="vector")
+            err = self.NewtonRaphsonError()
+            if self.print_info > 1:
+                print("     Subiter {} - Time: {:.5f} - Err: {:.5f}".format(subiter, self.time + self.dtime, err))
+            if err < tol_nr:
+                return 1, subiter, err
+            self.update(compute="matrix", updateWeakForm=False)
+            self.NewtonRaphsonIncrement()
+        return 0, subiter, err
+
+    def nlsolve(self, dt=0.1, update_dt=True, tmax=None, t0=None, dt_min=1e-6, max_subiter=None, dt_increase_niter=None,
+                tol_nr=None, print_info=None, **_ignored):  # fmt: skip
+        """fedoo/problem/non_linear.py:434-634 without outputs / callbacks.  Returns the number of increments."""
+        if tmax is not None:
+            self.tmax = tmax
+        if t0 is not None:
+            self.t0 = t0
+        max_subiter = self.nr_parameters["max_subiter"] if max_subiter is None else max_subiter
+        if dt_increase_niter is None:
+            dt_increase_niter = self.nr_parameters["dt_increase_niter"] or max_subiter // 3
+        tol_nr = self.nr_parameters["tol"] if tol_nr is None else tol_nr
+        if print_info is not None:
+            self.print_info = print_info
+        self.time = self.t0
+        if np.isscalar(self._U) and self._U == 0:
+            self.initialize()
+        restart, n_inc = False, 0
+        while self.time < self.tmax - self.err_num:
+            self.dtime = min(dt, self.tmax - self.time)
+            if restart:
+                self.to_start()
+                restart = False
+            else:
+                self.set_start()
+            convergence, n_iter, err = self.solve_time_increment(max_subiter, tol_nr)
+            if convergence:
+                self.time = self.time + self.dtime
+                n_inc += 1
+                if self.print_info > 0:
+                    print("Iter {} - Time: {:.5f} - dt {:.5f} - NR iter: {} - Err: {:.5f}".format(n_inc, self.time, dt, n_iter, err))
+                if update_dt and n_iter < dt_increase_niter and dt == self.dtime:
+                    dt *= 1.25
+            elif update_dt:
+                dt *= 0.25
+                if dt < dt_min:
+                    raise NameError("Current time step is inferior to the specified minimal time step (dt_min)")
+                restart = True
+            else:
+                raise NameError("Newton Raphson iteration has not converged (err: {:.5f})- Reduce the time step or use "
+                                "update_dt = True".format(err))  # fmt: skip
+        self.set_start()
         return n_inc
