@@ -165,6 +165,9 @@ class ElastoPlasticity(ConstitutiveLaw):
         ConstitutiveLaw.__init__(self, name)
         self.E, self.nu, self.yield_stress = E, nu, yield_stress
         self.k, self.m = 0.0, 1.0
+        # "consistent": algorithmic tangent of the radial return (quadratic Newton convergence);
+        # "continuum": L - (L:n)(n:L)/(n:L:n + R') at the end state, what simcoon's EPICP returns
+        self.tangent = "consistent"
 
     def set_hardening_function(self, function_type="power", **kargs):
         if function_type.lower() != "power":
@@ -202,6 +205,7 @@ class ElastoPlasticity(ConstitutiveLaw):
         statev = torch.empty((N, 8), dtype=torch.float64, device=dev)
         tangent = torch.empty(N * 36, dtype=torch.float64, device=dev)
         props = self.props
+        _lib.check(lib.fdk_set_option(b"j2_continuum_tangent", int(self.tangent == "continuum")), "fdk_set_option")
         _lib.check(
             lib.fdk_j2_update(
                 N, _lib.ptr(props), _lib.ptr(strain.device_tensor), _lib.ptr(sv0), _lib.ptr(stress), _lib.ptr(statev),
@@ -230,4 +234,5 @@ def Simcoon(umat_name, props, name=""):
     E, nu, _alpha, sigY, k, m = [float(x) for x in props]
     law = ElastoPlasticity(E, nu, sigY, name=name)
     law.set_hardening_function("power", H=k, beta=m)
+    law.tangent = "continuum"  # simcoon's cutting-plane umat returns the continuum tangent at the end state
     return law

@@ -28,6 +28,8 @@ int g_opt_mma = env_flag("FDK_MMA", 1);
 //   iso4    : hex8 + isotropic law + matrix requested (residual fused): the balanced 1024-thread kernel of
 //             fdk_assemble_iso.cuh (default 1; FDK_ISO4=0 -> 0: k_assemble, with or without mma)
 int g_opt_iso4 = env_flag("FDK_ISO4", 1);
+//   j2_continuum_tangent : fdk_j2_update returns the continuum elastoplastic tangent instead of the consistent one
+int g_opt_j2_continuum = env_flag("FDK_J2_CONTINUUM_TANGENT", 0);
 
 int check_plan(const fdk_plan* p) {
   FDK_REQUIRE(p != nullptr, FDK_EINVAL, "plan is NULL");
@@ -62,7 +64,8 @@ int fdk_set_option(const char* key, int value) {
   if (strcmp(key, "fuse_ku") == 0) { g_opt_fuse = value != 0; return 0; }
   if (strcmp(key, "mma") == 0) { g_opt_mma = value != 0; return 0; }
   if (strcmp(key, "iso4") == 0) { g_opt_iso4 = value != 0; return 0; }
-  set_error("unknown option '%s' (known: fuse_ku, mma, iso4)", key);
+  if (strcmp(key, "j2_continuum_tangent") == 0) { g_opt_j2_continuum = value != 0; return 0; }
+  set_error("unknown option '%s' (known: fuse_ku, mma, iso4, j2_continuum_tangent)", key);
   return FDK_EINVAL;
 }
 
@@ -71,7 +74,8 @@ int fdk_get_option(const char* key, int* value) {
   if (strcmp(key, "fuse_ku") == 0) { *value = g_opt_fuse; return 0; }
   if (strcmp(key, "mma") == 0) { *value = g_opt_mma; return 0; }
   if (strcmp(key, "iso4") == 0) { *value = g_opt_iso4; return 0; }
-  set_error("unknown option '%s' (known: fuse_ku, mma, iso4)", key);
+  if (strcmp(key, "j2_continuum_tangent") == 0) { *value = g_opt_j2_continuum; return 0; }
+  set_error("unknown option '%s' (known: fuse_ku, mma, iso4, j2_continuum_tangent)", key);
   return FDK_EINVAL;
 }
 
@@ -340,6 +344,7 @@ int fdk_j2_update(int64_t n_gp, const double* props_h, const double* strain_gp, 
   a.stress = stress_gp;
   a.statev = statev;
   a.tangent = tangent_gp;
+  a.continuum = g_opt_j2_continuum;
   k_j2_update<<<(unsigned)((n_gp + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
   FDK_CUDA(cudaGetLastError());
   return 0;

@@ -222,6 +222,7 @@ struct J2Args {
   double* stress;
   double* statev;
   double* tangent;
+  int continuum;  // 1: continuum elastoplastic tangent at the end state (beta = 1), 0: consistent (algorithmic) tangent
 };
 
 __global__ void __launch_bounds__(256) k_j2_update(const __grid_constant__ J2Args a) {
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(256) k_j2_update(const __grid_constant__ J2Arg
     // C = K 1(x)1 + 2 mu beta I_dev - 2 mu gamma n^(x)n^   (elastic: beta = 1, gamma = 0)
     double beta = 1.0, gam = 0.0;
     if (plastic) {
-      beta = 1.0 - 3.0 * mu * dp / q;
+      beta = a.continuum ? 1.0 : 1.0 - 3.0 * mu * dp / q;
       gam = 1.0 / (1.0 + Rp / (3.0 * mu)) - (1.0 - beta);
     }
     const double sc = sqrt(1.5) / qs;

@@ -19,7 +19,10 @@ Parity status:
     ``ElastoPlasticity`` class of the reference is dead code at this commit and
     the living path's arithmetic is in simcoon (C++, not vendored, not
     installed).  The restatement follows constitutivelaw/elasto_plasticity.py
-    and is checked against analytic uniaxial/shear cases only.
+    and is checked against analytic uniaxial/shear cases only.  (The reference's
+    one J2 known-answer test, tests/test_octet.py:80-81, is replayed on the CUDA
+    path by tests/test_gpu_parity.py::test_octet_replay_of_reference_j2_test and
+    lands within 1.4e-3 of its numbers, outside the test's own tolerance.)
 
 Conventions (reference): global dof = var * n_nodes + node
 (core/problem.py:89-91); Gauss-point index = gp * n_elements + element

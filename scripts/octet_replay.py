@@ -24,7 +24,8 @@ pb.set_solver(solver, rtol=1e-12)
 pb.bc.add(fd.constraint.PeriodicBC("small_strain", dim=3))
 pb.bc.add("Dirichlet", int(g["center"]), "Disp", 0)
 pb.bc.add("Dirichlet", 0, "MeanStrain", [0, 0, 0, 0.1, 0, 0])
-pb.nlsolve(dt=0.2, tmax=1, update_dt=False, tol_nr=0.1, print_info=2)
+tol_nr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.1
+pb.nlsolve(dt=0.2, tmax=1, update_dt=False, tol_nr=tol_nr, print_info=int(os.environ.get("PRINT_INFO", "2")))
 res = pb.get_results("Assembly", ["Strain", "Stress"], "GaussPoint")
 S, E = res.gausspoint_data["Stress"], res.gausspoint_data["Strain"]
 print("Stress[4][222] =", S[4][222], " (reference 72.3765265291865 +- 1e-3)")
