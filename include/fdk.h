@@ -50,7 +50,9 @@ int fdk_version(void);
  * residual is taken from the assembled rows, D = -K_row . U, instead of a second B^T sigma integration;
  * "mma" (default 1): hex8 + isotropic law in the generic cluster kernel: element matrices by FP64 tensor-core
  * DMMA.m8n8k4; "iso4" (default 1): hex8 + isotropic law + matrix requested (residual fused): the balanced
- * 1024-thread kernel (4 threads per incidence) instead of the generic one. */
+ * 1024-thread kernel (4 threads per incidence) instead of the generic one; "j2_continuum_tangent" (default 0):
+ * fdk_j2_update returns the continuum elastoplastic tangent L - (L:n)(n:L)/(n:L:n + R') at the end state (what
+ * simcoon's cutting-plane EPICP umat returns) instead of the consistent tangent of the radial return. */
 int fdk_set_option(const char* key, int value);
 int fdk_get_option(const char* key, int* value);
 
