@@ -20,7 +20,7 @@ fd.weakform.StressEquilibrium("ConstitutiveLaw", name="WeakForm", nlgeom=False)
 fd.Assembly.create("WeakForm", "Domain2", "tet4", name="Assembly")
 pb = fd.problem.NonLinear("Assembly")
 pb.set_nr_criterion(criterion="Work")
-pb.set_solver(solver, rtol=1e-12)
+pb.set_solver(solver, rtol=float(os.environ.get("RTOL", "1e-12")))
 pb.bc.add(fd.constraint.PeriodicBC("small_strain", dim=3))
 pb.bc.add("Dirichlet", int(g["center"]), "Disp", 0)
 pb.bc.add("Dirichlet", 0, "MeanStrain", [0, 0, 0, 0.1, 0, 0])
