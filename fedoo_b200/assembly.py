@@ -17,6 +17,8 @@ the vector as a NumPy array (device copy in ``global_vector_device``).
 
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 
 import numpy as np
@@ -28,6 +30,9 @@ from .core import DeviceCSR, GaussPointTensor, Mesh, _Named, as_device_f64, devi
 from .weakform import WeakFormBase
 
 _DEFAULT_NGP = {"hex8": 8, "tet4": 4, "tet10": 15, "quad4": 4}  # fedoo/lib_elements/element_list.py:50-84
+
+
+_RESIDUAL_KERNEL = os.environ.get("FDK_RESIDUAL_KERNEL", "1") != "0"  # 0: residual-only through the cluster kernels
 
 
 class Assembly(_Named):
@@ -194,7 +199,23 @@ class Assembly(_Named):
             if flags:
                 tangent_dev = law.tangent_device(self) if hasattr(law, "tangent_device") else None
                 peer = self.peer_vector
-                if (isinstance(law, ElasticIsotrop) and tangent_dev is None and peer is not None and flags == _lib.ALL
+                if flags == _lib.VECTOR and self.owned_nodes is None and peer is None and _RESIDUAL_KERNEL:
+                    # residual alone (every Newton sub-iteration): element forces + per-node gather, no cluster plan
+                    from .results import node_incidences
+
+                    node_ptr, node_inc = node_incidences(self.mesh)
+                    conn = self.mesh.device_arrays()[1]
+                    fe = self._scratch("fe", self.mesh.n_elements * conn.shape[1] * self.space.ndim)
+                    C_h = None
+                    if stress_dev is None and tangent_dev is None:
+                        C_h = np.ascontiguousarray(self.sv["TangentMatrix"], dtype=np.float64)
+                    rc = lib.fdk_residual_elastic(
+                        _lib.ELEM_IDS[self.elm_type], n_nodes, self.mesh.n_elements, _lib.ptr(conn), _lib.ptr(coords),
+                        _lib.ptr(C_h), _lib.ptr(tangent_dev if stress_dev is None else None), _lib.ptr(U_dev),
+                        _lib.ptr(stress_dev), _lib.ptr(node_ptr), _lib.ptr(node_inc), _lib.ptr(fe), _lib.ptr(D), stream,
+                    )  # fmt: skip
+                    _lib.check(rc, "fdk_residual_elastic")
+                elif (isinstance(law, ElasticIsotrop) and tangent_dev is None and peer is not None and flags == _lib.ALL
                         and U_dev is not None and stress_dev is None):
                     # multi-GPU: the kernel stores the owned residual entries straight into every rank's global vector
                     lam, mu = law.lame(dimension)
@@ -253,6 +274,14 @@ class Assembly(_Named):
             else:
                 self.global_vector_device = None
                 self.global_vector = 0
+
+    def _scratch(self, tag, n):
+        """Device scratch kept on the assembly between calls (never handed out)."""
+        b = self._bufs.get(tag)
+        if b is None or b.numel() != n:
+            b = torch.empty(n, dtype=torch.float64, device=device())
+            self._bufs[tag] = b
+        return b
 
     def _buffer(self, tag, n, zero=False):
         """Device output buffer.  Entries the kernels do not write (global dofs, halo nodes of a

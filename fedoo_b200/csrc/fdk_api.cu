@@ -306,6 +306,33 @@ int fdk_gp_strain_stress_fbar(int elem_type, int n_nodes, int64_t n_elems, const
                                strain_gp, stress_gp, stream);
 }
 
+int fdk_residual_elastic(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                         const double* C_h, const double* tangent_gp, const double* U, const double* stress_gp,
+                         const int64_t* node_ptr, const int32_t* node_inc, double* fe_scratch, double* D,
+                         fdk_stream_t stream) {
+  FDK_REQUIRE(conn && coords && node_ptr && node_inc && fe_scratch && D, FDK_EINVAL, "NULL argument");
+  FDK_REQUIRE(stress_gp || (U && (C_h || tangent_gp)), FDK_EINVAL, "need stress_gp, or U with C_h or tangent_gp");
+  ResArgs a{};
+  a.n_nodes = n_nodes;
+  a.n_elems = n_elems;
+  a.conn = conn;
+  a.coords = coords;
+  a.U = U;
+  a.stress_gp = stress_gp;
+  a.tangent_gp = tangent_gp;
+  a.fe = fe_scratch;
+  if (C_h)
+    for (int i = 0; i < 36; ++i) a.C[i] = C_h[i];
+  switch (elem_type) {
+    case FDK_HEX8: return launch_residual<Hex8>(a, node_ptr, node_inc, D, (cudaStream_t)stream);
+    case FDK_TET4: return launch_residual<Tet4>(a, node_ptr, node_inc, D, (cudaStream_t)stream);
+    case FDK_TET10: return launch_residual<Tet10>(a, node_ptr, node_inc, D, (cudaStream_t)stream);
+    case FDK_QUAD4: return launch_residual<Quad4>(a, node_ptr, node_inc, D, (cudaStream_t)stream);
+  }
+  set_error("unknown element type %d", elem_type);
+  return FDK_EINVAL;
+}
+
 int fdk_gp_temperature(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
                        const double* T, double* temp_gp, double* temp_gradient_gp, fdk_stream_t stream) {
   FDK_REQUIRE(conn && coords && T, FDK_EINVAL, "NULL input");

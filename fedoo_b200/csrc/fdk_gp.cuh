@@ -144,6 +144,124 @@ int launch_gp_fbar_center(const GpArgs& a, cudaStream_t stream) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Residual alone (compute = "vector": every Newton sub-iteration of fedoo/problem/non_linear.py:400-404 asks for it):
+// D = -int B^T sigma without the cluster machinery of the matrix kernels.  Pass 1, one thread per element: geometry at
+// every Gauss point, sigma from stress_gp or recomputed from U (grad u -> eps -> C eps), nodal forces of the element
+// into fe[e][k][d].  Pass 2, one thread per node: sum of its incidences in a fixed order (no atomics, bit-reproducible).
+// Replaces the vector branch of Assembly.assemble_global_mat (fedoo/core/assembly.py:400-411).
+struct ResArgs {
+  int n_nodes;
+  int64_t n_elems;
+  const int32_t* conn;
+  const double* coords;
+  const double* U;           // used when stress_gp == NULL
+  const double* stress_gp;   // (6, N) column-major, gp-major N, or NULL
+  const double* tangent_gp;  // (6, 6, N) Fortran order, or NULL -> C
+  double C[36];
+  double* fe;  // (n_elems, NNE, DIM)
+};
+
+template <class El>
+__global__ void __launch_bounds__(128) k_elem_force(const __grid_constant__ ResArgs a) {
+  constexpr int NNE = El::NNE, NGP = El::NGP, DIM = El::DIM;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n_elems) return;
+  const ElemTable& tab = c_tab[El::ID];
+  int nd[NNE];
+  double X[NNE][DIM];
+#pragma unroll
+  for (int k = 0; k < NNE; ++k) {
+    nd[k] = a.conn[e * NNE + k];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) X[k][d] = a.coords[(int64_t)nd[k] * DIM + d];
+  }
+  double f[NNE][DIM];
+#pragma unroll
+  for (int k = 0; k < NNE; ++k)
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) f[k][d] = 0.0;
+  const int64_t N = a.n_elems * NGP;
+#pragma unroll 1
+  for (int g = 0; g < NGP; ++g) {
+    double dN[DIM * NNE];
+#pragma unroll
+    for (int t = 0; t < DIM * NNE; ++t) dN[t] = tab.dN[g * DIM * NNE + t];
+    double G[NNE][DIM];
+    const double w = gp_geometry<NNE, DIM>(dN, tab.w[g], X, G);
+    const int64_t n = (int64_t)g * a.n_elems + e;
+    double sig[6];
+    if (a.stress_gp != nullptr) {
+#pragma unroll
+      for (int s = 0; s < 6; ++s) sig[s] = a.stress_gp[6 * n + s];
+    } else {
+      double gu[DIM][DIM];
+#pragma unroll
+      for (int v = 0; v < DIM; ++v)
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) gu[v][d] = 0.0;
+#pragma unroll
+      for (int k = 0; k < NNE; ++k)
+#pragma unroll
+        for (int v = 0; v < DIM; ++v) {
+          const double u = a.U[(int64_t)v * a.n_nodes + nd[k]];
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) gu[v][d] = fma(u, G[k][d], gu[v][d]);
+        }
+      double eps[6];
+      voigt_strain<DIM>(gu, eps);
+      if (a.tangent_gp != nullptr) apply_tangent(a.tangent_gp + 36 * n, 1, 6, eps, sig);
+      else apply_tangent(a.C, 6, 1, eps, sig);
+    }
+    (void)N;
+    // sigma as a tensor (Voigt xx, yy, zz, xy, xz, yz); f_k[d] += w sum_j sigma_dj dN_k/dx_j
+    const double S[3][3] = {{sig[0], sig[3], sig[4]}, {sig[3], sig[1], sig[5]}, {sig[4], sig[5], sig[2]}};
+#pragma unroll
+    for (int k = 0; k < NNE; ++k)
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        double t = 0.0;
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) t = fma(S[d][j], G[k][j], t);
+        f[k][d] = fma(w, t, f[k][d]);
+      }
+  }
+  double* out = a.fe + e * (NNE * DIM);
+#pragma unroll
+  for (int k = 0; k < NNE; ++k)
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) out[k * DIM + d] = f[k][d];
+}
+
+// D[d n_nodes + I] = -sum over the incidences (element, local node) of node I, in the order of the list
+template <int DIM>
+__global__ void __launch_bounds__(256) k_node_force_gather(int n_nodes, const int64_t* __restrict__ node_ptr,
+                                                            const int32_t* __restrict__ node_inc,
+                                                            const double* __restrict__ fe, double* __restrict__ D) {
+  const int I = blockIdx.x * blockDim.x + threadIdx.x;
+  if (I >= n_nodes) return;
+  double acc[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) acc[d] = 0.0;
+  for (int64_t t = node_ptr[I]; t < node_ptr[I + 1]; ++t) {
+    const double* src = fe + (int64_t)node_inc[t] * DIM;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) acc[d] += src[d];
+  }
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) D[(int64_t)d * n_nodes + I] = -acc[d];
+}
+
+template <class El>
+int launch_residual(const ResArgs& a, const int64_t* node_ptr, const int32_t* node_inc, double* D, cudaStream_t stream) {
+  if (a.n_elems == 0 || a.n_nodes == 0) return 0;
+  if (int rc = ensure_device_tables()) return rc;
+  k_elem_force<El><<<(unsigned)((a.n_elems + 127) / 128), 128, 0, stream>>>(a);
+  k_node_force_gather<El::DIM><<<(unsigned)((a.n_nodes + 255) / 256), 256, 0, stream>>>(a.n_nodes, node_ptr, node_inc, a.fe, D);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // Temperature and its gradient at the Gauss points (fedoo/weakform/heat_equation.py:64-70,149-152).
 template <class El>
 __global__ void __launch_bounds__(256) k_gp_temperature(const __grid_constant__ GpArgs a) {

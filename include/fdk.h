@@ -218,6 +218,17 @@ int fdk_gp_strain_stress_fbar(int elem_type, int n_nodes, int64_t n_elems, const
                               const double* U, const double* C_h, const double* tangent_gp, double* fbar_center,
                               double* grad_gp, double* strain_gp, double* stress_gp, fdk_stream_t stream);
 
+/* Residual alone, D = -int B^T sigma (compute = "vector" of Assembly.assemble_global_mat, fedoo/core/assembly.py:400-411;
+ * asked for at every Newton sub-iteration, fedoo/problem/non_linear.py:400-404) without the cluster plan of the matrix
+ * kernels: element forces into fe_scratch (n_elems * nne * dim doubles), then each node sums its incidences in the order
+ * of node_inc (node_ptr int64 [n_nodes+1], node_inc int32 = element * nne + local node): no atomics, reproducible.
+ * sigma from stress_gp (6,N), or recomputed from U with C_h (6x6 host) or tangent_gp (6,6,N).  Writes the nvar * n_nodes
+ * nodal entries of D. */
+int fdk_residual_elastic(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                         const double* C_h, const double* tangent_gp, const double* U, const double* stress_gp,
+                         const int64_t* node_ptr, const int32_t* node_inc, double* fe_scratch, double* D,
+                         fdk_stream_t stream);
+
 /* Thermal state: temp_gp [n_gp] and temp_gradient_gp [3][n_gp] (row-major)
  * (fedoo/weakform/heat_equation.py:64-70,149-152). */
 int fdk_gp_temperature(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--n", type=int, default=100)
     ap.add_argument("--mma", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--compute", default="all", choices=["all", "matrix", "vector"])
     ap.add_argument("--build-only", action="store_true")
     a = ap.parse_args()
     build()
@@ -68,7 +69,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(a.steps):
-        asm.assemble_global_mat("all")
+        asm.assemble_global_mat(a.compute)
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / a.steps

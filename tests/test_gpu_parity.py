@@ -794,3 +794,26 @@ def test_octet_replay_of_reference_j2_test(fd, golden_dir):
     assert abs(e - 0.03046909551762696) <= 5e-4 * 0.03046909551762696
     s2, e2 = out["consistent"]
     assert abs(s2 - 72.3765265291865) > abs(s - 72.3765265291865)  # the tangent definition is what the test discriminates
+
+
+@pytest.mark.parametrize("name,elm,space", [("hex8_jitter", "hex8", "3D"), ("tet10_box", "tet10", "3D"), ("quad4_plate", "quad4", "2Dstress")])
+def test_residual_only_paths_agree(fd, golden_dir, name, elm, space, monkeypatch):
+    """compute="vector": the dedicated residual kernels (element forces + per-node gather, fdk_residual_elastic) and
+    the cluster kernel's B^T sigma path give the reference's D; with a materialised Gauss-point stress too."""
+    import fedoo_b200.assembly as asm_mod
+
+    g = load(golden_dir, name)
+    out = {}
+    for fast in (True, False):
+        monkeypatch.setattr(asm_mod, "_RESIDUAL_KERNEL", fast)
+        law = fd.constitutivelaw.ElasticIsotrop(float(g["E"]), float(g["nu"]), name="law")
+        mesh, a, pb = _elastic_setup(fd, space, g["nodes"], g["elements"], elm, law)
+        pb.set_X(g["U"])
+        a.update(pb, compute="vector")
+        out[fast] = np.array(a.get_global_vector())
+        assert nrm(out[fast], g["D"]) <= TOL
+        # sigma given at the Gauss points (the J2 / F-bar route) instead of recomputed from U
+        a.sv["Stress"] = fd.GaussPointTensor(a.sv["Stress"].device_tensor.clone(), "stress")
+        a.assemble_global_mat("vector")
+        assert nrm(a.get_global_vector(), g["D"]) <= TOL
+    assert nrm(out[True], out[False]) <= 1e-13
