@@ -199,7 +199,16 @@ class Assembly(_Named):
             if flags:
                 tangent_dev = law.tangent_device(self) if hasattr(law, "tangent_device") else None
                 peer = self.peer_vector
-                if flags == _lib.VECTOR and self.owned_nodes is None and peer is None and _RESIDUAL_KERNEL:
+                fusable = isinstance(law, ElasticIsotrop) and tangent_dev is None and stress_dev is None
+                split = (flags == _lib.ALL and not fusable and self.owned_nodes is None and peer is None
+                         and _RESIDUAL_KERNEL)  # fmt: skip
+                if split:
+                    # K and D both wanted but the residual is not -K U (plastic stress, F-bar, general tangent):
+                    # matrix through the cluster kernel without its B^T sigma pass, residual through its own kernels
+                    flags = _lib.MATRIX
+                done_vec = False
+                if (flags == _lib.VECTOR or split) and self.owned_nodes is None and peer is None and _RESIDUAL_KERNEL:
+                    done_vec = True
                     # residual alone (every Newton sub-iteration): element forces + per-node gather, no cluster plan
                     from .results import node_incidences
 
@@ -215,6 +224,8 @@ class Assembly(_Named):
                         _lib.ptr(stress_dev), _lib.ptr(node_ptr), _lib.ptr(node_inc), _lib.ptr(fe), _lib.ptr(D), stream,
                     )  # fmt: skip
                     _lib.check(rc, "fdk_residual_elastic")
+                if flags == _lib.VECTOR and done_vec:
+                    pass
                 elif (isinstance(law, ElasticIsotrop) and tangent_dev is None and peer is not None and flags == _lib.ALL
                         and U_dev is not None and stress_dev is None):
                     # multi-GPU: the kernel stores the owned residual entries straight into every rank's global vector
