@@ -265,7 +265,19 @@ class Assembly(_Named):
             flags = (_lib.MATRIX if want_mat else 0) | (_lib.VECTOR if has_vec else 0)
             K = self._buffer("K", pattern.blk_nnz) if want_mat else None
             D = self._buffer("D", n_nodes + n_glob, zero=True) if has_vec else None
-            if flags:
+            if flags == _lib.VECTOR and self.owned_nodes is None and _RESIDUAL_KERNEL:
+                from .results import node_incidences
+
+                node_ptr, node_inc = node_incidences(self.mesh)
+                conn = self.mesh.device_arrays()[1]
+                fe = self._scratch("fe", self.mesh.n_elements * conn.shape[1])
+                rc = lib.fdk_residual_heat(
+                    _lib.ELEM_IDS[self.elm_type], n_nodes, self.mesh.n_elements, _lib.ptr(conn), _lib.ptr(coords),
+                    _lib.ptr(cond), rcdt, _lib.ptr(T_dev), _lib.ptr(self._T_start_dev if rcdt != 0.0 else None),
+                    _lib.ptr(node_ptr), _lib.ptr(node_inc), _lib.ptr(fe), _lib.ptr(D), stream,
+                )  # fmt: skip
+                _lib.check(rc, "fdk_residual_heat")
+            elif flags:
                 rc = lib.fdk_assemble_heat(
                     C.byref(plan.struct(1)), flags, _lib.ptr(coords), _lib.ptr(cond), rcdt, _lib.ptr(T_dev),
                     _lib.ptr(self._T_start_dev if rcdt != 0.0 else None), _lib.ptr(K), _lib.ptr(D), stream,

@@ -333,6 +333,32 @@ int fdk_residual_elastic(int elem_type, int n_nodes, int64_t n_elems, const int3
   return FDK_EINVAL;
 }
 
+int fdk_residual_heat(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                      const double* cond_h, double rho_c_over_dt, const double* T, const double* T_start,
+                      const int64_t* node_ptr, const int32_t* node_inc, double* fe_scratch, double* D,
+                      fdk_stream_t stream) {
+  FDK_REQUIRE(conn && coords && cond_h && T && node_ptr && node_inc && fe_scratch && D, FDK_EINVAL, "NULL argument");
+  FDK_REQUIRE(rho_c_over_dt == 0.0 || T_start, FDK_EINVAL, "the capacity term needs T_start");
+  ResHeatArgs a{};
+  a.n_nodes = n_nodes;
+  a.n_elems = n_elems;
+  a.conn = conn;
+  a.coords = coords;
+  a.T = T;
+  a.T_start = T_start;
+  a.rcdt = rho_c_over_dt;
+  a.fe = fe_scratch;
+  for (int i = 0; i < 9; ++i) a.cond[i] = cond_h[i];
+  switch (elem_type) {
+    case FDK_HEX8: return launch_residual_heat<Hex8>(a, node_ptr, node_inc, D, (cudaStream_t)stream);
+    case FDK_TET4: return launch_residual_heat<Tet4>(a, node_ptr, node_inc, D, (cudaStream_t)stream);
+    case FDK_TET10: return launch_residual_heat<Tet10>(a, node_ptr, node_inc, D, (cudaStream_t)stream);
+    case FDK_QUAD4: return launch_residual_heat<Quad4>(a, node_ptr, node_inc, D, (cudaStream_t)stream);
+  }
+  set_error("unknown element type %d", elem_type);
+  return FDK_EINVAL;
+}
+
 int fdk_gp_temperature(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
                        const double* T, double* temp_gp, double* temp_gradient_gp, fdk_stream_t stream) {
   FDK_REQUIRE(conn && coords && T, FDK_EINVAL, "NULL input");

@@ -233,6 +233,75 @@ __global__ void __launch_bounds__(128) k_elem_force(const __grid_constant__ ResA
     for (int d = 0; d < DIM; ++d) out[k * DIM + d] = f[k][d];
 }
 
+// Heat counterpart (fedoo/weakform/heat_equation.py:78-119,168-187): f_k = sum_g w [grad N_k . (cond grad T) +
+// (rho c / dt) N_k (T_g - T_start,g)], one dof per node.
+struct ResHeatArgs {
+  int n_nodes;
+  int64_t n_elems;
+  const int32_t* conn;
+  const double* coords;
+  const double* T;
+  const double* T_start;  // NULL when rcdt == 0
+  double cond[9];
+  double rcdt;
+  double* fe;  // (n_elems, NNE)
+};
+
+template <class El>
+__global__ void __launch_bounds__(128) k_elem_force_heat(const __grid_constant__ ResHeatArgs a) {
+  constexpr int NNE = El::NNE, NGP = El::NGP, DIM = El::DIM;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n_elems) return;
+  const ElemTable& tab = c_tab[El::ID];
+  double X[NNE][DIM], T[NNE], dT[NNE], f[NNE];
+#pragma unroll
+  for (int k = 0; k < NNE; ++k) {
+    const int nd = a.conn[e * NNE + k];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) X[k][d] = a.coords[(int64_t)nd * DIM + d];
+    T[k] = a.T[nd];
+    dT[k] = (a.rcdt != 0.0 && a.T_start != nullptr) ? T[k] - a.T_start[nd] : 0.0;
+    f[k] = 0.0;
+  }
+#pragma unroll 1
+  for (int g = 0; g < NGP; ++g) {
+    const double* dN = tab.dN + g * DIM * NNE;
+    double G[NNE][DIM];
+    const double w = gp_geometry<NNE, DIM>(dN, tab.w[g], X, G);
+    double gT[DIM], dTg = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) gT[d] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NNE; ++k) {
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) gT[d] = fma(T[k], G[k][d], gT[d]);
+      dTg = fma(tab.N[g * NNE + k], dT[k], dTg);
+    }
+    double q[DIM];
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      double t = 0.0;
+#pragma unroll
+      for (int j = 0; j < DIM; ++j) t = fma(a.cond[i * 3 + j], gT[j], t);
+      q[i] = t;
+    }
+    const double cap = a.rcdt * dTg;
+#pragma unroll
+    for (int k = 0; k < NNE; ++k) {
+      double t = tab.N[g * NNE + k] * cap;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) t = fma(G[k][d], q[d], t);
+      f[k] = fma(w, t, f[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NNE; ++k) a.fe[e * NNE + k] = f[k];
+}
+
+template <class El>
+int launch_residual_heat(const ResHeatArgs& a, const int64_t* node_ptr, const int32_t* node_inc, double* D,
+                         cudaStream_t stream);
+
 // D[d n_nodes + I] = -sum over the incidences (element, local node) of node I, in the order of the list
 template <int DIM>
 __global__ void __launch_bounds__(256) k_node_force_gather(int n_nodes, const int64_t* __restrict__ node_ptr,
@@ -250,6 +319,17 @@ __global__ void __launch_bounds__(256) k_node_force_gather(int n_nodes, const in
   }
 #pragma unroll
   for (int d = 0; d < DIM; ++d) D[(int64_t)d * n_nodes + I] = -acc[d];
+}
+
+template <class El>
+int launch_residual_heat(const ResHeatArgs& a, const int64_t* node_ptr, const int32_t* node_inc, double* D,
+                         cudaStream_t stream) {
+  if (a.n_elems == 0 || a.n_nodes == 0) return 0;
+  if (int rc = ensure_device_tables()) return rc;
+  k_elem_force_heat<El><<<(unsigned)((a.n_elems + 127) / 128), 128, 0, stream>>>(a);
+  k_node_force_gather<1><<<(unsigned)((a.n_nodes + 255) / 256), 256, 0, stream>>>(a.n_nodes, node_ptr, node_inc, a.fe, D);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 template <class El>

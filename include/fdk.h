@@ -229,6 +229,13 @@ int fdk_residual_elastic(int elem_type, int n_nodes, int64_t n_elems, const int3
                          const int64_t* node_ptr, const int32_t* node_inc, double* fe_scratch, double* D,
                          fdk_stream_t stream);
 
+/* The same for the heat equation (fedoo/weakform/heat_equation.py:78-119,168-187): D_I = -sum_g w [grad N_I . (cond
+ * grad T) + (rho c / dt) N_I (T_g - T_start,g)]; cond_h 3x3 row-major host; T_start may be NULL when rho_c_over_dt = 0. */
+int fdk_residual_heat(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                      const double* cond_h, double rho_c_over_dt, const double* T, const double* T_start,
+                      const int64_t* node_ptr, const int32_t* node_inc, double* fe_scratch, double* D,
+                      fdk_stream_t stream);
+
 /* Thermal state: temp_gp [n_gp] and temp_gradient_gp [3][n_gp] (row-major)
  * (fedoo/weakform/heat_equation.py:64-70,149-152). */
 int fdk_gp_temperature(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,

@@ -170,7 +170,7 @@ def test_uniform_anisotropic_matches_isotropic(fd, golden_dir):
 
 
 @pytest.mark.parametrize("name,mesh_from", [("tet4_box_heat", None), ("tet4_gyroid_heat", "tet4_gyroid")])
-def test_heat_against_reference(fd, golden_dir, name, mesh_from):
+def test_heat_against_reference(fd, golden_dir, name, mesh_from, monkeypatch):
     """Driving recipe of oracle/gen_golden.py:heat_case (= tests/test_thermal3D.py material)."""
     g = load(golden_dir, name)
     m = g if mesh_from is None else load(golden_dir, mesh_from)
@@ -195,6 +195,13 @@ def test_heat_against_reference(fd, golden_dir, name, mesh_from):
         assert nrm(K.data, g["K_data"]) <= TOL
     assert nrm(K @ g["v"], g["Kv"]) <= TOL
     assert nrm(a.get_global_vector(), g["D"]) <= TOL
+    # the residual alone: dedicated kernels (fdk_residual_heat) and the cluster kernel's path
+    import fedoo_b200.assembly as asm_mod
+
+    for fast in (True, False):
+        monkeypatch.setattr(asm_mod, "_RESIDUAL_KERNEL", fast)
+        a.assemble_global_mat("vector")
+        assert nrm(a.get_global_vector(), g["D"]) <= TOL, fast
     step = 1 if "K_data" in g else 97
     assert nrm(np.asarray(a.sv["Temp"])[::step], g["temp_gp"]) <= TOL
     assert nrm(np.asarray(a.sv["TempGradient"])[:, ::step], g["temp_gradient_gp"]) <= TOL
