@@ -84,6 +84,15 @@ def thermal(scale):
     torch.cuda.synchronize()
     first = time.perf_counter() - t0
     ms = timed(lambda: a.assemble_global_mat("all"))
+    import fedoo_b200.assembly as asm_mod
+
+    ms_res = timed(lambda: a.assemble_global_mat("vector"))  # residual alone: fdk_residual_heat
+    D_fast = a.global_vector.clone()
+    asm_mod._RESIDUAL_KERNEL = False
+    ms_res_cluster = timed(lambda: a.assemble_global_mat("vector"))  # the cluster kernel's path
+    res_paths_rel = float((a.global_vector - D_fast).abs().max() / D_fast.abs().max())
+    asm_mod._RESIDUAL_KERNEL = True
+    a.assemble_global_mat("all")
     K = a.get_global_matrix()
     A = csr(K)
     D = a.global_vector
@@ -111,8 +120,10 @@ def thermal(scale):
     return dict(
         config="configs[2]: tet4 HeatEquation (K=500, c=0.5, rho=7800, dt=10/3), 6-tet split of a jittered box",
         n_elems=len(elements), n_nodes=nn, nnz=nnz, first_call_s=first, ms_per_assembly=ms,
+        ms_residual_only=ms_res, ms_residual_only_cluster_kernel=ms_res_cluster,
         melem_per_s=len(elements) / ms / 1e3, algorithmic_gb=algo / 1e9, hbm_frac=algo / (ms * 1e-3) / 1e9 / peaks(),
         checks=dict(
+            residual_paths_rel=res_paths_rel,
             lumped_capacity_total_rel=abs(float(m.sum()) - rho * c / dt * vol) / (rho * c / dt * vol),
             capacity_positive=bool((m > 0).all()),
             D_conduction_balance_rel=float(resid.abs().max() / D0.abs().max()),
