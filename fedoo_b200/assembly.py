@@ -265,7 +265,9 @@ class Assembly(_Named):
             flags = (_lib.MATRIX if want_mat else 0) | (_lib.VECTOR if has_vec else 0)
             K = self._buffer("K", pattern.blk_nnz) if want_mat else None
             D = self._buffer("D", n_nodes + n_glob, zero=True) if has_vec else None
-            if flags == _lib.VECTOR and self.owned_nodes is None and _RESIDUAL_KERNEL:
+            split = (flags & _lib.VECTOR) and self.owned_nodes is None and _RESIDUAL_KERNEL
+            if split:
+                # the residual through its own kernels; with K also wanted the cluster kernel then runs matrix-only
                 from .results import node_incidences
 
                 node_ptr, node_inc = node_incidences(self.mesh)
@@ -277,7 +279,8 @@ class Assembly(_Named):
                     _lib.ptr(node_ptr), _lib.ptr(node_inc), _lib.ptr(fe), _lib.ptr(D), stream,
                 )  # fmt: skip
                 _lib.check(rc, "fdk_residual_heat")
-            elif flags:
+                flags &= ~_lib.VECTOR
+            if flags:
                 rc = lib.fdk_assemble_heat(
                     C.byref(plan.struct(1)), flags, _lib.ptr(coords), _lib.ptr(cond), rcdt, _lib.ptr(T_dev),
                     _lib.ptr(self._T_start_dev if rcdt != 0.0 else None), _lib.ptr(K), _lib.ptr(D), stream,
