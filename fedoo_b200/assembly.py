@@ -110,14 +110,23 @@ class Assembly(_Named):
     # ------------------------------------------------------------------ symbolic (one-time)
     def _symbolic(self):
         """Pattern, tiled CSR and cluster plan; cached per (mesh, element type) and per nvar."""
+        # the entry keeps the mesh and the mask alive, so their ids cannot be recycled while it is cached (the
+        # reference keys its caches on the mesh object itself); sizes are checked as well: a mesh edited in place
+        # (new connectivity) must not reuse a stale pattern
         key = (id(self.mesh), self.elm_type, id(self.owned_nodes))
         entry = Assembly._saved_plans.get(key)
+        if entry is not None and not (
+            entry["mesh"] is self.mesh and entry["owned"] is self.owned_nodes
+            and entry["sizes"] == (self.mesh.n_nodes, self.mesh.n_elements, id(self.mesh.elements))
+        ):  # fmt: skip
+            entry = None
         if entry is None:
             coords, conn = self.mesh.device_arrays()
             pattern = symbolic.build_pattern(conn, self.mesh.n_nodes)
             owned = None if self.owned_nodes is None else torch.from_numpy(np.asarray(self.owned_nodes, dtype=bool))
             plan = symbolic.build_plan(self.elm_type, coords, conn, pattern, owned=owned)
-            entry = {"pattern": pattern, "plan": plan, "csr": {}}
+            entry = {"pattern": pattern, "plan": plan, "csr": {}, "mesh": self.mesh, "owned": self.owned_nodes,
+                     "sizes": (self.mesh.n_nodes, self.mesh.n_elements, id(self.mesh.elements))}  # fmt: skip
             Assembly._saved_plans[key] = entry
         nvar = self.nvar
         n_glob = 0 if self._pb is None else getattr(self._pb, "n_global_dof", 0)
@@ -230,9 +239,10 @@ class Assembly(_Named):
                         and U_dev is not None and stress_dev is None):
                     # multi-GPU: the kernel stores the owned residual entries straight into every rank's global vector
                     lam, mu = law.lame(dimension)
+                    dst, n_dst = peer.begin_step()  # the half of the double-buffered symmetric vector this step writes
                     rc = lib.fdk_assemble_elastic_iso_dist(
                         C.byref(plan.struct(nvar)), flags, _lib.ptr(coords), lam, mu, _lib.ptr(U_dev), _lib.ptr(K),
-                        _lib.ptr(D), peer._ptr_array, len(peer.dst_ptrs), _lib.ptr(peer.node_gid), peer.n_global, stream,
+                        _lib.ptr(D), dst, n_dst, _lib.ptr(peer.node_gid), peer.n_global, stream,
                     )  # fmt: skip
                     _lib.check(rc, "fdk_assemble_elastic_iso_dist")
                     peer.barrier()
@@ -358,21 +368,30 @@ class Assembly(_Named):
         if self.weakform.constitutivelaw is not None:
             self.weakform.constitutivelaw.set_start(self, pb)
         self.sv_start = dict(self.sv)
-        self.assemble_global_mat("all")
+        self._assemble_current("all")
+
+    def _assemble_current(self, compute):
+        """fedoo/core/assembly.py:706,721,735: the lifecycle assembles ``self.current`` (the assembly on the deformed
+        configuration once ``set_disp`` has been called), which reads the state of this assembly."""
+        cur = self.current
+        if cur is not self:
+            cur.sv, cur.sv_start, cur._U_dev, cur._T_start_dev, cur._pb = (
+                self.sv, self.sv_start, self._U_dev, self._T_start_dev, self._pb)  # fmt: skip
+        cur.assemble_global_mat(compute)
 
     def update(self, pb, compute="all"):
         self.weakform.update(self, pb)
         if self.weakform.constitutivelaw is not None:
             self.weakform.constitutivelaw.update(self, pb)
         self.weakform.update_2(self, pb)
-        self.assemble_global_mat(compute)
+        self._assemble_current(compute)
 
     def to_start(self, pb):
         self.weakform.to_start(self, pb)
         if self.weakform.constitutivelaw is not None:
             self.weakform.constitutivelaw.to_start(self, pb)
         self.sv = dict(self.sv_start)
-        self.assemble_global_mat("all")
+        self._assemble_current("all")
 
     def reset(self):
         self.weakform.reset()

@@ -338,7 +338,6 @@ int fdk_residual_heat(int elem_type, int n_nodes, int64_t n_elems, const int32_t
                       const int64_t* node_ptr, const int32_t* node_inc, double* fe_scratch, double* D,
                       fdk_stream_t stream) {
   FDK_REQUIRE(conn && coords && cond_h && T && node_ptr && node_inc && fe_scratch && D, FDK_EINVAL, "NULL argument");
-  FDK_REQUIRE(rho_c_over_dt == 0.0 || T_start, FDK_EINVAL, "the capacity term needs T_start");
   ResHeatArgs a{};
   a.n_nodes = n_nodes;
   a.n_elems = n_elems;
@@ -354,6 +353,28 @@ int fdk_residual_heat(int elem_type, int n_nodes, int64_t n_elems, const int32_t
     case FDK_TET4: return launch_residual_heat<Tet4>(a, node_ptr, node_inc, D, (cudaStream_t)stream);
     case FDK_TET10: return launch_residual_heat<Tet10>(a, node_ptr, node_inc, D, (cudaStream_t)stream);
     case FDK_QUAD4: return launch_residual_heat<Quad4>(a, node_ptr, node_inc, D, (cudaStream_t)stream);
+  }
+  set_error("unknown element type %d", elem_type);
+  return FDK_EINVAL;
+}
+
+int fdk_residual_heat_gp(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                         const double* flux_gp, const double* src_gp, const int64_t* node_ptr, const int32_t* node_inc,
+                         double* fe_scratch, double* D, fdk_stream_t stream) {
+  FDK_REQUIRE(conn && coords && node_ptr && node_inc && fe_scratch && D, FDK_EINVAL, "NULL argument");
+  ResHeatGpArgs a{};
+  a.n_nodes = n_nodes;
+  a.n_elems = n_elems;
+  a.conn = conn;
+  a.coords = coords;
+  a.flux_gp = flux_gp;
+  a.src_gp = src_gp;
+  a.fe = fe_scratch;
+  switch (elem_type) {
+    case FDK_HEX8: return launch_residual_heat_gp<Hex8>(a, node_ptr, node_inc, D, (cudaStream_t)stream);
+    case FDK_TET4: return launch_residual_heat_gp<Tet4>(a, node_ptr, node_inc, D, (cudaStream_t)stream);
+    case FDK_TET10: return launch_residual_heat_gp<Tet10>(a, node_ptr, node_inc, D, (cudaStream_t)stream);
+    case FDK_QUAD4: return launch_residual_heat_gp<Quad4>(a, node_ptr, node_inc, D, (cudaStream_t)stream);
   }
   set_error("unknown element type %d", elem_type);
   return FDK_EINVAL;

@@ -241,7 +241,7 @@ struct ResHeatArgs {
   const int32_t* conn;
   const double* coords;
   const double* T;
-  const double* T_start;  // NULL when rcdt == 0
+  const double* T_start;  // NULL: zero start temperature
   double cond[9];
   double rcdt;
   double* fe;  // (n_elems, NNE)
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(128) k_elem_force_heat(const __grid_constant__
 #pragma unroll
     for (int d = 0; d < DIM; ++d) X[k][d] = a.coords[(int64_t)nd * DIM + d];
     T[k] = a.T[nd];
-    dT[k] = (a.rcdt != 0.0 && a.T_start != nullptr) ? T[k] - a.T_start[nd] : 0.0;
+    dT[k] = a.rcdt != 0.0 ? T[k] - (a.T_start != nullptr ? a.T_start[nd] : 0.0) : 0.0;  // NULL: T_start = 0 (heat_equation.py:140-147)
     f[k] = 0.0;
   }
 #pragma unroll 1
@@ -302,6 +302,56 @@ template <class El>
 int launch_residual_heat(const ResHeatArgs& a, const int64_t* node_ptr, const int32_t* node_inc, double* D,
                          cudaStream_t stream);
 
+// The same residual from GIVEN Gauss-point fields -- what the reference's weak forms hand to the assembly through
+// ``assembly.sv`` (heat_equation.py:99-117: grad v . (K TempGradient); :178-186: (rho c / dt) v (Temp - Temp_start)):
+// f_k = sum_g w [grad N_k . flux_g + N_k src_g], flux (3, N) row-major or NULL, src (N,) or NULL, gp-major columns.
+struct ResHeatGpArgs {
+  int n_nodes;
+  int64_t n_elems;
+  const int32_t* conn;
+  const double* coords;
+  const double* flux_gp;
+  const double* src_gp;
+  double* fe;  // (n_elems, NNE)
+};
+
+template <class El>
+__global__ void __launch_bounds__(128) k_elem_force_heat_gp(const __grid_constant__ ResHeatGpArgs a) {
+  constexpr int NNE = El::NNE, NGP = El::NGP, DIM = El::DIM;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n_elems) return;
+  const ElemTable& tab = c_tab[El::ID];
+  const int64_t N = a.n_elems * NGP;
+  double X[NNE][DIM], f[NNE];
+#pragma unroll
+  for (int k = 0; k < NNE; ++k) {
+    const int nd = a.conn[e * NNE + k];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) X[k][d] = a.coords[(int64_t)nd * DIM + d];
+    f[k] = 0.0;
+  }
+#pragma unroll 1
+  for (int g = 0; g < NGP; ++g) {
+    const double* dN = tab.dN + g * DIM * NNE;
+    double G[NNE][DIM];
+    const double w = gp_geometry<NNE, DIM>(dN, tab.w[g], X, G);
+    const int64_t n = (int64_t)g * a.n_elems + e;
+    double q[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) q[d] = a.flux_gp != nullptr ? a.flux_gp[(int64_t)d * N + n] : 0.0;
+    const double src = a.src_gp != nullptr ? a.src_gp[n] : 0.0;
+#pragma unroll
+    for (int k = 0; k < NNE; ++k) {
+      double t = tab.N[g * NNE + k] * src;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) t = fma(G[k][d], q[d], t);
+      f[k] = fma(w, t, f[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NNE; ++k) a.fe[e * NNE + k] = f[k];
+}
+
 // D[d n_nodes + I] = -sum over the incidences (element, local node) of node I, in the order of the list
 template <int DIM>
 __global__ void __launch_bounds__(256) k_node_force_gather(int n_nodes, const int64_t* __restrict__ node_ptr,
@@ -327,6 +377,17 @@ int launch_residual_heat(const ResHeatArgs& a, const int64_t* node_ptr, const in
   if (a.n_elems == 0 || a.n_nodes == 0) return 0;
   if (int rc = ensure_device_tables()) return rc;
   k_elem_force_heat<El><<<(unsigned)((a.n_elems + 127) / 128), 128, 0, stream>>>(a);
+  k_node_force_gather<1><<<(unsigned)((a.n_nodes + 255) / 256), 256, 0, stream>>>(a.n_nodes, node_ptr, node_inc, a.fe, D);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <class El>
+int launch_residual_heat_gp(const ResHeatGpArgs& a, const int64_t* node_ptr, const int32_t* node_inc, double* D,
+                            cudaStream_t stream) {
+  if (a.n_elems == 0 || a.n_nodes == 0) return 0;
+  if (int rc = ensure_device_tables()) return rc;
+  k_elem_force_heat_gp<El><<<(unsigned)((a.n_elems + 127) / 128), 128, 0, stream>>>(a);
   k_node_force_gather<1><<<(unsigned)((a.n_nodes + 255) / 256), 256, 0, stream>>>(a.n_nodes, node_ptr, node_inc, a.fe, D);
   FDK_CUDA(cudaGetLastError());
   return 0;

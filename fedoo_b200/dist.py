@@ -262,17 +262,39 @@ class PeerVector:
         self.group = group or dist.group.WORLD
         self.nvar, self.n_global = nvar, local.n_global_nodes
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.tensor = symm_mem.empty(nvar * self.n_global, dtype=torch.float64, device=dev)
-        self.tensor.zero_()
-        self.handle = symm_mem.rendezvous(self.tensor, self.group)
+        # DOUBLE-BUFFERED: step k stores into half k % 2.  A rank can only launch step k + 1 after it has passed the
+        # barrier of step k, which every rank enters after its own step-k kernel -- i.e. after everything it had
+        # queued on the stream to read the result of step k - 1 (the half step k + 1 overwrites).  One barrier per
+        # step therefore covers both the read-after-write and the write-after-read hazard.
+        n = nvar * self.n_global
+        self._n = n
+        self._both = symm_mem.empty(2 * n, dtype=torch.float64, device=dev)
+        self._both.zero_()
+        self.handle = symm_mem.rendezvous(self._both, self.group)
         mc = int(self.handle.multicast_ptr or 0)
-        self.dst_ptrs = [mc] if mc else [int(x) for x in self.handle.buffer_ptrs]
-        assert len(self.dst_ptrs) <= 8, "peer-address fallback is limited to 8 ranks"
+        base = [mc] if mc else [int(x) for x in self.handle.buffer_ptrs]
+        assert len(base) <= 8, "peer-address fallback is limited to 8 ranks"
         self.multicast = bool(mc)
+        self._dst = [[b + 8 * n * h for b in base] for h in (0, 1)]
+        self._arrays = [(C.c_void_p * len(d))(*d) for d in self._dst]
+        self._half = 1  # half written by the LAST step (begin_step flips it)
         self.node_gid = torch.from_numpy(np.ascontiguousarray(local.node_gid, dtype=np.int64)).to(dev)
-        self._ptr_array = (C.c_void_p * len(self.dst_ptrs))(*self.dst_ptrs)
         torch.cuda.synchronize()
         self.handle.barrier()
+
+    @property
+    def tensor(self):
+        """The global vector of the last completed step (valid after ``barrier()``, until the step after next)."""
+        return self._both[self._half * self._n : (self._half + 1) * self._n]
+
+    @property
+    def dst_ptrs(self):
+        return self._dst[self._half]
+
+    def begin_step(self):
+        """Flip to the other half; returns (ctypes pointer array, count) of the destinations of this step."""
+        self._half ^= 1
+        return self._arrays[self._half], len(self._dst[self._half])
 
     def barrier(self):
         """Device-side barrier on the current stream: after it every rank's stores have landed everywhere."""

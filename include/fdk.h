@@ -230,11 +230,19 @@ int fdk_residual_elastic(int elem_type, int n_nodes, int64_t n_elems, const int3
                          fdk_stream_t stream);
 
 /* The same for the heat equation (fedoo/weakform/heat_equation.py:78-119,168-187): D_I = -sum_g w [grad N_I . (cond
- * grad T) + (rho c / dt) N_I (T_g - T_start,g)]; cond_h 3x3 row-major host; T_start may be NULL when rho_c_over_dt = 0. */
+ * grad T) + (rho c / dt) N_I (T_g - T_start,g)]; cond_h 3x3 row-major host; T_start NULL = zero start temperature (the reference's __temp_start = 0, heat_equation.py:140-147). */
 int fdk_residual_heat(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
                       const double* cond_h, double rho_c_over_dt, const double* T, const double* T_start,
                       const int64_t* node_ptr, const int32_t* node_inc, double* fe_scratch, double* D,
                       fdk_stream_t stream);
+
+/* The heat residual from GIVEN Gauss-point fields, as the reference's weak forms pass them through assembly.sv
+ * (fedoo/weakform/heat_equation.py:99-117 "grad v . (K TempGradient)", :178-186 "(rho c / dt) v (Temp - Temp_start)"):
+ * D_I = -sum_g w [grad N_I . flux_g + N_I src_g]; flux_gp [3][n_gp] row-major (NULL = 0), src_gp [n_gp] (NULL = 0),
+ * gp-major columns g * n_elems + e.  This is the entry the adapter under the real fedoo.Assembly calls. */
+int fdk_residual_heat_gp(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                         const double* flux_gp, const double* src_gp, const int64_t* node_ptr, const int32_t* node_inc,
+                         double* fe_scratch, double* D, fdk_stream_t stream);
 
 /* Thermal state: temp_gp [n_gp] and temp_gradient_gp [3][n_gp] (row-major)
  * (fedoo/weakform/heat_equation.py:64-70,149-152). */

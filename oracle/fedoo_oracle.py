@@ -15,14 +15,16 @@ Parity status:
     and heat equation: PINNED against arrays produced by the reference itself
     (``oracle/gen_golden.py`` -> ``tests/golden/*.npz``; checked by
     ``tests/test_oracle_golden.py``).
-  * J2 plasticity (``j2_radial_return``): PARITY UNPINNED.  The in-tree
-    ``ElastoPlasticity`` class of the reference is dead code at this commit and
-    the living path's arithmetic is in simcoon (C++, not vendored, not
-    installed).  The restatement follows constitutivelaw/elasto_plasticity.py
-    and is checked against analytic uniaxial/shear cases only.  (The reference's
-    one J2 known-answer test, tests/test_octet.py:80-81, is replayed on the CUDA
-    path by tests/test_gpu_parity.py::test_octet_replay_of_reference_j2_test and
-    lands within 1.4e-3 of its numbers, outside the test's own tolerance.)
+  * J2 plasticity (``j2_radial_return``): the STATE UPDATE (sigma, p, eps_p) is PINNED on the reference's own
+    per-Gauss-point loop -- constitutivelaw/elasto_plasticity.py:303-376, dead code at this commit, driven standalone
+    by ``oracle/gen_golden_j2.py`` with its three breakages shimmed at run time (renamed tensor methods, hardening-slope
+    sign, local tolerance) -> ``tests/golden/j2_reference.npz``, agreement 5e-13.  The TANGENT is a definition, not a
+    result: the consistent tangent is checked by finite differences of sigma(eps); the continuum tangent
+    (``j2_continuum_tangent``) follows :275-300 with the corrected sign.  The living path's arithmetic is simcoon's
+    (C++, absent): the reference's one J2 known-answer test (tests/test_octet.py:80-81) is reproduced by the
+    REFERENCE'S OWN driver + this law (``oracle/gen_golden_octet_driver.py``) to 1.4e-3 / 2.7e-4 of its published
+    numbers, outside the test's tolerance -- that residual is simcoon's cutting-plane iteration at freshly yielded
+    points (one Newton correction per increment makes the answers tangent-dependent), and stays UNPINNED.
 
 Conventions (reference): global dof = var * n_nodes + node
 (core/problem.py:89-91); Gauss-point index = gp * n_elements + element
@@ -494,7 +496,7 @@ def residual_heat(G, wdet, elements, elm_type, conductivity, rho_c, dtime, T, T_
 
 
 # ---------------------------------------------------------------------------
-# J2 plasticity with isotropic power-law hardening -- PARITY UNPINNED
+# J2 plasticity with isotropic power-law hardening -- state update pinned on the reference's loop (header)
 # (constitutivelaw/elasto_plasticity.py:66-80 elastic H, :127-133 hardening,
 #  :154-164 yield function / flow direction, :303-376 trial state + return,
 #  :275-300 tangent; sv protocol constitutivelaw/simcoon_umat.py:463-580, EPICP
@@ -583,3 +585,24 @@ def j2_radial_return(eps, statev_start, props, tol=1e-12, max_iter=50):
         gamma = 1.0 / (1.0 + Rp / (3 * mu)) - (1.0 - beta)
         tang[:, :, idx] = vol + 2 * mu * beta * Idev[:, :, None] - 2 * mu * gamma * nn
     return sig, statev, tang
+
+
+def j2_continuum_tangent(sig, statev, statev_start, props):
+    """Continuum elasto-plastic tangent at the END state, (6, 6, N):  L - (L:n)(n:L) / (n:L:n + R'(p)) on the Gauss
+    points whose p grew during the increment, L elsewhere.  This is the operator the reference's legacy law builds
+    (elasto_plasticity.py:275-300, with the hardening-slope sign corrected) and the one a cutting-plane umat
+    returns; for J2, L:n = 3 mu s/q (stress Voigt) and n:L:n = 3 mu."""
+    E, nu, _alpha, _sigY, k, m = [float(x) for x in props]
+    mu = 0.5 * E / (1 + nu)
+    H = elastic_isotropic_H(E, nu)
+    N = sig.shape[1]
+    tang = np.repeat(H[:, :, None], N, axis=2)
+    idx = np.where(statev[1] > statev_start[1])[0]
+    if idx.size:
+        s = sig[:, idx].copy()
+        s[:3] -= s[:3].sum(axis=0) / 3.0
+        q = np.sqrt(1.5 * (_VOIGT_W[:, None] * s * s).sum(axis=0))
+        sh = s / q
+        Rp = k * m * np.power(statev[1, idx], m - 1.0)
+        tang[:, :, idx] -= (3 * mu) ** 2 / (3 * mu + Rp) * np.einsum("in,jn->ijn", sh, sh)
+    return tang
