@@ -68,6 +68,10 @@ class Assembly(_Named):
         self.reuse_buffers = kargs.pop("reuse_buffers", False)
         # leave the global vector in HBM (``global_vector`` is then the CUDA tensor): no D2H copy
         self.vector_on_device = kargs.pop("vector_on_device", False)
+        # pipeline the host copies (pinned dof vector in, residual out) on two copy streams with rotating buffers, so that
+        # step i + 1's H2D and step i's D2H overlap the kernels; ``global_vector`` is then a ``HostVector`` future
+        self.async_copies = kargs.pop("async_copies", False)
+        self._pipe = None
         # multi-GPU: a fedoo_b200.dist.PeerVector -> the residual exchange is fused into the assembly kernel
         self.peer_vector = kargs.pop("peer_vector", None)
         self._bufs = {}
@@ -198,7 +202,7 @@ class Assembly(_Named):
             has_vec = want_vec and not (np.isscalar(stress) and stress == 0)
             flags = (_lib.MATRIX if want_mat else 0) | (_lib.VECTOR if has_vec else 0)
             K = self._buffer("K", nvar * nvar * pattern.blk_nnz) if want_mat else None
-            D = self._buffer("D", nvar * n_nodes + n_glob, zero=True) if has_vec else None
+            D = self._buffer(self._d_tag(), nvar * n_nodes + n_glob, zero=True) if has_vec else None
             U_dev = stress_dev = None
             if has_vec:
                 if isinstance(stress, _FusedElasticStress):
@@ -274,7 +278,7 @@ class Assembly(_Named):
             has_vec = want_vec and T_dev is not None
             flags = (_lib.MATRIX if want_mat else 0) | (_lib.VECTOR if has_vec else 0)
             K = self._buffer("K", pattern.blk_nnz) if want_mat else None
-            D = self._buffer("D", n_nodes + n_glob, zero=True) if has_vec else None
+            D = self._buffer(self._d_tag(), n_nodes + n_glob, zero=True) if has_vec else None
             split = (flags & _lib.VECTOR) and self.owned_nodes is None and _RESIDUAL_KERNEL
             if split:
                 # the residual through its own kernels; with K also wanted the cluster kernel then runs matrix-only
@@ -299,6 +303,8 @@ class Assembly(_Named):
         else:
             raise NotImplementedError(f"weak form operator '{self.weakform.operator}'")
 
+        if self._pipe is not None:
+            self._pipe.kernel_finished()
         if want_mat:
             n_rows = nvar * n_nodes + n_glob
             block = (pattern.blk_indptr, pattern.blk_indices, nvar, n_nodes)
@@ -306,10 +312,27 @@ class Assembly(_Named):
         if want_vec:
             if has_vec:
                 self.global_vector_device = D
-                self.global_vector = D if self.vector_on_device else self._to_host(D)
+                if self.vector_on_device:
+                    self.global_vector = D
+                elif self.async_copies and self.reuse_buffers:
+                    self.global_vector = self._copy_pipe().d2h(D)
+                else:
+                    self.global_vector = self._to_host(D)
             else:
                 self.global_vector_device = None
                 self.global_vector = 0
+
+    def _copy_pipe(self):
+        if self._pipe is None:
+            self._pipe = _CopyPipe()
+        return self._pipe
+
+    def _d_tag(self):
+        """Output buffer of the residual: two of them in rotation when the D2H copies are pipelined (the kernel of step
+        i + 1 must not write the buffer step i's copy is still reading)."""
+        if self.async_copies and self.reuse_buffers and not self.vector_on_device:
+            return "D%d" % self._copy_pipe().begin_output()
+        return "D"
 
     def _scratch(self, tag, n):
         """Device scratch kept on the assembly between calls (never handed out)."""
@@ -404,7 +427,10 @@ class Assembly(_Named):
     def _strain_update(self, U):
         """StressEquilibrium.update (fedoo/weakform/stress_equilibrium.py:191-217): record the dof
         vector; sv['Strain'] / sv['DispGradient'] are produced lazily by ``fdk_gp_strain_stress``."""
-        self._U_dev = as_device_f64(U)
+        if self.async_copies and isinstance(U, torch.Tensor) and not U.is_cuda and U.is_pinned():
+            self._U_dev = self._copy_pipe().h2d(U)
+        else:
+            self._U_dev = as_device_f64(U)
         fbar = bool(getattr(self.weakform, "fbar", False))
         if fbar and self.space.ndim != 3:
             raise NotImplementedError("F-bar is available for the 3D modeling space")
@@ -496,7 +522,10 @@ class Assembly(_Named):
             if initialize:
                 self._T_start_dev = None
             return
-        self._U_dev = as_device_f64(T)
+        if self.async_copies and isinstance(T, torch.Tensor) and not T.is_cuda and T.is_pinned():
+            self._U_dev = self._copy_pipe().h2d(T)
+        else:
+            self._U_dev = as_device_f64(T)
         if initialize:
             self._T_start_dev = self._U_dev.clone()
         self.sv["Temp"] = _LazyTemp(self, self._U_dev, 0)
@@ -521,6 +550,83 @@ class Assembly(_Named):
             "fdk_gp_temperature",
         )  # fmt: skip
         return temp, grad
+
+
+class HostVector:
+    """The residual on its way to (pinned) host memory: ``result()`` / ``np.asarray()`` wait for the copy.  The
+    storage rotates: a result must be consumed before the assembly after next overwrites it."""
+
+    def __init__(self, host, event):
+        self._host, self._event = host, event
+
+    def result(self):
+        if self._event is not None:
+            self._event.synchronize()
+            self._event = None
+        return self._host.numpy()
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.result()
+        return a if dtype is None else a.astype(dtype)
+
+    def __len__(self):
+        return self._host.numel()
+
+    @property
+    def size(self):
+        return self._host.numel()
+
+
+class _CopyPipe:
+    """Two copy streams (H2D, D2H: PCIe is full duplex) and two-deep rotating buffers around the assembly kernel.
+    Ordering, all by events: H2D(i) waits for the kernel that last read its device buffer (i - 2); kernel(i) waits for
+    H2D(i) and for the D2H that last read its output buffer (i - 2); D2H(i) waits for kernel(i)."""
+
+    def __init__(self):
+        self.h2d_stream, self.d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
+        self.k_in = self.k_out = 0
+        self.U = [None, None]
+        self.kernel_done = [None, None]  # per input buffer: the assembly that read it has finished
+        self.host = [None, None]
+        self.d2h_done = [None, None]  # per output buffer
+
+    def h2d(self, U_host):
+        k = self.k_in = self.k_in ^ 1
+        if self.U[k] is None or self.U[k].numel() != U_host.numel():
+            self.U[k] = torch.empty(U_host.numel(), dtype=torch.float64, device=device())
+        if self.kernel_done[k] is not None:
+            self.h2d_stream.wait_event(self.kernel_done[k])
+        with torch.cuda.stream(self.h2d_stream):
+            self.U[k].copy_(U_host.reshape(-1), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.h2d_stream)
+        torch.cuda.current_stream().wait_event(ev)
+        return self.U[k]
+
+    def begin_output(self):
+        k = self.k_out = self.k_out ^ 1
+        if self.d2h_done[k] is not None:
+            torch.cuda.current_stream().wait_event(self.d2h_done[k])
+        return k
+
+    def kernel_finished(self):
+        """Called once per assembly, after its last launch on the current stream."""
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream())
+        self.kernel_done[self.k_in] = self.last_done = done
+
+    def d2h(self, D):
+        k = self.k_out
+        done = self.last_done
+        if self.host[k] is None or self.host[k].numel() != D.numel():
+            self.host[k] = torch.empty(D.numel(), dtype=torch.float64, pin_memory=True)
+        self.d2h_stream.wait_event(done)
+        with torch.cuda.stream(self.d2h_stream):
+            self.host[k].copy_(D, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.d2h_stream)
+        self.d2h_done[k] = ev
+        return HostVector(self.host[k], ev)
 
 
 class _LazyStrain(GaussPointTensor):

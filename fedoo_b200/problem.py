@@ -463,6 +463,8 @@ class NonLinear(_ProblemBase):
     def get_dof_solution(self, name="all"):
         if np.isscalar(self._U) and np.isscalar(self._dU):
             return self._U + self._dU
+        if name == "all" and np.isscalar(self._dU) and self._dU == 0:
+            return self._U  # as it is (a pinned / device tensor keeps its placement)
         return self._get_vect_component(np.asarray(self._U + self._dU), name)
 
     def get_X(self):

@@ -1,0 +1,245 @@
+"""The CUDA path under the REAL fedoo (north_star "drop-in backend under fd.problem.Linear/NonLinear").
+
+``import fedoo`` here is the UNMODIFIED reference copied to ``oracle/_ref`` by ``oracle/make_ref.py``;
+``fedoo_b200.install(fedoo)`` replaces ``Assembly.assemble_global_mat`` / ``get_gp_results`` with the kernels.  Two kinds
+of checks:
+  * the bodies of the reference's own tests (cantilever, plate with a hole, transient thermal gyroid) are executed
+    AS THEY ARE from ``oracle/_ref/tests`` -- they carry the reference's known answers and tolerances;
+  * the same assembly computed twice on one process, by the reference's NumPy/SciPy code and by the kernels:
+    ``indptr`` / ``indices`` identical, values and residual within 1e-12.
+``strict=True`` makes any assembly that is not on the accelerated path raise, so a pass cannot be a silent fall-through
+to the reference's own code; ``adapter.stats`` is asserted as well.
+"""
+
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _ref_available():
+    return os.path.isdir(os.path.join(REF, "fedoo"))
+
+
+@pytest.fixture(scope="module")
+def rf():
+    """(fedoo, adapter) with the backend installed."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    if not _ref_available():
+        pytest.fail("oracle/_ref is missing: __graft_entry__.build() (oracle/make_ref.py) creates it where /root/reference exists")
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import fedoo
+    from fedoo_b200 import adapter
+
+    adapter.install(fedoo, strict=True)
+    yield fedoo, adapter
+    adapter.uninstall(fedoo)
+
+
+def _run_reference_test(fname, func):
+    spec = importlib.util.spec_from_file_location("ref_" + fname[:-3], os.path.join(REF, "tests", fname))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    getattr(mod, func)()
+
+
+@pytest.mark.gpu
+def test_reference_cantilever_test_runs_on_the_kernels(rf):
+    fedoo, adapter = rf
+    fedoo.Assembly.delete_memory()
+    n0 = dict(adapter.stats)
+    _run_reference_test("test_cantilever_beam_3D_model.py", "test_cantilever_beam_3D_model")  # asserts -0.9007983467254552
+    assert adapter.stats["assembled"] > n0["assembled"] and adapter.stats["delegated"] == n0["delegated"]
+    assert adapter.stats["gp_results"] > n0["gp_results"]  # get_strain went through the device kernels
+
+
+@pytest.mark.gpu
+def test_reference_plate_with_hole_test_runs_on_the_kernels(rf):
+    fedoo, adapter = rf
+    fedoo.Assembly.delete_memory()
+    n0 = dict(adapter.stats)
+    _run_reference_test("test_platewithhol.py", "test_plate_with_hole")  # 2Dstress quad4, MeshChange=True, Stress_vm[282]
+    assert adapter.stats["assembled"] > n0["assembled"] and adapter.stats["delegated"] == n0["delegated"]
+
+
+@pytest.mark.gpu
+def test_reference_thermal3d_test_runs_on_the_kernels(rf, tmp_path, monkeypatch):
+    fedoo, adapter = rf
+    fedoo.Assembly.delete_memory()
+    monkeypatch.chdir(tmp_path)  # the test writes results/thermal3D.npz
+    n0 = dict(adapter.stats)
+    _run_reference_test("test_thermal3D.py", "test_thermal3D")  # NonLinear heat, Temp[8712] = 2.610859332847924
+    assert adapter.stats["assembled"] >= n0["assembled"] + 6 and adapter.stats["delegated"] == n0["delegated"]
+
+
+def _both(fedoo, adapter, build):
+    """Run ``build()`` (returns an assembly after update) with the reference's own code, then on the kernels."""
+    adapter.uninstall(fedoo)
+    try:
+        fedoo.Assembly.delete_memory()
+        a = build()
+        Kr, Dr = a.get_global_matrix().copy(), np.array(a.get_global_vector())
+    finally:
+        adapter.install(fedoo, strict=True)
+    fedoo.Assembly.delete_memory()
+    a = build()
+    return (Kr, Dr), (a.get_global_matrix(), np.array(a.get_global_vector())), a
+
+
+def _cmp(ref, got, tol=1e-12):
+    (Kr, Dr), (K, D) = ref, got
+    assert K.indptr.dtype == Kr.indptr.dtype == np.int32
+    assert np.array_equal(K.indptr, Kr.indptr) and np.array_equal(K.indices, Kr.indices) and K.shape == Kr.shape
+    assert np.abs(K.data - Kr.data).max() <= tol * np.abs(Kr.data).max()
+    assert np.abs(D - Dr).max() <= tol * max(np.abs(Dr).max(), 1e-300)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,elm,space", [("hex8_jitter", "hex8", "3D"), ("tet10_box", "tet10", "3D"), ("tet4_box", "tet4", "3D"),
+                                            ("quad4_jitter_pstrain", "quad4", "2Dplane")])  # fmt: skip
+def test_elastic_assembly_identical_to_reference(rf, golden_dir, name, elm, space):
+    fedoo, adapter = rf
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+
+    def build():
+        fedoo.ModelingSpace(space)
+        fedoo.Mesh(np.array(g["nodes"]), np.array(g["elements"]), elm, name="Domain")
+        fedoo.constitutivelaw.ElasticIsotrop(200e3, 0.3, name="law")
+        fedoo.weakform.StressEquilibrium("law", name="wf")
+        a = fedoo.Assembly.create("wf", "Domain", elm, name="A")
+        pb = fedoo.problem.Linear("A")
+        pb.set_X(np.random.default_rng(0).standard_normal(pb.n_dof) * 1e-3)
+        a.update(pb, compute="all")
+        return a
+
+    ref, got, a = _both(fedoo, adapter, build)
+    _cmp(ref, got)
+    # the Gauss-point state the reference's own weak form / law computed from the kernels' gradients
+    eps = a.sv["Strain"].asarray()
+    assert eps.shape == (6, a.n_gauss_points) and np.isfinite(eps).all()
+
+
+@pytest.mark.gpu
+def test_per_gp_tangent_and_global_dofs_identical_to_reference(rf):
+    """ElasticAnisotropic with a (6,6,N) tangent (the route a plastic tangent takes) and a problem with global dofs
+    (PeriodicBC adds six: K is resized with empty trailing rows, core/assembly.py:192-197,459-460)."""
+    fedoo, adapter = rf
+
+    def build():
+        fedoo.ModelingSpace("3D")
+        mesh = fedoo.mesh.box_mesh(nx=5, ny=4, nz=4, elm_type="hex8", name="Domain")
+        N = mesh.n_elements * 8
+        rng = np.random.default_rng(3)
+        H0 = fedoo.constitutivelaw.ElasticIsotrop(100e3, 0.25).get_tangent_matrix(None, "3D")
+        H = np.empty((6, 6, N), order="F")
+        H[...] = H0[:, :, None] * rng.uniform(0.5, 1.5, N)
+        fedoo.constitutivelaw.ElasticAnisotropic(H, name="law")
+        fedoo.weakform.StressEquilibrium("law", name="wf")
+        a = fedoo.Assembly.create("wf", "Domain", "hex8", name="A")
+        pb = fedoo.problem.Linear("A")
+        pb.bc.add(fedoo.constraint.PeriodicBC("small_strain", dim=3))
+        assert pb.n_global_dof == 6
+        X = np.zeros(pb.n_dof)
+        X[: 3 * mesh.n_nodes] = np.random.default_rng(0).standard_normal(3 * mesh.n_nodes) * 1e-3
+        pb.set_X(X)
+        a.update(pb, compute="all")
+        return a
+
+    ref, got, a = _both(fedoo, adapter, build)
+    _cmp(ref, got)
+    assert got[0].shape[0] == 3 * a.mesh.n_nodes + 6
+
+
+@pytest.mark.gpu
+def test_heat_assembly_identical_to_reference(rf):
+    fedoo, adapter = rf
+
+    def build():
+        fedoo.ModelingSpace("3D")
+        mesh = fedoo.mesh.box_mesh(nx=5, ny=5, nz=4, elm_type="hex8", name="Domain")
+        fedoo.constitutivelaw.ThermalProperties(500, 0.5, 7800, name="ThermalLaw")
+        fedoo.weakform.HeatEquation("ThermalLaw")
+        a = fedoo.Assembly.create("ThermalLaw", "Domain", name="A")
+        pb = fedoo.problem.NonLinear("A")
+        pb.dtime = 10 / 3  # the driving recipe of oracle/gen_golden.py:heat_case
+        pb._U = np.random.default_rng(2).uniform(0, 3, mesh.n_nodes)
+        pb._dU = 0
+        pb.initialize()
+        a.set_start(pb)
+        pb._dU = np.random.default_rng(4).uniform(-0.2, 0.2, mesh.n_nodes)
+        a.update(pb, "all")
+        return a
+
+    ref, got, a = _both(fedoo, adapter, build)
+    _cmp(ref, got)
+
+
+@pytest.mark.gpu
+def test_strict_mode_refuses_what_is_not_on_the_path(rf):
+    fedoo, adapter = rf
+    fedoo.Assembly.delete_memory()
+    fedoo.ModelingSpace("3D")
+    fedoo.mesh.box_mesh(nx=3, ny=3, nz=3, elm_type="hex20", name="Domain")
+    fedoo.constitutivelaw.ElasticIsotrop(1.0, 0.3, name="law")
+    fedoo.weakform.StressEquilibrium("law", name="wf")
+    a = fedoo.Assembly.create("wf", "Domain", "hex20", name="A")
+    fedoo.problem.Linear("A")  # initialises assembly.sv
+    with pytest.raises(NotImplementedError):
+        a.assemble_global_mat()
+    adapter.install(fedoo, strict=False)
+    try:
+        n0 = adapter.stats["delegated"]
+        a.assemble_global_mat()  # the reference's own method
+        assert adapter.stats["delegated"] == n0 + 1 and a.global_matrix.shape[0] == 3 * a.mesh.n_nodes
+    finally:
+        adapter.install(fedoo, strict=True)
+
+
+def test_adapter_classification_cpu():
+    """Host logic of the adapter on the CPU: what is routed to the kernels and what is not (no compute)."""
+    if not _ref_available():
+        pytest.skip("oracle/_ref not built in this environment")
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import fedoo
+    from fedoo_b200 import adapter
+
+    fedoo.Assembly.delete_memory()
+    fedoo.ModelingSpace("3D")
+    fedoo.mesh.box_mesh(nx=3, ny=3, nz=3, elm_type="hex8", name="Domain")
+    fedoo.constitutivelaw.ElasticIsotrop(1.0, 0.3, name="law")
+    fedoo.weakform.StressEquilibrium("law", name="wf")
+    a = fedoo.Assembly.create("wf", "Domain", "hex8", name="A")
+    assert adapter._classify(a) == "elastic"
+    a8 = fedoo.Assembly.create("wf", "Domain", "hex8", name="A27", n_elm_gp=27)
+    assert adapter._classify(a8) is None  # non-default quadrature
+    fedoo.ModelingSpace("3D")
+    fedoo.constitutivelaw.ThermalProperties(500, 0.5, 7800, name="ThermalLaw")
+    fedoo.weakform.HeatEquation("ThermalLaw")
+    h = fedoo.Assembly.create("ThermalLaw", "Domain", name="H")
+    assert adapter._classify(h) == "heat" and h.mat_lumping == [False, True]
+    # tangent formats of the reference (6x6 floats, object arrays with per-Gauss-point entries, (6,6,N))
+    H = fedoo.constitutivelaw.ElasticIsotrop(2.0, 0.3).get_tangent_matrix(None, "3D")
+    assert adapter._normalize_tangent(H, 8).shape == (6, 6)
+    Eg = np.linspace(1, 2, 8)
+    Hobj = fedoo.constitutivelaw.ElasticIsotrop(Eg, 0.3).get_tangent_matrix(None, "3D")
+    Hn = adapter._normalize_tangent(Hobj, 8)
+    assert Hn.shape == (6, 6, 8) and Hn.flags["F_CONTIGUOUS"] and np.allclose(Hn[0, 1], Eg * 0.3 / (1.3 * 0.4))
+    assert Hn[0, 3].max() == 0

@@ -1,0 +1,278 @@
+"""GPU tests added in round 2 for the paths the first round left unchecked (VERDICT r1 "what's weak" 2-3, "missing" 6-8):
+the fused multi-GPU kernel, the transient heat solve from the default zero start, ``Assembly.to_start``, the int64 branch
+of the CSR expansion, the reference's real tet10 mesh on the CUDA path, ``set_disp`` through the lifecycle."""
+
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-12
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def nrm(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def fd():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import fedoo_b200 as fd
+
+    return fd
+
+
+class _FakePeer:
+    """What Assembly needs from dist.PeerVector, on ONE process: the 'peers' are two plain device buffers (as if two
+    ranks' copies lived on this GPU), and ``node_gid`` is a PERMUTATION -- a kernel that ignored it, or wrote
+    v * n_local instead of v * n_global, would not reproduce the single-GPU residual."""
+
+    def __init__(self, n_local, n_global, nvar, seed=0):
+        import torch
+
+        self.n_global = n_global
+        self.gid = np.random.default_rng(seed).permutation(n_global)[:n_local].astype(np.int64)
+        self.node_gid = torch.from_numpy(self.gid).cuda()
+        self.bufs = [torch.full((nvar * n_global,), np.nan, dtype=torch.float64, device="cuda") for _ in range(2)]
+        self.arr = (C.c_void_p * 2)(*[b.data_ptr() for b in self.bufs])
+        self.steps = self.barriers = 0
+        self.multicast = False
+
+    def begin_step(self):
+        self.steps += 1
+        return self.arr, 2
+
+    def barrier(self):
+        self.barriers += 1
+
+
+def test_fused_exchange_kernel_against_single_gpu(fd, golden_dir):
+    """fdk_assemble_elastic_iso_dist (k_assemble_iso<..., DIST=true>): K and the local D identical to the plain kernel,
+    and every destination buffer holds D at var * n_global + node_gid[node] -- with a permuted node_gid, a global size
+    larger than the local one, and untouched (NaN) entries everywhere else."""
+    import torch
+
+    g = np.load(os.path.join(golden_dir, "hex8_jitter.npz"))
+
+    def setup(peer):
+        fd.Assembly.delete_memory()
+        fd.ModelingSpace("3D")
+        mesh = fd.Mesh(g["nodes"], g["elements"], "hex8", name="Domain")
+        law = fd.constitutivelaw.ElasticIsotrop(float(g["E"]), float(g["nu"]), name="law")
+        fd.weakform.StressEquilibrium(law, name="wf")
+        a = fd.Assembly.create("wf", "Domain", "hex8", name="A", peer_vector=peer)
+        pb = fd.problem.Linear("A")
+        pb.set_X(g["U"])
+        a.update(pb, compute="all")
+        return mesh, a
+
+    mesh, a = setup(None)
+    K0 = a.get_global_matrix().tocsr().data.copy()
+    D0 = np.array(a.get_global_vector())
+    n = mesh.n_nodes
+    peer = _FakePeer(n, n + 37, 3)
+    mesh, a = setup(peer)
+    torch.cuda.synchronize()
+    assert peer.steps == 1 and peer.barriers == 1
+    assert np.array_equal(a.get_global_matrix().tocsr().data, K0)  # same instantiation modulo the extra stores
+    assert np.array_equal(np.array(a.get_global_vector()), D0)
+    assert nrm(D0, g["D"]) <= TOL
+    for buf in peer.bufs:
+        h = buf.cpu().numpy().reshape(3, peer.n_global)
+        for v in range(3):
+            assert np.array_equal(h[v, peer.gid], D0[v * n : (v + 1) * n])
+        untouched = np.ones(peer.n_global, bool)
+        untouched[peer.gid] = False
+        assert np.isnan(h[:, untouched]).all()
+
+
+def test_heat_nlsolve_from_default_zero_start(fd, golden_dir):
+    """NonLinear + HeatEquation from the default scalar-0 temperature -- the first residual has
+    T_start = None (the reference's ``__temp_start = 0``, heat_equation.py:140-147).  Same run as
+    oracle/gen_golden_heat_nlsolve.py made with the reference (settings of tests/test_thermal3D.py:45,75)."""
+    g = np.load(os.path.join(golden_dir, "tet4_box.npz"))
+    ref = np.load(os.path.join(golden_dir, "heat_nlsolve_tet4.npz"))
+    fd.Assembly.delete_memory()
+    fd.ModelingSpace("3D")
+    mesh = fd.Mesh(g["nodes"], g["elements"], "tet4", name="Domain")
+    fd.constitutivelaw.ThermalProperties(500, 0.5, 7800, name="ThermalLaw")
+    fd.weakform.HeatEquation("ThermalLaw")
+    fd.Assembly.create("ThermalLaw", "Domain", name="Assembling")
+    pb = fd.problem.NonLinear("Assembling")
+    pb.set_nr_criterion("Displacement", tol=5e-2, max_subiter=5, err0=100)
+    right = mesh.find_nodes("X", mesh.bounding_box.xmax)
+    assert np.array_equal(right, ref["right"])
+    pb.bc.add("Dirichlet", right, "Temp", 3)
+    pb.nlsolve(dt=10 / 3, tmax=10, update_dt=True)
+    T = np.asarray(pb.get_dof_solution())
+    assert nrm(T, ref["T"]) <= 1e-10
+
+
+def test_to_start_restores_state_and_operators(fd, golden_dir):
+    """Assembly.to_start (core/assembly.py:724-735: the dt-cut restart of NonLinear): sv is rebound to the start state,
+    K and D are those of the start of the increment again -- checked on the plastic path, where both change."""
+    g = np.load(os.path.join(golden_dir, "hex8_jitter.npz"))
+    fd.Assembly.delete_memory()
+    fd.ModelingSpace("3D")
+    fd.Mesh(g["nodes"], g["elements"], "hex8", name="Domain")
+    law = fd.constitutivelaw.Simcoon("EPICP", [200e3, 0.3, 1e-5, 300.0, 1000.0, 0.3], name="law")
+    fd.weakform.StressEquilibrium(law, name="wf")
+    a = fd.Assembly.create("wf", "Domain", "hex8", name="A")
+    pb = fd.problem.NonLinear("A")
+    U1 = g["U"] * 20.0
+    pb._U, pb._dU = 0, U1
+    a.update(pb, compute="all")
+    pb._U, pb._dU = U1, 0
+    a.set_start(pb)  # commit increment 1: tangent back to elastic, state kept
+    K_start = a.get_global_matrix().tocsr().data.copy()
+    D_start = np.array(a.get_global_vector())
+    sv_start = a.sv["Statev"].clone()
+    stress_start = a.sv["Stress"].asarray().copy()
+    assert float(sv_start[:, 1].max()) > 0  # something yielded
+    pb._dU = g["U"] * 15.0
+    a.update(pb, compute="all")  # trial increment 2: state and operators move
+    assert nrm(a.get_global_matrix().tocsr().data, K_start) > 1e-3
+    assert float((a.sv["Statev"][:, 1] - sv_start[:, 1]).abs().max()) > 0
+    pb._dU = 0
+    a.to_start(pb)  # the increment is abandoned
+    assert a.sv is not a.sv_start and a.sv["Statev"] is a.sv_start["Statev"]
+    assert np.array_equal(a.sv["Statev"].cpu().numpy(), sv_start.cpu().numpy())
+    assert np.array_equal(a.sv["Stress"].asarray(), stress_start)
+    assert np.array_equal(a.get_global_matrix().tocsr().data, K_start)
+    assert np.array_equal(np.array(a.get_global_vector()), D_start)
+
+
+def test_expand_csr_int64_branch_against_scipy(fd, golden_dir):
+    """The int64 branch of fdk_sym_expand_csr (scipy's get_index_dtype rule switches at max(nnz, n) > 2^31 - 1; no test
+    mesh is that large) forced with index_bytes = 8 on a small mesh, against scipy.sparse.bmat built with int64
+    indices; the int32 result of the normal path must be the same numbers."""
+    import torch
+    from scipy import sparse
+
+    from fedoo_b200 import _lib, symbolic
+
+    g = np.load(os.path.join(golden_dir, "tet10_box.npz"))
+    conn = torch.from_numpy(g["elements"].astype(np.int32)).cuda()
+    n = len(g["nodes"])
+    pat = symbolic.build_pattern(conn, n)
+    lib = _lib.load()
+    for nvar, n_glob in ((3, 0), (3, 6), (1, 0), (2, 3)):
+        nnz = nvar * nvar * pat.blk_nnz
+        n_rows = nvar * n + n_glob
+        indptr = torch.empty(n_rows + 1, dtype=torch.int64, device="cuda")
+        indices = torch.empty(nnz, dtype=torch.int64, device="cuda")
+        _lib.check(
+            lib.fdk_sym_expand_csr(n, nvar, n_glob, pat.blk_nnz, _lib.ptr(pat.blk_indptr), _lib.ptr(pat.blk_indices), 8,
+                                   _lib.ptr(indptr), _lib.ptr(indices), _lib.current_stream()),
+            "fdk_sym_expand_csr",
+        )  # fmt: skip
+        bp, bi = pat.blk_indptr.cpu().numpy(), pat.blk_indices.cpu().numpy()
+        blk = sparse.csr_matrix((np.ones(len(bi)), bi.astype(np.int64), bp.astype(np.int64)), shape=(n, n))
+        ref = sparse.bmat([[blk] * nvar] * nvar, format="csr")
+        ref.resize(n_rows, n_rows)
+        assert np.array_equal(indptr.cpu().numpy(), ref.indptr.astype(np.int64))
+        assert np.array_equal(indices.cpu().numpy(), ref.indices.astype(np.int64))
+        ip32, ix32 = symbolic.expand_csr(pat, nvar, n_glob)
+        assert ip32.dtype == torch.int32
+        assert torch.equal(ip32.to(torch.int64), indptr) and torch.equal(ix32.to(torch.int64), indices)
+    assert symbolic.csr_index_dtype(2**31 - 1, 10) == torch.int32 and symbolic.csr_index_dtype(2**31, 10) == torch.int64
+    assert symbolic.csr_index_dtype(10, 2**31) == torch.int64
+
+
+def _read_msh_tet10(path):
+    """Minimal gmsh MSH 2.2 ASCII reader for 10-node tets (type 11); the reference swaps gmsh's last two mid-edge nodes
+    on import (mesh/importmesh.py:388-390,434-436).  Same reader as tests/test_oracle_golden.py."""
+    with open(path) as f:
+        lines = f.read().split("\n")
+    i = lines.index("$Nodes")
+    n = int(lines[i + 1])
+    nd = np.array([l.split() for l in lines[i + 2 : i + 2 + n]], dtype=float)
+    ids = nd[:, 0].astype(np.int64)
+    nodes = nd[:, 1:4]
+    i = lines.index("$Elements")
+    m = int(lines[i + 1])
+    tets = []
+    for l in lines[i + 2 : i + 2 + m]:
+        t = l.split()
+        if int(t[1]) == 11:
+            ntag = int(t[2])
+            tets.append([int(x) for x in t[3 + ntag :]])
+    e = np.array(tets, dtype=np.int64)
+    lut = np.full(ids.max() + 1, -1, dtype=np.int64)
+    lut[ids] = np.arange(n)
+    e = lut[e]
+    return nodes, e[:, [0, 1, 2, 3, 4, 5, 6, 7, 9, 8]]
+
+
+def test_reference_tet10_octet_mesh_on_the_cuda_path(fd, golden_dir):
+    """BASELINE config 5's real mesh (util/meshes/octet_truss_quad.msh, 24 911 tet10, 144 798 dofs, 10.1 M nnz):
+    pattern hashes, ||K||_F, K v and D of the reference (tests/golden/fingerprints.json)."""
+    fp = json.load(open(os.path.join(golden_dir, "fingerprints.json")))["tet10_octet"]
+    path = os.path.join(ROOT, "oracle", "_ref", fp["mesh_file"])
+    assert os.path.exists(path), "oracle/_ref is missing (oracle/make_ref.py copies the reference's mesh files)"
+    nodes, elements = _read_msh_tet10(path)
+    assert sha(nodes) == fp["nodes_sha"] and sha(elements.astype(np.int32)) == fp["elements_sha"]
+    fd.Assembly.delete_memory()
+    fd.ModelingSpace("3D")
+    fd.Mesh(nodes, elements.astype(np.int32), "tet10", name="Domain")
+    law = fd.constitutivelaw.ElasticIsotrop(fp["E"], fp["nu"], name="law")
+    fd.weakform.StressEquilibrium(law, name="wf")
+    a = fd.Assembly.create("wf", "Domain", "tet10", name="A")
+    pb = fd.problem.Linear("A")
+    U = np.random.default_rng(fp["U_seed"]).standard_normal(pb.n_dof) * 1e-3
+    pb.set_X(U)
+    a.update(pb, compute="all")
+    K = a.get_global_matrix().tocsr()
+    assert K.nnz == fp["K_nnz"] and list(K.shape) == fp["K_shape"]
+    assert sha(K.indptr) == fp["K_indptr_sha"] and sha(K.indices) == fp["K_indices_sha"]
+    assert abs(np.linalg.norm(K.data) - fp["K_fro"]) <= TOL * fp["K_fro"]
+    assert abs(np.abs(K.data).max() - fp["K_absmax"]) <= TOL * fp["K_absmax"]
+    v = np.random.default_rng(fp["v_seed"]).standard_normal(K.shape[0])
+    Kv = K @ v
+    assert abs(np.linalg.norm(Kv) - fp["Kv_norm"]) <= 1e-11 * fp["Kv_norm"]
+    assert nrm(Kv[:8], fp["Kv_head"]) <= 1e-10
+    D = np.array(a.get_global_vector())
+    if "D_norm" in fp:
+        assert abs(np.linalg.norm(D) - fp["D_norm"]) <= 1e-11 * fp["D_norm"]
+        assert nrm(D[: len(fp["D_head"])], fp["D_head"]) <= 1e-10
+
+
+def test_lifecycle_assembles_the_current_configuration(fd, golden_dir):
+    """after set_disp the lifecycle (update / set_start / to_start) assembles ``assembly.current``
+    (core/assembly.py:706,721,735) with the parent's state, so K and D follow the moved mesh at every call."""
+    from oracle import fedoo_oracle as fo
+
+    g = np.load(os.path.join(golden_dir, "hex8_jitter.npz"))
+    nodes, elements = g["nodes"], g["elements"]
+    fd.Assembly.delete_memory()
+    fd.ModelingSpace("3D")
+    fd.Mesh(nodes, elements, "hex8", name="Domain")
+    law = fd.constitutivelaw.ElasticIsotrop(float(g["E"]), float(g["nu"]), name="law")
+    fd.weakform.StressEquilibrium(law, name="wf")
+    a = fd.Assembly.create("wf", "Domain", "hex8", name="A")
+    pb = fd.problem.Linear("A")
+    H = fo.elastic_isotropic_H(float(g["E"]), float(g["nu"]))
+    n = len(nodes)
+    for k, scale in enumerate((0.5, 1.0)):  # two successive configurations: the second must not be stale
+        disp = (g["U"] * 20 * scale).reshape(3, n)
+        a.set_disp(disp)
+        pb.set_X(g["U"] * (k + 1))
+        a.update(pb, compute="all")
+        moved = nodes + disp.T
+        Kref = fo.assemble_stiffness(moved, elements, "hex8", H, 3)
+        assert a.current is not a
+        assert nrm(a.current.get_global_matrix().tocsr().data, Kref.data) <= TOL
+        assert nrm(np.array(a.current.get_global_vector()), -(Kref @ (g["U"] * (k + 1)))) <= 1e-11
