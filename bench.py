@@ -390,7 +390,7 @@ def run_hex8(args):
     torch.cuda.synchronize()
     t_first = time.perf_counter() - t0
     entry = asm._saved_bloc_structure
-    plan, pattern = entry["plan"], entry["pattern"]
+    plan, pattern = asm._plan(entry), entry["pattern"]
     # N > 1: the exchange of the residual.  Default: fused into the assembly kernel (stores over NVLink into a
     # symmetric, multicast-mapped, double-buffered global vector, fedoo_b200.dist.PeerVector); --exchange nccl, or a
     # failed symmetric-memory rendezvous: pack + NCCL all-gather + unpack (fedoo_b200.dist.VectorExchange)

@@ -33,6 +33,7 @@ _DEFAULT_NGP = {"hex8": 8, "tet4": 4, "tet10": 15, "quad4": 4}  # fedoo/lib_elem
 
 
 _RESIDUAL_KERNEL = os.environ.get("FDK_RESIDUAL_KERNEL", "1") != "0"  # 0: residual-only through the cluster kernels
+_HEAT_TET4_ROWS = os.environ.get("FDK_HEAT_TET4_ROWS", "1") != "0"  # 0: tet4 heat through the cluster kernel
 
 
 class Assembly(_Named):
@@ -127,9 +128,8 @@ class Assembly(_Named):
         if entry is None:
             coords, conn = self.mesh.device_arrays()
             pattern = symbolic.build_pattern(conn, self.mesh.n_nodes)
-            owned = None if self.owned_nodes is None else torch.from_numpy(np.asarray(self.owned_nodes, dtype=bool))
-            plan = symbolic.build_plan(self.elm_type, coords, conn, pattern, owned=owned)
-            entry = {"pattern": pattern, "plan": plan, "csr": {}, "mesh": self.mesh, "owned": self.owned_nodes,
+            # the cluster plan is built on first use (``_plan``): the row-owner kernels do not need one
+            entry = {"pattern": pattern, "plan": None, "csr": {}, "mesh": self.mesh, "owned": self.owned_nodes,
                      "sizes": (self.mesh.n_nodes, self.mesh.n_elements, id(self.mesh.elements))}  # fmt: skip
             Assembly._saved_plans[key] = entry
         nvar = self.nvar
@@ -138,6 +138,60 @@ class Assembly(_Named):
             entry["csr"][(nvar, n_glob)] = symbolic.expand_csr(entry["pattern"], nvar, n_glob)
         self._saved_bloc_structure = entry
         return entry, entry["csr"][(nvar, n_glob)], n_glob
+
+    def _plan(self, entry):
+        """Cluster plan of the pattern (fedoo_b200/plan.py), built on first use."""
+        if entry["plan"] is None:
+            coords, conn = self.mesh.device_arrays()
+            owned = None if self.owned_nodes is None else torch.from_numpy(np.asarray(self.owned_nodes, dtype=bool))
+            entry["plan"] = symbolic.build_plan(self.elm_type, coords, conn, entry["pattern"], owned=owned)
+        return entry["plan"]
+
+    def _row_positions(self, entry, node_ptr, node_inc):
+        """One-time table of the row-owner kernels: for every incidence (node I, element e) the record {element * nne +
+        local node, position of each column conn[e][j] inside row I of the block pattern packed 4 x u8} -- the row-local
+        counterpart of the reference's ``Matrix_convertCOOtoCSR`` (fedoo/core/_sparsematrix.py:256-274)."""
+        if "row_pos" not in entry:
+            pattern = entry["pattern"]
+            conn = self.mesh.device_arrays()[1].to(torch.int64)
+            nne = conn.shape[1]
+            assert nne == 4, "packed positions: four columns per incidence"
+            n = self.mesh.n_nodes
+            elem = node_inc.to(torch.int64) // nne
+            node = torch.repeat_interleave(torch.arange(n, device=conn.device), (node_ptr[1:] - node_ptr[:-1]))
+            keys = node[:, None] * n + conn[elem]  # (n_inc, 4) block keys I * n + J
+            slot = torch.searchsorted(pattern.keys, keys.reshape(-1)).reshape(-1, nne)
+            pos = slot - pattern.blk_indptr[node][:, None]
+            deg = pattern.blk_indptr[1:] - pattern.blk_indptr[:-1]
+            max_deg = int(deg.max()) if n else 0
+            if max_deg > 255:
+                raise _lib.FdkError(f"row degree {max_deg} exceeds the packed position format")
+            packed = pos[:, 0] | (pos[:, 1] << 8) | (pos[:, 2] << 16) | (pos[:, 3] << 24)
+            packed = torch.where(packed >= 2**31, packed - 2**32, packed).to(torch.int32)  # the same 32 bits, signed
+            # one 8-byte record per incidence: {element * nne + local node, packed positions}
+            entry["row_pos"] = (torch.stack([node_inc.to(torch.int32), packed], dim=1).contiguous(), max_deg)
+        return entry["row_pos"]
+
+    def _heavy_rows(self, entry, plan, flags, coords, iso, lam, mu, C_h, tangent_dev, U_dev, stress_dev, K, D):
+        """Rows of the nodes the cluster plan left out (more incident elements than one cluster holds): csrc/fdk_rows.cuh."""
+        rows = plan.heavy_nodes
+        if rows.numel() == 0 or not flags:
+            return
+        from .results import node_incidences
+
+        pattern = entry["pattern"]
+        node_ptr, node_inc = node_incidences(self.mesh)
+        conn = self.mesh.device_arrays()[1]
+        if "max_deg" not in entry:
+            entry["max_deg"] = int((pattern.blk_indptr[1:] - pattern.blk_indptr[:-1]).max())
+        rc = _lib.load().fdk_assemble_rows_elastic(
+            _lib.ELEM_IDS[self.elm_type], int(rows.numel()), _lib.ptr(rows), self.mesh.n_nodes, self.mesh.n_elements,
+            _lib.ptr(conn), _lib.ptr(coords), _lib.ptr(node_ptr), _lib.ptr(node_inc), _lib.ptr(pattern.blk_indptr),
+            _lib.ptr(pattern.blk_indices), pattern.blk_nnz, entry["max_deg"], int(iso), float(lam), float(mu), _lib.ptr(C_h),
+            _lib.ptr(tangent_dev), flags, _lib.ptr(U_dev), _lib.ptr(stress_dev), _lib.ptr(K), _lib.ptr(D),
+            _lib.current_stream(),
+        )  # fmt: skip
+        _lib.check(rc, "fdk_assemble_rows_elastic")
 
     def _small_plan(self, entry):
         """Second cluster plan of the same pattern with half-size (16-node hex8) clusters, built on first use."""
@@ -186,7 +240,7 @@ class Assembly(_Named):
             raise ValueError("compute must be 'all', 'matrix', 'vector' or 'none'")
         lib = _lib.load()
         entry, (indptr, indices), n_glob = self._symbolic()
-        plan, pattern = entry["plan"], entry["pattern"]
+        pattern = entry["pattern"]
         nvar = self.nvar
         n_nodes = self.mesh.n_nodes
         dev = device()
@@ -245,18 +299,21 @@ class Assembly(_Named):
                     lam, mu = law.lame(dimension)
                     dst, n_dst = peer.begin_step()  # the half of the double-buffered symmetric vector this step writes
                     rc = lib.fdk_assemble_elastic_iso_dist(
-                        C.byref(plan.struct(nvar)), flags, _lib.ptr(coords), lam, mu, _lib.ptr(U_dev), _lib.ptr(K),
+                        C.byref(self._plan(entry).struct(nvar)), flags, _lib.ptr(coords), lam, mu, _lib.ptr(U_dev), _lib.ptr(K),
                         _lib.ptr(D), dst, n_dst, _lib.ptr(peer.node_gid), peer.n_global, stream,
                     )  # fmt: skip
                     _lib.check(rc, "fdk_assemble_elastic_iso_dist")
+                    if self._plan(entry).heavy_nodes.numel():
+                        raise NotImplementedError("high-valence nodes with the fused multi-GPU exchange")
                     peer.barrier()
                 elif isinstance(law, ElasticIsotrop) and tangent_dev is None:
                     lam, mu = law.lame(dimension)
                     rc = lib.fdk_assemble_elastic_iso(
-                        C.byref(plan.struct(nvar)), flags, _lib.ptr(coords), lam, mu, _lib.ptr(U_dev),
+                        C.byref(self._plan(entry).struct(nvar)), flags, _lib.ptr(coords), lam, mu, _lib.ptr(U_dev),
                         _lib.ptr(stress_dev), _lib.ptr(K), _lib.ptr(D), stream,
                     )  # fmt: skip
                     _lib.check(rc, "fdk_assemble_elastic_iso")
+                    self._heavy_rows(entry, self._plan(entry), flags, coords, True, lam, mu, None, None, U_dev, stress_dev, K, D)
                 else:
                     H = self.sv["TangentMatrix"]
                     C_h = None if tangent_dev is not None else np.ascontiguousarray(H, dtype=np.float64)
@@ -264,11 +321,14 @@ class Assembly(_Named):
                         # general tangent on hex8: 16-node clusters, so that the 36 tangent entries of every (touched
                         # element, Gauss point) fit in shared memory next to the geometry (csrc/fdk_assemble_iso.cuh)
                         plan = self._small_plan(entry)
+                    else:
+                        plan = self._plan(entry)
                     rc = lib.fdk_assemble_elastic_general(
                         C.byref(plan.struct(nvar)), flags, _lib.ptr(coords), _lib.ptr(C_h), _lib.ptr(tangent_dev),
                         _lib.ptr(U_dev), _lib.ptr(stress_dev), _lib.ptr(K), _lib.ptr(D), stream,
                     )  # fmt: skip
                     _lib.check(rc, "fdk_assemble_elastic_general")
+                    self._heavy_rows(entry, plan, flags, coords, False, 0.0, 0.0, C_h, tangent_dev, U_dev, stress_dev, K, D)
         elif self.weakform.operator == "heat":
             law = self.weakform.constitutivelaw
             cond = np.ascontiguousarray(np.asarray(law.thermal_conductivity, dtype=np.float64).reshape(3, 3))
@@ -279,6 +339,21 @@ class Assembly(_Named):
             flags = (_lib.MATRIX if want_mat else 0) | (_lib.VECTOR if has_vec else 0)
             K = self._buffer("K", pattern.blk_nnz) if want_mat else None
             D = self._buffer(self._d_tag(), n_nodes + n_glob, zero=True) if has_vec else None
+            T_start = self._T_start_dev if rcdt != 0.0 else None
+            if flags and self.elm_type == "tet4" and self.owned_nodes is None and _HEAT_TET4_ROWS:
+                # constant-gradient element: the row-owner kernel does K and D in one launch, without a cluster plan
+                from .results import node_incidences
+
+                node_ptr, node_inc = node_incidences(self.mesh)
+                inc_rec, max_deg = self._row_positions(entry, node_ptr, node_inc)
+                conn = self.mesh.device_arrays()[1]
+                rc = lib.fdk_assemble_heat_tet4(
+                    flags, n_nodes, self.mesh.n_elements, _lib.ptr(conn), _lib.ptr(coords), _lib.ptr(cond), rcdt,
+                    _lib.ptr(T_dev), _lib.ptr(T_start), _lib.ptr(node_ptr), _lib.ptr(inc_rec),
+                    _lib.ptr(pattern.blk_indptr), max_deg, _lib.ptr(K), _lib.ptr(D), stream,
+                )  # fmt: skip
+                _lib.check(rc, "fdk_assemble_heat_tet4")
+                flags = 0
             split = (flags & _lib.VECTOR) and self.owned_nodes is None and _RESIDUAL_KERNEL
             if split:
                 # the residual through its own kernels; with K also wanted the cluster kernel then runs matrix-only
@@ -289,15 +364,21 @@ class Assembly(_Named):
                 fe = self._scratch("fe", self.mesh.n_elements * conn.shape[1])
                 rc = lib.fdk_residual_heat(
                     _lib.ELEM_IDS[self.elm_type], n_nodes, self.mesh.n_elements, _lib.ptr(conn), _lib.ptr(coords),
-                    _lib.ptr(cond), rcdt, _lib.ptr(T_dev), _lib.ptr(self._T_start_dev if rcdt != 0.0 else None),
+                    _lib.ptr(cond), rcdt, _lib.ptr(T_dev), _lib.ptr(T_start),
                     _lib.ptr(node_ptr), _lib.ptr(node_inc), _lib.ptr(fe), _lib.ptr(D), stream,
                 )  # fmt: skip
                 _lib.check(rc, "fdk_residual_heat")
                 flags &= ~_lib.VECTOR
             if flags:
+                plan = self._plan(entry)
+                if plan.heavy_nodes.numel():
+                    raise NotImplementedError(
+                        f"{int(plan.heavy_nodes.numel())} nodes of this mesh touch more elements than a cluster of the heat "
+                        "kernel holds (the row-owner kernel covers tet4 meshes of any valence)"
+                    )
                 rc = lib.fdk_assemble_heat(
                     C.byref(plan.struct(1)), flags, _lib.ptr(coords), _lib.ptr(cond), rcdt, _lib.ptr(T_dev),
-                    _lib.ptr(self._T_start_dev if rcdt != 0.0 else None), _lib.ptr(K), _lib.ptr(D), stream,
+                    _lib.ptr(T_start), _lib.ptr(K), _lib.ptr(D), stream,
                 )  # fmt: skip
                 _lib.check(rc, "fdk_assemble_heat")
         else:

@@ -6,7 +6,9 @@
 #include "fdk_assemble_iso.cuh"
 #include "fdk_color.cuh"
 #include "fdk_gp.cuh"
+#include "fdk_heat_tet4.cuh"
 #include "fdk_results.cuh"
+#include "fdk_rows.cuh"
 #include "fdk_solve.cuh"
 #include "fdk_symbolic.cuh"
 
@@ -233,6 +235,55 @@ int fdk_assemble_elastic_general(const fdk_plan* plan, int compute, const double
   return dispatch_assemble<PHYS_GENERAL>(a, (cudaStream_t)stream);
 }
 
+int fdk_assemble_rows_elastic(int elem_type, int n_rows, const int32_t* rows, int n_nodes, int64_t n_elems,
+                              const int32_t* conn, const double* coords, const int64_t* node_ptr, const int32_t* node_inc,
+                              const int64_t* blk_indptr, const int32_t* blk_indices, int64_t blk_nnz, int max_row_degree,
+                              int isotropic, double lam, double mu, const double* C_h, const double* tangent_gp,
+                              int compute, const double* U, const double* stress_gp, double* K_values, double* D,
+                              fdk_stream_t stream) {
+  if (n_rows == 0) return 0;
+  FDK_REQUIRE(rows && conn && coords && node_ptr && node_inc && blk_indptr && blk_indices, FDK_EINVAL, "NULL argument");
+  FDK_REQUIRE((compute & ~FDK_ALL) == 0 && compute != 0, FDK_EINVAL, "compute must be FDK_MATRIX, FDK_VECTOR or both");
+  FDK_REQUIRE(!(compute & FDK_MATRIX) || K_values, FDK_EINVAL, "matrix requested without K_values");
+  FDK_REQUIRE(!(compute & FDK_VECTOR) || (D && (U || stress_gp)), FDK_EINVAL, "the vector needs D and U or stress_gp");
+  FDK_REQUIRE(isotropic || C_h || tangent_gp, FDK_EINVAL, "need an isotropic law, C_h or tangent_gp");
+  RowArgs a{};
+  a.n_rows = n_rows;
+  a.rows = rows;
+  a.n_nodes = n_nodes;
+  a.n_elems = n_elems;
+  a.conn = conn;
+  a.coords = coords;
+  a.node_ptr = node_ptr;
+  a.node_inc = node_inc;
+  a.blk_indptr = blk_indptr;
+  a.blk_indices = blk_indices;
+  a.blk_nnz = blk_nnz;
+  a.max_deg = max_row_degree;
+  a.lam = lam;
+  a.mu = mu;
+  if (C_h)
+    for (int i = 0; i < 36; ++i) a.C[i] = C_h[i];
+  a.tangent_gp = tangent_gp;
+  a.U = U;
+  a.stress_gp = stress_gp;
+  a.compute = compute;
+  a.fuse_ku = ((compute & FDK_VECTOR) && stress_gp == nullptr) ? 1 : 0;  // linear in U: D_I = -K_row . U exactly
+  a.K = K_values;
+  a.D = D;
+  cudaStream_t st = (cudaStream_t)stream;
+#define FDK_ROWS(El) (isotropic ? launch_assemble_rows<El, PHYS_ISO>(a, st) : launch_assemble_rows<El, PHYS_GENERAL>(a, st))
+  switch (elem_type) {
+    case FDK_HEX8: return FDK_ROWS(Hex8);
+    case FDK_TET4: return FDK_ROWS(Tet4);
+    case FDK_TET10: return FDK_ROWS(Tet10);
+    case FDK_QUAD4: return FDK_ROWS(Quad4);
+  }
+#undef FDK_ROWS
+  set_error("unknown element type %d", elem_type);
+  return FDK_EINVAL;
+}
+
 int fdk_assemble_heat(const fdk_plan* plan, int compute, const double* coords, const double* cond_h,
                       double rho_c_over_dt, const double* T, const double* T_start, double* K_values, double* D,
                       fdk_stream_t stream) {
@@ -356,6 +407,32 @@ int fdk_residual_heat(int elem_type, int n_nodes, int64_t n_elems, const int32_t
   }
   set_error("unknown element type %d", elem_type);
   return FDK_EINVAL;
+}
+
+int fdk_assemble_heat_tet4(int compute, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                           const double* cond_h, double rho_c_over_dt, const double* T, const double* T_start,
+                           const int64_t* node_ptr, const int32_t* inc_rec, const int64_t* blk_indptr,
+                           int max_row_degree, double* K_values, double* D, fdk_stream_t stream) {
+  FDK_REQUIRE(conn && coords && cond_h && node_ptr && inc_rec && blk_indptr, FDK_EINVAL, "NULL argument");
+  FDK_REQUIRE((compute & ~FDK_ALL) == 0 && compute != 0, FDK_EINVAL, "compute must be FDK_MATRIX, FDK_VECTOR or both");
+  FDK_REQUIRE(!(compute & FDK_MATRIX) || K_values, FDK_EINVAL, "matrix requested without K_values");
+  FDK_REQUIRE(!(compute & FDK_VECTOR) || (D && T), FDK_EINVAL, "vector requested without D / T");
+  HeatTet4Args a{};
+  a.n_nodes = n_nodes;
+  a.n_elems = n_elems;
+  a.conn = conn;
+  a.coords = coords;
+  a.node_ptr = node_ptr;
+  a.inc_rec = reinterpret_cast<const int2*>(inc_rec);
+  a.blk_indptr = blk_indptr;
+  a.T = (compute & FDK_VECTOR) ? T : nullptr;
+  a.T_start = T_start;
+  a.rcdt = rho_c_over_dt;
+  a.max_deg = max_row_degree;
+  a.K = (compute & FDK_MATRIX) ? K_values : nullptr;
+  a.D = (compute & FDK_VECTOR) ? D : nullptr;
+  for (int i = 0; i < 9; ++i) a.cond[i] = cond_h[i];
+  return launch_heat_tet4(a, (cudaStream_t)stream);
 }
 
 int fdk_residual_heat_gp(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,

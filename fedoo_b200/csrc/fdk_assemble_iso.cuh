@@ -37,7 +37,40 @@
 #define FDK_P2_UNROLL 2  // Gauss points in flight per thread in the block phase (register budget: 64)
 #endif
 
+#ifndef FDK_HEX_REFLECT
+// 1: hex8 geometry phase without table loads (see HexRef below).  MEASURED on B200 (round 2, 8 M elements): 17.8 ms with
+// the permuted coordinate loads straight from sX (the eight Gauss-point lanes of an element then read eight different
+// nodes: +57 M bank-conflict wavefronts per million elements, exactly what the 49 M table wavefronts saved), 18.7 ms
+// with the element-local coordinate copy that removes those conflicts (one more dependent STS -> LDS round per task),
+// against 17.7 ms for the table version.  Kept as a compile-time option, off.
+#define FDK_HEX_REFLECT 0
+#endif
+
 namespace fdk {
+
+// hex8: the reference gradients at Gauss point g are those at Gauss point 0 of the element REFLECTED along the axes
+// where g sits on the + side (dN_k/dxi_r (g) = s_r dN_pi(k)/dxi_r (g0), s_r = -1 on a reflected axis; the signs cancel
+// in G = J^-1 dN).  A geometry task therefore runs the Gauss-point-0 formula -- 24 COMPILE-TIME constants as DFMA
+// operands instead of 24 + 24 table loads from shared memory (96 of the ~200 shared-memory wavefronts of a task) -- on a
+// node-permuted element, and stores position j = gradient of node pi_g(j).  Node k sits at position pi_g(k) (an
+// involution): the block phase reads it there.  In node codes c = b0 + 2 b1 + 4 b2 (sign bits of the reference
+// coordinates) the reflection is an XOR with the Gauss point's bits; code <-> local node: {0,1,3,2,4,5,7,6}.
+struct HexRef {
+  static constexpr unsigned CODES = 0x67542310u;  // nibble k: code of local node k, and local node of code k
+  __host__ __device__ static constexpr int bit(int k, int d) {
+    return d == 0 ? ((k ^ (k >> 1)) & 1) : (d == 1 ? ((k >> 1) & 1) : ((k >> 2) & 1));
+  }
+  // 1 + n_d x_d at Gauss point 0 (x = -a on every axis), as the table computes it (csrc/fdk_tables.cuh)
+  __host__ __device__ static constexpr double f(int k, int d) {
+    return 1.0 + (bit(k, d) ? 1.0 : -1.0) * (-1.0 * 0.5773502691896258);
+  }
+  __host__ __device__ static constexpr double dn(int r, int k) {  // dN_k / dxi_r at Gauss point 0
+    return 0.125 * (bit(k, r) ? 1.0 : -1.0) * f(k, r == 0 ? 1 : 0) * f(k, r == 2 ? 1 : 2);
+  }
+  // Gauss point g = ix * 4 + iy * 2 + iz (xi slowest): bits to flip in a node code
+  __host__ __device__ static constexpr int gx(int g) { return (g >> 2) | (g & 2) | ((g & 1) << 2); }
+  __device__ static __forceinline__ int perm(int code, int gxv) { return (int)((CODES >> (4 * (code ^ gxv))) & 7u); }
+};
 
 constexpr int P2_UNROLL = FDK_P2_UNROLL;
 #ifndef FDK_ISO_PART_UNIFORM
@@ -67,6 +100,12 @@ struct IsoLayout {
   // hex8, 4 threads per incidence: block positions come from the plan (csrc/fdk_color.cuh): the 16 blocks a half-warp
   // stores together share a window of 16 positions, permuted so that the gather is conflict-free as well
   static constexpr bool COLORED = NNE == 8 && TPI == 4 && !PART_UNIFORM;
+  // hex8: reflected geometry phase (HexRef) -- Gauss-point-0 constants on a node-permuted element.  The lanes of one
+  // element then read eight DIFFERENT nodes, so the coordinates are first copied into an element-local array
+  // [le][node][3] (stride 24 doubles: the 16 lanes of a half-warp = 2 elements x 8 Gauss points hit 16 distinct 8-byte banks)
+  static constexpr bool HEXREF = El::ID == FDK_HEX8 && COLORED && ISO_COLS_ADJ && (FDK_HEX_REFLECT != 0);
+  static constexpr int XESTR = NNE * DIM;
+  __host__ __device__ static long xe_doubles(const fdk_plan& p) { return HEXREF ? (long)p.cap_te * XESTR : 0; }
   __host__ __device__ static long stage_doubles(const fdk_plan& p) {
     return COLORED ? (long)((p.cap_inc + 3) / 4) * 32 * BLK : (long)p.cap_inc * ISTR;
   }
@@ -99,7 +138,8 @@ struct IsoLayout {
     return tangent_gp ? (long)p.cap_te * NGP * CSTR : 0;
   }
   static size_t smem_bytes(const fdk_plan& p, bool tangent_gp = false, bool bts = false) {
-    long doubles = TAB_DOUBLES + 2L * xu_doubles(p) + sr_offset(p) + rs_doubles(p, bts) + extra_doubles(p, tangent_gp) + p.cap_owned;
+    long doubles = TAB_DOUBLES + 2L * xu_doubles(p) + sr_offset(p) + rs_doubles(p, bts) + extra_doubles(p, tangent_gp) +
+                   xe_doubles(p) + p.cap_owned;
     size_t bytes = (size_t)doubles * 8;
     bytes += (size_t)(2 * (p.cap_owned + 1)) * 4;      // sSlotBase, sFinc
     bytes += (size_t)(p.cap_slots + 1) * 4;            // sRec
@@ -134,6 +174,7 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
   // column block jj of this thread: part*NH + jj (contiguous) or part + jj*TPI (interleaved)
   auto col = [&](int jj) { return PART_UNIFORM ? part * NH + jj : (COLORED ? iso_col(part, jj) : part + jj * TPI); };
   constexpr bool ADJ = COLORED && ISO_COLS_ADJ;  // the thread's two columns are adjacent: 6 contiguous doubles
+  constexpr bool HEXREF = IL::HEXREF;  // reflected geometry layout (HexRef)
 
   extern __shared__ __align__(16) double smem[];
   double* sdN = smem;              // [NGP][TSTR] reference gradients, [g][d][k]
@@ -147,7 +188,8 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
   double* sF = sR;
   double* sSig = sR;                       // [cap_te][NGP][6] sqrt(w) sigma (do_bts): shares the space of sF
   double* sC = sR + IL::rs_doubles(p, do_bts);  // [cap_te][NGP][36] tangent of every (touched element, gp) (per_gp)
-  long long* sBptr = reinterpret_cast<long long*>(sC + IL::extra_doubles(p, per_gp));  // [cap_owned]
+  double* sXe = sC + IL::extra_doubles(p, per_gp);  // [cap_te][NNE][DIM] element-local coordinates (HEXREF)
+  long long* sBptr = reinterpret_cast<long long*>(sXe + IL::xe_doubles(p));  // [cap_owned]
   int* sSlotBase = reinterpret_cast<int*>(sBptr + p.cap_owned);                                 // [cap_owned+1]
   int* sFinc = sSlotBase + (p.cap_owned + 1);                                                   // [cap_owned+1]
   unsigned* sRec = reinterpret_cast<unsigned*>(sFinc + (p.cap_owned + 1));                      // [cap_slots+1]
@@ -285,7 +327,26 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
       const unsigned char* lc = sLconn + le * NNE;
       const double* dN = sdN + g * TSTR;
       int ln[NNE];
-      if constexpr (NNE % 4 == 0) {
+      if constexpr (HEXREF) {
+        // lane (le, g) copies node g of its element into the element-local array; its 8 lanes sit in one warp
+        // (task = le * 8 + g, 8 | 32), so a warp-level sync publishes the copy.  Then position j works on node pi_g(j).
+        {
+          const double* xk = sX + (int)lc[g] * XSTR;
+          const double2 x01 = *reinterpret_cast<const double2*>(xk);
+          const double x2 = xk[2];
+          double* xe = sXe + le * IL::XESTR + g * DIM;
+          xe[0] = x01.x;
+          xe[1] = x01.y;
+          xe[2] = x2;
+        }
+        {
+          const int left = n_te * NGP - (task - (tid & 31));  // tasks of this warp's round: the first `left` lanes are here
+          __syncwarp(left >= 32 ? 0xffffffffu : ((1u << left) - 1u));
+        }
+        const int gxv = HexRef::gx(g);
+#pragma unroll
+        for (int j = 0; j < NNE; ++j) ln[j] = HexRef::perm((int)((HexRef::CODES >> (4 * j)) & 7u), gxv);
+      } else if constexpr (NNE % 4 == 0) {
         const unsigned* lc4 = reinterpret_cast<const unsigned*>(lc);
 #pragma unroll
         for (int q = 0; q < NNE / 4; ++q) {
@@ -307,15 +368,23 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
         double X[2][DIM];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const double* xk = sX + ln[k + h] * XSTR;
-          const double2 x01 = *reinterpret_cast<const double2*>(xk);
-          X[h][0] = x01.x;
-          X[h][1] = x01.y;
-          if constexpr (DIM == 3) X[h][2] = xk[2];
+          if constexpr (HEXREF) {
+            const double* xk = sXe + le * IL::XESTR + ln[k + h] * DIM;
+#pragma unroll
+            for (int x = 0; x < DIM; ++x) X[h][x] = xk[x];
+          } else {
+            const double* xk = sX + ln[k + h] * XSTR;
+            const double2 x01 = *reinterpret_cast<const double2*>(xk);
+            X[h][0] = x01.x;
+            X[h][1] = x01.y;
+            if constexpr (DIM == 3) X[h][2] = xk[2];
+          }
         }
 #pragma unroll
         for (int r = 0; r < DIM; ++r) {
-          const double2 dn = *reinterpret_cast<const double2*>(dN + r * NNE + k);  // nodes k, k+1
+          double2 dn;
+          if constexpr (HEXREF) dn = make_double2(HexRef::dn(r, k), HexRef::dn(r, k + 1));  // compile-time operands
+          else dn = *reinterpret_cast<const double2*>(dN + r * NNE + k);                     // nodes k, k+1
 #pragma unroll
           for (int x = 0; x < DIM; ++x) J[r][x] = fma(dn.y, X[1][x], fma(dn.x, X[0][x], J[r][x]));
         }
@@ -342,7 +411,10 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
       for (int k = 0; k < NNE; k += 2) {
         double2 dn[DIM];
 #pragma unroll
-        for (int r = 0; r < DIM; ++r) dn[r] = *reinterpret_cast<const double2*>(dN + r * NNE + k);
+        for (int r = 0; r < DIM; ++r) {
+          if constexpr (HEXREF) dn[r] = make_double2(HexRef::dn(r, k), HexRef::dn(r, k + 1));
+          else dn[r] = *reinterpret_cast<const double2*>(dN + r * NNE + k);
+        }
         double v[2 * DIM];  // [h][x]
 #pragma unroll
         for (int x = 0; x < DIM; ++x) {
@@ -393,13 +465,34 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
       const int le = my_desc & 0xFFF, i = my_desc >> 12;
       const double* gi_p = sG + le * ESTR + i * DIM;
       const double* gj_p = sG + le * ESTR + col(0) * DIM;
+      [[maybe_unused]] const int ci = (int)((HexRef::CODES >> (4 * i)) & 7u);  // node code of the row node
+      [[maybe_unused]] const double* ge_p = sG + le * ESTR;
       if constexpr (!GEN) {
-#pragma unroll P2_UNROLL
+        constexpr int UNR = HEXREF ? NGP : P2_UNROLL;  // reflected layout: the Gauss point must be a compile-time value
+#pragma unroll UNR
         for (int g = 0; g < NGP; ++g) {
           double gi[DIM];
+          double gj[NH][DIM];
+          if constexpr (HEXREF) {
+            // node i sits at position pi_g(i); the thread's column pair (2 part, 2 part + 1) at pair slot
+            // part ^ (iy + 2 iz), in swapped order when ix ^ iy (all of it folded at compile time but `part`, `ci`)
+            const int gxv = HexRef::gx(g);
+            const double* gp = ge_p + g * GSTR;
+            const double* gip = gp + HexRef::perm(ci, gxv) * DIM;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) gi[d] = gip[d];
+            const double2* g2 = reinterpret_cast<const double2*>(gp + ((part ^ (gxv >> 1)) * 2) * DIM);
+            const double2 v0 = g2[0], v1 = g2[1], v2 = g2[2];
+            const bool swp = ((gxv ^ (gxv >> 1)) & 1) != 0;
+            gj[swp ? 1 : 0][0] = v0.x;
+            gj[swp ? 1 : 0][1] = v0.y;
+            gj[swp ? 1 : 0][2] = v1.x;
+            gj[swp ? 0 : 1][0] = v1.y;
+            gj[swp ? 0 : 1][1] = v2.x;
+            gj[swp ? 0 : 1][2] = v2.y;
+          } else {
 #pragma unroll
           for (int d = 0; d < DIM; ++d) gi[d] = gi_p[g * GSTR + d];
-          double gj[NH][DIM];
           if constexpr ((PART_UNIFORM || ADJ) && (NH * DIM) % 2 == 0) {  // contiguous columns: 128-bit loads
             const double2* g2 = reinterpret_cast<const double2*>(gj_p + g * GSTR);
 #pragma unroll
@@ -413,6 +506,7 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
             for (int j = 0; j < NH; ++j)
 #pragma unroll
               for (int d = 0; d < DIM; ++d) gj[j][d] = gj_p[g * GSTR + (col(j) - col(0)) * DIM + d];
+          }
           }
 #pragma unroll
           for (int j = 0; j < NH; ++j)
@@ -430,8 +524,16 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
 #pragma unroll 1
         for (int g = 0; g < NGP; ++g) {
           double gi[3];
+          [[maybe_unused]] int gxv = 0;
+          if constexpr (HEXREF) {
+            gxv = HexRef::gx(g);
+            const double* gip = ge_p + g * GSTR + HexRef::perm(ci, gxv) * 3;
 #pragma unroll
-          for (int d = 0; d < 3; ++d) gi[d] = gi_p[g * GSTR + d];
+            for (int d = 0; d < 3; ++d) gi[d] = gip[d];
+          } else {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) gi[d] = gi_p[g * GSTR + d];
+          }
           if (do_bts && part == 0) {  // nodal force of this incidence: B_i^T (w sigma)
             const double* ws = s_p + g * SGS;
             f[0] += ws[0] * gi[0] + ws[3] * gi[1] + ws[4] * gi[2];
@@ -455,7 +557,17 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
             t[2][sc] = gi[2] * c2 + gi[0] * c4 + gi[1] * c5;
           }
           [[maybe_unused]] double gjv[NH * 3];
-          if constexpr (ADJ) {
+          if constexpr (HEXREF) {  // pair slot part ^ (iy + 2 iz); order swapped when ix ^ iy (run-time here)
+            const double2* g2 = reinterpret_cast<const double2*>(ge_p + g * GSTR + ((part ^ (gxv >> 1)) * 2) * 3);
+            const double2 v0 = g2[0], v1 = g2[1], v2 = g2[2];
+            const bool swp = ((gxv ^ (gxv >> 1)) & 1) != 0;
+            gjv[0] = swp ? v1.y : v0.x;
+            gjv[1] = swp ? v2.x : v0.y;
+            gjv[2] = swp ? v2.y : v1.x;
+            gjv[3] = swp ? v0.x : v1.y;
+            gjv[4] = swp ? v0.y : v2.x;
+            gjv[5] = swp ? v1.x : v2.y;
+          } else if constexpr (ADJ) {
             const double2* g2 = reinterpret_cast<const double2*>(gj_p + g * GSTR);
 #pragma unroll
             for (int q = 0; q < NH * 3 / 2; ++q) {

@@ -1,0 +1,150 @@
+// fdk_heat_tet4.cuh -- heat equation on tet4 meshes: row-owner kernel (BASELINE config [2]).
+//
+// tet4 has a CONSTANT gradient: the element matrix is V grad N_I . (k grad N_J) + delta_IJ (rho c / dt) V / 4 -- about
+// 100 flops -- while the cluster kernel of fdk_assemble.cuh pays its descriptors, staging and barriers per incidence as
+// if the element were expensive (measured: 13.7 ms for 20 M elements, 1 % of the HBM roofline; the compulsory traffic
+// is 51 B per element).  Here ONE THREAD OWNS ONE NODE ROW: it walks the incidences (element, local node) of its node,
+// recomputes the element's gradients from the four vertices (each element is visited by its four nodes: rho = 4 of a
+// 100-flop computation, cheaper than any exchange), and adds the four entries of its row into the row's accumulator,
+// which lives in shared memory as acc[slot][thread] (slot-major: the threads of a warp hit 32 consecutive banks).
+// The position of every entry inside the row comes from a one-time table (4 x u8 per incidence, fedoo_b200/assembly.py).
+// No atomics, a fixed summation order per row (element-ascending): bit-reproducible.  The residual
+// D_I = -sum_g w [grad N_I . (k grad T) + (rho c / dt) N_I (T_g - T_start,g)] is accumulated on the way (the four nodal
+// temperatures are the only extra loads), so K + D is one launch.
+//
+// Reference: fedoo/weakform/heat_equation.py:78-119 (conduction), :168-187 (capacity, lumped: assembly option
+// mat_lumping, core/_sparsematrix.py:91-98); tet4 tables fedoo/lib_elements/tetrahedron.py:21-29,72-73,106-130
+// (4 Gauss points of weight 1/24: for a constant integrand their sum is |det J| / 6 to rounding).
+#pragma once
+#include "fdk_assemble.cuh"
+
+namespace fdk {
+
+struct HeatTet4Args {
+  int n_nodes;
+  int64_t n_elems;
+  const int32_t* conn;        // (n_elems, 4)
+  const double* coords;       // (n_nodes, 3)
+  const int64_t* node_ptr;    // [n_nodes + 1] incidences of every node ...
+  const int2* inc_rec;        // ... {element * 4 + local node, 4 x u8 = position of column conn[e][j] in the node's row},
+                              // element-ascending
+  const int64_t* blk_indptr;  // [n_nodes + 1] block-CSR row pointers (nvar = 1: the CSR itself)
+  const double* T;            // nodal temperature (NULL: no vector)
+  const double* T_start;      // NULL = 0
+  double cond[9];
+  double rcdt;
+  int max_deg;
+  double* K;  // NULL: vector only
+  double* D;
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_heat_tet4_rows(const __grid_constant__ HeatTet4Args a) {
+  extern __shared__ double s_acc[];  // [max_deg][THREADS]
+  const int tid = threadIdx.x;
+  const int I = blockIdx.x * THREADS + tid;
+  if (I >= a.n_nodes) return;
+  const ElemTable& tab = c_tab[FDK_TET4];
+  const bool want_K = a.K != nullptr, want_D = a.D != nullptr && a.T != nullptr;
+  const int64_t bp = a.blk_indptr[I];
+  const int deg = (int)(a.blk_indptr[I + 1] - bp);
+  if (want_K) {
+    for (int s = 0; s < deg; ++s) s_acc[s * THREADS + tid] = 0.0;
+  }
+  double dsum = 0.0;
+  const int64_t t0 = a.node_ptr[I], t1 = a.node_ptr[I + 1];
+  for (int64_t t = t0; t < t1; ++t) {
+    const int2 rec = a.inc_rec[t];
+    const int inc = rec.x;
+    const int64_t e = inc >> 2;
+    const int i = inc & 3;
+    const int4 nd4 = *reinterpret_cast<const int4*>(a.conn + e * 4);
+    const int nd[4] = {nd4.x, nd4.y, nd4.z, nd4.w};
+    double X[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) X[k][d] = a.coords[(int64_t)nd[k] * 3 + d];
+    double G[4][3];
+    const double wdet = gp_geometry<4, 3>(tab.dN, 1.0, X, G);  // |det J|; the gradient is the same at every Gauss point
+    // gradient of the row node (selects, not a run-time index: G stays in registers)
+    double gi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) gi[d] = i == 0 ? G[0][d] : (i == 1 ? G[1][d] : (i == 2 ? G[2][d] : G[3][d]));
+    // k grad N_I (cond is symmetric in every use of the reference, but nothing here assumes it): row vector G_I . cond
+    double kg[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) kg[c] = gi[0] * a.cond[0 * 3 + c] + gi[1] * a.cond[1 * 3 + c] + gi[2] * a.cond[2 * 3 + c];
+    double wsum = 0.0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) wsum += tab.w[g];
+    const double V = wsum * wdet;
+    if (want_K) {
+      const uint32_t pos = (uint32_t)rec.y;
+      double cap = 0.0;
+      if (a.rcdt != 0.0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) cap = fma(tab.w[g], tab.N[g * 4 + i], cap);
+        cap *= a.rcdt * wdet;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double v = V * (kg[0] * G[j][0] + kg[1] * G[j][1] + kg[2] * G[j][2]);
+        if (j == i) v += cap;
+        s_acc[((pos >> (8 * j)) & 0xFF) * THREADS + tid] += v;
+      }
+    }
+    if (want_D) {
+      double Tk[4], gT[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        Tk[k] = a.T[nd[k]];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) gT[d] = fma(Tk[k], G[k][d], gT[d]);
+      }
+      // grad N_I . (cond grad T)
+      double q = 0.0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) q += gi[r] * (a.cond[r * 3 + 0] * gT[0] + a.cond[r * 3 + 1] * gT[1] + a.cond[r * 3 + 2] * gT[2]);
+      double f = V * q;
+      if (a.rcdt != 0.0) {
+        double dT[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dT[k] = Tk[k] - (a.T_start != nullptr ? a.T_start[nd[k]] : 0.0);
+        double c = 0.0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          double dTg = 0.0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dTg = fma(tab.N[g * 4 + k], dT[k], dTg);
+          c = fma(tab.w[g] * tab.N[g * 4 + i], dTg, c);
+        }
+        f = fma(a.rcdt * wdet, c, f);
+      }
+      dsum += f;
+    }
+  }
+  if (want_K) {
+    double* row = a.K + bp;
+    for (int s = 0; s < deg; ++s) __stcs(row + s, s_acc[s * THREADS + tid]);
+  }
+  if (want_D) a.D[I] = -dsum;
+}
+
+inline int launch_heat_tet4(const HeatTet4Args& a, cudaStream_t stream) {
+  if (a.n_nodes == 0) return 0;
+  if (int rc = ensure_device_tables()) return rc;
+  constexpr int THREADS = 128;
+  const size_t smem = (size_t)(a.K != nullptr ? a.max_deg : 0) * THREADS * sizeof(double);
+  FDK_REQUIRE(a.max_deg <= 255 && smem <= 200 * 1024, FDK_ECAP, "row degree %d exceeds the row-owner kernel's capacity", a.max_deg);
+  static thread_local size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    FDK_CUDA(cudaFuncSetAttribute(k_heat_tet4_rows<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  k_heat_tet4_rows<THREADS><<<(unsigned)((a.n_nodes + THREADS - 1) / THREADS), THREADS, smem, stream>>>(a);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fdk

@@ -180,6 +180,17 @@ class Plan:
         inc_ptr_node[1:] = torch.cumsum(inc_count, 0)
         deg = pattern.blk_indptr[1:] - pattern.blk_indptr[:-1]
 
+        # ---- high-valence nodes: one node alone must fit a cluster (its incident elements are the cluster's touched
+        # elements).  Nodes beyond that are left out of the clusters; their rows are assembled by the rows kernel
+        # (csrc/fdk_rows.cuh, Assembly._heavy_rows), one CTA per node.  Unstructured tet meshes have a few.
+        alone_max = min(cap["te_max"], cap["inc_max"])
+        heavy = inc_count > alone_max
+        if owned is not None:
+            heavy &= owned.to(dev)
+        self.heavy_nodes = torch.nonzero(heavy).reshape(-1).to(torch.int32)
+        if self.heavy_nodes.numel():
+            owned = (~heavy) if owned is None else (owned.to(dev) & ~heavy)
+
         # ---- Morton order with unique keys ----
         if owned is not None:
             # only owned nodes get clusters: build the curve on THEIR lattice, so that the Morton blocks are

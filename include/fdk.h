@@ -236,6 +236,33 @@ int fdk_residual_heat(int elem_type, int n_nodes, int64_t n_elems, const int32_t
                       const int64_t* node_ptr, const int32_t* node_inc, double* fe_scratch, double* D,
                       fdk_stream_t stream);
 
+/* Rows of HIGH-VALENCE nodes (csrc/fdk_rows.cuh): the cluster plan leaves out the nodes whose incident elements alone
+ * exceed a cluster's shared memory (unstructured tet meshes have a few; the reference's util/meshes/octet_truss_quad.msh
+ * does) and this entry assembles their block rows, one CTA per node, any valence.  rows[n_rows]: the nodes; node_ptr /
+ * node_inc: incidences element * nne + local node, element-ascending; K_values in the tiled layout of fdk_plan;
+ * law: isotropic (lam, mu), or C_h (6x6 row-major host) or tangent_gp (6,6,N).  Vector: -int B^T stress_gp, or
+ * -K_row . U when no stress is given (exact for every tangent, the state being linear in U).  Same arithmetic and the
+ * same reference lines as fdk_assemble_elastic_iso / _general. */
+int fdk_assemble_rows_elastic(int elem_type, int n_rows, const int32_t* rows, int n_nodes, int64_t n_elems,
+                              const int32_t* conn, const double* coords, const int64_t* node_ptr, const int32_t* node_inc,
+                              const int64_t* blk_indptr, const int32_t* blk_indices, int64_t blk_nnz, int max_row_degree,
+                              int isotropic, double lam, double mu, const double* C_h, const double* tangent_gp,
+                              int compute, const double* U, const double* stress_gp, double* K_values, double* D,
+                              fdk_stream_t stream);
+
+/* Heat equation on a tet4 mesh, matrix and / or residual in ONE launch of the row-owner kernel (csrc/fdk_heat_tet4.cuh):
+ * K_IJ = sum_e V_e grad N_I . (cond grad N_J) + delta_IJ (rho c / dt) V_e / 4 (lumped capacity, the reference's
+ * mat_lumping = [False, True], fedoo/weakform/heat_equation.py:78-119,168-227, core/_sparsematrix.py:91-98) and D as in
+ * fdk_residual_heat.  One thread per node row walks its incidences: node_ptr [n_nodes + 1] into inc_rec, an array of
+ * int32 pairs {element * 4 + local node, positions (4 x u8, little endian) of the columns conn[e][0..3] inside the
+ * node's row of the block pattern blk_indptr / blk_indices (fdk_sym_block_csr)}, element-ascending per node;
+ * max_row_degree <= 255.  K_values [blk_nnz] in the order of the pattern (nvar = 1: the CSR itself).  No cluster plan
+ * is needed.  T_start NULL = 0. */
+int fdk_assemble_heat_tet4(int compute, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                           const double* cond_h, double rho_c_over_dt, const double* T, const double* T_start,
+                           const int64_t* node_ptr, const int32_t* inc_rec, const int64_t* blk_indptr,
+                           int max_row_degree, double* K_values, double* D, fdk_stream_t stream);
+
 /* The heat residual from GIVEN Gauss-point fields, as the reference's weak forms pass them through assembly.sv
  * (fedoo/weakform/heat_equation.py:99-117 "grad v . (K TempGradient)", :178-186 "(rho c / dt) v (Temp - Temp_start)"):
  * D_I = -sum_g w [grad N_I . flux_g + N_I src_g]; flux_gp [3][n_gp] row-major (NULL = 0), src_gp [n_gp] (NULL = 0),

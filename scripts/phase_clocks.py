@@ -62,7 +62,7 @@ def main():
     pb.set_X(np.random.default_rng(0).standard_normal(pb.n_dof) * 1e-3)
     asm.update(pb, compute="all")
     asm.vector_on_device = True
-    plan = asm._saved_bloc_structure["plan"]
+    plan = asm._plan(asm._saved_bloc_structure)
     lib = _lib.load()
     out = (C.c_ulonglong * 16)()
     _lib.check(lib.fdk_debug_phase_clocks(out, 16, 1), "phase clocks")

@@ -293,13 +293,13 @@ def test_j2_closed_forms_and_tangent(fd):
     sig, sv, _ = _j2_kernel(fd, props, eps, np.zeros((8, eps.shape[1])))
     for n, a in enumerate(amps):
         # uniaxial isochoric: q = 3 mu (e - p)
-        p = 0.0 if 3 * mu * a <= sigY else brentq(lambda x: 3 * mu * (a - x) - sigY - k * x**m, 0.0, a)
-        assert abs(sv[1, n] - p) <= 1e-12 and abs(sig[0, n] - 2 * mu * (a - p)) <= 1e-9
+        p = 0.0 if 3 * mu * a <= sigY else brentq(lambda x: 3 * mu * (a - x) - sigY - k * x**m, 0.0, a, xtol=1e-17, rtol=1e-15)
+        assert abs(sv[1, n] - p) <= 1e-12 and abs(sig[0, n] - 2 * mu * (a - p)) <= 1e-9 * sigY
         # pure shear: tau = mu (gamma - sqrt(3) p), q = sqrt(3) tau
         r3 = np.sqrt(3.0)
-        p = 0.0 if r3 * mu * a <= sigY else brentq(lambda x: r3 * mu * (a - r3 * x) - sigY - k * x**m, 0.0, a / r3)
+        p = 0.0 if r3 * mu * a <= sigY else brentq(lambda x: r3 * mu * (a - r3 * x) - sigY - k * x**m, 0.0, a / r3, xtol=1e-17, rtol=1e-15)
         j = amps.size + n
-        assert abs(sv[1, j] - p) <= 1e-12 and abs(sig[3, j] - mu * (a - r3 * p)) <= 1e-9
+        assert abs(sv[1, j] - p) <= 1e-12 and abs(sig[3, j] - mu * (a - r3 * p)) <= 1e-9 * sigY
         assert abs(sv[5, j] - r3 * p) <= 1e-12  # engineering plastic shear
     # tangents by finite differences around plastically loading states
     rng = np.random.default_rng(5)
@@ -308,8 +308,8 @@ def test_j2_closed_forms_and_tangent(fd):
     sv0 = np.zeros((8, N))
     s0, sv1, Ccons = _j2_kernel(fd, props, e0, sv0, "consistent")
     _, _, Ccont = _j2_kernel(fd, props, e0, sv0, "continuum")
-    yielding = sv1[1] > 1e-5
-    assert yielding.sum() > N // 2
+    yielding = sv1[1] > 1e-4  # well past first yield: the hardening curvature p^(m-2) makes finite differences useless at p -> 0
+    assert yielding.sum() > N // 3
     h = 1e-7
     fd_C = np.zeros((6, 6, N))
     for j in range(6):
@@ -318,9 +318,14 @@ def test_j2_closed_forms_and_tangent(fd):
         sp, _, _ = _j2_kernel(fd, props, e0 + de, sv0)
         sm, _, _ = _j2_kernel(fd, props, e0 - de, sv0)
         fd_C[:, j, :] = (sp - sm) / (2 * h)
-    assert nrm(Ccons[:, :, yielding], fd_C[:, :, yielding]) <= 1e-6
-    assert nrm(Ccont[:, :, yielding], fd_C[:, :, yielding]) > 1e-3  # a different operator, on purpose
-    assert nrm(Ccont[:, :, ~yielding], fd_C[:, :, ~yielding]) <= 1e-6 or (~yielding).sum() == 0
+    err_cons = nrm(Ccons[:, :, yielding], fd_C[:, :, yielding])
+    err_cont = nrm(Ccont[:, :, yielding], fd_C[:, :, yielding])
+    assert err_cons <= 1e-5, err_cons
+    assert err_cont > 1e-3, err_cont  # a different operator, on purpose
+    vm = np.sqrt(0.5 * ((s0[0] - s0[1]) ** 2 + (s0[1] - s0[2]) ** 2 + (s0[0] - s0[2]) ** 2 + 6 * (s0[3] ** 2 + s0[4] ** 2 + s0[5] ** 2)))
+    elastic = (sv1[1] == 0) & (vm < 0.95 * sigY)  # clear of the yield surface: both tangents are the elastic matrix
+    if elastic.any():
+        assert nrm(Ccont[:, :, elastic], fd_C[:, :, elastic]) <= 1e-6 and nrm(Ccons[:, :, elastic], fd_C[:, :, elastic]) <= 1e-6
 
 
 def test_j2_update_against_oracle(fd):

@@ -276,3 +276,46 @@ def test_lifecycle_assembles_the_current_configuration(fd, golden_dir):
         assert a.current is not a
         assert nrm(a.current.get_global_matrix().tocsr().data, Kref.data) <= TOL
         assert nrm(np.array(a.current.get_global_vector()), -(Kref @ (g["U"] * (k + 1)))) <= 1e-11
+
+
+@pytest.mark.parametrize("name,elm,space", [("tet10_box", "tet10", "3D"), ("hex8_jitter", "hex8", "3D"), ("quad4_plate", "quad4", "2Dstress")])
+def test_high_valence_rows_kernel(fd, golden_dir, name, elm, space, monkeypatch):
+    """Nodes with more incident elements than one cluster holds are assembled by the rows kernel (csrc/fdk_rows.cuh).
+    Forced here by shrinking the cluster capacity, so that a good share of the rows goes through it: K, D of the
+    reference for the isotropic closed form, a uniform 6x6 tangent, and the residual integrated from a given stress."""
+    import fedoo_b200.assembly as asm_mod
+    import fedoo_b200.plan as plan_mod
+
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    n_inc = np.bincount(g["elements"].reshape(-1), minlength=len(g["nodes"]))
+    limit = max(1, int(np.median(n_inc[n_inc > 0])) - 1)  # the nodes of median valence and above become "heavy"
+    for table in (plan_mod._CAPS, plan_mod._CAPS_SMALL):
+        if elm in table:
+            monkeypatch.setitem(table, elm, dict(table[elm], te_max=limit))
+    E, nu = float(g["E"]), float(g["nu"])
+    for kind in ("iso", "uniform", "stress"):
+        fd.Assembly.delete_memory()
+        fd.ModelingSpace(space)
+        fd.Mesh(g["nodes"], g["elements"], elm, name="Domain")
+        if kind == "iso":
+            law = fd.constitutivelaw.ElasticIsotrop(E, nu, name="law")
+        else:
+            H = fd.constitutivelaw.ElasticIsotrop(E, nu).get_tangent_matrix(None, "3D")
+            law = fd.constitutivelaw.ElasticAnisotropic(H, name="law")
+        fd.weakform.StressEquilibrium(law, name="wf")
+        a = fd.Assembly.create("wf", "Domain", elm, name="A")
+        pb = fd.problem.Linear("A")
+        pb.set_X(g["U"])
+        if kind == "stress":
+            monkeypatch.setattr(asm_mod, "_RESIDUAL_KERNEL", False)  # K and B^T sigma both through the cluster / rows kernels
+            a.update(pb, compute="none")
+            a.sv["Stress"] = fd.GaussPointTensor(a.sv["Stress"].device_tensor.clone(), "stress")
+            a.assemble_global_mat("all")
+        else:
+            a.update(pb, compute="all")
+        plans = [p for p in (a._saved_bloc_structure.get("plan"), a._saved_bloc_structure.get("plan_small")) if p is not None]
+        assert plans and all(p.heavy_nodes.numel() > 0.2 * (n_inc > 0).sum() for p in plans)
+        K = a.get_global_matrix().tocsr()
+        assert np.array_equal(K.indptr, g["K_indptr"]) and np.array_equal(K.indices, g["K_indices"])
+        assert nrm(K.data, g["K_data"]) <= TOL, kind
+        assert nrm(np.array(a.get_global_vector()), g["D"]) <= TOL, kind

@@ -80,10 +80,16 @@ def test_plan_unreferenced_nodes_and_single_node_overflow():
     nodes = np.vstack([nodes, [[5.0, 5.0, 5.0], [6.0, 6.0, 6.0]]])  # two isolated nodes
     plan, pat = make_plan("hex8", nodes, el)
     assert plan.n_nodes == len(nodes)
-    from fedoo_b200._lib import FdkError
-
-    with pytest.raises(FdkError):
-        make_plan("hex8", nodes, el, caps=dict(inc_max=4, te_max=80))  # interior nodes have 8 incidences
+    # a node whose incident elements alone exceed a cluster's capacity is left out of the clusters: its row goes to the
+    # rows kernel (csrc/fdk_rows.cuh).  With inc_max = 4 every node touching more than 4 elements is such a node.
+    small, _ = make_plan("hex8", nodes, el, caps=dict(inc_max=4, te_max=80))
+    n_inc = np.bincount(el.reshape(-1), minlength=len(nodes))
+    heavy = np.flatnonzero(n_inc > 4)
+    assert heavy.size > 0 and np.array_equal(small.heavy_nodes.cpu().numpy(), heavy)
+    assert small.n_owned == len(nodes) - heavy.size
+    owned_by_clusters = small.t["cl_node"].cpu().numpy()
+    assert not np.intersect1d(owned_by_clusters, heavy).size
+    assert plan.heavy_nodes.numel() == 0
 
 
 def test_slab_ranks_get_the_same_bricks_as_one_gpu():
