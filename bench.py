@@ -46,7 +46,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="hex8", choices=list(METRICS))
-    ap.add_argument("--n", type=int, default=200, help="hex8: elements per box edge (200 -> 8 M hex8)")
+    ap.add_argument("--n", "--edge", dest="n", type=int, default=200,
+                    help="hex8: elements per box edge (200 -> 8 M hex8); --edge: the spelling torchrun does not mistake for its own")
     ap.add_argument("--scale", type=float, default=1.0, help="other configs: fraction of the full element count")
     ap.add_argument("--jitter", type=int, default=0, help="hex8: 1 = displace interior nodes (no identical elements)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

@@ -38,8 +38,33 @@ struct HeatTet4Args {
   double* D;
 };
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_heat_tet4_rows(const __grid_constant__ HeatTet4Args a) {
+// Gradients of the four shape functions of a tet4 and |det J|, specialised to the reference element of
+// fedoo/lib_elements/tetrahedron.py:106-130 (N = [eta, zeta, 1 - xi - eta - zeta, xi]: node 2 is the origin, xi runs to
+// node 3, eta to node 0, zeta to node 1).  The table's dN/dxi entries are 0 and +-1, so J = dN . X is three edge
+// vectors and G = J^-1 dN is the three columns of J^-1 and minus their sum: the same numbers, bit for bit, as the generic
+// gp_geometry<4, 3> (same cofactor formulas, same order of the additions) for a third of the FP64 work.
+__device__ __forceinline__ double tet4_gradients(const double (&X)[4][3], double (&G)[4][3]) {
+  double J[3][3];
+#pragma unroll
+  for (int x = 0; x < 3; ++x) {
+    J[0][x] = X[3][x] - X[2][x];
+    J[1][x] = X[0][x] - X[2][x];
+    J[2][x] = X[1][x] - X[2][x];
+  }
+  double iJ[3][3];
+  const double det = invert<3>(J, iJ);
+#pragma unroll
+  for (int x = 0; x < 3; ++x) {
+    G[3][x] = iJ[x][0];
+    G[0][x] = iJ[x][1];
+    G[1][x] = iJ[x][2];
+    G[2][x] = ((-iJ[x][0]) - iJ[x][1]) - iJ[x][2];
+  }
+  return fabs(det);
+}
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_heat_tet4_rows(const __grid_constant__ HeatTet4Args a) {
   extern __shared__ double s_acc[];  // [max_deg][THREADS]
   const int tid = threadIdx.x;
   const int I = blockIdx.x * THREADS + tid;
@@ -50,6 +75,16 @@ __global__ void __launch_bounds__(THREADS) k_heat_tet4_rows(const __grid_constan
   const int deg = (int)(a.blk_indptr[I + 1] - bp);
   if (want_K) {
     for (int s = 0; s < deg; ++s) s_acc[s * THREADS + tid] = 0.0;
+  }
+  // quadrature sums of the (symmetric) 4-point rule, from the table: sum_g w, sum_g w N_i, sum_g w N_i N_k (i = k, i != k)
+  double wsum = 0.0, wn = 0.0, m_diag = 0.0, m_off = 0.0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const double w = tab.w[g], n0 = tab.N[g * 4 + 0], n1 = tab.N[g * 4 + 1];
+    wsum += w;
+    wn = fma(w, n0, wn);
+    m_diag = fma(w * n0, n0, m_diag);
+    m_off = fma(w * n0, n1, m_off);
   }
   double dsum = 0.0;
   const int64_t t0 = a.node_ptr[I], t1 = a.node_ptr[I + 1];
@@ -66,27 +101,19 @@ __global__ void __launch_bounds__(THREADS) k_heat_tet4_rows(const __grid_constan
 #pragma unroll
       for (int d = 0; d < 3; ++d) X[k][d] = a.coords[(int64_t)nd[k] * 3 + d];
     double G[4][3];
-    const double wdet = gp_geometry<4, 3>(tab.dN, 1.0, X, G);  // |det J|; the gradient is the same at every Gauss point
+    const double wdet = tet4_gradients(X, G);  // |det J|; the gradient is the same at every Gauss point
     // gradient of the row node (selects, not a run-time index: G stays in registers)
     double gi[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) gi[d] = i == 0 ? G[0][d] : (i == 1 ? G[1][d] : (i == 2 ? G[2][d] : G[3][d]));
-    // k grad N_I (cond is symmetric in every use of the reference, but nothing here assumes it): row vector G_I . cond
-    double kg[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) kg[c] = gi[0] * a.cond[0 * 3 + c] + gi[1] * a.cond[1 * 3 + c] + gi[2] * a.cond[2 * 3 + c];
-    double wsum = 0.0;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) wsum += tab.w[g];
     const double V = wsum * wdet;
     if (want_K) {
-      const uint32_t pos = (uint32_t)rec.y;
-      double cap = 0.0;
-      if (a.rcdt != 0.0) {
+      // k grad N_I (nothing here assumes a symmetric conductivity): row vector G_I . cond
+      double kg[3];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) cap = fma(tab.w[g], tab.N[g * 4 + i], cap);
-        cap *= a.rcdt * wdet;
-      }
+      for (int c = 0; c < 3; ++c) kg[c] = gi[0] * a.cond[0 * 3 + c] + gi[1] * a.cond[1 * 3 + c] + gi[2] * a.cond[2 * 3 + c];
+      const uint32_t pos = (uint32_t)rec.y;
+      const double cap = a.rcdt * wdet * wn;  // lumped capacity: row sum of the consistent matrix (sum_k N_k = 1)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         double v = V * (kg[0] * G[j][0] + kg[1] * G[j][1] + kg[2] * G[j][2]);
@@ -108,18 +135,15 @@ __global__ void __launch_bounds__(THREADS) k_heat_tet4_rows(const __grid_constan
       for (int r = 0; r < 3; ++r) q += gi[r] * (a.cond[r * 3 + 0] * gT[0] + a.cond[r * 3 + 1] * gT[1] + a.cond[r * 3 + 2] * gT[2]);
       double f = V * q;
       if (a.rcdt != 0.0) {
-        double dT[4];
+        // sum_g w N_i(g) sum_k N_k(g) dT_k = m_off sum_k dT_k + (m_diag - m_off) dT_i
+        double dT[4], ssum = 0.0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dT[k] = Tk[k] - (a.T_start != nullptr ? a.T_start[nd[k]] : 0.0);
-        double c = 0.0;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          double dTg = 0.0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) dTg = fma(tab.N[g * 4 + k], dT[k], dTg);
-          c = fma(tab.w[g] * tab.N[g * 4 + i], dTg, c);
+        for (int k = 0; k < 4; ++k) {
+          dT[k] = Tk[k] - (a.T_start != nullptr ? a.T_start[nd[k]] : 0.0);
+          ssum += dT[k];
         }
-        f = fma(a.rcdt * wdet, c, f);
+        const double dTi = i == 0 ? dT[0] : (i == 1 ? dT[1] : (i == 2 ? dT[2] : dT[3]));
+        f = fma(a.rcdt * wdet, fma(m_diag - m_off, dTi, m_off * ssum), f);
       }
       dsum += f;
     }
@@ -131,20 +155,32 @@ __global__ void __launch_bounds__(THREADS) k_heat_tet4_rows(const __grid_constan
   if (want_D) a.D[I] = -dsum;
 }
 
+template <int THREADS, int MINB>
+int launch_heat_tet4_t(const HeatTet4Args& a, size_t smem, cudaStream_t stream) {
+  static thread_local size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    FDK_CUDA(cudaFuncSetAttribute(k_heat_tet4_rows<THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  k_heat_tet4_rows<THREADS, MINB><<<(unsigned)((a.n_nodes + THREADS - 1) / THREADS), THREADS, smem, stream>>>(a);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 inline int launch_heat_tet4(const HeatTet4Args& a, cudaStream_t stream) {
   if (a.n_nodes == 0) return 0;
   if (int rc = ensure_device_tables()) return rc;
   constexpr int THREADS = 128;
   const size_t smem = (size_t)(a.K != nullptr ? a.max_deg : 0) * THREADS * sizeof(double);
   FDK_REQUIRE(a.max_deg <= 255 && smem <= 200 * 1024, FDK_ECAP, "row degree %d exceeds the row-owner kernel's capacity", a.max_deg);
-  static thread_local size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    FDK_CUDA(cudaFuncSetAttribute(k_heat_tet4_rows<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
-  k_heat_tet4_rows<THREADS><<<(unsigned)((a.n_nodes + THREADS - 1) / THREADS), THREADS, smem, stream>>>(a);
-  FDK_CUDA(cudaGetLastError());
-  return 0;
+  // resident CTAs per SM the register allocation aims at (96 / 80 / 64 registers); FDK_HEAT_MINB overrides (diagnostic)
+  static const int minb = [] {
+    const char* e = getenv("FDK_HEAT_MINB");
+    return e ? atoi(e) : 6;
+  }();
+  if (minb >= 8) return launch_heat_tet4_t<THREADS, 8>(a, smem, stream);
+  if (minb >= 6) return launch_heat_tet4_t<THREADS, 6>(a, smem, stream);
+  return launch_heat_tet4_t<THREADS, 5>(a, smem, stream);
 }
 
 }  // namespace fdk
