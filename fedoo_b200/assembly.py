@@ -29,6 +29,7 @@ from .constitutivelaw import ElasticAnisotropic, ElasticIsotrop, ElastoPlasticit
 from .core import DeviceCSR, GaussPointTensor, Mesh, _Named, as_device_f64, device
 from .weakform import WeakFormBase
 
+_LAZY = object()  # a per-Gauss-point tangent exists in structured form; the (6,6,N) array is expanded only on demand
 _DEFAULT_NGP = {"hex8": 8, "tet4": 4, "tet10": 15, "quad4": 4}  # fedoo/lib_elements/element_list.py:50-84
 
 
@@ -264,7 +265,10 @@ class Assembly(_Named):
                 else:
                     stress_dev = stress.device_tensor
             if flags:
-                tangent_dev = law.tangent_device(self) if hasattr(law, "tangent_device") else None
+                if getattr(law, "tangent_r1_device", None) is not None and law.tangent_r1_device(self) is not None:
+                    tangent_dev = _LAZY
+                else:
+                    tangent_dev = law.tangent_device(self) if hasattr(law, "tangent_device") else None
                 peer = self.peer_vector
                 fusable = isinstance(law, ElasticIsotrop) and tangent_dev is None and stress_dev is None
                 split = (flags == _lib.ALL and not fusable and self.owned_nodes is None and peer is None
@@ -283,6 +287,8 @@ class Assembly(_Named):
                     conn = self.mesh.device_arrays()[1]
                     fe = self._scratch("fe", self.mesh.n_elements * conn.shape[1] * self.space.ndim)
                     C_h = None
+                    if stress_dev is None and tangent_dev is _LAZY:
+                        tangent_dev = law.tangent_device(self)
                     if stress_dev is None and tangent_dev is None:
                         C_h = np.ascontiguousarray(self.sv["TangentMatrix"], dtype=np.float64)
                     rc = lib.fdk_residual_elastic(
@@ -314,7 +320,21 @@ class Assembly(_Named):
                     )  # fmt: skip
                     _lib.check(rc, "fdk_assemble_elastic_iso")
                     self._heavy_rows(entry, self._plan(entry), flags, coords, True, lam, mu, None, None, U_dev, stress_dev, K, D)
+                elif (getattr(law, "tangent_r1_device", None) is not None and law.tangent_r1_device(self) is not None
+                        and self.elm_type == "hex8" and nvar == 3 and want_mat):
+                    # J2 tangent in its structured form: the balanced kernel reads 10 doubles per (element, Gauss point)
+                    plan = self._small_plan(entry)
+                    rc = lib.fdk_assemble_elastic_r1(
+                        C.byref(plan.struct(nvar)), flags, _lib.ptr(coords), _lib.ptr(law.tangent_r1_device(self)),
+                        _lib.ptr(stress_dev), _lib.ptr(K), _lib.ptr(D), stream,
+                    )  # fmt: skip
+                    _lib.check(rc, "fdk_assemble_elastic_r1")
+                    if plan.heavy_nodes.numel():
+                        self._heavy_rows(entry, plan, flags, coords, False, 0.0, 0.0, None, law.tangent_device(self), U_dev,
+                                         stress_dev, K, D)  # fmt: skip
                 else:
+                    if tangent_dev is _LAZY:
+                        tangent_dev = law.tangent_device(self)
                     H = self.sv["TangentMatrix"]
                     C_h = None if tangent_dev is not None else np.ascontiguousarray(H, dtype=np.float64)
                     if self.elm_type == "hex8" and nvar == 3 and want_mat:

@@ -168,6 +168,8 @@ class ElastoPlasticity(ConstitutiveLaw):
         # "consistent": algorithmic tangent of the radial return (quadratic Newton convergence);
         # "continuum": L - (L:n)(n:L)/(n:L:n + R') at the end state, what simcoon's EPICP returns
         self.tangent = "consistent"
+        # keep the per-Gauss-point tangent in its 10-double structured form (see StructuredTangent); 0: the (6,6,N) array
+        self.structured_tangent = True
 
     def set_hardening_function(self, function_type="power", **kargs):
         if function_type.lower() != "power":
@@ -203,27 +205,80 @@ class ElastoPlasticity(ConstitutiveLaw):
             sv0 = torch.zeros((N, 8), dtype=torch.float64, device=dev)
         stress = torch.empty((N, 6), dtype=torch.float64, device=dev)
         statev = torch.empty((N, 8), dtype=torch.float64, device=dev)
-        tangent = torch.empty(N * 36, dtype=torch.float64, device=dev)
         props = self.props
         _lib.check(lib.fdk_set_option(b"j2_continuum_tangent", int(self.tangent == "continuum")), "fdk_set_option")
-        _lib.check(
-            lib.fdk_j2_update(
-                N, _lib.ptr(props), _lib.ptr(strain.device_tensor), _lib.ptr(sv0), _lib.ptr(stress), _lib.ptr(statev),
-                _lib.ptr(tangent), _lib.current_stream(),
-            ),
-            "fdk_j2_update",
-        )  # fmt: skip
+        if self.structured_tangent:
+            # 10 doubles per Gauss point instead of 36 (csrc/fdk_gp.cuh); the (6,6,N) array is built only if somebody reads it
+            r1 = torch.empty((N, 10), dtype=torch.float64, device=dev)
+            _lib.check(
+                lib.fdk_j2_update_r1(
+                    N, _lib.ptr(props), _lib.ptr(strain.device_tensor), _lib.ptr(sv0), _lib.ptr(stress), _lib.ptr(statev),
+                    _lib.ptr(r1), _lib.current_stream(),
+                ),
+                "fdk_j2_update_r1",
+            )  # fmt: skip
+            assembly.sv["TangentMatrix"] = StructuredTangent(r1)
+        else:
+            tangent = torch.empty(N * 36, dtype=torch.float64, device=dev)
+            _lib.check(
+                lib.fdk_j2_update(
+                    N, _lib.ptr(props), _lib.ptr(strain.device_tensor), _lib.ptr(sv0), _lib.ptr(stress), _lib.ptr(statev),
+                    _lib.ptr(tangent), _lib.current_stream(),
+                ),
+                "fdk_j2_update",
+            )  # fmt: skip
+            assembly.sv["TangentMatrix"] = tangent
         assembly.sv["Stress"] = GaussPointTensor(stress)
         assembly.sv["Statev"] = statev
-        assembly.sv["TangentMatrix"] = tangent
 
     def set_start(self, assembly, pb):
         # elastic prediction for the next increment (simcoon_umat.py:591-593)
         assembly.sv["TangentMatrix"] = self.get_elastic_matrix()
 
     def tangent_device(self, assembly):
+        """(6,6,N) Fortran-ordered device tensor of the per-Gauss-point tangent, or None when it is uniform."""
         H = assembly.sv["TangentMatrix"]
+        if isinstance(H, StructuredTangent):
+            return H.full()
         return H if isinstance(H, torch.Tensor) else None
+
+    def tangent_r1_device(self, assembly):
+        """The structured form [lam', mu', kappa, n^(6), 0] per Gauss point, or None."""
+        H = assembly.sv["TangentMatrix"]
+        return H.r1 if isinstance(H, StructuredTangent) else None
+
+
+class StructuredTangent:
+    """sv["TangentMatrix"] of the J2 law in its structured form (N, 10): C = lam' 1(x)1 + 2 mu' I_sym - kappa n^(x)n^.
+    Indexing ``H[i][j]`` (what the reference's weak form does, stress_equilibrium.py:112-117), ``np.asarray`` and
+    ``full()`` expand it to the (6,6,N) array of the reference's protocol (simcoon_umat.py:556-580)."""
+
+    def __init__(self, r1):
+        self.r1 = r1
+        self._full = None
+        self._host = None
+
+    def full(self):
+        if self._full is None:
+            N = self.r1.shape[0]
+            out = torch.empty(N * 36, dtype=torch.float64, device=self.r1.device)
+            _lib.check(_lib.load().fdk_j2_tangent_expand(N, _lib.ptr(self.r1), _lib.ptr(out), _lib.current_stream()),
+                       "fdk_j2_tangent_expand")  # fmt: skip
+            self._full = out
+        return self._full
+
+    def __array__(self, dtype=None, copy=None):
+        if self._host is None:
+            N = self.r1.shape[0]
+            self._host = self.full().cpu().numpy().reshape(N, 6, 6).transpose(2, 1, 0)  # (i, j, n), Fortran (6,6,N)
+        return self._host
+
+    def __getitem__(self, i):
+        return np.asarray(self)[i]
+
+    @property
+    def shape(self):
+        return (6, 6, self.r1.shape[0])
 
 
 def Simcoon(umat_name, props, name=""):

@@ -284,6 +284,61 @@ int fdk_assemble_rows_elastic(int elem_type, int n_rows, const int32_t* rows, in
   return FDK_EINVAL;
 }
 
+int fdk_assemble_elastic_r1(const fdk_plan* plan, int compute, const double* coords, const double* tangent_r1,
+                            const double* stress_gp, double* K_values, double* D, fdk_stream_t stream) {
+  if (int rc = check_plan(plan)) return rc;
+  if (int rc = check_io(compute, coords, K_values, D)) return rc;
+  FDK_REQUIRE(tangent_r1 != nullptr, FDK_EINVAL, "tangent_r1 is NULL");
+  FDK_REQUIRE(compute & FDK_MATRIX, FDK_EINVAL, "the structured-tangent kernel assembles the matrix (residual alone: fdk_residual_elastic)");
+  FDK_REQUIRE(!(compute & FDK_VECTOR) || stress_gp, FDK_EINVAL, "the vector needs stress_gp");
+  FDK_REQUIRE(plan->elem_type == FDK_HEX8 && plan->nvar == 3 && plan->threads == Hex8::THREADS / 2 && plan->blk_slot &&
+                  plan->ent_pos,
+              FDK_EINVAL, "structured J2 tangent: hex8, 3 dofs per node, plan built with small = True");
+  AsmArgs a{};
+  a.p = *plan;
+  a.coords = coords;
+  a.stress_gp = stress_gp;
+  a.tangent_r1 = tangent_r1;
+  a.K = K_values;
+  a.D = D;
+  a.compute = compute;
+  a.fuse_ku = 0;
+  FDK_REQUIRE((assemble_iso_fits<Hex8, 512, 4, PHYS_R1>(a)), FDK_ECAP, "plan does not fit the balanced kernel");
+  return launch_assemble_iso<Hex8, 512, 4, PHYS_R1>(a, (cudaStream_t)stream);
+}
+
+int fdk_j2_update_r1(int64_t n_gp, const double* props_h, const double* strain_gp, const double* statev_start,
+                     double* stress_gp, double* statev, double* tangent_r1, fdk_stream_t stream) {
+  FDK_REQUIRE(props_h && strain_gp && statev_start && stress_gp && statev && tangent_r1, FDK_EINVAL, "NULL argument");
+  FDK_REQUIRE(n_gp >= 0, FDK_EINVAL, "negative n_gp");
+  if (n_gp == 0) return 0;
+  J2Args a{};
+  a.n_gp = n_gp;
+  a.E = props_h[0];
+  a.nu = props_h[1];
+  a.sigY = props_h[3];
+  a.k = props_h[4];
+  a.m = props_h[5];
+  a.strain = strain_gp;
+  a.statev0 = statev_start;
+  a.stress = stress_gp;
+  a.statev = statev;
+  a.tangent = nullptr;
+  a.tangent_r1 = tangent_r1;
+  a.continuum = g_opt_j2_continuum;
+  k_j2_update<<<(unsigned)((n_gp + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int fdk_j2_tangent_expand(int64_t n_gp, const double* tangent_r1, double* tangent_gp, fdk_stream_t stream) {
+  FDK_REQUIRE(n_gp >= 0 && (n_gp == 0 || (tangent_r1 && tangent_gp)), FDK_EINVAL, "bad argument");
+  if (n_gp == 0) return 0;
+  k_j2_tangent_expand<<<(unsigned)((n_gp + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_gp, tangent_r1, tangent_gp);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int fdk_assemble_heat(const fdk_plan* plan, int compute, const double* coords, const double* cond_h,
                       double rho_c_over_dt, const double* T, const double* T_start, double* K_values, double* D,
                       fdk_stream_t stream) {

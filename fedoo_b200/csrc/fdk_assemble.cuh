@@ -33,7 +33,7 @@
 
 namespace fdk {
 
-enum Physics { PHYS_ISO = 0, PHYS_GENERAL = 1, PHYS_HEAT = 2 };
+enum Physics { PHYS_ISO = 0, PHYS_GENERAL = 1, PHYS_HEAT = 2, PHYS_R1 = 3 };  // R1: structured J2 tangent (balanced kernel)
 
 constexpr int HEAVY_T = 4;  // slots with more contributions are pre-reduced (must match plan.py)
 
@@ -54,6 +54,7 @@ struct AsmArgs {
   const double* U2;          // heat: T_start
   const double* stress_gp;   // optional given stress (6,N)
   const double* tangent_gp;  // optional per-GP tangent (6,6,N)
+  const double* tangent_r1;  // PHYS_R1: structured J2 tangent, J2_R1 doubles per Gauss point
   double* K;
   double* D;
   double lam, mu;

@@ -134,11 +134,11 @@ struct IsoLayout {
     const long r = sr_doubles(p), g = bts ? (((long)p.cap_te * NGP * SGS + 1) & ~1L) : 0;
     return r > g ? r : g;
   }
-  __host__ __device__ static long extra_doubles(const fdk_plan& p, bool tangent_gp) {
-    return tangent_gp ? (long)p.cap_te * NGP * CSTR : 0;
+  __host__ __device__ static long extra_doubles(const fdk_plan& p, bool tangent_gp, int cstr = CSTR) {
+    return tangent_gp ? (long)p.cap_te * NGP * cstr : 0;
   }
-  static size_t smem_bytes(const fdk_plan& p, bool tangent_gp = false, bool bts = false) {
-    long doubles = TAB_DOUBLES + 2L * xu_doubles(p) + sr_offset(p) + rs_doubles(p, bts) + extra_doubles(p, tangent_gp) +
+  static size_t smem_bytes(const fdk_plan& p, bool tangent_gp = false, bool bts = false, int cstr = CSTR) {
+    long doubles = TAB_DOUBLES + 2L * xu_doubles(p) + sr_offset(p) + rs_doubles(p, bts) + extra_doubles(p, tangent_gp, cstr) +
                    xe_doubles(p) + p.cap_owned;
     size_t bytes = (size_t)doubles * 8;
     bytes += (size_t)(2 * (p.cap_owned + 1)) * 4;      // sSlotBase, sFinc
@@ -155,10 +155,11 @@ template <class El, int THREADS, int TPI, int PHYS = PHYS_ISO, bool DIST = false
 __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS > 0 ? 1024 / THREADS : 1))
     k_assemble_iso(const __grid_constant__ AsmArgs a) {
   using IL = IsoLayout<El, TPI>;
-  constexpr bool GEN = PHYS == PHYS_GENERAL;
+  constexpr bool R1 = PHYS == PHYS_R1;  // structured J2 tangent: [lam', mu', kappa, n^(6), 0] per (element, Gauss point)
+  constexpr bool GEN = PHYS == PHYS_GENERAL || R1;
   constexpr bool COLORED = IL::COLORED;
   static_assert(PHYS == PHYS_ISO || (GEN && El::DIM == 3), "balanced kernel: isotropic, or general tangent in 3D");
-  constexpr int CSTR = IL::CSTR, SGS = IL::SGS;
+  constexpr int CSTR = R1 ? J2_R1 : IL::CSTR, SGS = IL::SGS;
   constexpr int NNE = IL::NNE, NGP = IL::NGP, DIM = IL::DIM, NV = IL::NV, BLK = IL::BLK, ISTR = IL::ISTR;
   constexpr int GROW = IL::GROW, GSTR = IL::GSTR, ESTR = IL::ESTR, TSTR = IL::TSTR, NH = IL::NH, XSTR = IL::XSTR;
   constexpr int INC = THREADS / TPI;  // incidences per cluster <= INC
@@ -166,7 +167,8 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
   const int tid = threadIdx.x;
   const bool fuse_ku = a.fuse_ku != 0;
   const bool do_bts = GEN && (a.compute & FDK_VECTOR) && !fuse_ku;  // residual as B^T sigma from a given stress
-  const bool per_gp = GEN && a.tangent_gp != nullptr;
+  const bool per_gp = GEN && (R1 || a.tangent_gp != nullptr);
+  [[maybe_unused]] const double* tan_src = R1 ? a.tangent_r1 : a.tangent_gp;
   // the TPI threads of an incidence sit in adjacent lanes: a warp covers 32 / TPI incidences of 2-3 elements
   // (element-major order), so its own-row loads touch 32 / TPI addresses and its column loads ~10
   const int it = PART_UNIFORM ? tid % INC : tid / TPI;    // incidence of this thread (phase 2)
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
   double* sF = sR;
   double* sSig = sR;                       // [cap_te][NGP][6] sqrt(w) sigma (do_bts): shares the space of sF
   double* sC = sR + IL::rs_doubles(p, do_bts);  // [cap_te][NGP][36] tangent of every (touched element, gp) (per_gp)
-  double* sXe = sC + IL::extra_doubles(p, per_gp);  // [cap_te][NNE][DIM] element-local coordinates (HEXREF)
+  double* sXe = sC + IL::extra_doubles(p, per_gp, CSTR);  // [cap_te][NNE][DIM] element-local coordinates (HEXREF)
   long long* sBptr = reinterpret_cast<long long*>(sXe + IL::xe_doubles(p));  // [cap_owned]
   int* sSlotBase = reinterpret_cast<int*>(sBptr + p.cap_owned);                                 // [cap_owned+1]
   int* sFinc = sSlotBase + (p.cap_owned + 1);                                                   // [cap_owned+1]
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
       const int task = idx / PIECES, k = idx - task * PIECES;
       const int le = task / NGP, g = task - le * NGP;
       const int64_t e = p.cl_te_elem[h.te0 + le];
-      cp_async<16>(sC + (long)task * CSTR + 2 * k, a.tangent_gp + CSTR * ((int64_t)g * p.n_elems + e) + 2 * k);
+      cp_async<16>(sC + (long)task * CSTR + 2 * k, tan_src + CSTR * ((int64_t)g * p.n_elems + e) + 2 * k);
     }
   };
   ClusterHdr cur = load_hdr(p.cl_hdr, blockIdx.x);
@@ -540,6 +542,65 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
             f[1] += ws[1] * gi[1] + ws[3] * gi[0] + ws[5] * gi[2];
             f[2] += ws[2] * gi[2] + ws[4] * gi[0] + ws[5] * gi[1];
           }
+          if constexpr (R1) {
+            // K_ij += lam' g_i (x) g_j + mu' (g_j (x) g_i + (g_i . g_j) 1) - kappa (n^ g_i) (x) (n^ g_j); sqrt(w) sits in g
+            const double2* r2 = reinterpret_cast<const double2*>(c_p + g * CSTR);
+            const double2 q0 = r2[0], q1 = r2[1], q2 = r2[2], q3 = r2[3], q4 = r2[4];
+            const double lamp = q0.x, mup = q0.y, kap = q1.x;
+            const double n0 = q1.y, n1 = q2.x, n2 = q2.y, n3 = q3.x, n4 = q3.y, n5 = q4.x;
+            double li[3], mi[3], ki[3];
+            {
+              const double a0 = n0 * gi[0] + n3 * gi[1] + n4 * gi[2];
+              const double a1 = n3 * gi[0] + n1 * gi[1] + n5 * gi[2];
+              const double a2 = n4 * gi[0] + n5 * gi[1] + n2 * gi[2];
+              ki[0] = -kap * a0;
+              ki[1] = -kap * a1;
+              ki[2] = -kap * a2;
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                li[d] = lamp * gi[d];
+                mi[d] = mup * gi[d];
+              }
+            }
+            double gjv[NH * 3];
+            if constexpr (HEXREF) {
+              const double2* g2 = reinterpret_cast<const double2*>(ge_p + g * GSTR + ((part ^ (gxv >> 1)) * 2) * 3);
+              const double2 v0 = g2[0], v1 = g2[1], v2 = g2[2];
+              const bool swp = ((gxv ^ (gxv >> 1)) & 1) != 0;
+              gjv[0] = swp ? v1.y : v0.x;
+              gjv[1] = swp ? v2.x : v0.y;
+              gjv[2] = swp ? v2.y : v1.x;
+              gjv[3] = swp ? v0.x : v1.y;
+              gjv[4] = swp ? v0.y : v2.x;
+              gjv[5] = swp ? v1.x : v2.y;
+            } else {
+              static_assert(ADJ || !R1, "structured tangent path: adjacent column blocks");
+              const double2* g2 = reinterpret_cast<const double2*>(gj_p + g * GSTR);
+#pragma unroll
+              for (int q = 0; q < NH * 3 / 2; ++q) {
+                const double2 v = g2[q];
+                gjv[2 * q] = v.x;
+                gjv[2 * q + 1] = v.y;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < NH; ++j) {
+              const double* gj = gjv + 3 * j;
+              const double b0 = n0 * gj[0] + n3 * gj[1] + n4 * gj[2];
+              const double b1 = n3 * gj[0] + n1 * gj[1] + n5 * gj[2];
+              const double b2 = n4 * gj[0] + n5 * gj[1] + n2 * gj[2];
+              const double bj[3] = {b0, b1, b2};
+              const double dot = mi[0] * gj[0] + mi[1] * gj[1] + mi[2] * gj[2];
+#pragma unroll
+              for (int cc = 0; cc < 3; ++cc) {
+#pragma unroll
+                for (int aa = 0; aa < 3; ++aa)
+                  acc[j][cc * 3 + aa] += fma(li[cc], gj[aa], fma(mi[aa], gj[cc], ki[cc] * bj[aa]));
+                acc[j][cc * 3 + cc] += dot;
+              }
+            }
+            continue;
+          }
           double t[3][6];
 #pragma unroll
           for (int sc = 0; sc < 6; ++sc) {
@@ -757,9 +818,11 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
 template <class El, int THREADS, int TPI, int PHYS = PHYS_ISO>
 bool assemble_iso_fits(const AsmArgs& a) {
   using IL = IsoLayout<El, TPI>;
-  const bool bts = PHYS == PHYS_GENERAL && (a.compute & FDK_VECTOR) && !a.fuse_ku;
+  constexpr bool GENP = PHYS == PHYS_GENERAL || PHYS == PHYS_R1;
+  const bool bts = GENP && (a.compute & FDK_VECTOR) && !a.fuse_ku;
+  const bool staged = PHYS == PHYS_R1 || (PHYS == PHYS_GENERAL && a.tangent_gp != nullptr);
   return TPI * a.p.cap_inc <= THREADS &&
-         IL::smem_bytes(a.p, PHYS == PHYS_GENERAL && a.tangent_gp != nullptr, bts) <= 227 * 1024;
+         IL::smem_bytes(a.p, staged, bts, PHYS == PHYS_R1 ? J2_R1 : IL::CSTR) <= 227 * 1024;
 }
 
 template <class El, int THREADS, int TPI, int PHYS = PHYS_ISO, bool DIST = false>
@@ -774,8 +837,10 @@ int launch_assemble_iso(AsmArgs& a, cudaStream_t stream) {
   FDK_REQUIRE(p.nvar == IL::NV, FDK_EINVAL, "plan nvar %d does not match the operator (%d)", p.nvar, IL::NV);
   FDK_REQUIRE(!IL::COLORED || (p.blk_slot && p.ent_pos), FDK_EINVAL,
               "the plan carries no block colouring (fdk_plan_color_blocks)");
-  const bool bts = PHYS == PHYS_GENERAL && (a.compute & FDK_VECTOR) && !a.fuse_ku;
-  const size_t smem = IL::smem_bytes(p, PHYS == PHYS_GENERAL && a.tangent_gp != nullptr, bts);
+  constexpr bool GENP = PHYS == PHYS_GENERAL || PHYS == PHYS_R1;
+  const bool bts = GENP && (a.compute & FDK_VECTOR) && !a.fuse_ku;
+  const bool staged = PHYS == PHYS_R1 || (PHYS == PHYS_GENERAL && a.tangent_gp != nullptr);
+  const size_t smem = IL::smem_bytes(p, staged, bts, PHYS == PHYS_R1 ? J2_R1 : IL::CSTR);
   FDK_REQUIRE(smem <= 227 * 1024, FDK_ECAP, "cluster needs %zu bytes of shared memory (> 227 KB)", smem);
   if (p.n_clusters == 0) return 0;
   if (int rc = ensure_device_tables()) return rc;
@@ -787,7 +852,9 @@ int launch_assemble_iso(AsmArgs& a, cudaStream_t stream) {
   }
   // persistent CTAs: as many as are resident at once (one per SM for the 1024-thread variants)
   static thread_local int resident = 0;
-  if (resident == 0) {
+  static thread_local size_t resident_smem = 0;
+  if (resident == 0 || resident_smem != smem) {  // the occupancy depends on the plan's shared-memory footprint
+    resident_smem = smem;
     int dev = 0, sms = 0, per_sm = 0;
     FDK_CUDA(cudaGetDevice(&dev));
     FDK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

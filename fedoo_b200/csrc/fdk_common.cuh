@@ -40,6 +40,7 @@ using Tet10 = ElemTraits<FDK_TET10, 10, 15, 3, 256>;
 using Quad4 = ElemTraits<FDK_QUAD4, 4, 4, 2, 512>;
 
 constexpr int MAX_NGP = 15, MAX_NNE = 10, MAX_DIM = 3;
+constexpr int J2_R1 = 10;  // doubles per Gauss point of the structured J2 tangent (csrc/fdk_gp.cuh)
 
 // Gauss weights, shape functions and reference derivatives at the Gauss points.
 struct ElemTable {

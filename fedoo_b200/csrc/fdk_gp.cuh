@@ -481,8 +481,16 @@ struct J2Args {
   double* stress;
   double* statev;
   double* tangent;
+  double* tangent_r1;  // structured form of the same tangent, J2_R1 doubles per Gauss point (see below), or NULL
   int continuum;  // 1: continuum elastoplastic tangent at the end state (beta = 1), 0: consistent (algorithmic) tangent
 };
+
+// Both J2 tangents are an isotropic tensor minus a rank-one term on the unit deviatoric direction n^:
+//     C = lam' 1 (x) 1 + 2 mu' I_sym - kappa n^ (x) n^,   lam' = K - 2 mu beta / 3, mu' = mu beta, kappa = 2 mu gamma
+// (elastic points: beta = 1, gamma = 0).  Ten doubles per Gauss point carry it -- [lam', mu', kappa, n^ (6, stress Voigt),
+// 0] -- instead of the 36 of the (6,6,N) array the reference's protocol stores (simcoon_umat.py:556-580): 80 instead of
+// 288 bytes written by the update and read back by the assembly, and 10 instead of 36 shared-memory operands per
+// (element, Gauss point) in the block phase (csrc/fdk_assemble_iso.cuh, PHYS_R1).
 
 __global__ void __launch_bounds__(256) k_j2_update(const __grid_constant__ J2Args a) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -568,7 +576,7 @@ __global__ void __launch_bounds__(256) k_j2_update(const __grid_constant__ J2Arg
 #pragma unroll
     for (int i = 0; i < 4; ++i) vo[i] = make_double2(out_v[2 * i], out_v[2 * i + 1]);
   }
-  if (a.tangent != nullptr) {
+  if (a.tangent != nullptr || a.tangent_r1 != nullptr) {
     // C = K 1(x)1 + 2 mu beta I_dev - 2 mu gamma n^(x)n^   (elastic: beta = 1, gamma = 0)
     double beta = 1.0, gam = 0.0;
     if (plastic) {
@@ -579,8 +587,17 @@ __global__ void __launch_bounds__(256) k_j2_update(const __grid_constant__ J2Arg
     double nh[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) nh[i] = s[i] * sc;
-    double2* to = reinterpret_cast<double2*>(a.tangent + 36 * n);
     const double m2b = 2.0 * mu * beta, m2g = 2.0 * mu * gam;
+    if (a.tangent_r1 != nullptr) {
+      double2* ro = reinterpret_cast<double2*>(a.tangent_r1 + (int64_t)J2_R1 * n);
+      ro[0] = make_double2(kb - m2b / 3.0, 0.5 * m2b);
+      ro[1] = make_double2(m2g, nh[0]);
+      ro[2] = make_double2(nh[1], nh[2]);
+      ro[3] = make_double2(nh[3], nh[4]);
+      ro[4] = make_double2(nh[5], 0.0);
+    }
+    if (a.tangent == nullptr) return;
+    double2* to = reinterpret_cast<double2*>(a.tangent + 36 * n);
 #pragma unroll
     for (int j = 0; j < 6; ++j) {  // column j (Fortran order: C_ij at i + 6 j)
       double col[6];
@@ -594,6 +611,32 @@ __global__ void __launch_bounds__(256) k_j2_update(const __grid_constant__ J2Arg
 #pragma unroll
       for (int i = 0; i < 3; ++i) to[3 * j + i] = make_double2(col[2 * i], col[2 * i + 1]);
     }
+  }
+}
+
+// (6,6,N) array from the structured form (for whoever reads sv["TangentMatrix"], and for the kernels that take the full
+// tangent): the same expression as in k_j2_update
+__global__ void __launch_bounds__(256) k_j2_tangent_expand(int64_t n_gp, const double* __restrict__ r1, double* __restrict__ tangent) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_gp) return;
+  const double* r = r1 + (int64_t)J2_R1 * n;
+  const double lamp = r[0], m2b = 2.0 * r[1], kap = r[2];
+  double nh[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) nh[i] = r[3 + i];
+  double2* to = reinterpret_cast<double2*>(tangent + 36 * n);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double col[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double v = -kap * nh[i] * nh[j];
+      if (i < 3 && j < 3) v += lamp;
+      if (i == j) v += (i < 3) ? m2b : 0.5 * m2b;
+      col[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) to[3 * j + i] = make_double2(col[2 * i], col[2 * i + 1]);
   }
 }
 

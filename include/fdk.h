@@ -286,6 +286,20 @@ int fdk_gp_temperature(int elem_type, int n_nodes, int64_t n_elems, const int32_
 int fdk_j2_update(int64_t n_gp, const double* props_h, const double* strain_gp, const double* statev_start,
                   double* stress_gp, double* statev, double* tangent_gp, fdk_stream_t stream);
 
+/* The same update returning the tangent in its STRUCTURED form: both J2 tangents (consistent / continuum) are
+ * C = lam' 1(x)1 + 2 mu' I_sym - kappa n^(x)n^ with n^ the unit deviatoric stress direction; tangent_r1 holds, per
+ * Gauss point (gp-major), the 10 doubles [lam', mu', kappa, n^ (6, stress Voigt), 0] -- 80 bytes instead of the 288 of
+ * the (6,6,N) array of the reference's protocol (fedoo/constitutivelaw/simcoon_umat.py:556-580).
+ * fdk_j2_tangent_expand rebuilds the (6,6,N) array (for sv["TangentMatrix"] readers and the other kernels);
+ * fdk_assemble_elastic_r1 assembles K = int B^T C B straight from the structured form (hex8, 3D, plan built with
+ * small = True; balanced kernel, 10 instead of 36 tangent operands per element and Gauss point in shared memory),
+ * and D = -int B^T stress_gp when FDK_VECTOR is set. */
+int fdk_j2_update_r1(int64_t n_gp, const double* props_h, const double* strain_gp, const double* statev_start,
+                     double* stress_gp, double* statev, double* tangent_r1, fdk_stream_t stream);
+int fdk_j2_tangent_expand(int64_t n_gp, const double* tangent_r1, double* tangent_gp, fdk_stream_t stream);
+int fdk_assemble_elastic_r1(const fdk_plan* plan, int compute, const double* coords, const double* tangent_r1,
+                            const double* stress_gp, double* K_values, double* D, fdk_stream_t stream);
+
 /* ------------------------------------------------------------------------- *
  * What the callers of the assembly do with K, on the device.  Replaces the
  * host-side elimination + solve of Problem.solve (fedoo/core/problem.py:277-298: MatCB^T A MatCB,

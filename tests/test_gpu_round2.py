@@ -319,3 +319,70 @@ def test_high_valence_rows_kernel(fd, golden_dir, name, elm, space, monkeypatch)
         assert np.array_equal(K.indptr, g["K_indptr"]) and np.array_equal(K.indices, g["K_indices"])
         assert nrm(K.data, g["K_data"]) <= TOL, kind
         assert nrm(np.array(a.get_global_vector()), g["D"]) <= TOL, kind
+
+
+def test_structured_j2_tangent(fd, golden_dir):
+    """The J2 tangent in its structured form (10 doubles per Gauss point: lam', mu', kappa, n^) against the (6,6,N)
+    array of the reference's protocol: (1) fdk_j2_update_r1 + fdk_j2_tangent_expand reproduce fdk_j2_update's tangent,
+    state and stress bit for bit, for both tangent definitions; (2) K assembled straight from the structured form
+    (fdk_assemble_elastic_r1) equals K assembled from the full array, and the oracle's K."""
+    import torch
+
+    from fedoo_b200 import _lib
+    from oracle import fedoo_oracle as fo
+
+    lib = _lib.load()
+    props = np.array([200e3, 0.3, 1e-5, 300.0, 1000.0, 0.3])
+    rng = np.random.default_rng(2)
+    N = 5000
+    eps = torch.from_numpy(np.ascontiguousarray((rng.standard_normal((6, N)) * 2e-3).T)).cuda()
+    sv0 = torch.zeros((N, 8), dtype=torch.float64, device="cuda")
+    for cont in (0, 1):
+        _lib.set_option("j2_continuum_tangent", cont)
+        try:
+            s_a, v_a = torch.empty((N, 6), dtype=torch.float64, device="cuda"), torch.empty((N, 8), dtype=torch.float64, device="cuda")
+            s_b, v_b = torch.empty_like(s_a), torch.empty_like(v_a)
+            C_a = torch.empty(N * 36, dtype=torch.float64, device="cuda")
+            r1 = torch.empty((N, 10), dtype=torch.float64, device="cuda")
+            C_b = torch.empty_like(C_a)
+            _lib.check(lib.fdk_j2_update(N, _lib.ptr(props), _lib.ptr(eps), _lib.ptr(sv0), _lib.ptr(s_a), _lib.ptr(v_a),
+                                         _lib.ptr(C_a), _lib.current_stream()), "fdk_j2_update")  # fmt: skip
+            _lib.check(lib.fdk_j2_update_r1(N, _lib.ptr(props), _lib.ptr(eps), _lib.ptr(sv0), _lib.ptr(s_b), _lib.ptr(v_b),
+                                            _lib.ptr(r1), _lib.current_stream()), "fdk_j2_update_r1")  # fmt: skip
+            _lib.check(lib.fdk_j2_tangent_expand(N, _lib.ptr(r1), _lib.ptr(C_b), _lib.current_stream()), "expand")
+            assert torch.equal(s_a, s_b) and torch.equal(v_a, v_b)
+            assert float((C_a - C_b).abs().max()) <= 1e-15 * float(C_a.abs().max())
+            assert float((v_a[:, 1] > 0).double().mean()) > 0.3
+            nh = r1[:, 3:9]
+            w = torch.tensor([1, 1, 1, 2, 2, 2.0], device="cuda", dtype=torch.float64)
+            yielded = r1[:, 2] != 0
+            assert float(((nh[yielded] ** 2 * w).sum(1) - 1).abs().max()) < 1e-13  # unit deviatoric direction
+            assert float(r1[:, 9].abs().max()) == 0.0
+        finally:
+            _lib.set_option("j2_continuum_tangent", 0)
+    # K through the two routes
+    g = np.load(os.path.join(golden_dir, "hex8_jitter.npz"))
+    Ks = {}
+    for structured in (True, False):
+        fd.Assembly.delete_memory()
+        fd.ModelingSpace("3D")
+        fd.Mesh(g["nodes"], g["elements"], "hex8", name="Domain")
+        law = fd.constitutivelaw.Simcoon("EPICP", list(props), name="law")
+        law.tangent = "consistent"
+        law.structured_tangent = structured
+        fd.weakform.StressEquilibrium(law, name="wf")
+        a = fd.Assembly.create("wf", "Domain", "hex8", name="A")
+        pb = fd.problem.Linear("A")
+        pb.set_X(g["U"] * 30.0)
+        a.update(pb, compute="all")
+        H = a.sv["TangentMatrix"]
+        assert isinstance(H, fd.constitutivelaw.StructuredTangent) == structured
+        Ks[structured] = (a.get_global_matrix().tocsr().data.copy(), np.array(a.get_global_vector()))
+        if structured:
+            assert np.asarray(H).shape == (6, 6, a.n_gauss_points) and H[0][1].shape == (a.n_gauss_points,)
+    assert nrm(Ks[True][0], Ks[False][0]) <= 1e-13 and np.array_equal(Ks[True][1], Ks[False][1])
+    G, wdet = fo.geometry(g["nodes"], g["elements"], "hex8")
+    eps_o = fo.strain_gp(G, g["elements"], g["U"] * 30.0, len(g["nodes"]), 3)
+    _, _, Ct = fo.j2_radial_return(eps_o, np.zeros((8, eps_o.shape[1])), props)
+    Kref = fo.assemble_stiffness(g["nodes"], g["elements"], "hex8", Ct, 3)
+    assert nrm(Ks[True][0], Kref.data) <= 1e-10
