@@ -661,26 +661,54 @@ def distributed_checks(asm, pb, loc, peer, exch, D_nccl, n, world, rank, jitter)
 # configs [2]-[4]: one GPU (N > 1: rank 0 runs, the others exit -- these configurations are not sharded yet)
 # ----------------------------------------------------------------------------------------------
 def run_other(args):
-    if int(os.environ.get("RANK", "0")) != 0:
+    """configs [2]-[4].  One GPU, except tet10 (the configuration BASELINE names "across 8 GPUs"): under torchrun its
+    nodes are partitioned by recursive coordinate bisection, every rank assembles the complete rows of the nodes it owns
+    from its local mesh (one halo layer of elements; no matrix exchange) and the owned slices of D are all-gathered over
+    NCCL (fedoo_b200.dist: partition_rcb / extract_local / VectorExchange) -- strong scaling, the global mesh is fixed.
+    The other configurations are not sharded: rank 0 runs, the others exit."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    cfg = args.config
+    sharded = world > 1 and cfg == "tet10"
+    if rank != 0 and not sharded:
         return
     import torch
+    import torch.distributed as dist
 
     import fedoo_b200 as fd
+    from fedoo_b200 import dist as fdist
 
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    cfg = args.config
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if sharded:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     nodes, elements, elm, _ = make_inputs(cfg, scale=args.scale)
     T0, U = dof_vector(cfg, nodes)
-    nn, n_el = len(nodes), len(elements)
+    nn_global, n_el = len(nodes), len(elements)
+    nvar = 1 if cfg == "heat_tet4" else 3
+    loc = exch = D_global = None
+    part_stats = None
+    glob = None
+    if sharded:
+        if args.check and n_el <= 400_000:
+            glob = (nodes, elements, U)  # small enough to redo on one GPU for the comparison
+        part = fdist.partition_rcb(nodes, world)  # deterministic: every rank computes the same partition
+        loc = fdist.extract_local(nodes, elements, part, rank)
+        U = np.concatenate([U[v * nn_global + loc.node_gid] for v in range(nvar)])
+        part_stats = dict(owned_nodes=int(loc.owned.sum()), local_nodes=len(loc.nodes), local_elements=len(loc.elements),
+                          halo_element_share=float(len(loc.elements) * world / n_el - 1.0))  # fmt: skip
+        nodes, elements = loc.nodes, loc.elements.astype(np.int32)
+    nn = len(nodes)
     fd.Assembly.delete_memory()
     fd.ModelingSpace("3D")
     fd.Mesh(nodes, elements, elm, name="Domain")
     U_host = torch.empty(U.size, dtype=torch.float64, pin_memory=True)
     U_host.copy_(torch.from_numpy(U))
+    kargs = dict(reuse_buffers=True, owned_nodes=(loc.owned if sharded else None))
     if cfg == "heat_tet4":
         fd.constitutivelaw.ThermalProperties(500.0, 0.5, 7800.0, name="ThermalLaw")
         fd.weakform.HeatEquation("ThermalLaw")
-        a = fd.Assembly.create("ThermalLaw", "Domain", name="A", reuse_buffers=True)
+        a = fd.Assembly.create("ThermalLaw", "Domain", name="A", **kargs)
         pb = fd.problem.NonLinear("A")
         pb.dtime = 10.0 / 3.0
         pb._U, pb._dU = T0.copy(), 0
@@ -695,14 +723,13 @@ def run_other(args):
         else:
             law = fd.constitutivelaw.ElasticIsotrop(1e5, 0.3, name="law")
         fd.weakform.StressEquilibrium(law, name="wf")
-        a = fd.Assembly.create("wf", "Domain", elm, name="A", reuse_buffers=True)
+        a = fd.Assembly.create("wf", "Domain", elm, name="A", **kargs)
         pb = fd.problem.Linear("A")
 
         def set_state(host):
             pb.set_X(host)
 
     U_dev = U_host.cuda()
-    nvar = 1 if cfg == "heat_tet4" else 3
 
     def set_state_device():
         if cfg == "heat_tet4":
@@ -710,12 +737,20 @@ def run_other(args):
         else:
             pb.set_X(U_dev)
 
+    def barrier():
+        if sharded:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     a.vector_on_device = True
     set_state_device()
     t0 = time.perf_counter()
     a.update(pb, compute="all")
     torch.cuda.synchronize()
     t_first = time.perf_counter() - t0
+    if sharded:
+        exch = fdist.VectorExchange(loc, nvar)
+        D_global = torch.zeros(nvar * nn_global, dtype=torch.float64, device="cuda")
     # the step: state update (J2: strain + radial return + tangent; elastic / heat: lazy, nothing materialised) + K + D
     full_update = cfg == "j2_plate"
 
@@ -724,30 +759,39 @@ def run_other(args):
             a.update(pb, compute="all")
         else:
             a.assemble_global_mat("all")
+        if exch is not None:
+            exch.allgather(a.global_vector, D_global)
 
     W = max(args.warmup, 3)
     for _ in range(W):
         step_device()
-    torch.cuda.synchronize()
+    barrier()
     torch.cuda.profiler.start()
     with Clocks(torch.cuda.current_device()) as clk:
         ms_total, _ = time_loop(torch, step_device, args.steps)
+        barrier()
     torch.cuda.profiler.stop()
-    ms_step = ms_total / args.steps
     # the dominant kernel alone: the matrix assembly
     _, ms_matrix = time_loop(torch, lambda: a.assemble_global_mat("matrix"), max(3, args.steps // 2))
+    t = torch.tensor([ms_total, ms_matrix], dtype=torch.float64, device="cuda")
+    if sharded:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_matrix = float(t[0]), float(t[1])
+    ms_step = ms_total / args.steps
     K = a.get_global_matrix()
-    nnz = int(K.data.numel())
+    nnz = int(K.data.numel()) if not sharded else nvar * nvar * int(a._plan(a._saved_bloc_structure).t["cl_slot_ptr"][-1])
     nne = elements.shape[1]
+    n_own_nodes = int(loc.owned.sum()) if sharded else nn
+    n_own_elems = n_el / world
     if cfg == "heat_tet4":
-        algo_k = 8 * nnz + 4 * nne * n_el + 8 * 3 * nn
-        algo_step = algo_k + 16 * nn
+        algo_k = 8 * nnz + 4 * nne * n_own_elems + 8 * 3 * n_own_nodes
+        algo_step = algo_k + 16 * n_own_nodes
     elif cfg == "tet10":
-        algo_k = 8 * nnz + 4 * nne * n_el + 8 * 3 * nn
-        algo_step = algo_k + 16 * 3 * nn
-    else:  # SURVEY 8d, fused J2: statev in/out, stress out, K, conn, coords, U, D (the tangent never leaves the SM)
+        algo_k = 8 * nnz + 4 * nne * n_own_elems + 8 * 3 * n_own_nodes
+        algo_step = algo_k + 16 * 3 * n_own_nodes
+    else:  # SURVEY 8d, fused J2: statev in/out, stress out, K, conn, coords, U, D (+ the structured tangent: 80 B per GP)
         n_gp = 8 * n_el
-        algo_k = 8 * nnz + 4 * nne * n_el + 8 * 3 * nn + n_gp * 8 * 36  # as built today the matrix kernel READS the tangent
+        algo_k = 8 * nnz + 4 * nne * n_el + 8 * 3 * nn + n_gp * 8 * 10  # the matrix kernel reads the structured tangent
         algo_step = 8 * nnz + 4 * nne * n_el + 8 * 3 * nn + 16 * 3 * nn + n_gp * 8 * (8 + 8 + 6)
     peak, peak_src = hbm_peak()
 
@@ -767,40 +811,75 @@ def run_other(args):
         return prev.result() if prev is not None else out
 
     e2e_loop(2)
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     Dh = e2e_loop(args.steps)
-    torch.cuda.synchronize()
+    barrier()
     e2e_s = (time.perf_counter() - t0) / args.steps
+    if sharded:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
     a.async_copies = False
 
     checks = None
-    if args.check:
+    if args.check and not sharded:
         checks = other_checks(cfg, a, pb, U, T0, nn)
+    elif args.check:
+        a.vector_on_device = True
+        step_device()
+        torch.cuda.synchronize()
+        s3 = torch.stack([D_global[v * nn_global : (v + 1) * nn_global].sum() for v in range(nvar)])
+        spread = torch.stack([D_global.sum(), -D_global.sum()])
+        dist.all_reduce(spread, op=dist.ReduceOp.MAX)
+        checks = {"D_sum_rel": float(s3.abs().max() / D_global.abs().max()),
+                  "D_identical_on_all_ranks": bool(float(spread[0] + spread[1]) == 0.0),
+                  "D_nonzero_fraction": float((D_global != 0).double().mean())}  # fmt: skip
+        if glob is not None:  # the whole mesh on this GPU alone: the gathered residual must be the one-GPU residual
+            D_multi = D_global.clone()
+            fd.Assembly.delete_memory()
+            fd.Mesh(glob[0], glob[1], elm, name="Whole")
+            a1 = fd.Assembly.create("wf", "Whole", elm, name="One", vector_on_device=True)
+            pb1 = fd.problem.Linear("One")
+            pb1.set_X(glob[2])
+            a1.update(pb1, compute="all")
+            err = (D_multi - a1.global_vector).abs().max() / a1.global_vector.abs().max()
+            dist.all_reduce(err, op=dist.ReduceOp.MAX)
+            checks["D_vs_single_gpu_rel"] = float(err)
+    if sharded:
+        stats_all = [None] * world
+        dist.all_gather_object(stats_all, dict(part_stats, clusters=int(a._plan(a._saved_bloc_structure).n_clusters),
+                                               heavy_nodes=int(a._plan(a._saved_bloc_structure).heavy_nodes.numel())))  # fmt: skip
+    if rank != 0:
+        dist.destroy_process_group()
+        return
     cb = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and not sharded:
         cb = cpu_baseline(cfg, args.cpu_n or CPU_SAMPLE_EDGE[cfg], 3, 1)
         cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    kernels = {"heat_tet4": "fdk::k_assemble_heat_tet4 (row-owner kernel) / fdk::k_assemble<Tet4, PHYS_HEAT>",
-               "tet10": "fdk::k_assemble<Tet10, PHYS_ISO>", "j2_plate": "fdk::k_assemble_iso<Hex8, 512, 4, PHYS_GENERAL>"}  # fmt: skip
+    kernels = {"heat_tet4": "fdk::k_heat_tet4_rows (row-owner kernel, K + D in one launch)",
+               "tet10": "fdk::k_assemble<Tet10, PHYS_ISO>", "j2_plate": "fdk::k_assemble_iso<Hex8, 512, 4, PHYS_R1>"}  # fmt: skip
     line = {
         "metric": METRICS[cfg],
         "value": n_el / (ms_step * 1e-3) / 1e6,
         "unit": "Melem/s",
-        "n_gpus": 1,
+        "n_gpus": world if sharded else 1,
         "steps": args.steps,
         "warmup": W,
         "ms_per_step": ms_step,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong" if sharded else "weak",
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
         "config": {
             "workload": workload_label(args),
-            "n_elements": n_el, "n_nodes": nn, "nnz": nnz,
-            "l2": f"{algo_step / 1e9:.2f} GB of compulsory traffic per step against a 126 MB L2; no flush needed",
-            "partition": "one GPU (this configuration is not sharded)",
+            "n_elements": n_el, "n_nodes": nn_global, "nnz": nnz if not sharded else None,
+            "l2": f"{algo_step / 1e9:.2f} GB of compulsory traffic per step and GPU against a 126 MB L2; no flush needed",
+            "partition": ("one GPU (this configuration is not sharded)" if not sharded else
+                          f"recursive coordinate bisection of the nodes over {world} GPUs, owner-computes rows, one halo layer of "
+                          "elements per rank, residual exchange: pack + NCCL all-gather of D + unpack"),
+            "ranks": stats_all if sharded else None,
             "first_call_s": t_first,
             "step": "Assembly.update(pb, 'all')" if full_update else "Assembly.assemble_global_mat('all')",
         },
@@ -827,12 +906,14 @@ def run_other(args):
             "note": "every step: pinned host dof vector -> HBM, state update + K + D, residual -> pinned host (async_copies); "
             "K and the Gauss-point state stay in HBM",
         },
-        "gpu_launches": args.steps * {"heat_tet4": 3, "tet10": 1, "j2_plate": 5}[cfg],
+        "gpu_launches": args.steps * ({"heat_tet4": 1, "tet10": 1, "j2_plate": 5}[cfg] + (2 if sharded else 0)),
         "clocks": clk.summary(),
     }
     if checks is not None:
         line["checks"] = checks
     print(json.dumps(line), flush=True)
+    if sharded:
+        dist.destroy_process_group()
 
 
 def other_checks(cfg, a, pb, U, T0, nn):

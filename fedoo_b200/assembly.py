@@ -34,6 +34,7 @@ _DEFAULT_NGP = {"hex8": 8, "tet4": 4, "tet10": 15, "quad4": 4}  # fedoo/lib_elem
 
 
 _RESIDUAL_KERNEL = os.environ.get("FDK_RESIDUAL_KERNEL", "1") != "0"  # 0: residual-only through the cluster kernels
+_TET10_BIG = os.environ.get("FDK_TET10_BIG", "0") != "0"  # tet10 + isotropic law through the balanced 1024-thread kernel
 _HEAT_TET4_ROWS = os.environ.get("FDK_HEAT_TET4_ROWS", "1") != "0"  # 0: tet4 heat through the cluster kernel
 
 
@@ -194,6 +195,15 @@ class Assembly(_Named):
         )  # fmt: skip
         _lib.check(rc, "fdk_assemble_rows_elastic")
 
+    def _big_plan(self, entry):
+        """Plan with clusters for 1024-thread CTAs (tet10 + isotropic law: csrc/fdk_assemble_iso.cuh with 5 threads per
+        incidence), built on first use."""
+        if "plan_big" not in entry:
+            coords, conn = self.mesh.device_arrays()
+            owned = None if self.owned_nodes is None else torch.from_numpy(np.asarray(self.owned_nodes, dtype=bool))
+            entry["plan_big"] = symbolic.build_plan(self.elm_type, coords, conn, entry["pattern"], owned=owned, big=True)
+        return entry["plan_big"]
+
     def _small_plan(self, entry):
         """Second cluster plan of the same pattern with half-size (16-node hex8) clusters, built on first use."""
         if "plan_small" not in entry:
@@ -314,12 +324,16 @@ class Assembly(_Named):
                     peer.barrier()
                 elif isinstance(law, ElasticIsotrop) and tangent_dev is None:
                     lam, mu = law.lame(dimension)
+                    plan = self._plan(entry)
+                    if (self.elm_type == "tet10" and _TET10_BIG and want_mat and (U_dev is not None or not has_vec)
+                            and stress_dev is None):
+                        plan = self._big_plan(entry)  # 1024-thread clusters for the balanced kernel
                     rc = lib.fdk_assemble_elastic_iso(
-                        C.byref(self._plan(entry).struct(nvar)), flags, _lib.ptr(coords), lam, mu, _lib.ptr(U_dev),
+                        C.byref(plan.struct(nvar)), flags, _lib.ptr(coords), lam, mu, _lib.ptr(U_dev),
                         _lib.ptr(stress_dev), _lib.ptr(K), _lib.ptr(D), stream,
                     )  # fmt: skip
                     _lib.check(rc, "fdk_assemble_elastic_iso")
-                    self._heavy_rows(entry, self._plan(entry), flags, coords, True, lam, mu, None, None, U_dev, stress_dev, K, D)
+                    self._heavy_rows(entry, plan, flags, coords, True, lam, mu, None, None, U_dev, stress_dev, K, D)
                 elif (getattr(law, "tangent_r1_device", None) is not None and law.tangent_r1_device(self) is not None
                         and self.elm_type == "hex8" and nvar == 3 and want_mat):
                     # J2 tangent in its structured form: the balanced kernel reads 10 doubles per (element, Gauss point)

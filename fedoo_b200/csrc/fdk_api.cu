@@ -172,6 +172,12 @@ int fdk_assemble_elastic_iso(const fdk_plan* plan, int compute, const double* co
   if (g_opt_iso4 && (compute & FDK_MATRIX) && !bts && plan->elem_type == FDK_HEX8 && plan->threads == Hex8::THREADS &&
       plan->blk_slot && plan->ent_pos && assemble_iso_fits<Hex8, 1024, 4>(a))
     return launch_assemble_iso<Hex8, 1024, 4>(a, (cudaStream_t)stream);
+  // tet10 plans built for 1024-thread CTAs (fedoo_b200/plan.py, _CAPS_BIG): the balanced organisation with 5 threads
+  // per incidence (two column blocks each, as for hex8) -- 32 warps per SM instead of the generic kernel's 8
+  if (g_opt_iso4 && (compute & FDK_MATRIX) && !bts && plan->elem_type == FDK_TET10 && plan->threads == 1024 &&
+      assemble_iso_fits<Tet10, 1024, 5>(a))
+    return launch_assemble_iso<Tet10, 1024, 5>(a, (cudaStream_t)stream);
+  FDK_REQUIRE(plan->threads != 1024, FDK_ECAP, "plan built for 1024-thread clusters does not fit the balanced kernel");
   return dispatch_assemble<PHYS_ISO>(a, (cudaStream_t)stream);
 }
 

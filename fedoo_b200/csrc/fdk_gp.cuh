@@ -530,30 +530,39 @@ __global__ void __launch_bounds__(256) k_j2_update(const __grid_constant__ J2Arg
   const double pm = (sig[0] + sig[1] + sig[2]) / 3.0;
   double s[6] = {sig[0] - pm, sig[1] - pm, sig[2] - pm, sig[3], sig[4], sig[5]};
   const double q = sqrt(1.5 * (s[0] * s[0] + s[1] * s[1] + s[2] * s[2] + 2.0 * (s[3] * s[3] + s[4] * s[4] + s[5] * s[5])));
-  const double R0 = (p0 > 0.0) ? a.k * pow(p0, a.m) : 0.0;
+  // x^m as exp(m log x): half the cost of pow(), and the logarithm is all the iteration needs beside it
+  const double R0 = (p0 > 0.0) ? a.k * exp(a.m * log(p0)) : 0.0;
   const double ftr = q - a.sigY - R0;
   double dp = 0.0;
   double Rp = 0.0;
   const bool plastic = ftr > 0.0;
   if (plastic) {
+    // root of f(x) = q - 3 mu x - sigY - k (p0 + x)^m on (0, hi]: f is convex and decreasing, so Newton from a point where
+    // f > 0 climbs monotonically to the root; from f < 0 it lands left of it first.  Two upper bounds of the root:
+    // 3 mu x <= f_trial, and k (p0 + x)^m - R0 <= f_trial (the second one is the tight one just past first yield, where
+    // the hardening slope k m p^(m-1) is huge).  Safeguarded by bisection on [lo, hi].
     const double m3 = 3.0 * mu;
-    double lo = 0.0, hi = ftr / m3, x = hi;
+    double hi = ftr / m3;
+    if (a.k > 0.0) {
+      const double h2 = exp(log((ftr + R0) / a.k) / a.m) - p0;
+      if (h2 > 0.0 && h2 < hi) hi = h2;
+    }
+    double lo = 0.0, x = hi, dR = 1e300;
     for (int it = 0; it < 60; ++it) {
       const double pp = p0 + x;
-      const double pw = (pp > 0.0) ? pow(pp, a.m) : 0.0;
+      const double pw = (pp > 0.0) ? exp(a.m * log(pp)) : 0.0;
       const double fx = q - m3 * x - a.sigY - a.k * pw;
       if (fx < 0.0) hi = fmin(hi, x);
       if (fx > 0.0) lo = fmax(lo, x);
-      const double dR = (pp > 0.0) ? a.k * a.m * pw / pp : 1e300;
+      dR = (pp > 0.0) ? a.k * a.m * pw / pp : 1e300;
       double xn = x + fx / (m3 + dR);
-      if (!(xn > lo && xn < hi) || !isfinite(xn)) xn = 0.5 * (lo + hi);
+      if (!(xn >= lo && xn <= hi) || !isfinite(xn)) xn = 0.5 * (lo + hi);
       const bool done = fabs(xn - x) <= 1e-14 * fmax(fabs(xn), 1e-300);
       x = xn;
       if (done) break;
     }
     dp = x;
-    const double pn = p0 + dp;
-    Rp = (pn > 0.0) ? a.k * a.m * pow(pn, a.m - 1.0) : 1e300;
+    Rp = dR;  // k m p^(m-1) at the last iterate: equal to the end-state slope to the iteration's own tolerance
   }
   const double qs = (q > 0.0) ? q : 1.0;
   double nf[6];

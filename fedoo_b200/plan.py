@@ -30,7 +30,7 @@ from . import _lib
 _CAPS = {
     "hex8": dict(nne=8, ngp=8, dim=3, inc_max=256, te_max=80, shift=5),
     "tet4": dict(nne=4, ngp=4, dim=3, inc_max=256, te_max=256, shift=4),
-    "tet10": dict(nne=10, ngp=15, dim=3, inc_max=128, te_max=36, shift=3),
+    "tet10": dict(nne=10, ngp=15, dim=3, inc_max=128, te_max=36, shift=5),
     "quad4": dict(nne=4, ngp=4, dim=2, inc_max=256, te_max=400, shift=6),
 }
 # CTA sizes the kernels are instantiated for (csrc/fdk_common.cuh ElemTraits::THREADS and half of it):
@@ -43,6 +43,8 @@ _CAPS_SMALL = {
     "quad4": dict(inc_max=128, te_max=200, shift=5),
 }
 HEAVY_T = 4  # slots with more contributions are pre-reduced by a balanced pass (csrc/fdk_assemble.cuh)
+# "big" variant (tet10 + isotropic law): clusters for the balanced 1024-thread kernel, 5 threads per incidence
+_CAPS_BIG = {"tet10": dict(inc_max=204, te_max=32, shift=4)}
 TN_MAX = 255
 ENT_MAX = 65535
 
@@ -140,7 +142,7 @@ class Plan:
     """Cluster plan for one (mesh connectivity, element type).  Holds the device tensors and
     the C struct handed to the kernels."""
 
-    def __init__(self, elem_type, coords, conn, pattern, caps=None, verbose=False, owned=None, small=None):
+    def __init__(self, elem_type, coords, conn, pattern, caps=None, verbose=False, owned=None, small=None, big=False):
         """``owned``: optional bool mask (n_nodes,) -- only these nodes get clusters (their rows are
         assembled); used by the multi-GPU partition where a rank's local mesh carries halo nodes.
         ``small``: half-size clusters / CTAs, two resident per SM (default: env FDK_SMALL_CTA, else on)."""
@@ -153,11 +155,16 @@ class Plan:
             small = (elem_type != "hex8") if env is None else (env != "0")
         cap = dict(_CAPS[elem_type])
         self.threads = _THREADS[elem_type]
-        if small and elem_type in _CAPS_SMALL:  # tet10: one vertex node alone can touch > 18 elements
+        if big and elem_type in _CAPS_BIG:
+            cap.update(_CAPS_BIG[elem_type])
+            self.threads = 1024
+        elif small and elem_type in _CAPS_SMALL:  # tet10: one vertex node alone can touch > 18 elements
             cap.update(_CAPS_SMALL[elem_type])
             self.threads //= 2
         if caps:
             cap.update(caps)
+        if os.environ.get("FDK_PLAN_SHIFT"):  # diagnostic: initial cluster size (log2 of Morton cells), refined down as needed
+            cap["shift"] = int(os.environ["FDK_PLAN_SHIFT"])
         assert 2 * cap["inc_max"] <= self.threads
         self.elem_type = elem_type
         dev = conn.device
