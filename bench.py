@@ -53,8 +53,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-n", type=int, default=0, help="edge of the bounded CPU sample (0: per-config default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: residual exchange fused into the kernel over NVLink peer memory, or NCCL all-gather")
+    ap.add_argument("--exchange", default="copy", choices=["copy", "peer", "nccl"],
+                    help="N > 1, residual exchange: copy = one coalesced copy of the owned slices to the NVLink multicast "
+                    "address after the kernel; peer = stores fused into the assembly kernel; nccl = pack + all-gather + unpack")
     ap.add_argument("--check", action="store_true", help="verify size-independent properties of the assembled K, D")
     return ap.parse_args()
 
@@ -397,9 +398,9 @@ def run_hex8(args):
     # failed symmetric-memory rendezvous: pack + NCCL all-gather + unpack (fedoo_b200.dist.VectorExchange)
     exch = peer = D_nccl = None
     if world > 1:
-        if args.exchange == "peer":
+        if args.exchange in ("peer", "copy"):
             try:
-                peer = fdist.PeerVector(loc, 3)
+                peer = fdist.PeerVector(loc, 3, mode=("fused" if args.exchange == "peer" else "copy"))
                 asm.peer_vector = peer
             except Exception as e:  # noqa: BLE001
                 if rank == 0:
@@ -522,8 +523,10 @@ def run_hex8(args):
                 "l2": "working set (>= 16 GB written per step at n=200) far exceeds the 126 MB L2; no flush needed",
                 "partition": f"z-slabs of nodes over {world} GPU(s), owner-computes rows, residual exchange: "
                 + ("none (1 GPU)" if world == 1 else
-                   ("fused into the assembly kernel: stores over NVLink into a symmetric, double-buffered global vector ("
-                    + ("NVSwitch multicast" if peer.multicast else "peer addresses") + ") + device barrier"
+                   ((("fused into the assembly kernel: stores" if peer.mode == "fused" else
+                      "one coalesced segment copy of the owned slices after the kernel")
+                     + " over NVLink into a symmetric, double-buffered global vector ("
+                     + ("NVSwitch multicast" if peer.multicast else "peer addresses") + ") + device barrier")
                     if peer is not None else "pack + NCCL all-gather of D + unpack")),
                 "nnz": 9 * pattern.blk_nnz if world == 1 else None,
                 "nnz_per_s": (9 * (3 * n + 1) ** 3) / (ms_step * 1e-3),
@@ -557,7 +560,8 @@ def run_hex8(args):
                 "buffers (async_copies); K stays in HBM (DeviceCSR, materialised to scipy only on demand)",
             },
             # the assembly kernel, plus pack / unpack of the residual exchange (NCCL's own kernels not counted)
-            "gpu_launches": args.steps * (1 if exch is None else (3 if exch.seg_pack is not None else 6)),
+            "gpu_launches": args.steps * ((1 if peer is None or peer.mode == "fused" else 2) if exch is None
+                                          else (3 if exch.seg_pack is not None else 6)),
             "clocks": clk.summary(),
         }
         if checks is not None:

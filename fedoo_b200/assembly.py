@@ -310,7 +310,7 @@ class Assembly(_Named):
                 if flags == _lib.VECTOR and done_vec:
                     pass
                 elif (isinstance(law, ElasticIsotrop) and tangent_dev is None and peer is not None and flags == _lib.ALL
-                        and U_dev is not None and stress_dev is None):
+                        and U_dev is not None and stress_dev is None and getattr(peer, "mode", "fused") == "fused"):
                     # multi-GPU: the kernel stores the owned residual entries straight into every rank's global vector
                     lam, mu = law.lame(dimension)
                     dst, n_dst = peer.begin_step()  # the half of the double-buffered symmetric vector this step writes
@@ -334,6 +334,9 @@ class Assembly(_Named):
                     )  # fmt: skip
                     _lib.check(rc, "fdk_assemble_elastic_iso")
                     self._heavy_rows(entry, plan, flags, coords, True, lam, mu, None, None, U_dev, stress_dev, K, D)
+                    if peer is not None and has_vec:  # multi-GPU, "copy" mode: one coalesced copy of the owned slices
+                        peer.publish(D)
+                        peer.barrier()
                 elif (getattr(law, "tangent_r1_device", None) is not None and law.tangent_r1_device(self) is not None
                         and self.elm_type == "hex8" and nvar == 3 and want_mat):
                     # J2 tangent in its structured form: the balanced kernel reads 10 doubles per (element, Gauss point)

@@ -255,11 +255,17 @@ class PeerVector:
     own addresses when no multicast object could be created.  Replaces pack + NCCL all-gather + unpack
     (``VectorExchange``) by ``fdk_assemble_elastic_iso_dist`` + a device-side barrier."""
 
-    def __init__(self, local: LocalMesh, nvar: int, group=None):
+    def __init__(self, local: LocalMesh, nvar: int, group=None, mode="copy"):
+        """``mode``: "fused" -- the assembly kernel itself stores every owned entry to the multicast / peer addresses as
+        soon as its cluster is done (8-byte stores scattered in Morton order: the transfer overlaps the assembly, but
+        every store is its own NVLink packet); "copy" -- the kernel writes the rank-local vector only and ONE
+        segment-copy launch then streams the owned slices (contiguous for slab partitions) to the multicast address with
+        coalesced stores.  Measured on 8 B200 (round 2, 200^3 hex8): see DESIGN.md section 5."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
 
         self.group = group or dist.group.WORLD
+        self.mode = mode
         self.nvar, self.n_global = nvar, local.n_global_nodes
         dev = torch.device("cuda", torch.cuda.current_device())
         # DOUBLE-BUFFERED: step k stores into half k % 2.  A rank can only launch step k + 1 after it has passed the
@@ -279,8 +285,28 @@ class PeerVector:
         self._arrays = [(C.c_void_p * len(d))(*d) for d in self._dst]
         self._half = 1  # half written by the LAST step (begin_step flips it)
         self.node_gid = torch.from_numpy(np.ascontiguousarray(local.node_gid, dtype=np.int64)).to(dev)
+        # "copy" mode: the owned nodes must be one run of local AND of global ids (slab partitions)
+        own_l = np.nonzero(local.owned)[0]
+        self._seg = None
+        if len(own_l) and np.array_equal(own_l, np.arange(own_l[0], own_l[0] + len(own_l))):
+            g = np.asarray(local.node_gid)[own_l]
+            if np.array_equal(g, np.arange(g[0], g[0] + len(g))):
+                n_loc = len(local.nodes)
+                rows = np.array([(v * n_loc + own_l[0], v * self.n_global + g[0], len(own_l)) for v in range(nvar)], dtype=np.int64)
+                self._seg = tuple(torch.from_numpy(np.ascontiguousarray(rows[:, k])).to(dev) for k in range(3)) + (len(own_l),)
+        if mode == "copy" and self._seg is None:
+            raise ValueError("PeerVector(mode='copy') needs owned nodes that are contiguous in local and global numbering")
         torch.cuda.synchronize()
         self.handle.barrier()
+
+    def publish(self, D_local):
+        """"copy" mode: stream the owned slices of the rank-local vector into this step's half of every rank's copy."""
+        lib = _lib.load()
+        self._half ^= 1
+        ss, sd, sl, mx = self._seg
+        for dst in self._dst[self._half]:
+            _lib.check(lib.fdk_copy_segments(self.nvar, _lib.ptr(ss), _lib.ptr(sd), _lib.ptr(sl), mx, _lib.ptr(D_local),
+                                             C.c_void_p(dst), _lib.current_stream()), "fdk_copy_segments")  # fmt: skip
 
     @property
     def tensor(self):
