@@ -177,7 +177,11 @@ int fdk_assemble_elastic_iso(const fdk_plan* plan, int compute, const double* co
   if (g_opt_iso4 && (compute & FDK_MATRIX) && !bts && plan->elem_type == FDK_TET10 && plan->threads == 1024 &&
       assemble_iso_fits<Tet10, 1024, 5>(a))
     return launch_assemble_iso<Tet10, 1024, 5>(a, (cudaStream_t)stream);
-  FDK_REQUIRE(plan->threads != 1024, FDK_ECAP, "plan built for 1024-thread clusters does not fit the balanced kernel");
+  if (g_opt_iso4 && (compute & FDK_MATRIX) && !bts && plan->elem_type == FDK_TET10 && plan->threads == 768 &&
+      assemble_iso_fits<Tet10, 768, 5>(a))
+    return launch_assemble_iso<Tet10, 768, 5>(a, (cudaStream_t)stream);
+  FDK_REQUIRE(plan->threads != 1024 && plan->threads != 768, FDK_ECAP,
+              "plan built for %d-thread clusters does not fit the balanced kernel", plan->threads);
   return dispatch_assemble<PHYS_ISO>(a, (cudaStream_t)stream);
 }
 

@@ -109,12 +109,24 @@ struct IsoLayout {
   __host__ __device__ static long stage_doubles(const fdk_plan& p) {
     return COLORED ? (long)((p.cap_inc + 3) / 4) * 32 * BLK : (long)p.cap_inc * ISTR;
   }
-  static constexpr int ESTR = (NNE == 8 && DIM == 3) ? 216 : L::ESTR;
-  static constexpr int TSTR = (GROW + 2) & ~1;  // even: the reference gradients are read as 128-bit node pairs
+  // Gauss points per geometry CHUNK: an element's sqrt(w) dN/dx takes NGP * GSTR doubles of shared memory (tet10: 15 x 34 =
+  // 4 KB), which caps the touched elements of a cluster -- tet10 clusters then hold one vertex node and its mid-edge
+  // neighbours (8 nodes, 60 incidences) and most threads idle.  With GCH < NGP the geometry and block phases run NGP / GCH
+  // times over GCH Gauss points each (the accumulators stay in registers across the chunks), so a cluster can touch
+  // NGP / GCH times more elements for the same shared memory.
+  static constexpr int GCH = (El::ID == FDK_TET10) ? 5 : NGP;
+  static constexpr int NCH = NGP / GCH;
+  static_assert(NGP % GCH == 0, "chunks cover the Gauss points");
+  static constexpr int ESTR_C = ((GCH * GSTR) / 2) % 2 ? GCH * GSTR : GCH * GSTR + 2;
+  static constexpr int ESTR = (NNE == 8 && DIM == 3) ? 216 : (NCH == 1 ? L::ESTR : ESTR_C);
+  // even (the reference gradients are read as 128-bit node pairs) and an ODD number of 16-byte units, so that the rows
+  // of the Gauss points the lanes of a warp work on start in different bank groups (hex8: 26, tet10: 34 -- 32 would put
+  // every Gauss point's row on the same banks)
+  static constexpr int TSTR = (((GROW + 2) & ~1) / 2) % 2 ? ((GROW + 2) & ~1) : ((GROW + 2) & ~1) + 2;
   static_assert(NNE % 2 == 0, "node pairs");
   static constexpr int XSTR = 4;  // padded coordinates of a touched node: one 128-bit + one 64-bit load
   static constexpr int TAB_DOUBLES = (NGP * TSTR + NGP + 1) & ~1;
-  static_assert(ISTR >= NNE * BLK && ESTR >= NGP * GSTR, "strides cover the rows");
+  static_assert(ISTR >= NNE * BLK && ESTR >= GCH * GSTR, "strides cover the rows");
 
   __host__ __device__ static int xu_doubles(const fdk_plan& p) { return (p.cap_tn * (XSTR + NV) + 1) & ~1; }
   // staging of the blocks; the per-slot K.u products live BEHIND both views of the big region so that the
@@ -163,6 +175,8 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
   constexpr int NNE = IL::NNE, NGP = IL::NGP, DIM = IL::DIM, NV = IL::NV, BLK = IL::BLK, ISTR = IL::ISTR;
   constexpr int GROW = IL::GROW, GSTR = IL::GSTR, ESTR = IL::ESTR, TSTR = IL::TSTR, NH = IL::NH, XSTR = IL::XSTR;
   constexpr int INC = THREADS / TPI;  // incidences per cluster <= INC
+  constexpr int GCH = IL::GCH, NCH = IL::NCH;  // Gauss points per chunk, chunks
+  static_assert(NCH == 1 || PHYS == PHYS_ISO, "chunked Gauss points: isotropic path only");
   const fdk_plan& p = a.p;
   const int tid = threadIdx.x;
   const bool fuse_ku = a.fuse_ku != 0;
@@ -174,8 +188,9 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
   const int it = PART_UNIFORM ? tid % INC : tid / TPI;    // incidence of this thread (phase 2)
   const int part = PART_UNIFORM ? tid / INC : tid % TPI;  // its column blocks
   // column block jj of this thread: part*NH + jj (contiguous) or part + jj*TPI (interleaved)
-  auto col = [&](int jj) { return PART_UNIFORM ? part * NH + jj : (COLORED ? iso_col(part, jj) : part + jj * TPI); };
-  constexpr bool ADJ = COLORED && ISO_COLS_ADJ;  // the thread's two columns are adjacent: 6 contiguous doubles
+  // the thread's two columns are adjacent (2 part, 2 part + 1): 6 contiguous doubles of dN/dx, three 128-bit loads
+  constexpr bool ADJ = ISO_COLS_ADJ && NH == 2 && !PART_UNIFORM && DIM == 3;
+  auto col = [&](int jj) { return PART_UNIFORM ? part * NH + jj : ((COLORED || ADJ) ? iso_col(part, jj) : part + jj * TPI); };
   constexpr bool HEXREF = IL::HEXREF;  // reflected geometry layout (HexRef)
 
   extern __shared__ __align__(16) double smem[];
@@ -319,13 +334,18 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
       for (int t = first; t < (n_ent + 1) / 2; t += stride) cp_async<4>(sEnt + 2 * t, esrc + 2 * t);
       for (int t = first; t < n_heavy; t += stride) cp_async<4>(sHeavy + t, p.heavy_slot + h0 + t);
     };
-    const int n_task = n_te * NGP;
+    const int n_task = n_te * GCH;
     const bool desc_early = n_task + 128 <= THREADS;  // uniform over the CTA
     if (desc_early && tid >= n_task) fetch_desc(tid - n_task, THREADS - n_task);
 
+    double acc[NH][BLK];
+    [[maybe_unused]] double f[NV];
+
+#pragma unroll 1
+    for (int ch = 0; ch < NCH; ++ch) {  // chunks of GCH Gauss points (one chunk unless IL::GCH < NGP)
     // ---------------- phase 1: sqrt(w) dN/dx per (touched element, Gauss point) ----------------
-    for (int task = tid; task < n_te * NGP; task += THREADS) {
-      const int le = task / NGP, g = task - le * NGP;
+    for (int task = tid; task < n_te * GCH; task += THREADS) {
+      const int le = task / GCH, gl = task - le * GCH, g = ch * GCH + gl;
       const unsigned char* lc = sLconn + le * NNE;
       const double* dN = sdN + g * TSTR;
       int ln[NNE];
@@ -342,7 +362,7 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
           xe[2] = x2;
         }
         {
-          const int left = n_te * NGP - (task - (tid & 31));  // tasks of this warp's round: the first `left` lanes are here
+          const int left = n_te * GCH - (task - (tid & 31));  // tasks of this warp's round: the first `left` lanes are here
           __syncwarp(left >= 32 ? 0xffffffffu : ((1u << left) - 1u));
         }
         const int gxv = HexRef::gx(g);
@@ -408,7 +428,7 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
         }
       }
       // G[k][x] = sum_r iJ[x][r] dN[r][k], stored [k][x] as 128-bit pairs
-      double2* out = reinterpret_cast<double2*>(sG + le * ESTR + g * GSTR);
+      double2* out = reinterpret_cast<double2*>(sG + le * ESTR + gl * GSTR);
 #pragma unroll
       for (int k = 0; k < NNE; k += 2) {
         double2 dn[DIM];
@@ -433,15 +453,17 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
         for (int t = 0; t < DIM; ++t) out[(k * DIM) / 2 + t] = make_double2(v[2 * t], v[2 * t + 1]);
       }
     }
-    if (has_next) load_node_ids(nxt);  // consumed after phase 2
-    if constexpr (GEN) {
-      if (has_next && (per_gp || do_bts)) nxt_te_elem = load_te_elem(nxt);
+    if (ch == 0) {
+      if (has_next) load_node_ids(nxt);  // consumed after phase 2
+      if constexpr (GEN) {
+        if (has_next && (per_gp || do_bts)) nxt_te_elem = load_te_elem(nxt);
+      }
     }
-    __syncthreads();                   // B2: geometry complete
+    __syncthreads();                   // B2: geometry (of this chunk) complete
     FDK_CLK(2)
 
     // ---------------- the rest of the gather descriptors (land during phase 2) ----------------
-    {
+    if (ch == 0) {
       if (!desc_early) fetch_desc(tid, THREADS);
       for (int t = tid; t < n_owned; t += THREADS) {  // read by the residual reduction of the previous cluster:
         cp_async<4>(sSlotBase + t, p.cl_slot_loc + q0 + t);  // only now, after every warp has passed it
@@ -455,14 +477,14 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
     }
 
     // ---------------- phase 2: NH column blocks of one incidence per thread ----------------
-    double acc[NH][BLK];
+    if (ch == 0) {
 #pragma unroll
-    for (int j = 0; j < NH; ++j)
+      for (int j = 0; j < NH; ++j)
 #pragma unroll
-      for (int b = 0; b < BLK; ++b) acc[j][b] = 0.0;
-    [[maybe_unused]] double f[NV];
+        for (int b = 0; b < BLK; ++b) acc[j][b] = 0.0;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) f[v] = 0.0;
+      for (int v = 0; v < NV; ++v) f[v] = 0.0;
+    }
     if (it < n_inc) {
       const int le = my_desc & 0xFFF, i = my_desc >> 12;
       const double* gi_p = sG + le * ESTR + i * DIM;
@@ -472,14 +494,15 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
       if constexpr (!GEN) {
         constexpr int UNR = HEXREF ? NGP : P2_UNROLL;  // reflected layout: the Gauss point must be a compile-time value
 #pragma unroll UNR
-        for (int g = 0; g < NGP; ++g) {
+        for (int gl = 0; gl < GCH; ++gl) {
+          [[maybe_unused]] const int g = ch * GCH + gl;  // Gauss point; gl = its row in the chunk's geometry
           double gi[DIM];
           double gj[NH][DIM];
           if constexpr (HEXREF) {
             // node i sits at position pi_g(i); the thread's column pair (2 part, 2 part + 1) at pair slot
             // part ^ (iy + 2 iz), in swapped order when ix ^ iy (all of it folded at compile time but `part`, `ci`)
             const int gxv = HexRef::gx(g);
-            const double* gp = ge_p + g * GSTR;
+            const double* gp = ge_p + gl * GSTR;
             const double* gip = gp + HexRef::perm(ci, gxv) * DIM;
 #pragma unroll
             for (int d = 0; d < DIM; ++d) gi[d] = gip[d];
@@ -494,9 +517,9 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
             gj[swp ? 0 : 1][2] = v2.y;
           } else {
 #pragma unroll
-          for (int d = 0; d < DIM; ++d) gi[d] = gi_p[g * GSTR + d];
+          for (int d = 0; d < DIM; ++d) gi[d] = gi_p[gl * GSTR + d];
           if constexpr ((PART_UNIFORM || ADJ) && (NH * DIM) % 2 == 0) {  // contiguous columns: 128-bit loads
-            const double2* g2 = reinterpret_cast<const double2*>(gj_p + g * GSTR);
+            const double2* g2 = reinterpret_cast<const double2*>(gj_p + gl * GSTR);
 #pragma unroll
             for (int t = 0; t < NH * DIM / 2; ++t) {
               const double2 v = g2[t];
@@ -507,7 +530,7 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
 #pragma unroll
             for (int j = 0; j < NH; ++j)
 #pragma unroll
-              for (int d = 0; d < DIM; ++d) gj[j][d] = gj_p[g * GSTR + (col(j) - col(0)) * DIM + d];
+              for (int d = 0; d < DIM; ++d) gj[j][d] = gj_p[gl * GSTR + (col(j) - col(0)) * DIM + d];
           }
           }
 #pragma unroll
@@ -652,6 +675,8 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
         }
       }
     }
+    if (ch + 1 < NCH) __syncthreads();  // the next chunk's geometry overwrites this one
+    }  // chunks
     if (has_next) fetch_inputs(nxt, buf ^ 1);  // lands during the gather
     else cp_async_commit();
     __syncthreads();  // B3: everyone is done reading the geometry; the region becomes the staging array

@@ -44,7 +44,7 @@ _CAPS_SMALL = {
 }
 HEAVY_T = 4  # slots with more contributions are pre-reduced by a balanced pass (csrc/fdk_assemble.cuh)
 # "big" variant (tet10 + isotropic law): clusters for the balanced 1024-thread kernel, 5 threads per incidence
-_CAPS_BIG = {"tet10": dict(inc_max=204, te_max=32, shift=4)}
+_CAPS_BIG = {"tet10": dict(inc_max=204, te_max=80, shift=7)}  # 5 Gauss points per geometry chunk: 1.4 KB per element
 TN_MAX = 255
 ENT_MAX = 65535
 
@@ -157,7 +157,8 @@ class Plan:
         self.threads = _THREADS[elem_type]
         if big and elem_type in _CAPS_BIG:
             cap.update(_CAPS_BIG[elem_type])
-            self.threads = 1024
+            self.threads = int(os.environ.get("FDK_BIG_THREADS", "1024"))  # 1024 or 768 threads, 5 per incidence
+            cap["inc_max"] = min(cap["inc_max"], self.threads // 5)
         elif small and elem_type in _CAPS_SMALL:  # tet10: one vertex node alone can touch > 18 elements
             cap.update(_CAPS_SMALL[elem_type])
             self.threads //= 2
