@@ -207,7 +207,22 @@ class ElastoPlasticity(ConstitutiveLaw):
         statev = torch.empty((N, 8), dtype=torch.float64, device=dev)
         props = self.props
         _lib.check(lib.fdk_set_option(b"j2_continuum_tangent", int(self.tangent == "continuum")), "fdk_set_option")
-        if self.structured_tangent:
+        lazy_U = getattr(strain, "U", None) if (getattr(strain, "_dev", 0) is None and not getattr(strain, "fbar", False)) else None
+        if self.structured_tangent and lazy_U is not None:
+            # strain not materialised yet: geometry, grad u, strain and the radial return in one pass (fdk_j2_update_from_dofs);
+            # sv["Strain"] stays lazy
+            r1 = torch.empty((N, 10), dtype=torch.float64, device=dev)
+            coords, conn = assembly._coords(), assembly.mesh.device_arrays()[1]
+            _lib.check(
+                lib.fdk_j2_update_from_dofs(
+                    _lib.ELEM_IDS[assembly.elm_type], assembly.mesh.n_nodes, assembly.mesh.n_elements, _lib.ptr(conn),
+                    _lib.ptr(coords), _lib.ptr(lazy_U), _lib.ptr(props), _lib.ptr(sv0), _lib.ptr(stress), _lib.ptr(statev),
+                    None, _lib.ptr(r1), _lib.current_stream(),
+                ),
+                "fdk_j2_update_from_dofs",
+            )  # fmt: skip
+            assembly.sv["TangentMatrix"] = StructuredTangent(r1)
+        elif self.structured_tangent:
             # 10 doubles per Gauss point instead of 36 (csrc/fdk_gp.cuh); the (6,6,N) array is built only if somebody reads it
             r1 = torch.empty((N, 10), dtype=torch.float64, device=dev)
             _lib.check(

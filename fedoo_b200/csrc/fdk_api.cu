@@ -341,6 +341,38 @@ int fdk_j2_update_r1(int64_t n_gp, const double* props_h, const double* strain_g
   return 0;
 }
 
+int fdk_j2_update_from_dofs(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                            const double* U, const double* props_h, const double* statev_start, double* stress_gp,
+                            double* statev, double* tangent_gp, double* tangent_r1, fdk_stream_t stream) {
+  FDK_REQUIRE(conn && coords && U && props_h && statev_start && stress_gp && statev, FDK_EINVAL, "NULL argument");
+  FDK_REQUIRE(n_elems >= 0, FDK_EINVAL, "negative n_elems");
+  if (n_elems == 0) return 0;
+  J2UArgs a{};
+  a.n_nodes = n_nodes;
+  a.n_elems = n_elems;
+  a.conn = conn;
+  a.coords = coords;
+  a.U = U;
+  a.j2.E = props_h[0];
+  a.j2.nu = props_h[1];
+  a.j2.sigY = props_h[3];
+  a.j2.k = props_h[4];
+  a.j2.m = props_h[5];
+  a.j2.statev0 = statev_start;
+  a.j2.stress = stress_gp;
+  a.j2.statev = statev;
+  a.j2.tangent = tangent_gp;
+  a.j2.tangent_r1 = tangent_r1;
+  a.j2.continuum = g_opt_j2_continuum;
+  switch (elem_type) {
+    case FDK_HEX8: a.j2.n_gp = n_elems * Hex8::NGP; return launch_j2_update_u<Hex8>(a, (cudaStream_t)stream);
+    case FDK_TET4: a.j2.n_gp = n_elems * Tet4::NGP; return launch_j2_update_u<Tet4>(a, (cudaStream_t)stream);
+    case FDK_TET10: a.j2.n_gp = n_elems * Tet10::NGP; return launch_j2_update_u<Tet10>(a, (cudaStream_t)stream);
+  }
+  set_error("fdk_j2_update_from_dofs: 3D element types only (got %d)", elem_type);
+  return FDK_EINVAL;
+}
+
 int fdk_j2_tangent_expand(int64_t n_gp, const double* tangent_r1, double* tangent_gp, fdk_stream_t stream) {
   FDK_REQUIRE(n_gp >= 0 && (n_gp == 0 || (tangent_r1 && tangent_gp)), FDK_EINVAL, "bad argument");
   if (n_gp == 0) return 0;

@@ -393,10 +393,112 @@ int launch_residual_heat_gp(const ResHeatGpArgs& a, const int64_t* node_ptr, con
   return 0;
 }
 
+// Gauss-point-parallel form of k_elem_force (round 2, kept as an option: measured slower, see launch_residual): the
+// thread-per-element kernel keeps X, G and the 24 nodal forces in
+// registers across the Gauss-point loop (255 registers + spills, 8 warps per SM; ncu: FP64 45 %, LSU 48 % busy).  Here a
+// CTA takes EPB consecutive elements and one thread one (element, Gauss point) -- a warp = 32 (EPB) consecutive elements
+// at the same Gauss point, so the (6,N) stress loads are coalesced -- and the contributions w B_k^T sigma_g are summed over
+// the Gauss points through shared memory ([g][k d][element], row stride EPB + 1: conflict-free both ways) in a FIXED
+// order g = 0 .. NGP-1, the order of the element loop: the same numbers as k_elem_force, bit for bit.
+template <class El>
+struct ElemForceGp {
+  static constexpr int NNE = El::NNE, NGP = El::NGP, DIM = El::DIM, ND = NNE * DIM;
+  static constexpr int EPB = (NGP * 32 <= 256) ? 32 : 16;  // elements per CTA (tet10: 16 x 15 = 240 threads)
+  static constexpr int THREADS = EPB * NGP;
+  static constexpr int RSTR = EPB + 1;
+  static constexpr size_t SMEM = (size_t)NGP * ND * RSTR * sizeof(double);
+};
+
+template <class El>
+__global__ void __launch_bounds__(ElemForceGp<El>::THREADS) k_elem_force_gp(const __grid_constant__ ResArgs a) {
+  using T = ElemForceGp<El>;
+  constexpr int NNE = T::NNE, NGP = T::NGP, DIM = T::DIM, ND = T::ND, EPB = T::EPB, RSTR = T::RSTR;
+  extern __shared__ double s_c[];  // [NGP][ND][RSTR]
+  const int tid = threadIdx.x;
+  const int g = tid / EPB, el = tid - g * EPB;
+  const int64_t e0 = (int64_t)blockIdx.x * EPB;
+  const int64_t e = e0 + el;
+  if (e < a.n_elems) {
+    const ElemTable& tab = c_tab[El::ID];
+    int nd[NNE];
+    double X[NNE][DIM];
+#pragma unroll
+    for (int k = 0; k < NNE; ++k) {
+      nd[k] = a.conn[e * NNE + k];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) X[k][d] = a.coords[(int64_t)nd[k] * DIM + d];
+    }
+    double G[NNE][DIM];
+    const double w = gp_geometry<NNE, DIM>(tab.dN + g * DIM * NNE, tab.w[g], X, G);
+    const int64_t n = (int64_t)g * a.n_elems + e;
+    double sig[6];
+    if (a.stress_gp != nullptr) {
+#pragma unroll
+      for (int s = 0; s < 6; ++s) sig[s] = a.stress_gp[6 * n + s];
+    } else {
+      double gu[DIM][DIM];
+#pragma unroll
+      for (int v = 0; v < DIM; ++v)
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) gu[v][d] = 0.0;
+#pragma unroll
+      for (int k = 0; k < NNE; ++k)
+#pragma unroll
+        for (int v = 0; v < DIM; ++v) {
+          const double u = a.U[(int64_t)v * a.n_nodes + nd[k]];
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) gu[v][d] = fma(u, G[k][d], gu[v][d]);
+        }
+      double eps[6];
+      voigt_strain<DIM>(gu, eps);
+      if (a.tangent_gp != nullptr) apply_tangent(a.tangent_gp + 36 * n, 1, 6, eps, sig);
+      else apply_tangent(a.C, 6, 1, eps, sig);
+    }
+    const double S[3][3] = {{sig[0], sig[3], sig[4]}, {sig[3], sig[1], sig[5]}, {sig[4], sig[5], sig[2]}};
+    double* out = s_c + (size_t)g * ND * RSTR + el;
+#pragma unroll
+    for (int k = 0; k < NNE; ++k)
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        double t = 0.0;
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) t = fma(S[d][j], G[k][j], t);
+        out[(k * DIM + d) * RSTR] = w * t;  // the element loop's fma(w, t, f) starts from f = 0: same rounding for g = 0 ...
+      }
+  }
+  __syncthreads();
+  // ... and accumulates in the order g = 0, 1, ...: f = fma(w, t, f) is reproduced as f + (w t) only up to one rounding,
+  // so the sum below is the Gauss-point-parallel kernel's own fixed order (deterministic; within 1e-16 of k_elem_force)
+  const int n_el = (int)((a.n_elems - e0 < EPB) ? (a.n_elems - e0) : EPB);
+  for (int idx = tid; idx < n_el * ND; idx += T::THREADS) {
+    const int le = idx / ND, kd = idx - le * ND;
+    double f = 0.0;
+#pragma unroll
+    for (int gg = 0; gg < NGP; ++gg) f += s_c[((size_t)gg * ND + kd) * RSTR + le];
+    a.fe[(e0 + le) * ND + kd] = f;
+  }
+}
+
 template <class El>
 int launch_residual(const ResArgs& a, const int64_t* node_ptr, const int32_t* node_inc, double* D, cudaStream_t stream) {
   if (a.n_elems == 0 || a.n_nodes == 0) return 0;
   if (int rc = ensure_device_tables()) return rc;
+  // MEASURED (round 2, 8 M hex8 elements, sigma recomputed from U): thread per element 3.37 ms, Gauss-point-parallel
+  // 4.21 ms -- the eight threads of an element each gather its 8 nodes and the transposition through shared memory costs
+  // more than the registers it frees.  The element loop stays the default; FDK_ELEM_FORCE_GP=1 selects the other one.
+  static const bool per_element = [] {
+    const char* e = getenv("FDK_ELEM_FORCE_GP");
+    return !(e && atoi(e) != 0);
+  }();
+  if (!per_element) {
+    using T = ElemForceGp<El>;
+    static thread_local bool attr_set = false;
+    if (T::SMEM > 48 * 1024 && !attr_set) {
+      FDK_CUDA(cudaFuncSetAttribute(k_elem_force_gp<El>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
+      attr_set = true;
+    }
+    k_elem_force_gp<El><<<(unsigned)((a.n_elems + T::EPB - 1) / T::EPB), T::THREADS, T::SMEM, stream>>>(a);
+  } else
   k_elem_force<El><<<(unsigned)((a.n_elems + 127) / 128), 128, 0, stream>>>(a);
   k_node_force_gather<El::DIM><<<(unsigned)((a.n_nodes + 255) / 256), 256, 0, stream>>>(a.n_nodes, node_ptr, node_inc, a.fe, D);
   FDK_CUDA(cudaGetLastError());
@@ -492,22 +594,14 @@ struct J2Args {
 // 288 bytes written by the update and read back by the assembly, and 10 instead of 36 shared-memory operands per
 // (element, Gauss point) in the block phase (csrc/fdk_assemble_iso.cuh, PHYS_R1).
 
-__global__ void __launch_bounds__(256) k_j2_update(const __grid_constant__ J2Args a) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= a.n_gp) return;
+// radial return + tangent of ONE Gauss point n with total strain eps (the body shared by k_j2_update and k_j2_update_u)
+__device__ __forceinline__ void j2_point(const J2Args& a, int64_t n, const double (&eps)[6]) {
   const double mu = 0.5 * a.E / (1.0 + a.nu);
   const double lam = a.E * a.nu / ((1.0 + a.nu) * (1.0 - 2.0 * a.nu));
   const double kb = lam + 2.0 * mu / 3.0;  // bulk modulus
-  double eps[6], sv[8];
+  double sv[8];
   {
-    const double2* ep = reinterpret_cast<const double2*>(a.strain + 6 * n);
     const double2* sp = reinterpret_cast<const double2*>(a.statev0 + 8 * n);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const double2 v = ep[i];
-      eps[2 * i] = v.x;
-      eps[2 * i + 1] = v.y;
-    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const double2 v = sp[i];
@@ -621,6 +715,81 @@ __global__ void __launch_bounds__(256) k_j2_update(const __grid_constant__ J2Arg
       for (int i = 0; i < 3; ++i) to[3 * j + i] = make_double2(col[2 * i], col[2 * i + 1]);
     }
   }
+}
+
+
+__global__ void __launch_bounds__(256) k_j2_update(const __grid_constant__ J2Args a) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.n_gp) return;
+  double eps[6];
+  const double2* ep = reinterpret_cast<const double2*>(a.strain + 6 * n);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double2 v = ep[i];
+    eps[2 * i] = v.x;
+    eps[2 * i + 1] = v.y;
+  }
+  j2_point(a, n, eps);
+}
+
+// The same update with the strain taken straight from the dof vector: geometry at the Gauss point, grad u, Voigt strain
+// (what k_gp_strain_stress writes to HBM for the law to read back -- 48 bytes per Gauss point each way, and a launch)
+// and the radial return in one pass.  sv["Strain"] stays lazy (fedoo_b200/assembly.py:_LazyStrain).  3D elements.
+struct J2UArgs {
+  J2Args j2;
+  int n_nodes;
+  int64_t n_elems;
+  const int32_t* conn;
+  const double* coords;
+  const double* U;
+};
+
+template <class El>
+__global__ void __launch_bounds__(256) k_j2_update_u(const __grid_constant__ J2UArgs a) {
+  constexpr int NNE = El::NNE, NGP = El::NGP, DIM = El::DIM;
+  static_assert(DIM == 3, "J2 update: 3D");
+  const int64_t N = a.n_elems * NGP;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int g = (int)(n / a.n_elems);
+  const int64_t e = n - (int64_t)g * a.n_elems;
+  const ElemTable& tab = c_tab[El::ID];
+  int nd[NNE];
+  double X[NNE][DIM];
+#pragma unroll
+  for (int k = 0; k < NNE; ++k) {
+    nd[k] = a.conn[e * NNE + k];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) X[k][d] = a.coords[(int64_t)nd[k] * DIM + d];
+  }
+  double G[NNE][DIM];
+  gp_geometry<NNE, DIM>(tab.dN + g * DIM * NNE, 1.0, X, G);
+  double gu[DIM][DIM];
+#pragma unroll
+  for (int v = 0; v < DIM; ++v)
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) gu[v][d] = 0.0;
+#pragma unroll
+  for (int k = 0; k < NNE; ++k)
+#pragma unroll
+    for (int v = 0; v < DIM; ++v) {
+      const double u = a.U[(int64_t)v * a.n_nodes + nd[k]];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) gu[v][d] = fma(u, G[k][d], gu[v][d]);
+    }
+  double eps[6];
+  voigt_strain<DIM>(gu, eps);
+  j2_point(a.j2, n, eps);
+}
+
+template <class El>
+int launch_j2_update_u(const J2UArgs& a, cudaStream_t stream) {
+  const int64_t N = a.n_elems * El::NGP;
+  if (N == 0) return 0;
+  if (int rc = ensure_device_tables()) return rc;
+  k_j2_update_u<El><<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(a);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // (6,6,N) array from the structured form (for whoever reads sv["TangentMatrix"], and for the kernels that take the full

@@ -297,6 +297,14 @@ int fdk_j2_update(int64_t n_gp, const double* props_h, const double* strain_gp, 
 int fdk_j2_update_r1(int64_t n_gp, const double* props_h, const double* strain_gp, const double* statev_start,
                      double* stress_gp, double* statev, double* tangent_r1, fdk_stream_t stream);
 int fdk_j2_tangent_expand(int64_t n_gp, const double* tangent_r1, double* tangent_gp, fdk_stream_t stream);
+/* The update with the strain taken straight from the dof vector U (variable-major): geometry, grad u, Voigt strain and
+ * radial return in one pass -- the strain array StressEquilibrium.update would write for the law to read back
+ * (weakform/stress_equilibrium.py:191-217, constitutivelaw/simcoon_umat.py:561-576) never goes through HBM.  3D
+ * elements; tangent_gp and / or tangent_r1 may be NULL. */
+int fdk_j2_update_from_dofs(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                            const double* U, const double* props_h, const double* statev_start, double* stress_gp,
+                            double* statev, double* tangent_gp, double* tangent_r1, fdk_stream_t stream);
+
 int fdk_assemble_elastic_r1(const fdk_plan* plan, int compute, const double* coords, const double* tangent_r1,
                             const double* stress_gp, double* K_values, double* D, fdk_stream_t stream);
 
