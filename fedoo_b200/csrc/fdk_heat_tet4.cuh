@@ -88,13 +88,25 @@ __global__ void __launch_bounds__(THREADS, MINB) k_heat_tet4_rows(const __grid_c
   }
   double dsum = 0.0;
   const int64_t t0 = a.node_ptr[I], t1 = a.node_ptr[I + 1];
+  // software pipeline over the incidences: the record and the connectivity of incidence t + 1 are in flight while
+  // incidence t computes (the chain record -> connectivity -> coordinates is three dependent global loads, and at 24
+  // warps per SM there is little else to hide it behind)
+  int2 rec_n = make_int2(0, 0);
+  int4 nd_n = make_int4(0, 0, 0, 0);
+  if (t0 < t1) {
+    rec_n = a.inc_rec[t0];
+    nd_n = *reinterpret_cast<const int4*>(a.conn + (int64_t)(rec_n.x >> 2) * 4);
+  }
   for (int64_t t = t0; t < t1; ++t) {
-    const int2 rec = a.inc_rec[t];
+    const int2 rec = rec_n;
     const int inc = rec.x;
-    const int64_t e = inc >> 2;
     const int i = inc & 3;
-    const int4 nd4 = *reinterpret_cast<const int4*>(a.conn + e * 4);
+    const int4 nd4 = nd_n;
     const int nd[4] = {nd4.x, nd4.y, nd4.z, nd4.w};
+    if (t + 1 < t1) {  // (a second record in flight was measured too: no further gain)
+      rec_n = a.inc_rec[t + 1];
+      nd_n = *reinterpret_cast<const int4*>(a.conn + (int64_t)(rec_n.x >> 2) * 4);
+    }
     double X[4][3];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
