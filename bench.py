@@ -13,6 +13,8 @@ One "step" = one pass of the hot path over the whole mesh.
   j2_plate  (configs[3]) hex8 plate with a hole: strain, J2 radial return + tangent at every Gauss point, K with the
             per-Gauss-point tangent, D = -int B^T sigma (one Newton iteration's work).
   tet10     (configs[4]) tet10 (15 Gauss points) elastic K + D (one load case of the homogenisation).
+            heat_tet4 / j2_plate / tet10 with N > 1: nodes partitioned by recursive coordinate bisection, owner-computes
+            rows, the owned slices of D all-gathered over NCCL.
 --impl reference: the UNMODIFIED reference (oracle/_ref, copied by oracle/make_ref.py) timed on the host cores on a
 bounded sample of the same workload (the J2 law lives in simcoon, absent: that config times the NumPy port instead).
 
@@ -662,20 +664,17 @@ def distributed_checks(asm, pb, loc, peer, exch, D_nccl, n, world, rank, jitter)
 
 
 # ----------------------------------------------------------------------------------------------
-# configs [2]-[4]: one GPU (N > 1: rank 0 runs, the others exit -- these configurations are not sharded yet)
+# configs [2]-[4]: one GPU, or (torchrun) the unstructured partition of fedoo_b200.dist over N GPUs
 # ----------------------------------------------------------------------------------------------
 def run_other(args):
-    """configs [2]-[4].  One GPU, except tet10 (the configuration BASELINE names "across 8 GPUs"): under torchrun its
-    nodes are partitioned by recursive coordinate bisection, every rank assembles the complete rows of the nodes it owns
-    from its local mesh (one halo layer of elements; no matrix exchange) and the owned slices of D are all-gathered over
-    NCCL (fedoo_b200.dist: partition_rcb / extract_local / VectorExchange) -- strong scaling, the global mesh is fixed.
-    The other configurations are not sharded: rank 0 runs, the others exit."""
+    """configs [2]-[4].  Under torchrun the nodes are partitioned by recursive coordinate bisection, every rank
+    assembles the complete rows of the nodes it owns from its local mesh (one halo layer of elements, whose Gauss-point
+    state it updates itself; no matrix exchange) and the owned slices of D are all-gathered over NCCL (fedoo_b200.dist:
+    partition_rcb / extract_local / VectorExchange) -- strong scaling, the global mesh is fixed."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     cfg = args.config
-    sharded = world > 1 and cfg == "tet10"
-    if rank != 0 and not sharded:
-        return
+    sharded = world > 1
     import torch
     import torch.distributed as dist
 
@@ -695,51 +694,56 @@ def run_other(args):
     glob = None
     if sharded:
         if args.check and n_el <= 400_000:
-            glob = (nodes, elements, U)  # small enough to redo on one GPU for the comparison
+            glob = (nodes, elements, U, T0)  # small enough to redo on one GPU for the comparison
         part = fdist.partition_rcb(nodes, world)  # deterministic: every rank computes the same partition
         loc = fdist.extract_local(nodes, elements, part, rank)
         U = np.concatenate([U[v * nn_global + loc.node_gid] for v in range(nvar)])
+        if T0 is not None:
+            T0 = T0[loc.node_gid]
         part_stats = dict(owned_nodes=int(loc.owned.sum()), local_nodes=len(loc.nodes), local_elements=len(loc.elements),
                           halo_element_share=float(len(loc.elements) * world / n_el - 1.0))  # fmt: skip
         nodes, elements = loc.nodes, loc.elements.astype(np.int32)
     nn = len(nodes)
-    fd.Assembly.delete_memory()
-    fd.ModelingSpace("3D")
-    fd.Mesh(nodes, elements, elm, name="Domain")
     U_host = torch.empty(U.size, dtype=torch.float64, pin_memory=True)
     U_host.copy_(torch.from_numpy(U))
-    kargs = dict(reuse_buffers=True, owned_nodes=(loc.owned if sharded else None))
-    if cfg == "heat_tet4":
-        fd.constitutivelaw.ThermalProperties(500.0, 0.5, 7800.0, name="ThermalLaw")
-        fd.weakform.HeatEquation("ThermalLaw")
-        a = fd.Assembly.create("ThermalLaw", "Domain", name="A", **kargs)
-        pb = fd.problem.NonLinear("A")
-        pb.dtime = 10.0 / 3.0
-        pb._U, pb._dU = T0.copy(), 0
-        pb.initialize()
-        a.set_start(pb)
 
-        def set_state(host):  # the iterate; the start temperature stays what set_start recorded (T0)
-            pb._U, pb._dU = host, 0
-    else:
-        if cfg == "j2_plate":
-            law = fd.constitutivelaw.Simcoon("EPICP", J2_PROPS, name="law")
+    def build(nodes, elements, T_start, **kargs):
+        """Mesh, law, weak form, assembly and problem of this configuration -> (assembly, problem, set_state)."""
+        fd.Assembly.delete_memory()
+        fd.ModelingSpace("3D")
+        fd.Mesh(nodes, elements, elm, name="Domain")
+        if cfg == "heat_tet4":
+            fd.constitutivelaw.ThermalProperties(500.0, 0.5, 7800.0, name="ThermalLaw")
+            fd.weakform.HeatEquation("ThermalLaw")
+            a = fd.Assembly.create("ThermalLaw", "Domain", name="A", **kargs)
+            pb = fd.problem.NonLinear("A")
+            pb.dtime = 10.0 / 3.0
+            pb._U, pb._dU = T_start.copy(), 0
+            pb.initialize()
+            a.set_start(pb)
+
+            def set_state(x):  # the iterate; the start temperature stays what set_start recorded
+                pb._U, pb._dU = x, 0
         else:
-            law = fd.constitutivelaw.ElasticIsotrop(1e5, 0.3, name="law")
-        fd.weakform.StressEquilibrium(law, name="wf")
-        a = fd.Assembly.create("wf", "Domain", elm, name="A", **kargs)
-        pb = fd.problem.Linear("A")
+            if cfg == "j2_plate":
+                law = fd.constitutivelaw.Simcoon("EPICP", J2_PROPS, name="law")
+            else:
+                law = fd.constitutivelaw.ElasticIsotrop(1e5, 0.3, name="law")
+            fd.weakform.StressEquilibrium(law, name="wf")
+            a = fd.Assembly.create("wf", "Domain", elm, name="A", **kargs)
+            pb = fd.problem.Linear("A")
 
-        def set_state(host):
-            pb.set_X(host)
+            def set_state(x):
+                pb.set_X(x)
+
+        return a, pb, set_state
+
+    a, pb, set_state = build(nodes, elements, T0, reuse_buffers=True, owned_nodes=(loc.owned if sharded else None))
 
     U_dev = U_host.cuda()
 
     def set_state_device():
-        if cfg == "heat_tet4":
-            pb._U, pb._dU = U_dev, 0
-        else:
-            pb.set_X(U_dev)
+        set_state(U_dev)
 
     def barrier():
         if sharded:
@@ -783,7 +787,11 @@ def run_other(args):
     ms_total, ms_matrix = float(t[0]), float(t[1])
     ms_step = ms_total / args.steps
     K = a.get_global_matrix()
-    nnz = int(K.data.numel()) if not sharded else nvar * nvar * int(a._plan(a._saved_bloc_structure).t["cl_slot_ptr"][-1])
+    if sharded:  # the blocks of the rows this rank owns
+        ip = a._saved_bloc_structure["pattern"].blk_indptr
+        nnz = nvar * nvar * int((ip[1:] - ip[:-1])[torch.from_numpy(loc.owned).to(ip.device)].sum())
+    else:
+        nnz = int(K.data.numel())
     nne = elements.shape[1]
     n_own_nodes = int(loc.owned.sum()) if sharded else nn
     n_own_elems = n_el / world
@@ -794,9 +802,9 @@ def run_other(args):
         algo_k = 8 * nnz + 4 * nne * n_own_elems + 8 * 3 * n_own_nodes
         algo_step = algo_k + 16 * 3 * n_own_nodes
     else:  # SURVEY 8d, fused J2: statev in/out, stress out, K, conn, coords, U, D (+ the structured tangent: 80 B per GP)
-        n_gp = 8 * n_el
-        algo_k = 8 * nnz + 4 * nne * n_el + 8 * 3 * nn + n_gp * 8 * 10  # the matrix kernel reads the structured tangent
-        algo_step = 8 * nnz + 4 * nne * n_el + 8 * 3 * nn + 16 * 3 * nn + n_gp * 8 * (8 + 8 + 6)
+        n_gp = 8 * n_own_elems
+        algo_k = 8 * nnz + 4 * nne * n_own_elems + 8 * 3 * n_own_nodes + n_gp * 8 * 10  # the matrix kernel reads the structured tangent
+        algo_step = 8 * nnz + 4 * nne * n_own_elems + 8 * 3 * n_own_nodes + 16 * 3 * n_own_nodes + n_gp * 8 * (8 + 8 + 6)
     peak, peak_src = hbm_peak()
 
     # ---- e2e: pinned host dof vector in, residual out, every step ----
@@ -836,24 +844,22 @@ def run_other(args):
         s3 = torch.stack([D_global[v * nn_global : (v + 1) * nn_global].sum() for v in range(nvar)])
         spread = torch.stack([D_global.sum(), -D_global.sum()])
         dist.all_reduce(spread, op=dist.ReduceOp.MAX)
-        checks = {"D_sum_rel": float(s3.abs().max() / D_global.abs().max()),
+        checks = {"D_sum_rel": float(s3.abs().max() / D_global.abs().max()) if cfg != "heat_tet4" else None,
                   "D_identical_on_all_ranks": bool(float(spread[0] + spread[1]) == 0.0),
                   "D_nonzero_fraction": float((D_global != 0).double().mean())}  # fmt: skip
         if glob is not None:  # the whole mesh on this GPU alone: the gathered residual must be the one-GPU residual
             D_multi = D_global.clone()
-            fd.Assembly.delete_memory()
-            fd.Mesh(glob[0], glob[1], elm, name="Whole")
-            a1 = fd.Assembly.create("wf", "Whole", elm, name="One", vector_on_device=True)
-            pb1 = fd.problem.Linear("One")
-            pb1.set_X(glob[2])
+            a1, pb1, set1 = build(glob[0], glob[1], glob[3], vector_on_device=True)
+            set1(glob[2])
             a1.update(pb1, compute="all")
             err = (D_multi - a1.global_vector).abs().max() / a1.global_vector.abs().max()
             dist.all_reduce(err, op=dist.ReduceOp.MAX)
             checks["D_vs_single_gpu_rel"] = float(err)
     if sharded:
         stats_all = [None] * world
-        dist.all_gather_object(stats_all, dict(part_stats, clusters=int(a._plan(a._saved_bloc_structure).n_clusters),
-                                               heavy_nodes=int(a._plan(a._saved_bloc_structure).heavy_nodes.numel())))  # fmt: skip
+        plan = a._saved_bloc_structure["plan"]  # None: the row-owner kernel needs no cluster plan
+        dist.all_gather_object(stats_all, dict(part_stats, clusters=None if plan is None else int(plan.n_clusters),
+                                               heavy_nodes=None if plan is None else int(plan.heavy_nodes.numel())))  # fmt: skip
     if rank != 0:
         dist.destroy_process_group()
         return
@@ -880,7 +886,7 @@ def run_other(args):
             "workload": workload_label(args),
             "n_elements": n_el, "n_nodes": nn_global, "nnz": nnz if not sharded else None,
             "l2": f"{algo_step / 1e9:.2f} GB of compulsory traffic per step and GPU against a 126 MB L2; no flush needed",
-            "partition": ("one GPU (this configuration is not sharded)" if not sharded else
+            "partition": ("one GPU" if not sharded else
                           f"recursive coordinate bisection of the nodes over {world} GPUs, owner-computes rows, one halo layer of "
                           "elements per rank, residual exchange: pack + NCCL all-gather of D + unpack"),
             "ranks": stats_all if sharded else None,

@@ -128,7 +128,7 @@ def load():
     lib.fdk_assemble_elastic_iso_dist.argtypes = [pp, i32, vp, dbl, dbl, vp, vp, vp, vp, i32, vp, i64, vp]
     lib.fdk_assemble_elastic_general.argtypes = [pp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.fdk_assemble_heat.argtypes = [pp, i32, vp, vp, dbl, vp, vp, vp, vp, vp]
-    lib.fdk_assemble_heat_tet4.argtypes = [i32, i32, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp, i32, vp, vp, vp]
+    lib.fdk_assemble_heat_tet4.argtypes = [i32, i32, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
     lib.fdk_assemble_rows_elastic.argtypes = [i32, i32, vp, i32, i64, vp, vp, vp, vp, vp, vp, i64, i32, i32, dbl, dbl, vp, vp,
                                               i32, vp, vp, vp, vp, vp]
     lib.fdk_gp_strain_stress.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]

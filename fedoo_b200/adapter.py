@@ -106,10 +106,26 @@ def _classify(a):
     return None
 
 
-def _normalize_tangent(H, n_gp):
+def _to_gauss_points(v, a):
+    """One material coefficient given at nodes, elements or Gauss points -> Gauss points, with the reference's own rule
+    for telling them apart (core/mesh.py:1222-1265: the LAST matching of n_nodes, n_elements, n_gauss_points wins;
+    element values are tiled over the gp-major order, nodal values interpolated with the shape functions)."""
+    n_gp, mesh = a.n_gauss_points, a.mesh
+    if v.shape[-1] == n_gp:
+        return v
+    if v.shape[-1] == mesh.n_elements:
+        return np.tile(v, a.n_elm_gp)
+    if v.shape[-1] == mesh.n_nodes:
+        _, N, _ = _lib.element_table(a.elm_type)  # (n_elm_gp, nne)
+        return np.einsum("gk,ek->ge", N, v[np.asarray(mesh.elements)]).reshape(-1)
+    raise ValueError("data doesn't match with the number of nodes, number of elements or number of gauss points.")
+
+
+def _normalize_tangent(H, a):
     """sv['TangentMatrix'] in any of the reference's formats (6x6 floats, 6x6 object array / list of lists with
-    per-Gauss-point entries, (6,6,N) ndarray -- all indexed H[i][j], stress_equilibrium.py:112-117) ->
-    (6,6) float array or (6,6,N) Fortran-ordered array."""
+    per-Gauss-point, per-element or per-node entries, (6,6,N) ndarray -- all indexed H[i][j],
+    stress_equilibrium.py:112-117) -> (6,6) float array or (6,6,N) Fortran-ordered array."""
+    n_gp = a.n_gauss_points
     if isinstance(H, np.ndarray) and H.dtype != object:
         if H.ndim == 2:
             return np.ascontiguousarray(H, dtype=np.float64)
@@ -123,9 +139,7 @@ def _normalize_tangent(H, n_gp):
     for i in range(6):
         for j in range(6):
             v = np.asarray(H[i][j], dtype=np.float64)
-            if v.ndim > 0 and v.shape[0] != n_gp:
-                raise NotImplementedError("per-node / per-element material data: convert it to Gauss points first")
-            out[i, j, :] = v
+            out[i, j, :] = _to_gauss_points(v, a) if v.ndim > 0 else v
     return out
 
 
@@ -204,7 +218,7 @@ def _assemble(a, compute, strict, orig):
     n_gp = a.n_gauss_points
     want_mat, want_vec = compute != "vector", compute != "matrix"
     if kind == "elastic":
-        H = _normalize_tangent(a.sv["TangentMatrix"], n_gp)
+        H = _normalize_tangent(a.sv["TangentMatrix"], a)
         m = be.elastic(a, H)
         m._pb = pb
         stress = a.sv.get("Stress", 0)

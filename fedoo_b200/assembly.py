@@ -174,6 +174,15 @@ class Assembly(_Named):
             entry["row_pos"] = (torch.stack([node_inc.to(torch.int32), packed], dim=1).contiguous(), max_deg)
         return entry["row_pos"]
 
+    def _owned_rows(self, entry):
+        """int32 list of the owned node rows on the device (None: every node is owned)."""
+        if self.owned_nodes is None:
+            return None
+        if "owned_rows" not in entry:
+            own = np.flatnonzero(np.asarray(self.owned_nodes, dtype=bool)).astype(np.int32)
+            entry["owned_rows"] = torch.from_numpy(own).to(device())
+        return entry["owned_rows"]
+
     def _heavy_rows(self, entry, plan, flags, coords, iso, lam, mu, C_h, tangent_dev, U_dev, stress_dev, K, D):
         """Rows of the nodes the cluster plan left out (more incident elements than one cluster holds): csrc/fdk_rows.cuh."""
         rows = plan.heavy_nodes
@@ -266,7 +275,7 @@ class Assembly(_Named):
             stress = self.sv.get("Stress", 0)
             has_vec = want_vec and not (np.isscalar(stress) and stress == 0)
             flags = (_lib.MATRIX if want_mat else 0) | (_lib.VECTOR if has_vec else 0)
-            K = self._buffer("K", nvar * nvar * pattern.blk_nnz) if want_mat else None
+            K = self._buffer("K", nvar * nvar * pattern.blk_nnz, zero=self.owned_nodes is not None) if want_mat else None
             D = self._buffer(self._d_tag(), nvar * n_nodes + n_glob, zero=True) if has_vec else None
             U_dev = stress_dev = None
             if has_vec:
@@ -374,20 +383,23 @@ class Assembly(_Named):
             T_dev = self._U_dev
             has_vec = want_vec and T_dev is not None
             flags = (_lib.MATRIX if want_mat else 0) | (_lib.VECTOR if has_vec else 0)
-            K = self._buffer("K", pattern.blk_nnz) if want_mat else None
+            K = self._buffer("K", pattern.blk_nnz, zero=self.owned_nodes is not None) if want_mat else None
             D = self._buffer(self._d_tag(), n_nodes + n_glob, zero=True) if has_vec else None
             T_start = self._T_start_dev if rcdt != 0.0 else None
-            if flags and self.elm_type == "tet4" and self.owned_nodes is None and _HEAT_TET4_ROWS:
-                # constant-gradient element: the row-owner kernel does K and D in one launch, without a cluster plan
+            if flags and self.elm_type == "tet4" and _HEAT_TET4_ROWS:
+                # constant-gradient element: the row-owner kernel does K and D in one launch, without a cluster plan;
+                # on a rank of a multi-GPU partition it computes the rows of the owned nodes only
                 from .results import node_incidences
 
                 node_ptr, node_inc = node_incidences(self.mesh)
                 inc_rec, max_deg = self._row_positions(entry, node_ptr, node_inc)
                 conn = self.mesh.device_arrays()[1]
+                rows = self._owned_rows(entry)
                 rc = lib.fdk_assemble_heat_tet4(
                     flags, n_nodes, self.mesh.n_elements, _lib.ptr(conn), _lib.ptr(coords), _lib.ptr(cond), rcdt,
                     _lib.ptr(T_dev), _lib.ptr(T_start), _lib.ptr(node_ptr), _lib.ptr(inc_rec),
-                    _lib.ptr(pattern.blk_indptr), max_deg, _lib.ptr(K), _lib.ptr(D), stream,
+                    _lib.ptr(pattern.blk_indptr), max_deg, n_nodes if rows is None else int(rows.numel()), _lib.ptr(rows),
+                    _lib.ptr(K), _lib.ptr(D), stream,
                 )  # fmt: skip
                 _lib.check(rc, "fdk_assemble_heat_tet4")
                 flags = 0

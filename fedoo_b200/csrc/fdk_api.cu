@@ -509,8 +509,11 @@ int fdk_residual_heat(int elem_type, int n_nodes, int64_t n_elems, const int32_t
 int fdk_assemble_heat_tet4(int compute, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
                            const double* cond_h, double rho_c_over_dt, const double* T, const double* T_start,
                            const int64_t* node_ptr, const int32_t* inc_rec, const int64_t* blk_indptr,
-                           int max_row_degree, double* K_values, double* D, fdk_stream_t stream) {
+                           int max_row_degree, int n_rows, const int32_t* rows, double* K_values, double* D,
+                           fdk_stream_t stream) {
   FDK_REQUIRE(conn && coords && cond_h && node_ptr && inc_rec && blk_indptr, FDK_EINVAL, "NULL argument");
+  FDK_REQUIRE(rows ? (n_rows >= 0 && n_rows <= n_nodes) : (n_rows == n_nodes || n_rows == 0), FDK_EINVAL,
+              "n_rows: the length of rows, or n_nodes (0 is accepted too) when rows is NULL");
   FDK_REQUIRE((compute & ~FDK_ALL) == 0 && compute != 0, FDK_EINVAL, "compute must be FDK_MATRIX, FDK_VECTOR or both");
   FDK_REQUIRE(!(compute & FDK_MATRIX) || K_values, FDK_EINVAL, "matrix requested without K_values");
   FDK_REQUIRE(!(compute & FDK_VECTOR) || (D && T), FDK_EINVAL, "vector requested without D / T");
@@ -526,6 +529,8 @@ int fdk_assemble_heat_tet4(int compute, int n_nodes, int64_t n_elems, const int3
   a.T_start = T_start;
   a.rcdt = rho_c_over_dt;
   a.max_deg = max_row_degree;
+  a.rows = rows;
+  a.n_rows = rows ? n_rows : n_nodes;
   a.K = (compute & FDK_MATRIX) ? K_values : nullptr;
   a.D = (compute & FDK_VECTOR) ? D : nullptr;
   for (int i = 0; i < 9; ++i) a.cond[i] = cond_h[i];

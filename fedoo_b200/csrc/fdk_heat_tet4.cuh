@@ -34,6 +34,8 @@ struct HeatTet4Args {
   double cond[9];
   double rcdt;
   int max_deg;
+  int n_rows;                 // rows this launch computes: all n_nodes, or ...
+  const int32_t* rows;        // ... the listed ones (a rank's owned nodes; NULL = 0 .. n_nodes - 1)
   double* K;  // NULL: vector only
   double* D;
 };
@@ -67,8 +69,9 @@ template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_heat_tet4_rows(const __grid_constant__ HeatTet4Args a) {
   extern __shared__ double s_acc[];  // [max_deg][THREADS]
   const int tid = threadIdx.x;
-  const int I = blockIdx.x * THREADS + tid;
-  if (I >= a.n_nodes) return;
+  const int r = blockIdx.x * THREADS + tid;
+  if (r >= a.n_rows) return;
+  const int I = a.rows != nullptr ? a.rows[r] : r;
   const ElemTable& tab = c_tab[FDK_TET4];
   const bool want_K = a.K != nullptr, want_D = a.D != nullptr && a.T != nullptr;
   const int64_t bp = a.blk_indptr[I];
@@ -174,13 +177,13 @@ int launch_heat_tet4_t(const HeatTet4Args& a, size_t smem, cudaStream_t stream) 
     FDK_CUDA(cudaFuncSetAttribute(k_heat_tet4_rows<THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  k_heat_tet4_rows<THREADS, MINB><<<(unsigned)((a.n_nodes + THREADS - 1) / THREADS), THREADS, smem, stream>>>(a);
+  k_heat_tet4_rows<THREADS, MINB><<<(unsigned)((a.n_rows + THREADS - 1) / THREADS), THREADS, smem, stream>>>(a);
   FDK_CUDA(cudaGetLastError());
   return 0;
 }
 
 inline int launch_heat_tet4(const HeatTet4Args& a, cudaStream_t stream) {
-  if (a.n_nodes == 0) return 0;
+  if (a.n_nodes == 0 || a.n_rows == 0) return 0;
   if (int rc = ensure_device_tables()) return rc;
   constexpr int THREADS = 128;
   const size_t smem = (size_t)(a.K != nullptr ? a.max_deg : 0) * THREADS * sizeof(double);

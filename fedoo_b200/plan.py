@@ -198,6 +198,12 @@ class Plan:
         self.heavy_nodes = torch.nonzero(heavy).reshape(-1).to(torch.int32)
         if self.heavy_nodes.numel():
             owned = (~heavy) if owned is None else (owned.to(dev) & ~heavy)
+        # ---- nodes no element refers to (the parts of an AssemblySum share one node array, fedoo/core/assembly_sum.py:
+        # 35-40; isolated nodes of an imported mesh): their rows are empty, nothing to compute.  They stay out of the
+        # clusters -- a cluster's slot records assume that every owned node has at least its diagonal block, and nothing
+        # would bound the number of such nodes in one cluster.
+        if bool((inc_count == 0).any()):
+            owned = (inc_count > 0) if owned is None else (owned.to(dev) & (inc_count > 0))
 
         # ---- Morton order with unique keys ----
         if owned is not None:

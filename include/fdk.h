@@ -257,11 +257,14 @@ int fdk_assemble_rows_elastic(int elem_type, int n_rows, const int32_t* rows, in
  * int32 pairs {element * 4 + local node, positions (4 x u8, little endian) of the columns conn[e][0..3] inside the
  * node's row of the block pattern blk_indptr / blk_indices (fdk_sym_block_csr)}, element-ascending per node;
  * max_row_degree <= 255.  K_values [blk_nnz] in the order of the pattern (nvar = 1: the CSR itself).  No cluster plan
- * is needed.  T_start NULL = 0. */
+ * is needed.  T_start NULL = 0.  rows [n_rows] (device) restricts the launch to the listed node rows -- a rank's owned
+ * nodes in a multi-GPU partition; the other rows of K_values and D are left untouched; NULL = every row (n_rows =
+ * n_nodes or 0). */
 int fdk_assemble_heat_tet4(int compute, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
                            const double* cond_h, double rho_c_over_dt, const double* T, const double* T_start,
                            const int64_t* node_ptr, const int32_t* inc_rec, const int64_t* blk_indptr,
-                           int max_row_degree, double* K_values, double* D, fdk_stream_t stream);
+                           int max_row_degree, int n_rows, const int32_t* rows, double* K_values, double* D,
+                           fdk_stream_t stream);
 
 /* The heat residual from GIVEN Gauss-point fields, as the reference's weak forms pass them through assembly.sv
  * (fedoo/weakform/heat_equation.py:99-117 "grad v . (K TempGradient)", :178-186 "(rho c / dt) v (Temp - Temp_start)"):

@@ -214,6 +214,166 @@ def test_heat_assembly_identical_to_reference(rf):
     _cmp(ref, got)
 
 
+def _heterogeneous_plate(fedoo, method):
+    """examples/heterogeneous/heterogeneous_struct.py of the reference: a plate with a stiff disk glued into its hole,
+    described in the reference's three ways."""
+    fd = fedoo
+    mesh = fd.mesh.hole_plate_mesh(nr=11, nt=11, length=100, height=100, radius=20, elm_type="quad4", name="Domain")
+    mesh.element_sets["matrix"] = np.arange(0, mesh.n_elements)
+    disk = fd.mesh.disk_mesh(20, 11, 11)
+    disk.element_sets["inclusion"] = np.arange(0, disk.n_elements)
+    mesh = mesh + disk
+    mesh.merge_nodes(np.c_[mesh.node_sets["hole_edge"], mesh.node_sets["boundary"]])
+    fd.ModelingSpace("2Dstress")
+    if method == 1:  # sum of two assemblies on element subsets of one node array
+        wf1 = fd.weakform.StressEquilibrium(fd.constitutivelaw.ElasticIsotrop(2e4, 0.3))
+        wf2 = fd.weakform.StressEquilibrium(fd.constitutivelaw.ElasticIsotrop(1e5, 0.3))
+        assembly = fd.Assembly.create(wf1, mesh.extract_elements("matrix")) + fd.Assembly.create(wf2, mesh.extract_elements("inclusion"))
+    elif method == 2:  # material data per element
+        E = np.empty(mesh.n_elements)
+        E[mesh.element_sets["matrix"]] = 2e4
+        E[mesh.element_sets["inclusion"]] = 1e5
+        assembly = fd.Assembly.create(fd.weakform.StressEquilibrium(fd.constitutivelaw.ElasticIsotrop(E, 0.3)), mesh)
+    else:  # heterogeneous law: per-Gauss-point tangent assembled from the two laws
+        mat = fd.constitutivelaw.Heterogeneous(
+            (fd.constitutivelaw.ElasticIsotrop(2e4, 0.3), fd.constitutivelaw.ElasticIsotrop(1e5, 0.3)), ("matrix", "inclusion"))  # fmt: skip
+        assembly = fd.Assembly.create(fd.weakform.StressEquilibrium(mat), mesh)
+    pb = fd.problem.Linear(assembly)
+    bb = mesh.bounding_box
+    pb.bc.add("Dirichlet", mesh.find_nodes("X", bb.xmin), "DispX", 0)
+    pb.bc.add("Dirichlet", mesh.find_nodes("Y", bb.ymin), "DispY", 0)
+    pb.bc.add("Dirichlet", mesh.find_nodes("X", bb.xmax), "DispX", 5)
+    pb.apply_boundary_conditions()
+    pb.solve()
+    return assembly, pb
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", [1, 2, 3])
+def test_heterogeneous_structure_example_identical_to_reference(rf, method):
+    """The reference's heterogeneous-structure example in its three formulations: AssemblySum over element subsets
+    (nodes without elements in each part), per-ELEMENT Young modulus (tiled to Gauss points as Mesh.data_to_gausspoint
+    does) and the Heterogeneous law (per-Gauss-point tangent).  Matrix and solution against the reference's own run."""
+    fedoo, adapter = rf
+    adapter.uninstall(fedoo)
+    try:
+        fedoo.Assembly.delete_memory()
+        a, pb = _heterogeneous_plate(fedoo, method)
+        Kr, Ur = a.get_global_matrix().copy(), np.array(pb.get_dof_solution())
+    finally:
+        adapter.install(fedoo, strict=True)
+    fedoo.Assembly.delete_memory()
+    n0 = dict(adapter.stats)
+    a, pb = _heterogeneous_plate(fedoo, method)
+    K, U = a.get_global_matrix(), np.array(pb.get_dof_solution())
+    assert adapter.stats["assembled"] >= n0["assembled"] + (2 if method == 1 else 1) and adapter.stats["delegated"] == n0["delegated"]
+    assert K.shape == Kr.shape and abs(K - Kr).max() <= 1e-12 * abs(Kr).max()
+    if method != 1:  # one assembly: the pattern is the reference's too (a sum of two matrices goes through scipy's add)
+        assert np.array_equal(K.indptr, Kr.indptr) and np.array_equal(K.indices, Kr.indices)
+    assert np.abs(U - Ur).max() <= 1e-9 * np.abs(Ur).max()
+
+
+def _twice(fedoo, adapter, run):
+    """``run()`` with the reference's own assembly, then on the kernels; (reference result, kernel result)."""
+    adapter.uninstall(fedoo)
+    try:
+        fedoo.Assembly.delete_memory()
+        ref = run()
+    finally:
+        adapter.install(fedoo, strict=True)
+    fedoo.Assembly.delete_memory()
+    return ref, run()
+
+
+@pytest.mark.gpu
+def test_transient_heat_2d_example_identical_to_reference(rf):
+    """examples/thermal/thermal_condution_2D.py of the reference (quad4 in a 2Dplane space, transient, ten adaptive time
+    steps of Newton-Raphson; its vtk output left out -- pyvista is absent): final temperature field."""
+    fedoo, adapter = rf
+
+    def run():
+        fd = fedoo
+        fd.ModelingSpace("2Dplane")
+        mesh = fd.mesh.rectangle_mesh(nx=21, ny=21, x_min=0, x_max=1, y_min=0, y_max=1, elm_type="quad4", name="Domain")
+        fd.constitutivelaw.ThermalProperties(18, 0.5, 7800, name="ThermalLaw")
+        fd.weakform.HeatEquation("ThermalLaw")
+        fd.Assembly.create("ThermalLaw", "Domain", name="Assembling")
+        pb = fd.problem.NonLinear("Assembling")
+        pb.set_nr_criterion("Displacement", tol=1e-2, max_subiter=5, err0=100)
+        pb.bc.add("Dirichlet", mesh.find_nodes("X", 0), "Temp", 100, start_value=0)
+        pb.bc.add("Dirichlet", mesh.find_nodes("X", 1), "Temp", 50, start_value=0)
+        pb.nlsolve(dt=20, tmax=200, update_dt=True, print_info=0)
+        return np.array(pb.get_dof_solution())
+
+    n0 = dict(adapter.stats)
+    Tr, T = _twice(fedoo, adapter, run)
+    assert adapter.stats["assembled"] > n0["assembled"] + 10 and adapter.stats["delegated"] == n0["delegated"]
+    assert Tr.min() > 49.9 and Tr.max() < 100.1
+    assert np.abs(T - Tr).max() <= 1e-9 * np.abs(Tr).max()
+
+
+@pytest.mark.gpu
+def test_periodic_plate_example_identical_to_reference(rf):
+    """examples/02-constraints/Periodic_BC_2D_Plate_with_hole.py of the reference: 2Dstress quad4 plate with a hole,
+    PeriodicBC (three global mean-strain dofs), enforced mean shear; solution and mean stress."""
+    fedoo, adapter = rf
+
+    def run():
+        fd = fedoo
+        fd.ModelingSpace("2Dstress")
+        mesh = fd.mesh.hole_plate_mesh()
+        fd.constitutivelaw.ElasticIsotrop(1e5, 0.3, name="ElasticLaw")
+        wf = fd.weakform.StressEquilibrium("ElasticLaw")
+        fd.Assembly.create(wf, mesh, name="Assembly")
+        pb = fd.problem.Linear("Assembly")
+        pb.bc.add(fd.constraint.PeriodicBC(periodicity_type="small_strain"))
+        pb.bc.add("Dirichlet", "E_xx", 0)
+        pb.bc.add("Dirichlet", "E_xy", 0.1)
+        pb.bc.add("Dirichlet", "E_yy", 0)
+        pb.bc.add("Dirichlet", mesh.nearest_node(mesh.bounding_box.center), "Disp", 0)
+        pb.solve()
+        res = pb.get_results("Assembly", ["Disp", "Stress", "MeanStrain"])
+        surf = mesh.bounding_box.volume
+        mean_stress = np.array([1 / surf * mesh.integrate_field(res["Stress"][i]) for i in [0, 1, 3]])
+        return np.array(pb.get_dof_solution()), mean_stress
+
+    n0 = dict(adapter.stats)
+    (Ur, sr), (U, s) = _twice(fedoo, adapter, run)
+    assert adapter.stats["assembled"] > n0["assembled"] and adapter.stats["delegated"] == n0["delegated"]
+    assert abs(sr[2] - 2497.66802) < 1e-3  # the value the reference prints for this example
+    assert np.abs(U - Ur).max() <= 1e-9 * np.abs(Ur).max()
+    assert np.abs(s - sr).max() <= 1e-9 * np.abs(sr).max()
+
+
+@pytest.mark.gpu
+def test_reference_homogenized_stiffness_on_the_kernels(rf):
+    """fedoo.homogen.get_homogenized_stiffness (homogen/tangent_stiffness.py:18-160: PeriodicBC, six load cases, mean
+    stress) of the UNMODIFIED reference on a hex8 cell with a stiff spherical inclusion given as a per-ELEMENT Young
+    modulus; K comes from the kernels, everything else is the reference's code."""
+    fedoo, adapter = rf
+    from scipy.sparse.linalg import spsolve
+
+    def direct(A, B, **kargs):  # the reference forwards solver_type=None to scipy's spsolve, which refuses it
+        return spsolve(A, B)
+
+    def run():
+        fd = fedoo
+        fd.ModelingSpace("3D")
+        mesh = fd.mesh.box_mesh(nx=7, ny=7, nz=7, elm_type="hex8", name="Domain")
+        ctr = mesh.nodes[mesh.elements].mean(axis=1)
+        E = np.where(np.linalg.norm(ctr - 0.5, axis=1) < 0.3, 1e6, 1e5)
+        fd.constitutivelaw.ElasticIsotrop(E, 0.3, name="law")
+        fd.weakform.StressEquilibrium("law", name="wf")
+        a = fd.Assembly.create("wf", "Domain", "hex8", name="A")
+        return np.array(fd.homogen.get_homogenized_stiffness(a, solver=direct))
+
+    n0 = dict(adapter.stats)
+    Cr, C = _twice(fedoo, adapter, run)
+    assert adapter.stats["assembled"] > n0["assembled"] and adapter.stats["delegated"] == n0["delegated"]
+    assert Cr.shape == (6, 6) and Cr[0, 0] > 1.3e5 and np.abs(Cr - Cr.T).max() < 1e-6 * Cr[0, 0]
+    assert np.abs(C - Cr).max() <= 1e-9 * np.abs(Cr).max()
+
+
 @pytest.mark.gpu
 def test_strict_mode_refuses_what_is_not_on_the_path(rf):
     fedoo, adapter = rf
@@ -262,11 +422,18 @@ def test_adapter_classification_cpu():
     fedoo.weakform.HeatEquation("ThermalLaw")
     h = fedoo.Assembly.create("ThermalLaw", "Domain", name="H")
     assert adapter._classify(h) == "heat" and h.mat_lumping == [False, True]
-    # tangent formats of the reference (6x6 floats, object arrays with per-Gauss-point entries, (6,6,N))
+    # tangent formats of the reference (6x6 floats, object arrays with per-Gauss-point / per-element / per-node entries,
+    # (6,6,N)); the conversion to Gauss points is the reference's own (Mesh.data_to_gausspoint)
     H = fedoo.constitutivelaw.ElasticIsotrop(2.0, 0.3).get_tangent_matrix(None, "3D")
-    assert adapter._normalize_tangent(H, 8).shape == (6, 6)
-    Eg = np.linspace(1, 2, 8)
-    Hobj = fedoo.constitutivelaw.ElasticIsotrop(Eg, 0.3).get_tangent_matrix(None, "3D")
-    Hn = adapter._normalize_tangent(Hobj, 8)
-    assert Hn.shape == (6, 6, 8) and Hn.flags["F_CONTIGUOUS"] and np.allclose(Hn[0, 1], Eg * 0.3 / (1.3 * 0.4))
-    assert Hn[0, 3].max() == 0
+    assert adapter._normalize_tangent(H, a).shape == (6, 6)
+    n_gp = a.n_gauss_points
+    assert (a.mesh.n_nodes, a.mesh.n_elements, n_gp) == (27, 8, 64)
+    for n in (n_gp, a.mesh.n_elements, a.mesh.n_nodes):
+        Eg = np.linspace(1, 2, n)
+        Hobj = fedoo.constitutivelaw.ElasticIsotrop(Eg, 0.3).get_tangent_matrix(None, "3D")
+        Hn = adapter._normalize_tangent(Hobj, a)
+        assert Hn.shape == (6, 6, n_gp) and Hn.flags["F_CONTIGUOUS"]
+        assert np.abs(Hn[0, 1] - a.mesh.data_to_gausspoint(Eg, 8) * 0.3 / (1.3 * 0.4)).max() < 1e-15
+        assert Hn[0, 3].max() == 0
+    with pytest.raises(ValueError):
+        adapter._normalize_tangent(fedoo.constitutivelaw.ElasticIsotrop(np.ones(5), 0.3).get_tangent_matrix(None, "3D"), a)

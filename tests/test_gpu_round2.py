@@ -121,6 +121,80 @@ def test_heat_nlsolve_from_default_zero_start(fd, golden_dir):
     assert nrm(T, ref["T"]) <= 1e-10
 
 
+def test_heat_row_owner_kernel_on_owned_rows(fd, golden_dir):
+    """A rank of a multi-GPU partition assembles the rows of its OWNED nodes only (fdk_assemble_heat_tet4 with a row
+    list): those rows of K and entries of D are bit-identical to the full assembly, everything else is left zero."""
+    g = np.load(os.path.join(golden_dir, "tet4_box_heat.npz"))
+    nodes, elements = g["nodes"], g["elements"]
+    owned = np.random.default_rng(5).random(len(nodes)) < 0.6
+
+    def run(own):
+        fd.Assembly.delete_memory()
+        fd.ModelingSpace("3D")
+        fd.Mesh(nodes, elements, "tet4", name="Domain")
+        fd.constitutivelaw.ThermalProperties(500, 0.5, 7800, name="ThermalLaw")
+        fd.weakform.HeatEquation("ThermalLaw")
+        a = fd.Assembly.create("ThermalLaw", "Domain", name="A", owned_nodes=own)
+        pb = fd.problem.NonLinear("A")
+        pb.dtime = 10 / 3
+        pb._U, pb._dU = np.random.default_rng(2).uniform(0, 3, len(nodes)), 0
+        pb.initialize()
+        a.set_start(pb)
+        pb._dU = np.random.default_rng(4).uniform(-0.2, 0.2, len(nodes))
+        a.update(pb, "all")
+        return a.get_global_matrix().tocsr(), np.array(a.get_global_vector())
+
+    K0, D0 = run(None)
+    K1, D1 = run(owned)
+    assert np.array_equal(K0.indptr, K1.indptr) and np.array_equal(K0.indices, K1.indices)
+    row_of = np.repeat(np.arange(len(nodes)), np.diff(K0.indptr))
+    assert np.array_equal(K1.data[owned[row_of]], K0.data[owned[row_of]])
+    assert np.array_equal(D1[owned], D0[owned]) and np.abs(D0[owned]).max() > 0
+    assert not K1.data[~owned[row_of]].any() and not D1[~owned].any()
+
+
+@pytest.mark.parametrize("name,elm,space", [("hex8_jitter", "hex8", "3D"), ("tet10_box", "tet10", "3D"), ("quad4_plate", "quad4", "2Dstress")])
+def test_nodes_without_elements(fd, golden_dir, name, elm, space):
+    """A mesh whose node array holds nodes no element refers to (each part of the reference's AssemblySum is one,
+    core/assembly_sum.py:35-40), numbered before, between and after the referenced ones: same K values and D as the
+    mesh without them, empty rows and zero residual for the extra nodes."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    nodes, elements, U = g["nodes"], g["elements"].astype(np.int64), g["U"]
+    n, dim = nodes.shape
+    rng = np.random.default_rng(1)
+    n_new = n + 300 + n // 3
+    new_id = np.sort(rng.choice(np.arange(150, n_new - 50), n, replace=False))  # 150 first, 50+ last and many between: unreferenced
+    nodes2 = rng.uniform(nodes.min(axis=0), nodes.max(axis=0), (n_new, dim))
+    nodes2[new_id] = nodes
+    U2 = np.zeros(dim * n_new)
+    for v in range(dim):
+        U2[v * n_new + new_id] = U[v * n : (v + 1) * n]
+
+    def run(nodes, elements, U):
+        fd.Assembly.delete_memory()
+        fd.ModelingSpace(space)
+        fd.Mesh(nodes, elements, elm, name="Domain")
+        law = fd.constitutivelaw.ElasticIsotrop(float(g["E"]), float(g["nu"]), name="law")
+        fd.weakform.StressEquilibrium(law, name="wf")
+        a = fd.Assembly.create("wf", "Domain", elm, name="A")
+        pb = fd.problem.Linear("A")
+        pb.set_X(U)
+        a.update(pb, compute="all")
+        return a.get_global_matrix().tocsr(), np.array(a.get_global_vector())
+
+    K0, D0 = run(nodes, elements, U)
+    K1, D1 = run(nodes2, new_id[elements], U2)
+    dof = np.concatenate([v * n_new + new_id for v in range(dim)])
+    sub = K1[dof][:, dof]
+    assert K1.nnz == K0.nnz and sub.nnz == K0.nnz  # nothing stored in the rows / columns of the extra nodes
+    assert abs(sub - K0).max() <= 1e-14 * abs(K0).max()
+    assert np.abs(D1[dof] - D0).max() <= 1e-14 * np.abs(D0).max()
+    rest = np.ones(dim * n_new, bool)
+    rest[dof] = False
+    assert not D1[rest].any()
+    assert nrm(D0, g["D"]) <= TOL
+
+
 def test_to_start_restores_state_and_operators(fd, golden_dir):
     """Assembly.to_start (core/assembly.py:724-735: the dt-cut restart of NonLinear): sv is rebound to the start state,
     K and D are those of the start of the increment again -- checked on the plastic path, where both change."""

@@ -77,19 +77,52 @@ def test_plan_forced_refinement():
 
 def test_plan_unreferenced_nodes_and_single_node_overflow():
     nodes, el = _mesh("hex8")
+    n_ref = len(nodes)
     nodes = np.vstack([nodes, [[5.0, 5.0, 5.0], [6.0, 6.0, 6.0]]])  # two isolated nodes
     plan, pat = make_plan("hex8", nodes, el)
     assert plan.n_nodes == len(nodes)
+    # nodes without elements have empty rows: they are not part of any cluster
+    assert plan.n_owned == n_ref and plan.t["cl_node"].cpu().numpy().max() < n_ref
     # a node whose incident elements alone exceed a cluster's capacity is left out of the clusters: its row goes to the
     # rows kernel (csrc/fdk_rows.cuh).  With inc_max = 4 every node touching more than 4 elements is such a node.
     small, _ = make_plan("hex8", nodes, el, caps=dict(inc_max=4, te_max=80))
     n_inc = np.bincount(el.reshape(-1), minlength=len(nodes))
     heavy = np.flatnonzero(n_inc > 4)
     assert heavy.size > 0 and np.array_equal(small.heavy_nodes.cpu().numpy(), heavy)
-    assert small.n_owned == len(nodes) - heavy.size
+    assert small.n_owned == n_ref - heavy.size
     owned_by_clusters = small.t["cl_node"].cpu().numpy()
     assert not np.intersect1d(owned_by_clusters, heavy).size
     assert plan.heavy_nodes.numel() == 0
+
+
+@pytest.mark.parametrize("where", ["inside", "far", "few", "first"])
+def test_plan_with_nodes_no_element_refers_to(where):
+    """The parts of an AssemblySum share one node array (fedoo/core/assembly_sum.py:35-40): each part's mesh carries the
+    other parts' nodes without any element.  Hundreds of them inside the bounding box, far away, a handful, or numbered
+    BEFORE the referenced ones: K from the plan arrays must stay the reference K (rows of those nodes empty)."""
+    nodes, el = _mesh("quad4")
+    rng = np.random.default_rng(0)
+    lo, hi = nodes.min(axis=0), nodes.max(axis=0)
+    if where == "inside":
+        extra = rng.uniform(lo, hi, (600, 2))
+    elif where == "far":
+        extra = np.full((600, 2), 500.0)
+    else:
+        extra = rng.uniform(lo, hi, (5, 2))
+    if where == "first":
+        nodes, el = np.vstack([extra, nodes]), el + len(extra)
+    else:
+        nodes = np.vstack([nodes, extra])
+    plan, pat = make_plan("quad4", nodes, el)
+    assert plan.n_owned == len(nodes) - len(extra)
+    K = emulate_iso(plan, pat, nodes, el, 1.5, 0.7, allow_unwritten=False)
+    H = np.zeros((6, 6))
+    H[:3, :3] = 1.5
+    H[np.arange(3), np.arange(3)] += 1.4
+    H[np.arange(3, 6), np.arange(3, 6)] = 0.7
+    Kref = fo.assemble_stiffness(nodes, el, "quad4", H, 2)
+    assert np.array_equal(Kref.indptr[: len(nodes) + 1] // 2, pat.blk_indptr.numpy())
+    assert np.abs(K - Kref.data).max() <= 1e-12 * np.abs(Kref.data).max()
 
 
 def test_slab_ranks_get_the_same_bricks_as_one_gpu():
