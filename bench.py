@@ -857,7 +857,8 @@ def run_other(args):
             checks["D_vs_single_gpu_rel"] = float(err)
     if sharded:
         stats_all = [None] * world
-        plan = a._saved_bloc_structure["plan"]  # None: the row-owner kernel needs no cluster plan
+        ent = a._saved_bloc_structure  # no plan at all: the row-owner kernel needs none
+        plan = next((ent[k] for k in ("plan", "plan_big", "plan_small") if ent.get(k) is not None), None)
         dist.all_gather_object(stats_all, dict(part_stats, clusters=None if plan is None else int(plan.n_clusters),
                                                heavy_nodes=None if plan is None else int(plan.heavy_nodes.numel())))  # fmt: skip
     if rank != 0:

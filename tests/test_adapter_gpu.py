@@ -375,6 +375,38 @@ def test_reference_homogenized_stiffness_on_the_kernels(rf):
 
 
 @pytest.mark.gpu
+def test_nonlinear_driver_with_elastic_law_identical_to_reference(rf):
+    """The reference's NonLinear problem (Newton-Raphson over four time increments: set_start / update / to_start, the
+    initial-stress term of the residual read from assembly.sv['Stress']) around a bi-material hex8 beam; the reference's
+    own post-processing (get_results at nodes) on top."""
+    fedoo, adapter = rf
+
+    def run():
+        fd = fedoo
+        fd.ModelingSpace("3D")
+        mesh = fd.mesh.box_mesh(nx=11, ny=4, nz=4, x_min=0, x_max=10, y_min=0, y_max=1, z_min=0, z_max=1, elm_type="hex8", name="Domain")  # fmt: skip
+        ctr = mesh.nodes[mesh.elements].mean(axis=1)
+        fd.constitutivelaw.ElasticIsotrop(np.where(ctr[:, 0] < 5, 1e5, 3e5), 0.3, name="law")
+        fd.weakform.StressEquilibrium("law", name="wf")
+        a = fd.Assembly.create("wf", "Domain", "hex8", name="A")
+        pb = fd.problem.NonLinear("A")
+        pb.set_nr_criterion("Displacement", tol=1e-8, max_subiter=5)
+        pb.bc.add("Dirichlet", mesh.find_nodes("X", 0), "Disp", 0)
+        pb.bc.add("Dirichlet", mesh.find_nodes("X", 10), "DispY", -0.5)
+        pb.nlsolve(dt=0.25, tmax=1, update_dt=False, print_info=0)
+        res = pb.get_results("A", ["Disp", "Stress", "Strain"], "Node")
+        return np.array(pb.get_dof_solution()), np.array(res["Stress"]), np.array(a.get_global_vector())
+
+    n0 = dict(adapter.stats)
+    (Ur, Sr, Dr), (U, S, D) = _twice(fedoo, adapter, run)
+    assert adapter.stats["assembled"] >= n0["assembled"] + 8 and adapter.stats["delegated"] == n0["delegated"]
+    assert abs(np.abs(Ur).max() - 0.5) < 1e-12
+    assert np.abs(U - Ur).max() <= 1e-9 * np.abs(Ur).max()
+    assert np.abs(S - Sr).max() <= 1e-9 * np.abs(Sr).max()
+    assert np.abs(D - Dr).max() <= 1e-9 * np.abs(Dr).max()
+
+
+@pytest.mark.gpu
 def test_strict_mode_refuses_what_is_not_on_the_path(rf):
     fedoo, adapter = rf
     fedoo.Assembly.delete_memory()
