@@ -275,6 +275,8 @@ class Assembly(_Named):
             stress = self.sv.get("Stress", 0)
             has_vec = want_vec and not (np.isscalar(stress) and stress == 0)
             flags = (_lib.MATRIX if want_mat else 0) | (_lib.VECTOR if has_vec else 0)
+            if self.mesh.n_elements == 0:
+                flags = 0  # nothing to integrate: K has no entry, D stays zero
             K = self._buffer("K", nvar * nvar * pattern.blk_nnz, zero=self.owned_nodes is not None) if want_mat else None
             D = self._buffer(self._d_tag(), nvar * n_nodes + n_glob, zero=True) if has_vec else None
             U_dev = stress_dev = None
@@ -383,6 +385,8 @@ class Assembly(_Named):
             T_dev = self._U_dev
             has_vec = want_vec and T_dev is not None
             flags = (_lib.MATRIX if want_mat else 0) | (_lib.VECTOR if has_vec else 0)
+            if self.mesh.n_elements == 0:
+                flags = 0
             K = self._buffer("K", pattern.blk_nnz, zero=self.owned_nodes is not None) if want_mat else None
             D = self._buffer(self._d_tag(), n_nodes + n_glob, zero=True) if has_vec else None
             T_start = self._T_start_dev if rcdt != 0.0 else None

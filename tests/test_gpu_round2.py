@@ -195,6 +195,64 @@ def test_nodes_without_elements(fd, golden_dir, name, elm, space):
     assert nrm(D0, g["D"]) <= TOL
 
 
+@pytest.mark.parametrize("elm", ["hex8", "tet4", "tet10", "quad4"])
+def test_smallest_meshes(fd, elm):
+    """One element, two disconnected elements, and a mesh with nodes but no element at all (the reference raises an
+    IndexError on that one; here it yields an empty matrix and a zero vector, no launch): K and D against the oracle."""
+    from fedoo_b200 import meshgen
+    from oracle import fedoo_oracle as fo
+
+    if elm == "quad4":
+        nodes, el = meshgen.rect_quad4(2, 2)
+        nodes = nodes + np.array([[0.0, 0.0], [0.1, -0.05], [0.05, 0.1], [-0.1, 0.02]])[: len(nodes)]
+    else:
+        nodes, hexes = meshgen.box_hex8(2, 2, 2)
+        nodes = nodes + np.random.default_rng(0).uniform(-0.1, 0.1, nodes.shape)
+        if elm == "hex8":
+            el = hexes
+        else:
+            el = meshgen.hex8_to_tet4(hexes)[:1]
+            if elm == "tet10":
+                nodes, el = meshgen.tet4_to_tet10(nodes, el, bulge=0.03)
+            used = np.unique(el)
+            renum = np.full(len(nodes), -1)
+            renum[used] = np.arange(len(used))
+            nodes, el = nodes[used], renum[el]
+    dim = nodes.shape[1]
+    space = "3D" if dim == 3 else "2Dplane"
+    H = fo.elastic_isotropic_H(200e3, 0.3)
+
+    def run(nodes, el):
+        fd.Assembly.delete_memory()
+        fd.ModelingSpace(space)
+        fd.Mesh(nodes, el, elm, name="Domain")
+        law = fd.constitutivelaw.ElasticIsotrop(200e3, 0.3, name="law")
+        fd.weakform.StressEquilibrium(law, name="wf")
+        a = fd.Assembly.create("wf", "Domain", elm, name="A")
+        pb = fd.problem.Linear("A")
+        U = np.random.default_rng(3).standard_normal(dim * len(nodes)) * 1e-3
+        pb.set_X(U)
+        a.update(pb, compute="all")
+        return a.get_global_matrix().tocsr(), a.get_global_vector(), U
+
+    for case in ("one", "two", "none"):
+        if case == "one":
+            nn, ee = nodes, el
+        elif case == "two":
+            nn, ee = np.vstack([nodes, nodes + 7.0]), np.vstack([el, el + len(nodes)])
+        else:
+            nn, ee = nodes, el[:0]
+        K, D, U = run(nn, ee)
+        assert K.shape == (dim * len(nn),) * 2
+        if case == "none":
+            assert K.nnz == 0 and (np.isscalar(D) or not np.asarray(D).any())
+            continue
+        Kref = fo.assemble_stiffness(nn, ee, elm, H, dim)
+        assert np.array_equal(K.indptr, Kref.indptr) and np.array_equal(K.indices, Kref.indices)
+        assert nrm(K.data, Kref.data) <= TOL
+        assert nrm(np.asarray(D), -(Kref @ U)) <= 1e-11
+
+
 def test_to_start_restores_state_and_operators(fd, golden_dir):
     """Assembly.to_start (core/assembly.py:724-735: the dt-cut restart of NonLinear): sv is rebound to the start state,
     K and D are those of the start of the increment again -- checked on the plastic path, where both change."""
