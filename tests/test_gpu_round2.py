@@ -253,6 +253,72 @@ def test_smallest_meshes(fd, elm):
         assert nrm(np.asarray(D), -(Kref @ U)) <= 1e-11
 
 
+@pytest.mark.parametrize("elm,n_points", [("tet4", 3000), ("tet10", 700)])
+def test_delaunay_meshes_elastic(fd, elm, n_points):
+    """Unstructured tetrahedra from a Delaunay triangulation of random points: vertex valence up to ~55, so the tet10
+    mesh has nodes beyond a cluster's capacity (rows kernel) and the rest spread over irregular clusters.  Pattern, K
+    and D against the oracle."""
+    from fedoo_b200 import meshgen
+    from mesh_util import delaunay_tet4
+    from oracle import fedoo_oracle as fo
+
+    nodes, el = delaunay_tet4(n_points, 11)
+    if elm == "tet10":
+        nodes, el = meshgen.tet4_to_tet10(nodes, el, bulge=0.02)
+    fd.Assembly.delete_memory()
+    fd.ModelingSpace("3D")
+    fd.Mesh(nodes, el, elm, name="Domain")
+    law = fd.constitutivelaw.ElasticIsotrop(200e3, 0.3, name="law")
+    fd.weakform.StressEquilibrium(law, name="wf")
+    a = fd.Assembly.create("wf", "Domain", elm, name="A")
+    pb = fd.problem.Linear("A")
+    U = np.random.default_rng(3).standard_normal(3 * len(nodes)) * 1e-3
+    pb.set_X(U)
+    a.update(pb, compute="all")
+    K, D = a.get_global_matrix().tocsr(), np.array(a.get_global_vector())
+    plan = a._plan(a._saved_bloc_structure)
+    if elm == "tet10":
+        assert plan.heavy_nodes.numel() > 0
+    Kref = fo.assemble_stiffness(nodes, el, elm, fo.elastic_isotropic_H(200e3, 0.3), 3)
+    assert np.array_equal(K.indptr, Kref.indptr) and np.array_equal(K.indices, Kref.indices)
+    # Delaunay tets are badly shaped (volumes down to 2 % of the mean are kept): the rounding of J^-1 is amplified in both
+    # implementations, 1.5e-12 of max|K| was observed for the curved tet10 -- hence 5e-12 here instead of the usual 1e-12
+    assert nrm(K.data, Kref.data) <= (5e-12 if elm == "tet10" else TOL)
+    assert nrm(D, -(Kref @ U)) <= 1e-11
+
+
+def test_delaunay_mesh_heat(fd):
+    """The row-owner heat kernel on unstructured tet4 (row degree and incidence count vary from node to node; anisotropic
+    conductivity): K with lumped capacity and the transient residual against the oracle."""
+    from mesh_util import delaunay_tet4
+    from oracle import fedoo_oracle as fo
+
+    nodes, el = delaunay_tet4(3000, 5)
+    cond = np.array([[500.0, 30.0, 0.0], [30.0, 200.0, -10.0], [0.0, -10.0, 350.0]])
+    fd.Assembly.delete_memory()
+    fd.ModelingSpace("3D")
+    fd.Mesh(nodes, el, "tet4", name="Domain")
+    fd.constitutivelaw.ThermalProperties(cond, 0.5, 7800, name="ThermalLaw")
+    fd.weakform.HeatEquation("ThermalLaw")
+    a = fd.Assembly.create("ThermalLaw", "Domain", name="A")
+    pb = fd.problem.NonLinear("A")
+    pb.dtime = 0.25
+    T0 = np.random.default_rng(2).uniform(0, 3, len(nodes))
+    dT = np.random.default_rng(4).uniform(-0.2, 0.2, len(nodes))
+    pb._U, pb._dU = T0, 0
+    pb.initialize()
+    a.set_start(pb)
+    pb._dU = dT
+    a.update(pb, "all")
+    K, D = a.get_global_matrix().tocsr(), np.array(a.get_global_vector())
+    Kref = fo.assemble_heat(nodes, el, "tet4", cond, 7800 * 0.5, 0.25)
+    G, wdet = fo.geometry(nodes, el, "tet4")
+    Dref = fo.residual_heat(G, wdet, el, "tet4", cond, 7800 * 0.5, 0.25, T0 + dT, T0, len(nodes))
+    assert np.array_equal(K.indptr, Kref.indptr) and np.array_equal(K.indices, Kref.indices)
+    assert nrm(K.data, Kref.data) <= TOL
+    assert nrm(D, Dref) <= 1e-11
+
+
 def test_to_start_restores_state_and_operators(fd, golden_dir):
     """Assembly.to_start (core/assembly.py:724-735: the dt-cut restart of NonLinear): sv is rebound to the start state,
     K and D are those of the start of the increment again -- checked on the plastic path, where both change."""

@@ -11,6 +11,7 @@ from fedoo_b200 import meshgen
 from fedoo_b200.plan import TN_MAX, _CAPS
 from oracle import fedoo_oracle as fo
 
+from mesh_util import delaunay_tet4
 from plan_emulator import emulate_iso, make_plan
 
 
@@ -122,6 +123,16 @@ def test_plan_with_nodes_no_element_refers_to(where):
     H[np.arange(3, 6), np.arange(3, 6)] = 0.7
     Kref = fo.assemble_stiffness(nodes, el, "quad4", H, 2)
     assert np.array_equal(Kref.indptr[: len(nodes) + 1] // 2, pat.blk_indptr.numpy())
+    assert np.abs(K - Kref.data).max() <= 1e-12 * np.abs(Kref.data).max()
+
+
+def test_plan_on_delaunay_tets():
+    """Unstructured tetrahedra (valence up to ~40 per vertex): the plan arrays alone reproduce the reference K."""
+    pts, el = delaunay_tet4(300, 0)
+    assert np.bincount(el.reshape(-1)).max() > 36
+    plan, pat = make_plan("tet4", pts, el)
+    K = emulate_iso(plan, pat, pts, el, 115384.61538461539, 76923.07692307692)
+    Kref = fo.assemble_stiffness(pts, el, "tet4", fo.elastic_isotropic_H(200e3, 0.3), 3)
     assert np.abs(K - Kref.data).max() <= 1e-12 * np.abs(Kref.data).max()
 
 
