@@ -821,11 +821,22 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
         const unsigned r0 = sRec[s], r1 = sRec[s + 1];
         const int e0 = r0 & 0xFFFF;
         const int e1 = (int)(r1 & 0xFFFF) - (((r0 ^ r1) >> 24) ? 1 : 0);
-        double v = 0.0;
-        for (int e = e0; e < e1; ++e) {
-          const int src = sEnt[e];
-          v += sBlk[(src / NNE) * ISTR + (src % NNE) * BLK + b];
+        // four independent chains: the lookups and loads of four contributions are in flight together (a vertex node
+        // of a tet mesh gathers 20-40 contributions in its diagonal slot; one dependent chain was latency-bound)
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        int e = e0;
+        for (; e + 3 < e1; e += 4) {
+          const int s0 = sEnt[e], s1 = sEnt[e + 1], s2 = sEnt[e + 2], s3 = sEnt[e + 3];
+          v0 += sBlk[(s0 / NNE) * ISTR + (s0 % NNE) * BLK + b];
+          v1 += sBlk[(s1 / NNE) * ISTR + (s1 % NNE) * BLK + b];
+          v2 += sBlk[(s2 / NNE) * ISTR + (s2 % NNE) * BLK + b];
+          v3 += sBlk[(s3 / NNE) * ISTR + (s3 % NNE) * BLK + b];
         }
+        for (; e < e1; ++e) {
+          const int src = sEnt[e];
+          v0 += sBlk[(src / NNE) * ISTR + (src % NNE) * BLK + b];
+        }
+        const double v = (v0 + v1) + (v2 + v3);
         const int src0 = sEnt[e0];
         sBlk[(src0 / NNE) * ISTR + (src0 % NNE) * BLK + b] = v;
       }
@@ -902,18 +913,30 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   if (fuse_ku) __syncthreads();  // sR complete (uniform)
   FDK_CLK(6)  // phase 3b
   if (do_vec) {
-    for (int n = tid; n < n_owned; n += THREADS) {
+    // one group of 8 lanes per owned node: the lanes stride over the node's per-slot products (or per-incidence nodal
+    // forces) and a three-step shuffle closes the sum -- a fixed order, so D stays bit-reproducible.  (One thread per
+    // node was a chain of up to ~90 dependent shared-memory loads for a tet10 vertex node.)
+    const int sub = tid & 7;
+    for (int n0 = (tid >> 3); n0 < ((n_owned + 3) & ~3); n0 += THREADS / 8) {  // whole warps iterate together
+      const bool live = n0 < n_owned;
+      const int n = live ? n0 : 0;
       double s[NV];
 #pragma unroll
       for (int v = 0; v < NV; ++v) s[v] = 0.0;
-      const int k0 = fuse_ku ? sSlotBase[n] : sFinc[n], k1 = fuse_ku ? sSlotBase[n + 1] : sFinc[n + 1];
+      const int k0 = fuse_ku ? sSlotBase[n] : sFinc[n], k1 = live ? (fuse_ku ? sSlotBase[n + 1] : sFinc[n + 1]) : k0;
       const double* src = fuse_ku ? sR : sF;
-      for (int k = k0; k < k1; ++k)
+      for (int k = k0 + sub; k < k1; k += 8)
 #pragma unroll
         for (int v = 0; v < NV; ++v) s[v] += src[k * NV + v];
-      const int node = p.cl_node[q0 + n];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) a.D[(int64_t)v * p.n_nodes + node] = -s[v];
+      for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) s[v] += __shfl_xor_sync(0xffffffffu, s[v], o);
+      if (live && sub == 0) {
+        const int node = p.cl_node[q0 + n];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) a.D[(int64_t)v * p.n_nodes + node] = -s[v];
+      }
     }
   }
   __syncthreads();  // staging, descriptors and row buffers are free for the next cluster
