@@ -298,7 +298,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
 
   // ---- persistent CTA: clusters blockIdx.x, blockIdx.x + gridDim.x, ... ----
   const int half = tid / HT;       // warp-uniform
-  const int it = tid - half * HT;  // incidence of this thread (phase 2)
+  // incidence of this thread (phase 2).  The second half is rotated by two warps: a cluster usually has far fewer
+  // incidences than HT, so only the first warps of each half have work -- unrotated, those are warps 0, 1 and HT/32,
+  // HT/32 + 1, which sit on the SAME two of the SM's four sub-partitions (warp id mod 4) and leave the FP64 pipes of
+  // the other two idle through the whole block phase (tet10: 62 incidences -> warps {0, 1, 4, 5} of 8)
+  static_assert(HT % 64 == 0, "rotation by two warps");
+  const int it = MMA ? tid - half * HT : (half == 0 ? tid : (tid - HT + 64) % HT);
   const int j0 = half * NH;        // its column blocks: j0 .. j0 + NH - 1
 
   extern __shared__ __align__(16) double smem[];
