@@ -485,6 +485,7 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
 #pragma unroll
       for (int v = 0; v < NV; ++v) f[v] = 0.0;
     }
+    [[maybe_unused]] const unsigned p2_lanes = __ballot_sync(0xffffffffu, it < n_inc);  // this warp's working lanes
     if (it < n_inc) {
       const int le = my_desc & 0xFFF, i = my_desc >> 12;
       const double* gi_p = sG + le * ESTR + i * DIM;
@@ -568,8 +569,53 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
           if constexpr (R1) {
             // K_ij += lam' g_i (x) g_j + mu' (g_j (x) g_i + (g_i . g_j) 1) - kappa (n^ g_i) (x) (n^ g_j); sqrt(w) sits in g
             const double2* r2 = reinterpret_cast<const double2*>(c_p + g * CSTR);
-            const double2 q0 = r2[0], q1 = r2[1], q2 = r2[2], q3 = r2[3], q4 = r2[4];
+            const double2 q0 = r2[0], q1 = r2[1];
             const double lamp = q0.x, mup = q0.y, kap = q1.x;
+            if (!__any_sync(p2_lanes, kap != 0.0)) {
+              // every Gauss point this warp works on in this step is elastic (kappa is exactly 0 there, and the plastic
+              // zone of a structure is spatially coherent, so whole warps are): the flow direction is neither loaded nor
+              // multiplied -- 48 instead of 102 DFMA and 6 fewer operands per thread and Gauss point
+              static_assert(ADJ || !R1, "structured tangent path: adjacent column blocks");
+              double gjv[NH * 3];
+              if constexpr (HEXREF) {
+                const double2* g2 = reinterpret_cast<const double2*>(ge_p + g * GSTR + ((part ^ (gxv >> 1)) * 2) * 3);
+                const double2 v0 = g2[0], v1 = g2[1], v2 = g2[2];
+                const bool swp = ((gxv ^ (gxv >> 1)) & 1) != 0;
+                gjv[0] = swp ? v1.y : v0.x;
+                gjv[1] = swp ? v2.x : v0.y;
+                gjv[2] = swp ? v2.y : v1.x;
+                gjv[3] = swp ? v0.x : v1.y;
+                gjv[4] = swp ? v0.y : v2.x;
+                gjv[5] = swp ? v1.x : v2.y;
+              } else {
+                const double2* g2 = reinterpret_cast<const double2*>(gj_p + g * GSTR);
+#pragma unroll
+                for (int q = 0; q < NH * 3 / 2; ++q) {
+                  const double2 v = g2[q];
+                  gjv[2 * q] = v.x;
+                  gjv[2 * q + 1] = v.y;
+                }
+              }
+              double li[3], mi[3];
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                li[d] = lamp * gi[d];
+                mi[d] = mup * gi[d];
+              }
+#pragma unroll
+              for (int j = 0; j < NH; ++j) {
+                const double* gj = gjv + 3 * j;
+                const double dot = mi[0] * gj[0] + mi[1] * gj[1] + mi[2] * gj[2];
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+#pragma unroll
+                  for (int aa = 0; aa < 3; ++aa) acc[j][cc * 3 + aa] += fma(li[cc], gj[aa], mi[aa] * gj[cc]);
+                  acc[j][cc * 3 + cc] += dot;
+                }
+              }
+              continue;
+            }
+            const double2 q2 = r2[2], q3 = r2[3], q4 = r2[4];
             const double n0 = q1.y, n1 = q2.x, n2 = q2.y, n3 = q3.x, n4 = q3.y, n5 = q4.x;
             double li[3], mi[3], ki[3];
             {
