@@ -407,6 +407,54 @@ def test_nonlinear_driver_with_elastic_law_identical_to_reference(rf):
 
 
 @pytest.mark.gpu
+def test_octet_truss_cells_of_the_reference_through_the_adapter(rf):
+    """The reference's own unstructured meshes, read by its own importer: tests/octet_truss.msh (tet4; the cell of
+    tests/test_octet.py, here with an elastic law: PeriodicBC, mean shear 0.1, direct solve, mean stress) and
+    util/meshes/octet_truss_quad.msh (tet10, 24 911 elements, vertices beyond a cluster's capacity: K and D of one update)."""
+    fedoo, adapter = rf
+    from scipy.sparse.linalg import spsolve
+
+    def tet4_cell():
+        fd = fedoo
+        fd.ModelingSpace("3D")
+        fd.mesh.import_file(os.path.join(REF, "tests", "octet_truss.msh"), name="Domain")
+        mesh = fd.Mesh["Domain2"]
+        fd.constitutivelaw.ElasticIsotrop(1e5, 0.3, name="law")
+        fd.weakform.StressEquilibrium("law", name="wf")
+        fd.Assembly.create("wf", "Domain2", "tet4", name="A")
+        pb = fd.problem.Linear("A")
+        pb.set_solver(lambda A, B, **kargs: spsolve(A, B))
+        pb.bc.add(fd.constraint.PeriodicBC("small_strain", dim=3))
+        pb.bc.add("Dirichlet", mesh.nearest_node(mesh.bounding_box.center), "Disp", 0)
+        pb.bc.add("Dirichlet", "MeanStrain", [0, 0, 0, 0.1, 0, 0])
+        pb.solve()
+        res = pb.get_results("A", ["Disp", "Stress"])
+        vol = mesh.bounding_box.volume
+        return np.array(pb.get_dof_solution()), np.array([mesh.integrate_field(res["Stress"][i]) / vol for i in range(6)])
+
+    def tet10_cell():
+        fd = fedoo
+        fd.ModelingSpace("3D")
+        fd.mesh.import_file(os.path.join(REF, "util", "meshes", "octet_truss_quad.msh"), name="Domain")
+        mesh = fd.Mesh["Domain2"]
+        fd.constitutivelaw.ElasticIsotrop(1e5, 0.3, name="law")
+        fd.weakform.StressEquilibrium("law", name="wf")
+        a = fd.Assembly.create("wf", "Domain2", "tet10", name="A")
+        pb = fd.problem.Linear("A")
+        pb.set_X(np.random.default_rng(0).standard_normal(3 * mesh.n_nodes) * 1e-3)
+        a.update(pb, compute="all")
+        return a.get_global_matrix().copy(), np.array(a.get_global_vector())
+
+    n0 = dict(adapter.stats)
+    (Ur, sr), (U, sg) = _twice(fedoo, adapter, tet4_cell)
+    assert abs(sr[3]) > 100 and np.abs(U - Ur).max() <= 1e-9 * np.abs(Ur).max() and np.abs(sg - sr).max() <= 1e-9 * np.abs(sr).max()
+    ref, got = _twice(fedoo, adapter, tet10_cell)
+    assert got[0].shape == (144798, 144798) and got[0].nnz == 10103202
+    _cmp(ref, got)
+    assert adapter.stats["assembled"] >= n0["assembled"] + 2 and adapter.stats["delegated"] == n0["delegated"]
+
+
+@pytest.mark.gpu
 def test_strict_mode_refuses_what_is_not_on_the_path(rf):
     fedoo, adapter = rf
     fedoo.Assembly.delete_memory()
