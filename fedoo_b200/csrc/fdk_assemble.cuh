@@ -121,7 +121,7 @@ struct Layout {
     bytes += (size_t)(2 * (p.cap_owned + 1)) * 4;     // sSlotBase, sFinc
     bytes += (size_t)(p.cap_slots + 1) * 4;           // sRec
     bytes += (size_t)p.cap_heavy * 4;                 // sHeavy
-    bytes += 2 * (size_t)((p.cap_te * NNE + 3) & ~3); // sLconn (double-buffered)
+    bytes += 2 * (size_t)((p.cap_te * NNE + 7) & ~3); // sLconn (double-buffered; + one word: unaligned starts)
     return bytes;
   }
 };
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   unsigned* sRec = reinterpret_cast<unsigned*>(sFinc + (p.cap_owned + 1)); // [cap_slots+1]
   unsigned* sHeavy = sRec + (p.cap_slots + 1);                             // [cap_heavy]
   unsigned char* sLbuf = reinterpret_cast<unsigned char*>(sHeavy + p.cap_heavy);  // [2][lc_bytes]
-  const int lc_bytes = (p.cap_te * NNE + 3) & ~3;
+  const int lc_bytes = (p.cap_te * NNE + 7) & ~3;
   // tensor-core path extras
   [[maybe_unused]] double* sJ = reinterpret_cast<double*>(sBptr + ((p.cap_owned + 1) & ~1));  // [cap_te][JSTR]
   unsigned short* sEnt = reinterpret_cast<unsigned short*>(sLbuf + 2 * lc_bytes);  // [cap_ent] slot-sorted sources
@@ -368,7 +368,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
     if constexpr (NNE % 4 == 0) {
       for (int t = tid; t < h.n_te * NNE / 4; t += THREADS) cp_async<4>(dL + 4 * t, lc + 4 * t);
     } else {
-      for (int t = tid; t < h.n_te * NNE; t += THREADS) dL[t] = lc[t];
+      // tet10: a cluster's byte range starts anywhere.  The aligned words that cover it are copied asynchronously (the
+      // buffer keeps the misalignment, readers add it back; the plan pads the array by one word) -- plain byte loads
+      // here made every cluster wait one global-memory latency between its block phase and its staging stores
+      const int sh = (int)(((int64_t)h.te0 * NNE) & 3);
+      const int n_w = (sh + h.n_te * NNE + 3) / 4;
+      for (int t = tid; t < n_w; t += THREADS) cp_async<4>(dL + 4 * t, lc - sh + 4 * t);
     }
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
@@ -410,7 +415,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble(const __grid_constan
   const int64_t slot0 = cur.slot0;
   const double* sX = sXbuf + buf * xu_doubles;
   const double* sU = sX + p.cap_tn * DIM;
-  const unsigned char* sLconn = sLbuf + buf * lc_bytes;
+  const unsigned char* sLconn = sLbuf + buf * lc_bytes + (NNE % 4 == 0 ? 0 : (int)(((int64_t)te0 * NNE) & 3));
   const int c_next = c + gridDim.x;
   const bool has_next = c_next < p.n_clusters;
   ClusterHdr nxt = cur;

@@ -115,6 +115,17 @@ __global__ void __launch_bounds__(THREADS, MINB) k_heat_tet4_rows(const __grid_c
     for (int k = 0; k < 4; ++k)
 #pragma unroll
       for (int d = 0; d < 3; ++d) X[k][d] = a.coords[(int64_t)nd[k] * 3 + d];
+    // the nodal temperatures are requested together with the coordinates, before the geometry is computed: they sit
+    // behind a run-time flag, so the compiler leaves them where they are written (ncu had them as the top stall)
+    double Tk[4] = {0.0, 0.0, 0.0, 0.0}, Ts[4] = {0.0, 0.0, 0.0, 0.0};
+    if (want_D) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) Tk[k] = a.T[nd[k]];
+      if (a.rcdt != 0.0 && a.T_start != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) Ts[k] = a.T_start[nd[k]];
+      }
+    }
     double G[4][3];
     const double wdet = tet4_gradients(X, G);  // |det J|; the gradient is the same at every Gauss point
     // gradient of the row node (selects, not a run-time index: G stays in registers)
@@ -137,10 +148,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_heat_tet4_rows(const __grid_c
       }
     }
     if (want_D) {
-      double Tk[4], gT[3] = {0.0, 0.0, 0.0};
+      double gT[3] = {0.0, 0.0, 0.0};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        Tk[k] = a.T[nd[k]];
 #pragma unroll
         for (int d = 0; d < 3; ++d) gT[d] = fma(Tk[k], G[k][d], gT[d]);
       }
@@ -154,7 +164,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_heat_tet4_rows(const __grid_c
         double dT[4], ssum = 0.0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          dT[k] = Tk[k] - (a.T_start != nullptr ? a.T_start[nd[k]] : 0.0);
+          dT[k] = Tk[k] - Ts[k];
           ssum += dT[k];
         }
         const double dTi = i == 0 ? dT[0] : (i == 1 ? dT[1] : (i == 2 ? dT[2] : dT[3]));
@@ -188,14 +198,16 @@ inline int launch_heat_tet4(const HeatTet4Args& a, cudaStream_t stream) {
   constexpr int THREADS = 128;
   const size_t smem = (size_t)(a.K != nullptr ? a.max_deg : 0) * THREADS * sizeof(double);
   FDK_REQUIRE(a.max_deg <= 255 && smem <= 200 * 1024, FDK_ECAP, "row degree %d exceeds the row-owner kernel's capacity", a.max_deg);
-  // resident CTAs per SM the register allocation aims at (96 / 80 / 64 registers); FDK_HEAT_MINB overrides (diagnostic)
+  // resident CTAs per SM the register allocation aims at (128 / 96 / 80 / 64 registers); FDK_HEAT_MINB overrides
+  // (diagnostic).  Measured at 20 M elements, K + D: 5 -> 1.38 ms (no spills), 6 -> 1.64 ms, 8 slower still
   static const int minb = [] {
     const char* e = getenv("FDK_HEAT_MINB");
-    return e ? atoi(e) : 6;
+    return e ? atoi(e) : 5;
   }();
   if (minb >= 8) return launch_heat_tet4_t<THREADS, 8>(a, smem, stream);
   if (minb >= 6) return launch_heat_tet4_t<THREADS, 6>(a, smem, stream);
-  return launch_heat_tet4_t<THREADS, 5>(a, smem, stream);
+  if (minb >= 5) return launch_heat_tet4_t<THREADS, 5>(a, smem, stream);
+  return launch_heat_tet4_t<THREADS, 4>(a, smem, stream);
 }
 
 }  // namespace fdk

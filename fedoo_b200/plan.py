@@ -450,7 +450,8 @@ class Plan:
             cl_te_ptr=cl_te_ptr.to(i32),
             cl_te_elem=te_elem.to(i32),
             cl_te_own=te_own.to(u8),
-            cl_lconn=lconn.to(u8).contiguous(),
+            # one row of padding: the kernel copies the aligned 4-byte words that cover a cluster's byte range
+            cl_lconn=torch.cat([lconn.to(u8), torch.zeros((1, nne), dtype=u8, device=dev)]).contiguous(),
             te_desc=((te_inc & 0xFFFF) | ((te_mask & 0xFFFF) << 16)).to(torch.uint32),
             cl_tn_ptr=cl_tn_ptr.to(i32),
             cl_tn_node=tn_node.to(i32),
