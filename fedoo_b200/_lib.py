@@ -18,7 +18,7 @@ EXPORTS = [
     "fdk_last_error_string", "fdk_version", "fdk_set_option", "fdk_get_option", "fdk_debug_phase_clocks", "fdk_element_info", "fdk_element_table",
     "fdk_sym_block_keys", "fdk_sym_block_csr", "fdk_sym_expand_csr", "fdk_plan_color_blocks",
     "fdk_assemble_elastic_iso", "fdk_assemble_elastic_iso_dist", "fdk_assemble_elastic_general", "fdk_assemble_heat", "fdk_assemble_heat_tet4", "fdk_assemble_rows_elastic",
-    "fdk_gp_strain_stress", "fdk_gp_strain_stress_fbar", "fdk_residual_elastic", "fdk_residual_heat", "fdk_residual_heat_gp", "fdk_gp_temperature", "fdk_j2_update", "fdk_j2_update_r1", "fdk_j2_update_from_dofs", "fdk_j2_tangent_expand", "fdk_assemble_elastic_r1",
+    "fdk_gp_strain_stress", "fdk_gp_strain_stress_fbar", "fdk_residual_elastic", "fdk_residual_heat", "fdk_residual_heat_gp", "fdk_gp_temperature", "fdk_gp_deformation_gradient", "fdk_j2_update", "fdk_j2_update_r1", "fdk_j2_update_from_dofs", "fdk_j2_tangent_expand", "fdk_assemble_elastic_r1",
     "fdk_gather_f64", "fdk_scatter_add_f64", "fdk_copy_segments",
     "fdk_csr_spmv", "fdk_csr_diagonal", "fdk_pcg_work_doubles", "fdk_pcg_jacobi", "fdk_bcsr_spmv", "fdk_bcsr_pcg_jacobi",
     "fdk_mpc_expand", "fdk_mpc_fold", "fdk_bcsr_pcg_jacobi_mpc", "fdk_pcg_multi_work_doubles", "fdk_bcsr_pcg_jacobi_multi",
@@ -137,6 +137,7 @@ def load():
     lib.fdk_residual_elastic.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.fdk_gp_strain_stress_fbar.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.fdk_gp_temperature.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, vp]
+    lib.fdk_gp_deformation_gradient.argtypes = [i32, i32, i64, vp, vp, vp, i32, vp, vp]
     lib.fdk_j2_update.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp]
     lib.fdk_j2_update_r1.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp]
     lib.fdk_j2_tangent_expand.argtypes = [i64, vp, vp, vp]

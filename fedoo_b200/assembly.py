@@ -645,6 +645,29 @@ class Assembly(_Named):
         ndim = self.space.ndim
         return [[g[a * 3 + b] if (a < ndim and b < ndim) else 0 for b in range(3)] for a in range(3)]
 
+    def get_deformation_gradient(self, U, fbar=None):
+        """F = 1 + grad u at the Gauss points as a device tensor (N, 3, 3)[n, j, i] -- the memory of the reference's
+        Fortran-ordered ``sv["F"]`` of shape (3, 3, N) -- or, with ``fbar`` (default: the weak form's ``fbar`` flag), the
+        F-bar form F (J_mean / J)^(1/3) (fedoo/weakform/stress_equilibrium.py:542-586, ``_comp_F`` / ``_comp_Fbar``).
+        ``result.permute(2, 1, 0)`` is the (3, 3, N) view.  These are the finite-strain kinematics the reference computes
+        itself; the strain measures and objective rates that follow live in simcoon and are not on this path."""
+        if fbar is None:
+            fbar = bool(getattr(self.weakform, "fbar", False))
+        coords, conn = self._coords(), self.mesh.device_arrays()[1]
+        U_dev = as_device_f64(U)
+        n_nodes = self.mesh.n_nodes
+        if U_dev.numel() < self.space.ndim * n_nodes:
+            raise ValueError("the dof vector is shorter than ndim * n_nodes")
+        F = torch.empty((self.n_gauss_points, 3, 3), dtype=torch.float64, device=device())
+        _lib.check(
+            _lib.load().fdk_gp_deformation_gradient(
+                _lib.ELEM_IDS[self.elm_type], n_nodes, self.mesh.n_elements, _lib.ptr(conn), _lib.ptr(coords),
+                _lib.ptr(U_dev), 1 if fbar else 0, _lib.ptr(F), _lib.current_stream(),
+            ),
+            "fdk_gp_deformation_gradient",
+        )  # fmt: skip
+        return F
+
     def _thermal_state_update(self, pb, initialize=False):
         """SteadyHeatEquation.update / TemperatureTimeDerivative.update
         (fedoo/weakform/heat_equation.py:54-70,140-152)."""

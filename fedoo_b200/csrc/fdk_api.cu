@@ -537,6 +537,27 @@ int fdk_assemble_heat_tet4(int compute, int n_nodes, int64_t n_elems, const int3
   return launch_heat_tet4(a, (cudaStream_t)stream);
 }
 
+int fdk_gp_deformation_gradient(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                                const double* U, int fbar, double* F_gp, fdk_stream_t stream) {
+  FDK_REQUIRE(conn && coords && U && F_gp, FDK_EINVAL, "NULL argument");
+  DefGradArgs a{};
+  a.n_nodes = n_nodes;
+  a.n_elems = n_elems;
+  a.conn = conn;
+  a.coords = coords;
+  a.U = U;
+  a.fbar = fbar;
+  a.F_gp = F_gp;
+  switch (elem_type) {
+    case FDK_HEX8: return launch_gp_defgrad<Hex8>(a, (cudaStream_t)stream);
+    case FDK_TET4: return launch_gp_defgrad<Tet4>(a, (cudaStream_t)stream);
+    case FDK_TET10: return launch_gp_defgrad<Tet10>(a, (cudaStream_t)stream);
+    case FDK_QUAD4: return launch_gp_defgrad<Quad4>(a, (cudaStream_t)stream);
+  }
+  set_error("unknown element type %d", elem_type);
+  return FDK_EINVAL;
+}
+
 int fdk_residual_heat_gp(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
                          const double* flux_gp, const double* src_gp, const int64_t* node_ptr, const int32_t* node_inc,
                          double* fe_scratch, double* D, fdk_stream_t stream) {

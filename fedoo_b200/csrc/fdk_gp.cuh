@@ -144,6 +144,91 @@ int launch_gp_fbar_center(const GpArgs& a, cudaStream_t stream) {
   return 0;
 }
 
+// Deformation gradient at the Gauss points, F = 1 + grad u, and its F-bar form F (J_mean / J)^(1/3) with J = det F and
+// J_mean the mean of J over the element's Gauss points -- the two finite-strain kinematic quantities the reference
+// computes in its own Python before it hands over to simcoon (fedoo/weakform/stress_equilibrium.py:542-586, _comp_F /
+// _comp_Fbar).  One thread per element, Gauss points in order (np.mean over the gp axis).  F_gp is (N, 9), entry
+// i + 3 j of Gauss point n = F_ij: the memory layout of the reference's Fortran-ordered (3, 3, N) array.  2-D meshes:
+// F_33 = 1, the out-of-plane shears 0.
+struct DefGradArgs {
+  int n_nodes;
+  int64_t n_elems;
+  const int32_t* conn;
+  const double* coords;
+  const double* U;
+  int fbar;
+  double* F_gp;
+};
+
+template <class El>
+__global__ void __launch_bounds__(128) k_gp_defgrad(const __grid_constant__ DefGradArgs a) {
+  constexpr int NNE = El::NNE, NGP = El::NGP, DIM = El::DIM;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n_elems) return;
+  const ElemTable& tab = c_tab[El::ID];
+  int nd[NNE];
+  double X[NNE][DIM];
+#pragma unroll
+  for (int k = 0; k < NNE; ++k) {
+    nd[k] = a.conn[e * NNE + k];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) X[k][d] = a.coords[(int64_t)nd[k] * DIM + d];
+  }
+  double Jg[NGP];
+  double Jsum = 0.0;
+#pragma unroll 1
+  for (int g = 0; g < NGP; ++g) {
+    double dN[DIM * NNE];
+#pragma unroll
+    for (int t = 0; t < DIM * NNE; ++t) dN[t] = tab.dN[g * DIM * NNE + t];
+    double G[NNE][DIM];
+    gp_geometry<NNE, DIM>(dN, 1.0, X, G);
+    double F[3][3] = {{1.0, 0.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 0.0, 1.0}};
+#pragma unroll
+    for (int v = 0; v < DIM; ++v) {
+      double gu[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) gu[d] = 0.0;
+#pragma unroll
+      for (int k = 0; k < NNE; ++k) {
+        const double u = a.U[(int64_t)v * a.n_nodes + nd[k]];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) gu[d] = fma(u, G[k][d], gu[d]);
+      }
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) F[v][d] += gu[d];
+    }
+    const double J = F[0][0] * (F[1][1] * F[2][2] - F[1][2] * F[2][1]) - F[0][1] * (F[1][0] * F[2][2] - F[1][2] * F[2][0]) +
+                     F[0][2] * (F[1][0] * F[2][1] - F[1][1] * F[2][0]);
+    Jg[g] = J;
+    Jsum += J;
+    double* out = a.F_gp + 9 * ((int64_t)g * a.n_elems + e);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) out[i + 3 * j] = F[i][j];
+  }
+  if (a.fbar) {
+    const double Jc = Jsum / NGP;
+#pragma unroll 1
+    for (int g = 0; g < NGP; ++g) {
+      const double sc = pow(Jc / Jg[g], 1.0 / 3.0);
+      double* out = a.F_gp + 9 * ((int64_t)g * a.n_elems + e);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) out[t] *= sc;
+    }
+  }
+}
+
+template <class El>
+int launch_gp_defgrad(const DefGradArgs& a, cudaStream_t stream) {
+  if (a.n_elems == 0) return 0;
+  if (int rc = ensure_device_tables()) return rc;
+  k_gp_defgrad<El><<<(unsigned)((a.n_elems + 127) / 128), 128, 0, stream>>>(a);
+  FDK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Residual alone (compute = "vector": every Newton sub-iteration of fedoo/problem/non_linear.py:400-404 asks for it):
 // D = -int B^T sigma without the cluster machinery of the matrix kernels.  Pass 1, one thread per element: geometry at

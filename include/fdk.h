@@ -279,6 +279,14 @@ int fdk_residual_heat_gp(int elem_type, int n_nodes, int64_t n_elems, const int3
 int fdk_gp_temperature(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
                        const double* T, double* temp_gp, double* temp_gradient_gp, fdk_stream_t stream);
 
+/* Finite-strain kinematics the reference computes in its own Python before handing over to simcoon
+ * (fedoo/weakform/stress_equilibrium.py:542-586, _comp_F / _comp_Fbar): F = 1 + grad u at every Gauss point and, with
+ * fbar != 0, the F-bar form F (J_mean / J)^(1/3), J = det F, J_mean = the mean of J over the element's Gauss points.
+ * F_gp [n_gp][9], entry i + 3 j of Gauss point g * n_elems + e = F_ij (the memory of the reference's Fortran-ordered
+ * (3, 3, N) array sv["F"]).  quad4: F_33 = 1. */
+int fdk_gp_deformation_gradient(int elem_type, int n_nodes, int64_t n_elems, const int32_t* conn, const double* coords,
+                                const double* U, int fbar, double* F_gp, fdk_stream_t stream);
+
 /* J2 plasticity (isotropic power-law hardening sigma_Y + k p^m), backward-Euler radial
  * return + consistent tangent, one thread per Gauss point.  Follows the Simcoon("EPICP")
  * state-variable protocol of fedoo/constitutivelaw/simcoon_umat.py:463-580 (props

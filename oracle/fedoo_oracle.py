@@ -404,6 +404,22 @@ def strain_gp(G, elements, U, n_nodes, ndim):
     return eps
 
 
+def deformation_gradient(G, elements, U, n_nodes, ndim, fbar=False):
+    """F = 1 + grad u at the Gauss points, (3, 3, N) gp-major; with ``fbar`` scaled by (J_mean / J)^(1/3), J_mean the
+    mean of det F over the element's Gauss points (weakform/stress_equilibrium.py:542-586, _comp_F / _comp_Fbar)."""
+    g = grad_disp_gp(G, elements, U, n_nodes, ndim)  # (ndim, ndim, N)
+    N = g.shape[-1]
+    F = np.zeros((3, 3, N))
+    F[np.arange(3), np.arange(3)] = 1.0
+    F[:ndim, :ndim] += g
+    if fbar:
+        n_el = len(elements)
+        J = np.linalg.det(F.transpose(2, 0, 1))
+        Jc = np.mean(J.reshape(-1, n_el), axis=0)
+        F = F * ((Jc / J.reshape(-1, n_el)).ravel() ** (1 / 3))
+    return F
+
+
 def stress_gp(H, eps):
     """sigma_i = sum_j eps_j H_ij, H 6x6 or (6,6,N)."""
     H = np.asarray(H)

@@ -319,6 +319,28 @@ def test_delaunay_mesh_heat(fd):
     assert nrm(D, Dref) <= 1e-11
 
 
+@pytest.mark.parametrize("name,elm", [("hex8_jitter", "hex8"), ("tet10_box", "tet10")])
+def test_deformation_gradient_and_fbar(fd, golden_dir, name, elm):
+    """fdk_gp_deformation_gradient: F = 1 + grad u at the Gauss points and the finite-strain F-bar form
+    F (J_mean / J)^(1/3) against arrays made by the reference's own `_comp_F` / `_comp_Fbar`
+    (weakform/stress_equilibrium.py:542-586; det F between 0.63 and 1.48 in these vectors)."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    ref = np.load(os.path.join(golden_dir, "defgrad.npz"))
+    fd.Assembly.delete_memory()
+    fd.ModelingSpace("3D")
+    fd.Mesh(g["nodes"], g["elements"], elm, name="Domain")
+    law = fd.constitutivelaw.ElasticIsotrop(200e3, 0.3, name="law")
+    wf = fd.weakform.StressEquilibrium(law, name="wf")
+    a = fd.Assembly.create("wf", "Domain", elm, name="A")
+    U = ref[name + "_U"]
+    F = a.get_deformation_gradient(U).permute(2, 1, 0).cpu().numpy()  # (3, 3, N)
+    assert F.shape == ref[name + "_F"].shape and np.abs(F - ref[name + "_F"]).max() <= 1e-13
+    Fb = a.get_deformation_gradient(U, fbar=True).permute(2, 1, 0).cpu().numpy()
+    assert np.abs(Fb - ref[name + "_Fbar"]).max() <= 1e-13
+    wf.fbar = True  # the weak form's flag is the default
+    assert np.array_equal(a.get_deformation_gradient(U).permute(2, 1, 0).cpu().numpy(), Fb)
+
+
 def test_to_start_restores_state_and_operators(fd, golden_dir):
     """Assembly.to_start (core/assembly.py:724-735: the dt-cut restart of NonLinear): sv is rebound to the start state,
     K and D are those of the start of the increment again -- checked on the plastic path, where both change."""
