@@ -10,7 +10,7 @@ All numeric work happens in hand-written CUDA kernels behind the C ABI of ``incl
 (``fedoo_b200/_fdk.so``); there is no CPU fallback.
 """
 
-from . import adapter, constitutivelaw, constraint, homogen, mesh, meshgen, problem, weakform
+from . import adapter, constitutivelaw, constraint, homogen, mesh, meshgen, problem, solver, weakform
 from ._lib import FdkError
 from .adapter import install, uninstall
 from .assembly import Assembly
@@ -24,6 +24,6 @@ WeakForm = WeakFormBase
 __version__ = "0.1.0"
 
 __all__ = [
-    "install", "uninstall", "adapter", "Assembly", "ConstitutiveLaw", "DeviceCSR", "FdkError", "GaussPointTensor", "Mesh", "ModelingSpace", "Problem",
+    "install", "uninstall", "adapter", "solver", "Assembly", "ConstitutiveLaw", "DeviceCSR", "FdkError", "GaussPointTensor", "Mesh", "ModelingSpace", "Problem",
     "WeakForm", "WeakFormBase", "constitutivelaw", "constraint", "homogen", "mesh", "meshgen", "problem", "weakform",
 ]  # fmt: skip

@@ -455,6 +455,57 @@ def test_octet_truss_cells_of_the_reference_through_the_adapter(rf):
 
 
 @pytest.mark.gpu
+def test_device_pcg_through_the_reference_solver_hook(rf):
+    """``pb.set_solver(fedoo_b200.solver.pcg, rtol=...)``: the reference hands its reduced system (MatCB^T A MatCB, a host
+    scipy matrix; fedoo/core/problem.py:277-298, core/base.py:512-537) to the device Jacobi-PCG.  The reference's own
+    cantilever case, solved by its scipy direct solver and by the device solver, K from the kernels both times; and a
+    periodic cell, whose reduced system carries the multi-point constraints."""
+    fedoo, adapter = rf
+    import fedoo_b200
+    from scipy.sparse.linalg import spsolve
+
+    def beam(solver, **kargs):
+        fd = fedoo
+        fd.Assembly.delete_memory()
+        fd.ModelingSpace("3D")
+        mesh = fd.mesh.box_mesh(nx=21, ny=5, nz=5, x_min=0, x_max=1000, y_min=0, y_max=100, z_min=0, z_max=100, elm_type="hex8", name="Domain")  # fmt: skip
+        fd.constitutivelaw.ElasticIsotrop(200e3, 0.3, name="ElasticLaw")
+        fd.weakform.StressEquilibrium("ElasticLaw", name="wf")
+        fd.Assembly.create("wf", "Domain", "hex8", name="Assembling")
+        pb = fd.problem.Linear("Assembling")
+        pb.set_solver(solver, **kargs)
+        pb.bc.add("Dirichlet", mesh.find_nodes("X", 0), "Disp", 0)
+        pb.bc.add("Dirichlet", mesh.find_nodes("X", 1000), "DispY", -10)
+        pb.apply_boundary_conditions()
+        pb.solve()
+        return np.array(pb.get_dof_solution())
+
+    def cell(solver, **kargs):
+        fd = fedoo
+        fd.Assembly.delete_memory()
+        fd.ModelingSpace("3D")
+        mesh = fd.mesh.box_mesh(nx=7, ny=7, nz=7, elm_type="hex8", name="Domain")
+        ctr = mesh.nodes[mesh.elements].mean(axis=1)
+        fd.constitutivelaw.ElasticIsotrop(np.where(np.linalg.norm(ctr - 0.5, axis=1) < 0.3, 1e6, 1e5), 0.3, name="law")
+        fd.weakform.StressEquilibrium("law", name="wf")
+        fd.Assembly.create("wf", "Domain", "hex8", name="A")
+        pb = fd.problem.Linear("A")
+        pb.set_solver(solver, **kargs)
+        pb.bc.add(fd.constraint.PeriodicBC("small_strain", dim=3))
+        pb.bc.add("Dirichlet", mesh.nearest_node(mesh.bounding_box.center), "Disp", 0)
+        pb.bc.add("Dirichlet", "MeanStrain", [0, 0.01, 0, 0.02, 0, 0])
+        pb.solve()
+        return np.array(pb.get_dof_solution())
+
+    direct = lambda A, B, **kargs: spsolve(A, B)  # noqa: E731
+    for case in (beam, cell):
+        Ud = case(direct)
+        Ug = case(fedoo_b200.solver.pcg, rtol=1e-12)
+        assert fedoo_b200.solver.info["iterations"] > 10 and fedoo_b200.solver.info["relative_residual"] <= 1e-12
+        assert np.abs(Ug - Ud).max() <= 1e-8 * np.abs(Ud).max()
+
+
+@pytest.mark.gpu
 def test_strict_mode_refuses_what_is_not_on_the_path(rf):
     fedoo, adapter = rf
     fedoo.Assembly.delete_memory()
