@@ -41,7 +41,7 @@ from . import core as _core
 from . import weakform as _wf
 
 _SUPPORTED = {"hex8": (8, 3), "tet4": (4, 3), "tet10": (15, 3), "quad4": (4, 2)}  # default n_elm_gp, ndim
-stats = {"assembled": 0, "delegated": 0, "gp_results": 0, "gp_state": 0}
+stats = {"assembled": 0, "delegated": 0, "gp_results": 0, "gp_state": 0, "device_solves": 0}
 _installed = {}
 
 
@@ -204,6 +204,21 @@ def _backend(a, kind):
     return be
 
 
+_device_K = {}  # id(host csr_matrix handed to the reference) -> (weakref to it, the DeviceCSR it was fetched from)
+
+
+def _remember_device_matrix(host, dev_csr):
+    import weakref
+
+    key = id(host)
+    _device_K[key] = (weakref.ref(host, lambda _r, k=key: _device_K.pop(k, None)), dev_csr)
+
+
+def _device_matrix_of(host):
+    rec = _device_K.get(id(host))
+    return rec[1] if rec is not None and rec[0]() is host else None
+
+
 _CHUNK = 64 * 1024 * 1024  # elements of the pinned staging buffers (512 MB of float64)
 _staging = {}
 
@@ -253,7 +268,9 @@ def _to_host_csr(dev_csr, be):
     _, indptr, indices = be.host_index
     idx = np.empty_like(indices)
     torch.from_numpy(idx).copy_(torch.from_numpy(indices))  # multi-threaded host copy
-    return sparse.csr_matrix((_fetch(dev_csr.data), idx, indptr.copy()), shape=dev_csr.shape)
+    host = sparse.csr_matrix((_fetch(dev_csr.data), idx, indptr.copy()), shape=dev_csr.shape)
+    _remember_device_matrix(host, dev_csr)  # Problem.solve with the device solver finds K still in HBM
+    return host
 
 
 def _assemble(a, compute, strict, orig):
@@ -456,6 +473,39 @@ def _gp_results(a, operator, U, n_elm_gp, use_local_dof, orig):
     return _fetch(res)
 
 
+def _problem_solve(pb, orig, kargs):
+    """Problem.solve (fedoo/core/problem.py:277-300) when the problem's solver is ``fedoo_b200.solver.pcg``, the matrix
+    is one this adapter assembled (its device copy is still in HBM) and the constraints are plain Dirichlet conditions
+    (MatCB is then a selection of the free dofs): K_ff x_f = (B + D - K Xbc)_f by the masked Jacobi-PCG on the device,
+    without forming MatCB^T A MatCB on the host or sending K anywhere.  Anything else goes to the reference's own
+    method, which hands the host reduced system to the solver callable."""
+    from . import solver as _solver
+
+    spec = getattr(pb, "_ProblemBase__solver", None)
+    A = getattr(pb, "_Problem__A", None)
+    K = _device_matrix_of(A) if A is not None else None
+    if (spec is None or len(spec) < 3 or spec[1] is not _solver.pcg or K is None or getattr(pb, "_MFext", None) is not None
+            or len(pb._dof_free) == 0 or tuple(A.shape) != (pb.n_dof, pb.n_dof)):  # fmt: skip
+        return orig(pb, **kargs)
+    opts = spec[2]
+    rtol = opts.get("rtol", opts.get("tol", 1e-8))
+    dev = K.data.device
+    n = pb.n_dof
+    Xbc = _core.as_device_f64(np.asarray(pb._Xbc, dtype=np.float64), dev)
+    rhs = -K.matvec(Xbc)
+    for v in (pb._Problem__B, pb._Problem__D):
+        if not (np.isscalar(v) and v == 0):
+            rhs += _core.as_device_f64(np.asarray(v, dtype=np.float64), dev)
+    free = torch.zeros(n, dtype=torch.uint8, device=dev)
+    free[torch.from_numpy(np.asarray(pb._dof_free, dtype=np.int64)).to(dev)] = 1
+    x, it, rel = K.pcg(rhs, free_mask=free, rtol=rtol, maxiter=opts.get("maxiter"), check_every=opts.get("check_every", 10))
+    _solver.info["iterations"], _solver.info["relative_residual"], _solver.info["on_device_matrix"] = it, rel, True
+    if rel > rtol:
+        print(f"Warning: fedoo_b200.solver.pcg: convergence to tolerance not achieved ({rel:.2e} after {it} iterations)")
+    pb._Problem__X = _fetch(x * free + Xbc)  # x is 0 on the imposed dofs already; the mask makes it explicit
+    stats["device_solves"] += 1
+
+
 def install(fedoo=None, strict=True, state_updates=True):
     """Put the CUDA path under ``fedoo.Assembly`` (the reference package, unmodified).  Returns the module.
     ``state_updates=False`` leaves ``StressEquilibrium.update`` / ``ElasticAnisotropic.update`` to the reference's own
@@ -470,8 +520,9 @@ def install(fedoo=None, strict=True, state_updates=True):
         return fedoo
     W = fedoo.weakform.stress_equilibrium.StressEquilibrium
     L = fedoo.constitutivelaw.elastic_anisotropic.ElasticAnisotropic
+    P = fedoo.core.problem.Problem
     TL = fedoo.util.voigt_tensors  # the reference's own containers of Gauss-point tensors
-    orig_asm, orig_gp, orig_wf, orig_law = A.assemble_global_mat, A.get_gp_results, W.update, L.update
+    orig_asm, orig_gp, orig_wf, orig_law, orig_solve = A.assemble_global_mat, A.get_gp_results, W.update, L.update, P.solve
     flag, state = [strict], [state_updates]
 
     def assemble_global_mat(self, compute="all"):
@@ -486,6 +537,10 @@ def install(fedoo=None, strict=True, state_updates=True):
     def law_update(self, assembly, pb):
         return _law_update(self, assembly, pb, orig_law, TL.StressTensorList) if state[0] else orig_law(self, assembly, pb)
 
+    def problem_solve(self, **kargs):
+        return _problem_solve(self, orig_solve, kargs)
+
+    problem_solve.__doc__ = orig_solve.__doc__
     assemble_global_mat.__doc__ = orig_asm.__doc__
     get_gp_results.__doc__ = orig_gp.__doc__
     wf_update.__doc__ = orig_wf.__doc__
@@ -494,8 +549,9 @@ def install(fedoo=None, strict=True, state_updates=True):
     A.get_gp_results = get_gp_results
     W.update = wf_update
     L.update = law_update
+    P.solve = problem_solve
     _installed[id(A)] = {"cls": A, "orig": (orig_asm, orig_gp), "strict": flag, "state": state,
-                         "wf": (W, orig_wf), "law": (L, orig_law)}  # fmt: skip
+                         "wf": (W, orig_wf), "law": (L, orig_law), "solve": (P, orig_solve)}  # fmt: skip
     return fedoo
 
 
@@ -508,3 +564,4 @@ def uninstall(fedoo=None):
         A.assemble_global_mat, A.get_gp_results = rec["orig"]
         rec["wf"][0].update = rec["wf"][1]
         rec["law"][0].update = rec["law"][1]
+        rec["solve"][0].solve = rec["solve"][1]

@@ -12,6 +12,11 @@ runs the Jacobi-preconditioned conjugate gradient of libfdk (``fdk_pcg_jacobi``;
     pb.set_solver(fedoo_b200.solver.pcg, rtol=1e-10)
     pb.solve()
 
+With ``install`` in place, ``Problem.solve`` short-cuts further when it can (adapter._problem_solve): if the matrix is
+one the adapter assembled -- its values are still in HBM -- and the constraints are plain Dirichlet conditions, the
+masked PCG runs on that device matrix directly; the reduced system is never formed on the host and K is not uploaded
+(``info["on_device_matrix"]`` says which way the last solve went).
+
 There is no CPU implementation behind it: without the CUDA extension and a device it raises.
 """
 
@@ -22,7 +27,7 @@ import torch
 
 from .core import DeviceCSR, device
 
-info = {"iterations": 0, "relative_residual": 0.0}  # of the last call
+info = {"iterations": 0, "relative_residual": 0.0, "on_device_matrix": False}  # of the last call
 
 
 def pcg(A, B, rtol=1e-8, maxiter=None, check_every=10, **kargs):
@@ -50,7 +55,7 @@ def pcg(A, B, rtol=1e-8, maxiter=None, check_every=10, **kargs):
         (n, n),
     )
     x, it, rel = M.pcg(torch.from_numpy(b).to(dev), rtol=rtol, maxiter=maxiter, check_every=check_every)
-    info["iterations"], info["relative_residual"] = it, rel
+    info["iterations"], info["relative_residual"], info["on_device_matrix"] = it, rel, False
     if rel > rtol:
         print(f"Warning: fedoo_b200.solver.pcg: convergence to tolerance not achieved ({rel:.2e} after {it} iterations)")
     return x.cpu().numpy()

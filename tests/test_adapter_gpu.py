@@ -456,10 +456,10 @@ def test_octet_truss_cells_of_the_reference_through_the_adapter(rf):
 
 @pytest.mark.gpu
 def test_device_pcg_through_the_reference_solver_hook(rf):
-    """``pb.set_solver(fedoo_b200.solver.pcg, rtol=...)``: the reference hands its reduced system (MatCB^T A MatCB, a host
-    scipy matrix; fedoo/core/problem.py:277-298, core/base.py:512-537) to the device Jacobi-PCG.  The reference's own
-    cantilever case, solved by its scipy direct solver and by the device solver, K from the kernels both times; and a
-    periodic cell, whose reduced system carries the multi-point constraints."""
+    """``pb.set_solver(fedoo_b200.solver.pcg, rtol=...)``: the reference's solver hook (fedoo/core/base.py:512-537).  The
+    reference's own cantilever case, solved by its scipy direct solver and by the device Jacobi-PCG, K from the kernels
+    both times; and a periodic cell, whose reduced system MatCB^T A MatCB (core/problem.py:277-298) carries the multi-point
+    constraints and is formed by the reference on the host."""
     fedoo, adapter = rf
     import fedoo_b200
     from scipy.sparse.linalg import spsolve
@@ -500,9 +500,14 @@ def test_device_pcg_through_the_reference_solver_hook(rf):
     direct = lambda A, B, **kargs: spsolve(A, B)  # noqa: E731
     for case in (beam, cell):
         Ud = case(direct)
+        n0 = adapter.stats["device_solves"]
         Ug = case(fedoo_b200.solver.pcg, rtol=1e-12)
         assert fedoo_b200.solver.info["iterations"] > 10 and fedoo_b200.solver.info["relative_residual"] <= 1e-12
         assert np.abs(Ug - Ud).max() <= 1e-8 * np.abs(Ud).max()
+        # plain Dirichlet conditions: the masked PCG ran on the matrix still in HBM (no host reduced system, no upload);
+        # multi-point constraints: the reference formed MatCB^T A MatCB on the host and the callable solved that
+        assert fedoo_b200.solver.info["on_device_matrix"] == (case is beam)
+        assert adapter.stats["device_solves"] == n0 + (1 if case is beam else 0)
 
 
 @pytest.mark.gpu
