@@ -1,7 +1,8 @@
 """Drop-in backend under the REAL fedoo: ``fedoo_b200.install(fedoo)``.
 
 The reference has no plugin interface; its seam is duck-typed Python.  ``install`` replaces, on the
-reference's own ``fedoo.core.assembly.Assembly`` class, the two methods behind which the whole hot path sits:
+reference's own ``fedoo.core.assembly.Assembly`` class, the two methods behind which the whole hot path sits --
+and three more methods whose host cost would otherwise dominate once the assembly is fast:
 
   * ``Assembly.assemble_global_mat(compute)``   fedoo/core/assembly.py:143-470
         -> one-time symbolic pattern + cluster plan, then the sm_100a kernels of libfdk; results are handed back in the
@@ -10,14 +11,16 @@ reference's own ``fedoo.core.assembly.Assembly`` class, the two methods behind w
   * ``Assembly.get_gp_results(operator, U)``    fedoo/core/assembly.py:1045-1112  (and with it ``get_grad_disp``
         :1285-1336, ``StressEquilibrium.update`` :191-217, ``SteadyHeatEquation.update`` heat_equation.py:64-70)
         -> Gauss-point values / first derivatives of nodal fields on the device, without the elementary-operator
-        matrices the reference builds (37 s at 1 M elements).
-
+        matrices the reference builds (37 s at 1 M elements);
   * ``StressEquilibrium.update(assembly, pb)``  fedoo/weakform/stress_equilibrium.py:191-217 (small strain) and
     ``ElasticAnisotropic.update(assembly, pb)`` fedoo/constitutivelaw/elastic_anisotropic.py:36-56 (inherited by
     ``ElasticIsotrop``): grad u, strain and sigma = H eps at the Gauss points come from ONE kernel each and are handed back
     in the reference's own containers (``sv["DispGradient"]`` 3x3 list of arrays, ``StrainTensorList`` /
     ``StressTensorList`` over Fortran-ordered (6, N) arrays); the device copy of the stress is kept for the residual.
     (The reference's own versions cost 0.6 s + 1.5 s per update at 1 M elements -- Python sums over 8 M Gauss points.)
+  * ``Problem.solve()``  fedoo/core/problem.py:277-300, only when the problem's solver is ``fedoo_b200.solver.pcg``, the
+    matrix is one this adapter assembled and the constraints are plain Dirichlet conditions: the masked Jacobi-PCG then
+    runs on the matrix still in HBM instead of the host forming ``MatCB.T @ A @ MatCB`` (``_problem_solve``).
 
 Everything else -- ``Problem``, boundary conditions, ``DiffOp``, the other constitutive laws, outputs -- stays the reference's own
 code and talks to the kernels only through ``assembly.sv`` (``TangentMatrix``, ``Stress``, ``TempGradient``, ``Temp``),
