@@ -19,8 +19,9 @@ and three more methods whose host cost would otherwise dominate once the assembl
     ``StressTensorList`` over Fortran-ordered (6, N) arrays); the device copy of the stress is kept for the residual.
     (The reference's own versions cost 0.6 s + 1.5 s per update at 1 M elements -- Python sums over 8 M Gauss points.)
   * ``Problem.solve()``  fedoo/core/problem.py:277-300, only when the problem's solver is ``fedoo_b200.solver.pcg``, the
-    matrix is one this adapter assembled and the constraints are plain Dirichlet conditions: the masked Jacobi-PCG then
-    runs on the matrix still in HBM instead of the host forming ``MatCB.T @ A @ MatCB`` (``_problem_solve``).
+    matrix is one this adapter assembled and the constraints are Dirichlet conditions and / or PeriodicBC's multi-point
+    constraints: the masked / constrained Jacobi-PCG then runs on the matrix still in HBM instead of the host forming
+    ``MatCB.T @ A @ MatCB`` (``_problem_solve``).
 
 Everything else -- ``Problem``, boundary conditions, ``DiffOp``, the other constitutive laws, outputs -- stays the reference's own
 code and talks to the kernels only through ``assembly.sv`` (``TangentMatrix``, ``Stress``, ``TempGradient``, ``Temp``),
@@ -476,32 +477,82 @@ def _gp_results(a, operator, U, n_elm_gp, use_local_dof, orig):
     return _fetch(res)
 
 
+def _mpc_map(pb, n_nodal, n_glob):
+    """The reference's multi-point constraints (``pb._MFext``: X_slave = M X + Xbc after ``M + M @ M``,
+    fedoo/core/problem.py:375-393) as the device constraint map of csrc/fdk_solve.cuh, when they have the form PeriodicBC
+    generates: every eliminated dof follows ONE free nodal dof with factor 1 plus any combination of the global
+    (mean-strain) dofs.  Entries that point at imposed or eliminated dofs carry no unknown (their share is in Xbc
+    already).  Returns None when a constraint does not fit."""
+    from . import constraint as _constraint
+
+    M = pb._MFext.tocoo()
+    blocked = np.fromiter(pb._dof_blocked, dtype=np.int64, count=len(pb._dof_blocked))
+    eliminated = np.zeros(n_nodal + n_glob, dtype=bool)
+    eliminated[np.asarray(pb._dof_slave, dtype=np.int64)] = True  # Dirichlet dofs and MPC slaves
+    is_blocked = np.zeros(n_nodal + n_glob, dtype=bool)
+    is_blocked[blocked] = True
+    slaves = np.flatnonzero(eliminated & ~is_blocked)
+    if slaves.size == 0 or slaves.max() >= n_nodal:
+        return None
+    pos = np.full(n_nodal + n_glob, -1, dtype=np.int64)
+    pos[slaves] = np.arange(slaves.size)
+    r, c, v = M.row.astype(np.int64), M.col.astype(np.int64), M.data
+    if (pos[r] < 0).any():
+        return None  # a constraint row that is not an eliminated dof
+    glob = c >= n_nodal
+    coef = np.zeros((slaves.size, n_glob))
+    np.add.at(coef, (pos[r[glob]], c[glob] - n_nodal), v[glob])
+    coef[:, is_blocked[n_nodal:]] = 0.0  # imposed global dofs: in Xbc
+    nodal = ~glob & ~eliminated[c]
+    master = np.full(slaves.size, -1, dtype=np.int64)
+    count = np.bincount(pos[r[nodal]], minlength=slaves.size)
+    if (count != 1).any() or not np.all(v[nodal] == 1.0):
+        return None
+    master[pos[r[nodal]]] = c[nodal]
+    return _constraint.MpcMap(n_nodal, n_glob, slaves, master, coef)
+
+
 def _problem_solve(pb, orig, kargs):
     """Problem.solve (fedoo/core/problem.py:277-300) when the problem's solver is ``fedoo_b200.solver.pcg``, the matrix
-    is one this adapter assembled (its device copy is still in HBM) and the constraints are plain Dirichlet conditions
-    (MatCB is then a selection of the free dofs): K_ff x_f = (B + D - K Xbc)_f by the masked Jacobi-PCG on the device,
-    without forming MatCB^T A MatCB on the host or sending K anywhere.  Anything else goes to the reference's own
-    method, which hands the host reduced system to the solver callable."""
+    is one this adapter assembled (its device copy is still in HBM) and the constraints are Dirichlet conditions (MatCB
+    is then a selection of the free dofs) and / or multi-point constraints of the periodic form (``_mpc_map``):
+    MatCB^T K MatCB y = MatCB^T (B + D - K Xbc) by the masked / constrained Jacobi-PCG on the device, matrix-free in the
+    constraints, without forming the reduced matrix on the host or sending K anywhere.  Anything else goes to the
+    reference's own method, which hands the host reduced system to the solver callable."""
     from . import solver as _solver
 
     spec = getattr(pb, "_ProblemBase__solver", None)
     A = getattr(pb, "_Problem__A", None)
     K = _device_matrix_of(A) if A is not None else None
-    if (spec is None or len(spec) < 3 or spec[1] is not _solver.pcg or K is None or getattr(pb, "_MFext", None) is not None
-            or len(pb._dof_free) == 0 or tuple(A.shape) != (pb.n_dof, pb.n_dof)):  # fmt: skip
+    if (spec is None or len(spec) < 3 or spec[1] is not _solver.pcg or K is None or len(pb._dof_free) == 0
+            or tuple(A.shape) != (pb.n_dof, pb.n_dof)):  # fmt: skip
         return orig(pb, **kargs)
+    n = pb.n_dof
+    mpc = None
+    if getattr(pb, "_MFext", None) is not None:  # multi-point constraints: the periodic form runs on the device too
+        n_glob = int(getattr(pb, "n_global_dof", 0) or 0)
+        mpc = _mpc_map(pb, n - n_glob, n_glob) if K.block is not None and K.n_glob == n_glob else None
+        if mpc is None:
+            return orig(pb, **kargs)
     opts = spec[2]
     rtol = opts.get("rtol", opts.get("tol", 1e-8))
     dev = K.data.device
-    n = pb.n_dof
-    Xbc = _core.as_device_f64(np.asarray(pb._Xbc, dtype=np.float64), dev)
+    Xbc = _core.as_device_f64(np.asarray(pb._Xbc, dtype=np.float64), dev)  # already expanded through the constraints
     rhs = -K.matvec(Xbc)
     for v in (pb._Problem__B, pb._Problem__D):
         if not (np.isscalar(v) and v == 0):
             rhs += _core.as_device_f64(np.asarray(v, dtype=np.float64), dev)
     free = torch.zeros(n, dtype=torch.uint8, device=dev)
     free[torch.from_numpy(np.asarray(pb._dof_free, dtype=np.int64)).to(dev)] = 1
-    x, it, rel = K.pcg(rhs, free_mask=free, rtol=rtol, maxiter=opts.get("maxiter"), check_every=opts.get("check_every", 10))
+    if mpc is not None:  # T^T K T y = T^T (B + D - K Xbc), X = T y + Xbc (fedoo/core/problem.py:286-298 with MatCB = T)
+        load = rhs[mpc.n_nodal :].clone()  # loads on the global dofs (fold overwrites those rows)
+        mpc.fold(rhs)
+        rhs[mpc.n_nodal :] += load
+    x, it, rel = K.pcg(rhs, free_mask=free, rtol=rtol, maxiter=opts.get("maxiter"), check_every=opts.get("check_every", 10),
+                       mpc=mpc)  # fmt: skip
+    if mpc is not None:
+        mpc.expand(x)
+        free = 1  # every entry of T y is meaningful
     _solver.info["iterations"], _solver.info["relative_residual"], _solver.info["on_device_matrix"] = it, rel, True
     if rel > rtol:
         print(f"Warning: fedoo_b200.solver.pcg: convergence to tolerance not achieved ({rel:.2e} after {it} iterations)")

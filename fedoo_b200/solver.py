@@ -13,8 +13,9 @@ runs the Jacobi-preconditioned conjugate gradient of libfdk (``fdk_pcg_jacobi``;
     pb.solve()
 
 With ``install`` in place, ``Problem.solve`` short-cuts further when it can (adapter._problem_solve): if the matrix is
-one the adapter assembled -- its values are still in HBM -- and the constraints are plain Dirichlet conditions, the
-masked PCG runs on that device matrix directly; the reduced system is never formed on the host and K is not uploaded
+one the adapter assembled -- its values are still in HBM -- and the constraints are Dirichlet conditions and / or the
+multi-point constraints PeriodicBC generates, the masked / constrained PCG runs on that device matrix directly; the
+reduced system is never formed on the host and K is not uploaded
 (``info["on_device_matrix"]`` says which way the last solve went).
 
 There is no CPU implementation behind it: without the CUDA extension and a device it raises.

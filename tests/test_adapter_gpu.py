@@ -412,9 +412,10 @@ def test_octet_truss_cells_of_the_reference_through_the_adapter(rf):
     tests/test_octet.py, here with an elastic law: PeriodicBC, mean shear 0.1, direct solve, mean stress) and
     util/meshes/octet_truss_quad.msh (tet10, 24 911 elements, vertices beyond a cluster's capacity: K and D of one update)."""
     fedoo, adapter = rf
+    import fedoo_b200
     from scipy.sparse.linalg import spsolve
 
-    def tet4_cell():
+    def tet4_cell(device_solver=False):
         fd = fedoo
         fd.ModelingSpace("3D")
         fd.mesh.import_file(os.path.join(REF, "tests", "octet_truss.msh"), name="Domain")
@@ -423,7 +424,10 @@ def test_octet_truss_cells_of_the_reference_through_the_adapter(rf):
         fd.weakform.StressEquilibrium("law", name="wf")
         fd.Assembly.create("wf", "Domain2", "tet4", name="A")
         pb = fd.problem.Linear("A")
-        pb.set_solver(lambda A, B, **kargs: spsolve(A, B))
+        if device_solver:
+            pb.set_solver(fedoo_b200.solver.pcg, rtol=1e-12)
+        else:
+            pb.set_solver(lambda A, B, **kargs: spsolve(A, B))
         pb.bc.add(fd.constraint.PeriodicBC("small_strain", dim=3))
         pb.bc.add("Dirichlet", mesh.nearest_node(mesh.bounding_box.center), "Disp", 0)
         pb.bc.add("Dirichlet", "MeanStrain", [0, 0, 0, 0.1, 0, 0])
@@ -448,6 +452,10 @@ def test_octet_truss_cells_of_the_reference_through_the_adapter(rf):
     n0 = dict(adapter.stats)
     (Ur, sr), (U, sg) = _twice(fedoo, adapter, tet4_cell)
     assert abs(sr[3]) > 100 and np.abs(U - Ur).max() <= 1e-9 * np.abs(Ur).max() and np.abs(sg - sr).max() <= 1e-9 * np.abs(sr).max()
+    fedoo.Assembly.delete_memory()
+    Up, sp = tet4_cell(device_solver=True)  # the periodic constraints of a real unstructured cell, solved on the device
+    assert fedoo_b200.solver.info["on_device_matrix"]
+    assert np.abs(Up - Ur).max() <= 1e-7 * np.abs(Ur).max() and np.abs(sp - sr).max() <= 1e-7 * np.abs(sr).max()
     ref, got = _twice(fedoo, adapter, tet10_cell)
     assert got[0].shape == (144798, 144798) and got[0].nnz == 10103202
     _cmp(ref, got)
@@ -459,7 +467,7 @@ def test_device_pcg_through_the_reference_solver_hook(rf):
     """``pb.set_solver(fedoo_b200.solver.pcg, rtol=...)``: the reference's solver hook (fedoo/core/base.py:512-537).  The
     reference's own cantilever case, solved by its scipy direct solver and by the device Jacobi-PCG, K from the kernels
     both times; and a periodic cell, whose reduced system MatCB^T A MatCB (core/problem.py:277-298) carries the multi-point
-    constraints and is formed by the reference on the host."""
+    constraints of PeriodicBC -- converted to the device constraint map and solved matrix-free."""
     fedoo, adapter = rf
     import fedoo_b200
     from scipy.sparse.linalg import spsolve
@@ -504,10 +512,18 @@ def test_device_pcg_through_the_reference_solver_hook(rf):
         Ug = case(fedoo_b200.solver.pcg, rtol=1e-12)
         assert fedoo_b200.solver.info["iterations"] > 10 and fedoo_b200.solver.info["relative_residual"] <= 1e-12
         assert np.abs(Ug - Ud).max() <= 1e-8 * np.abs(Ud).max()
-        # plain Dirichlet conditions: the masked PCG ran on the matrix still in HBM (no host reduced system, no upload);
-        # multi-point constraints: the reference formed MatCB^T A MatCB on the host and the callable solved that
-        assert fedoo_b200.solver.info["on_device_matrix"] == (case is beam)
-        assert adapter.stats["device_solves"] == n0 + (1 if case is beam else 0)
+        # Dirichlet conditions, and the multi-point constraints PeriodicBC generates: the masked / constrained PCG ran on
+        # the matrix still in HBM (no reduced system on the host, no upload)
+        assert fedoo_b200.solver.info["on_device_matrix"] and adapter.stats["device_solves"] == n0 + 1
+    # the callable on its own (what the reference calls when the short-cut does not apply): a host reduced system
+    from scipy import sparse
+
+    rng = np.random.default_rng(0)
+    B = sparse.random(400, 400, density=0.02, random_state=1, format="csr")
+    A = (B @ B.T + sparse.identity(400) * 5.0).tocsr()
+    b = rng.standard_normal(400)
+    x = fedoo_b200.solver.pcg(A, b, rtol=1e-12, solver_type=None)  # foreign keyword arguments are ignored
+    assert not fedoo_b200.solver.info["on_device_matrix"] and np.abs(A @ x - b).max() <= 1e-9 * np.abs(b).max()
 
 
 @pytest.mark.gpu
