@@ -524,24 +524,33 @@ def _problem_solve(pb, orig, kargs):
     spec = getattr(pb, "_ProblemBase__solver", None)
     A = getattr(pb, "_Problem__A", None)
     K = _device_matrix_of(A) if A is not None else None
-    if (spec is None or len(spec) < 3 or spec[1] is not _solver.pcg or K is None or len(pb._dof_free) == 0
-            or tuple(A.shape) != (pb.n_dof, pb.n_dof)):  # fmt: skip
+    func = spec[1] if spec is not None and len(spec) >= 3 else None
+    bound = dict(getattr(func, "keywords", None) or {})  # functools.partial(fedoo_b200.solver.pcg, rtol=...) is fine too
+    if (getattr(func, "func", func) is not _solver.pcg or K is None or len(pb._dof_free) == 0
+            or not hasattr(A, "shape") or len(A.shape) != 2):  # fmt: skip
         return orig(pb, **kargs)
     n = pb.n_dof
+    n_glob = int(getattr(pb, "n_global_dof", 0) or 0)
+    n_mat = int(K.shape[0])  # n, or the nodal size when the matrix was assembled before the global dofs existed (the
+    # reference resizes it at this point, core/problem.py:283-284: empty trailing rows and columns)
     mpc = None
     if getattr(pb, "_MFext", None) is not None:  # multi-point constraints: the periodic form runs on the device too
-        n_glob = int(getattr(pb, "n_global_dof", 0) or 0)
-        mpc = _mpc_map(pb, n - n_glob, n_glob) if K.block is not None and K.n_glob == n_glob else None
+        ok = K.block is not None and ((n_mat == n and K.n_glob == n_glob) or (n_mat == n - n_glob and K.n_glob == 0))
+        mpc = _mpc_map(pb, n - n_glob, n_glob) if ok else None
         if mpc is None:
             return orig(pb, **kargs)
-    opts = spec[2]
+    elif n_mat != n:
+        return orig(pb, **kargs)
+    opts = {**bound, **{k: v for k, v in spec[2].items() if v is not None}}
     rtol = opts.get("rtol", opts.get("tol", 1e-8))
     dev = K.data.device
     Xbc = _core.as_device_f64(np.asarray(pb._Xbc, dtype=np.float64), dev)  # already expanded through the constraints
-    rhs = -K.matvec(Xbc)
+    rhs = torch.zeros(n, dtype=torch.float64, device=dev)
+    rhs[:n_mat] -= K.matvec(Xbc[:n_mat] if n_mat < n else Xbc)[:n_mat]
     for v in (pb._Problem__B, pb._Problem__D):
         if not (np.isscalar(v) and v == 0):
-            rhs += _core.as_device_f64(np.asarray(v, dtype=np.float64), dev)
+            vd = _core.as_device_f64(np.asarray(v, dtype=np.float64), dev)
+            rhs[: vd.numel()] += vd
     free = torch.zeros(n, dtype=torch.uint8, device=dev)
     free[torch.from_numpy(np.asarray(pb._dof_free, dtype=np.int64)).to(dev)] = 1
     if mpc is not None:  # T^T K T y = T^T (B + D - K Xbc), X = T y + Xbc (fedoo/core/problem.py:286-298 with MatCB = T)

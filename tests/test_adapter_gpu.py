@@ -356,7 +356,7 @@ def test_reference_homogenized_stiffness_on_the_kernels(rf):
     def direct(A, B, **kargs):  # the reference forwards solver_type=None to scipy's spsolve, which refuses it
         return spsolve(A, B)
 
-    def run():
+    def run(solver=direct):
         fd = fedoo
         fd.ModelingSpace("3D")
         mesh = fd.mesh.box_mesh(nx=7, ny=7, nz=7, elm_type="hex8", name="Domain")
@@ -365,13 +365,24 @@ def test_reference_homogenized_stiffness_on_the_kernels(rf):
         fd.constitutivelaw.ElasticIsotrop(E, 0.3, name="law")
         fd.weakform.StressEquilibrium("law", name="wf")
         a = fd.Assembly.create("wf", "Domain", "hex8", name="A")
-        return np.array(fd.homogen.get_homogenized_stiffness(a, solver=direct))
+        return np.array(fd.homogen.get_homogenized_stiffness(a, solver=solver))
 
     n0 = dict(adapter.stats)
     Cr, C = _twice(fedoo, adapter, run)
     assert adapter.stats["assembled"] > n0["assembled"] and adapter.stats["delegated"] == n0["delegated"]
     assert Cr.shape == (6, 6) and Cr[0, 0] > 1.3e5 and np.abs(Cr - Cr.T).max() < 1e-6 * Cr[0, 0]
     assert np.abs(C - Cr).max() <= 1e-9 * np.abs(Cr).max()
+    # the six load cases on the device: the reference's perturbation problem with the device PCG as its solver
+    import functools
+
+    import fedoo_b200
+
+    fedoo.Assembly.delete_memory()
+    fedoo.Problem.get_all().pop("_perturbation", None)
+    n1 = adapter.stats["device_solves"]
+    Cd = run(functools.partial(fedoo_b200.solver.pcg, rtol=1e-11))
+    assert adapter.stats["device_solves"] == n1 + 6 and fedoo_b200.solver.info["on_device_matrix"]
+    assert np.abs(Cd - Cr).max() <= 1e-7 * np.abs(Cr).max()
 
 
 @pytest.mark.gpu
