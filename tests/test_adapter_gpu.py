@@ -392,7 +392,7 @@ def test_nonlinear_driver_with_elastic_law_identical_to_reference(rf):
     own post-processing (get_results at nodes) on top."""
     fedoo, adapter = rf
 
-    def run():
+    def run(solver=None):
         fd = fedoo
         fd.ModelingSpace("3D")
         mesh = fd.mesh.box_mesh(nx=11, ny=4, nz=4, x_min=0, x_max=10, y_min=0, y_max=1, z_min=0, z_max=1, elm_type="hex8", name="Domain")  # fmt: skip
@@ -401,6 +401,8 @@ def test_nonlinear_driver_with_elastic_law_identical_to_reference(rf):
         fd.weakform.StressEquilibrium("law", name="wf")
         a = fd.Assembly.create("wf", "Domain", "hex8", name="A")
         pb = fd.problem.NonLinear("A")
+        if solver is not None:
+            pb.set_solver(solver, rtol=1e-12)
         pb.set_nr_criterion("Displacement", tol=1e-8, max_subiter=5)
         pb.bc.add("Dirichlet", mesh.find_nodes("X", 0), "Disp", 0)
         pb.bc.add("Dirichlet", mesh.find_nodes("X", 10), "DispY", -0.5)
@@ -415,6 +417,14 @@ def test_nonlinear_driver_with_elastic_law_identical_to_reference(rf):
     assert np.abs(U - Ur).max() <= 1e-9 * np.abs(Ur).max()
     assert np.abs(S - Sr).max() <= 1e-9 * np.abs(Sr).max()
     assert np.abs(D - Dr).max() <= 1e-9 * np.abs(Dr).max()
+    # the same Newton-Raphson run with every linear solve on the device (tangent matrix still in HBM)
+    import fedoo_b200
+
+    fedoo.Assembly.delete_memory()
+    n1 = adapter.stats["device_solves"]
+    Up, Sp, _ = run(fedoo_b200.solver.pcg)
+    assert adapter.stats["device_solves"] >= n1 + 4
+    assert np.abs(Up - Ur).max() <= 1e-7 * np.abs(Ur).max() and np.abs(Sp - Sr).max() <= 1e-6 * np.abs(Sr).max()
 
 
 @pytest.mark.gpu
