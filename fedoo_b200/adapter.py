@@ -524,6 +524,8 @@ def _problem_solve(pb, orig, kargs):
     spec = getattr(pb, "_ProblemBase__solver", None)
     A = getattr(pb, "_Problem__A", None)
     K = _device_matrix_of(A) if A is not None else None
+    if not all(hasattr(pb, name) for name in ("_Problem__B", "_Problem__D", "_Xbc", "_dof_free", "_dof_slave")):
+        return orig(pb, **kargs)  # not the Problem this short-cut was written against (fedoo/core/problem.py:56-70)
     func = spec[1] if spec is not None and len(spec) >= 3 else None
     bound = dict(getattr(func, "keywords", None) or {})  # functools.partial(fedoo_b200.solver.pcg, rtol=...) is fine too
     if (getattr(func, "func", func) is not _solver.pcg or K is None or len(pb._dof_free) == 0
