@@ -610,3 +610,44 @@ def test_adapter_classification_cpu():
         assert Hn[0, 3].max() == 0
     with pytest.raises(ValueError):
         adapter._normalize_tangent(fedoo.constitutivelaw.ElasticIsotrop(np.ones(5), 0.3).get_tangent_matrix(None, "3D"), a)
+
+
+@pytest.mark.parametrize("kind", ["box", "octet"])
+@pytest.mark.parametrize("imposed", [True, False])
+def test_reference_constraints_as_device_map_cpu(kind, imposed):
+    """adapter._mpc_map on the CPU: the multi-point constraints the reference's PeriodicBC generates (after its
+    ``M + M @ M`` coupling, fedoo/core/problem.py:375-393), converted to the device constraint map, give the SAME
+    change-of-basis matrix as the reference's MatCB on the free dofs -- structured hex8 cell and the reference's
+    unstructured octet-truss cell, mean strain imposed (those columns move to Xbc) or loaded (they stay unknowns)."""
+    if not _ref_available():
+        pytest.skip("oracle/_ref not built in this environment")
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import fedoo as fd
+    from fedoo_b200 import adapter
+
+    fd.Assembly.delete_memory()
+    fd.ModelingSpace("3D")
+    if kind == "box":
+        mesh, et, name = fd.mesh.box_mesh(nx=5, ny=4, nz=4, elm_type="hex8", name="Domain"), "hex8", "Domain"
+    else:
+        fd.mesh.import_file(os.path.join(REF, "tests", "octet_truss.msh"), name="Domain")
+        mesh, et, name = fd.Mesh["Domain2"], "tet4", "Domain2"
+    fd.constitutivelaw.ElasticIsotrop(1e5, 0.3, name="law")
+    fd.weakform.StressEquilibrium("law", name="wf")
+    fd.Assembly.create("wf", name, et, name="A")
+    pb = fd.problem.Linear("A")
+    pb.bc.add(fd.constraint.PeriodicBC("small_strain", dim=3))
+    pb.bc.add("Dirichlet", mesh.nearest_node(mesh.bounding_box.center), "Disp", 0)
+    pb.bc.add("Dirichlet" if imposed else "Neumann", "MeanStrain", [0, 0.01, 0, 0.02, 0, 0])
+    pb.apply_boundary_conditions()
+    n, ng = pb.n_dof, pb.n_global_dof
+    mpc = adapter._mpc_map(pb, n - ng, ng)
+    assert mpc is not None and len(mpc.slave_h) > 100
+    free = np.asarray(pb._dof_free)
+    d = abs(mpc.to_scipy().tocsc()[:, free] - pb._Problem__MatCB)
+    assert d.nnz == 0 or d.max() == 0.0
