@@ -605,6 +605,13 @@ def install(fedoo=None, strict=True, state_updates=True):
     def problem_solve(self, **kargs):
         return _problem_solve(self, orig_solve, kargs)
 
+    orig_del = A.__dict__.get("delete_memory")  # a staticmethod object (core/assembly.py:755-774)
+
+    def delete_memory():
+        (orig_del.__func__ if isinstance(orig_del, staticmethod) else orig_del)()
+        _asm.Assembly.delete_memory()  # patterns, plans and device meshes cached behind the reference's assemblies
+        _device_K.clear()
+
     problem_solve.__doc__ = orig_solve.__doc__
     assemble_global_mat.__doc__ = orig_asm.__doc__
     get_gp_results.__doc__ = orig_gp.__doc__
@@ -615,8 +622,10 @@ def install(fedoo=None, strict=True, state_updates=True):
     W.update = wf_update
     L.update = law_update
     P.solve = problem_solve
+    if orig_del is not None:
+        A.delete_memory = staticmethod(delete_memory)
     _installed[id(A)] = {"cls": A, "orig": (orig_asm, orig_gp), "strict": flag, "state": state,
-                         "wf": (W, orig_wf), "law": (L, orig_law), "solve": (P, orig_solve)}  # fmt: skip
+                         "wf": (W, orig_wf), "law": (L, orig_law), "solve": (P, orig_solve), "del": orig_del}  # fmt: skip
     return fedoo
 
 
@@ -630,3 +639,5 @@ def uninstall(fedoo=None):
         rec["wf"][0].update = rec["wf"][1]
         rec["law"][0].update = rec["law"][1]
         rec["solve"][0].solve = rec["solve"][1]
+        if rec["del"] is not None:
+            A.delete_memory = rec["del"]
