@@ -46,6 +46,18 @@
 #define FDK_HEX_REFLECT 0
 #endif
 
+#ifndef FDK_HEX_MONO
+// 1: hex8 geometry phase in the monomial basis of the trilinear element (see the kernel, phase 1): twelve lanes of a warp
+// compute the coefficient vectors of the warp's four elements, every task then forms J in 27 FMA and builds the
+// reference gradients from the Gauss point's signs -- 124 instead of 194 shared-memory wavefronts per warp-task and no
+// table.  MEASURED on B200 (round 2, 8 M elements): 20.5 ms against 17.65 ms for the table version (J2 plate: 22.5
+// against 19.8 ms).  A warp runs ONE geometry task per cluster, so the phase follows the length of its dependency chain,
+// not the wavefront count: coordinate loads -> 8-term sums on 12 of 32 lanes -> store -> warp sync -> loads -> J is
+// longer than loads -> J.  (The same basis is a clear win where one thread integrates a whole element: the
+// residual-only kernel k_elem_force_hex8, 3.37 -> 2.49 ms.)  Kept as a compile-time option, off.
+#define FDK_HEX_MONO 0
+#endif
+
 namespace fdk {
 
 // hex8: the reference gradients at Gauss point g are those at Gauss point 0 of the element REFLECTED along the axes
@@ -105,7 +117,9 @@ struct IsoLayout {
   // [le][node][3] (stride 24 doubles: the 16 lanes of a half-warp = 2 elements x 8 Gauss points hit 16 distinct 8-byte banks)
   static constexpr bool HEXREF = El::ID == FDK_HEX8 && COLORED && ISO_COLS_ADJ && (FDK_HEX_REFLECT != 0);
   static constexpr int XESTR = NNE * DIM;
-  __host__ __device__ static long xe_doubles(const fdk_plan& p) { return HEXREF ? (long)p.cap_te * XESTR : 0; }
+  // hex8: monomial-basis geometry (phase 1 of the kernel): 7 coefficient vectors per touched element share the array
+  static constexpr bool MONO = El::ID == FDK_HEX8 && !HEXREF && (FDK_HEX_MONO != 0);
+  __host__ __device__ static long xe_doubles(const fdk_plan& p) { return (HEXREF || MONO) ? (long)p.cap_te * XESTR : 0; }
   __host__ __device__ static long stage_doubles(const fdk_plan& p) {
     return COLORED ? (long)((p.cap_inc + 3) / 4) * 32 * BLK : (long)p.cap_inc * ISTR;
   }
@@ -347,6 +361,96 @@ __global__ void __launch_bounds__(THREADS, (PHYS == PHYS_ISO && 1024 / THREADS >
     for (int task = tid; task < n_te * GCH; task += THREADS) {
       const int le = task / GCH, gl = task - le * GCH, g = ch * GCH + gl;
       const unsigned char* lc = sLconn + le * NNE;
+      if constexpr (IL::MONO && GCH == NGP) {
+        // ---- monomial basis of the trilinear element.  A nodal field is c0 + c1 xi + c2 eta + c3 zeta + c4 xi eta +
+        // c5 eta zeta + c6 xi zeta + c7 xi eta zeta with c_m = 1/8 sum_k h_m(k) x_k (h_m: products of the nodes' signs).
+        // The 32 tasks of a warp are the 8 Gauss points of 4 elements: twelve of its lanes first compute the seven
+        // coefficient vectors of those elements, one (element, component) each -- 8 coordinate loads instead of the 24
+        // every task made -- and park them in shared memory; after a warp-level sync every task reads its element's 21
+        // coefficients, forms J in 27 FMA (instead of 72 from 24 coordinates and 24 table entries) and builds the
+        // reference gradients of the eight shape functions from the Gauss point's signs: no table loads at all.
+        const int lane = tid & 31;
+        {
+          const int left = n_te * GCH - (task - lane);  // tasks of this warp's round: the first `left` lanes are here
+          if (lane < 12 && (lane / 3) * 8 < left) {
+            const int el = le - (lane >> 3) + lane / 3;  // first element of the warp + lane / 3
+            const int d = lane - (lane / 3) * 3;
+            const unsigned char* l8 = sLconn + el * NNE;
+            double c[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const double x = sX[(int)l8[k] * XSTR + d];
+              const double s0 = HexRef::bit(k, 0) ? 1.0 : -1.0, s1 = HexRef::bit(k, 1) ? 1.0 : -1.0, s2 = HexRef::bit(k, 2) ? 1.0 : -1.0;
+              c[0] += s0 * x;
+              c[1] += s1 * x;
+              c[2] += s2 * x;
+              c[3] += (s0 * s1) * x;
+              c[4] += (s1 * s2) * x;
+              c[5] += (s0 * s2) * x;
+              c[6] += (s0 * s1 * s2) * x;
+            }
+            double2* co = reinterpret_cast<double2*>(sXe + el * IL::XESTR + d * 8);  // [component][8]: 7 coefficients + pad
+            co[0] = make_double2(0.125 * c[0], 0.125 * c[1]);
+            co[1] = make_double2(0.125 * c[2], 0.125 * c[3]);
+            co[2] = make_double2(0.125 * c[4], 0.125 * c[5]);
+            co[3] = make_double2(0.125 * c[6], 0.0);
+          }
+          __syncwarp(left >= 32 ? 0xffffffffu : ((1u << left) - 1u));
+        }
+        constexpr double GA = 0.5773502691896258;
+        const double xi = (g & 4) ? GA : -GA, et = (g & 2) ? GA : -GA, ze = (g & 1) ? GA : -GA;
+        double J[3][3];
+        {
+          const double xe_ = xi * et, ez = et * ze, xz = xi * ze;
+#pragma unroll
+          for (int x = 0; x < 3; ++x) {  // one component at a time: eight doubles live
+            const double2* c2 = reinterpret_cast<const double2*>(sXe + le * IL::XESTR + x * 8);
+            const double2 c01 = c2[0], c23 = c2[1], c45 = c2[2], c6_ = c2[3];
+            // c0..c6 = coefficients of xi, eta, zeta, xi eta, eta zeta, xi zeta, xi eta zeta
+            J[0][x] = fma(c6_.x, ez, fma(c45.y, ze, fma(c23.y, et, c01.x)));
+            J[1][x] = fma(c6_.x, xz, fma(c45.x, ze, fma(c23.y, xi, c01.y)));
+            J[2][x] = fma(c6_.x, xe_, fma(c45.y, xi, fma(c45.x, et, c23.x)));
+          }
+        }
+        double iJ[3][3];
+        const double det = invert<3>(J, iJ);
+        const double s = sqrt(sW[g] * fabs(det));
+        if constexpr (GEN) {
+          if (do_bts) {  // sqrt(w) sigma of this Gauss point: with sqrt(w) dN/dx it gives w B^T sigma
+            const int64_t e = task == tid ? my_te_elem : p.cl_te_elem[cur.te0 + le];
+            const double* sp = a.stress_gp + 6 * ((int64_t)g * p.n_elems + e);
+            double* so = sSig + (long)task * SGS;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) so[k] = s * sp[k];
+          }
+        }
+        {
+          const double s8 = 0.125 * s;
+#pragma unroll
+          for (int x = 0; x < 3; ++x)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) iJ[x][r] *= s8;
+        }
+        // 8 dN_k / dxi_r = s_kr f_a(k) f_b(k), f_d(k) = 1 + s_kd xi_d: two values per axis, four products per direction
+        const double fx[2] = {1.0 - xi, 1.0 + xi}, fy[2] = {1.0 - et, 1.0 + et}, fz[2] = {1.0 - ze, 1.0 + ze};
+        double2* out = reinterpret_cast<double2*>(sG + le * ESTR + gl * GSTR);
+#pragma unroll
+        for (int k = 0; k < NNE; k += 2) {
+          double v[6];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int b0 = HexRef::bit(k + h, 0), b1 = HexRef::bit(k + h, 1), b2 = HexRef::bit(k + h, 2);
+            const double A = (b0 ? 1.0 : -1.0) * (fy[b1] * fz[b2]);
+            const double B = (b1 ? 1.0 : -1.0) * (fx[b0] * fz[b2]);
+            const double C = (b2 ? 1.0 : -1.0) * (fx[b0] * fy[b1]);
+#pragma unroll
+            for (int x = 0; x < 3; ++x) v[3 * h + x] = fma(iJ[x][2], C, fma(iJ[x][1], B, iJ[x][0] * A));
+          }
+#pragma unroll
+          for (int t = 0; t < 3; ++t) out[(k * 3) / 2 + t] = make_double2(v[2 * t], v[2 * t + 1]);
+        }
+        continue;
+      }
       const double* dN = sdN + g * TSTR;
       int ln[NNE];
       if constexpr (HEXREF) {
