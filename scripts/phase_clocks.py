@@ -16,7 +16,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-CLK_LIB = os.path.join(ROOT, "fedoo_b200", "_fdk_clk.so")
+CLK_LIB = os.environ.get("FDK_CLK_LIB") or os.path.join(ROOT, "fedoo_b200", "_fdk_clk.so")  # FDK_CLK_LIB: a library built by hand
 os.environ["FDK_LIB"] = CLK_LIB  # before fedoo_b200 is imported (fedoo_b200/_lib.py reads it at import time)
 
 NAMES = ["-", "phase 0 wait", "phase 1 (geometry)", "phase 2 (blocks)", "staging / phase 2m", "phase 3a heavy",
@@ -26,6 +26,8 @@ NAMES = ["-", "phase 0 wait", "phase 1 (geometry)", "phase 2 (blocks)", "staging
 def build():
     from fedoo_b200 import build as b
 
+    if os.environ.get("FDK_CLK_LIB"):
+        return
     cmd = b.nvcc_command(out=CLK_LIB)
     cmd.insert(1, "-DFDK_PHASE_CLOCKS")
     if not os.path.exists(CLK_LIB) or any(os.path.getmtime(CLK_LIB) < os.path.getmtime(d) for d in b.DEPS):
