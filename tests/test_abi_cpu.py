@@ -75,6 +75,27 @@ def test_no_cpu_fallback():
         a.assemble_global_mat()
 
 
+def test_solver_callable_has_no_cpu_fallback():
+    """fedoo_b200.solver.pcg (the callable handed to the reference's Problem.set_solver) validates its arguments on the
+    host and then needs the device: without one it raises, it does not quietly solve on the CPU."""
+    import numpy as np
+    import torch
+    from scipy import sparse
+
+    import fedoo_b200 as fd
+
+    A = sparse.identity(5, format="csr") * 2.0
+    with pytest.raises(ValueError):
+        fd.solver.pcg(sparse.csr_matrix(np.ones((3, 4))), np.ones(3))
+    with pytest.raises(ValueError):
+        fd.solver.pcg(A, np.ones(4))
+    assert fd.solver.pcg(sparse.csr_matrix((0, 0)), np.zeros(0)).shape == (0,)
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(fd.FdkError):
+        fd.solver.pcg(A, np.ones(5))
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "fedoo_b200")
     for dirpath, _, files in os.walk(pkg):
